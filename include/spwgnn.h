@@ -1,0 +1,121 @@
+/* spwgnn.h -- C ABI of libspwgnn.so: the B200 (sm_100a) hot path of SPWGNN's tower-stability
+ * propagation network.  Plain pointers and sizes only; no torch / C++ types cross this boundary.
+ *
+ * What each entry point replaces in the reference (paths under /root/reference/src):
+ *   spw_edges_*        the relation-matrix loops            main.py:66-81, TowerCreator.py:415-428,
+ *                                                           JengaBuilder.py:313-326
+ *   spw_forward        the Keras graph behind .predict/.fit Networks.py:22-99 (+ Blocks.py:12-91)
+ *   spw_bce_grad       loss + its gradient seed             Networks.py:102 (binary_crossentropy)
+ *   spw_backward       TF autodiff of that graph            Networks.py:101-102 (compile/fit)
+ * The reference has no FFI of its own (pure Python on Keras); INTEGRATION.md shows the ctypes
+ * binding a maintainer would add to Networks.py.
+ *
+ * Conventions
+ *   - every pointer is a DEVICE pointer unless the name ends in _host; the caller owns all memory;
+ *     the library allocates nothing persistent and never synchronises the device.
+ *   - every call enqueues kernels on `stream` (a cudaStream_t passed as void*) and returns.
+ *   - return value: 0 = ok, negative = SpwStatus; spw_last_error() gives a thread-local message.
+ *   - towers are ragged: tower t owns nodes [node_off[t], node_off[t+1]); 2 <= N_t <= SPW_MAX_NODES
+ *     is not required (N_t may be 0 or 1: such towers simply have no edges), N_t <= SPW_MAX_NODES is.
+ *   - float tensors are fp32, row-major; all pointers must be 16-byte aligned.
+ */
+#ifndef SPWGNN_H
+#define SPWGNN_H
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SPW_VERSION 1
+#define SPW_MAX_NODES 64      /* blocks per tower handled by the edge builder's per-tower CTA */
+#define SPW_N_STEPS 5         /* Networks.py:83 */
+#define SPW_PROP_DIM 100      /* Networks.py:29 */
+
+typedef enum {
+  SPW_OK = 0,
+  SPW_ERR_BAD_ARG = -1,       /* null / misaligned pointer, negative size */
+  SPW_ERR_UNSUPPORTED = -2,   /* shape outside the limits above */
+  SPW_ERR_WORKSPACE = -3,     /* workspace too small */
+  SPW_ERR_LAUNCH = -4         /* CUDA launch failure (message carries cudaGetErrorString) */
+} SpwStatus;
+
+/* The 22 parameter tensors, Keras Dense layout kernel[in][out], bias[out] (Blocks.py:22-27):
+ *   rm  2->150->150->150->150   om 2->100->100   rmp 350->150->150->100   omp 300->100->101
+ * Used const for weights, mutable for gradients (same struct, same shapes). */
+typedef struct {
+  float* rm_w[4];  float* rm_b[4];
+  float* om_w[2];  float* om_b[2];
+  float* rmp_w[3]; float* rmp_b[3];
+  float* omp_w[2]; float* omp_b[2];
+} SpwParams;
+
+/* A packed batch of tower graphs.  Built by spw_edges_count + spw_edges_fill. */
+typedef struct {
+  int32_t n_towers;
+  int32_t n_nodes;            /* sum of N_t */
+  int32_t n_edges;            /* active edges (host copy of edge_off[n_towers]) */
+  const int32_t* node_off;    /* [n_towers+1] */
+  const int32_t* in_off;      /* [n_nodes+1]  receiver-major CSR: in-edges of node i are [in_off[i], in_off[i+1]) */
+  const int32_t* in_snd;      /* [n_edges]    sender node (global id) of receiver-major edge */
+  const int32_t* in_rcv;      /* [n_edges]    receiver node of receiver-major edge */
+  const int32_t* out_off;     /* [n_nodes+1]  slot-order (sender-major) CSR: out-edges of node i */
+  const int32_t* out_pos;     /* [n_edges]    receiver-major position of slot-order edge e */
+} SpwGraph;
+
+int spw_version(void);
+const char* spw_last_error(void);
+
+/* ---- edge-index construction (replaces main.py:66-81) ------------------------------------
+ * Edge m->j (m != j, same tower) is active iff sqrt(dx*dx + dy*dy) < thr evaluated in IEEE
+ * double with separately rounded multiplies/add/sqrt -- numpy's np.linalg.norm(...,axis=1) --
+ * or unconditionally when fully_connected != 0.  Slot order: sender m outer, receiver j inner,
+ * slot = m*(N-1) + (j < m ? j : j-1)  (main.py:69-81).
+ *
+ * spw_edges_count: per-node degrees and the per-tower edge prefix sum.
+ *   deg_out/deg_in [n_nodes], edge_off [n_towers+1] (edge_off[n_towers] = total active edges).
+ *   max_nodes_per_tower: the caller's max N_t (host value; checked against SPW_MAX_NODES).     */
+int spw_edges_count(const double* pos_xy /*[n_nodes][2]*/, const int32_t* node_off, int32_t n_towers,
+                    int32_t n_nodes, int32_t max_nodes_per_tower, double thr, int fully_connected,
+                    int32_t* deg_out, int32_t* deg_in, int32_t* edge_off, void* stream);
+
+/* spw_edges_fill: the edge list in slot order (snd/rcv/slot, the reference's non-zero columns)
+ * plus the receiver-major / sender-major CSR views the kernels consume.  Any of snd/rcv/slot may
+ * be NULL.  All outputs sized by edge_off[n_towers] (read it back from spw_edges_count, or size
+ * for the worst case sum N_t*(N_t-1)).                                                          */
+int spw_edges_fill(const double* pos_xy, const int32_t* node_off, int32_t n_towers, int32_t n_nodes,
+                   int32_t max_nodes_per_tower, double thr, int fully_connected, const int32_t* edge_off,
+                   int32_t* snd, int32_t* rcv, int32_t* slot,
+                   int32_t* in_off, int32_t* in_snd, int32_t* in_rcv,
+                   int32_t* out_off, int32_t* out_pos, void* stream);
+
+/* ---- network ---------------------------------------------------------------------------- */
+/* Bytes of workspace spw_forward/spw_backward need.  training != 0 also reserves the node-level
+ * state the backward pass reads (5 propagation steps x per-node activations) and per-edge
+ * gradient staging.  The same workspace must be passed, untouched, to spw_backward.            */
+size_t spw_workspace_bytes(int32_t n_nodes, int32_t n_edges, int training);
+
+/* Forward (Networks.py:58-96).  obj [n_nodes][3] = [x, y, width]/170 (main.py:91).
+ * logits [n_nodes] (channel 0 of the last object-propagator output, Networks.py:94);
+ * probs  [n_nodes] sigmoid(logits) or NULL.  training: keep state for spw_backward
+ * (dropout is not applied: see DESIGN.md).                                                     */
+int spw_forward(const SpwParams* w, const SpwGraph* g, const float* obj, float* logits, float* probs,
+                void* workspace, size_t workspace_bytes, int training, void* stream);
+
+/* Keras binary_crossentropy on probabilities clipped to [1e-7, 1-1e-7] (Networks.py:102), mean over
+ * `count` outputs (pass the GLOBAL number of blocks when data-parallel).  Writes dlogits [n_nodes]
+ * = d(mean loss)/d(logit) and adds the summed loss and the number of correct (p>0.5)==target
+ * predictions into stats[0], stats[1] (double[2], must be zeroed by the caller).               */
+int spw_bce_grad(const float* logits, const float* target, int32_t n_nodes, double count,
+                 float* dlogits, double* stats, void* stream);
+
+/* Backward: gradients of sum_i dlogits[i]*logit[i] w.r.t. all 22 tensors, written (not
+ * accumulated) to grads.  Deterministic: fixed tile->CTA assignment, fixed-order reductions.   */
+int spw_backward(const SpwParams* w, const SpwGraph* g, const float* obj, const float* dlogits,
+                 void* workspace, size_t workspace_bytes, const SpwParams* grads, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SPWGNN_H */

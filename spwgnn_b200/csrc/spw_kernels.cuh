@@ -1,0 +1,680 @@
+// spw_kernels.cuh -- forward / backward kernels of the propagation network (fp32, sm_100a).
+//
+// Math (reference: /root/reference/src/Networks.py:58-96, restated in SURVEY.md section 3.3), with
+// two exact algebraic refactorings that remove 2.5x of the per-edge multiply-adds:
+//   (1) the first relation-propagator layer is linear in its concatenated input
+//       (Networks.py:86-87):  W1.[c_e, p_s, p_r] + b1 = (W1a.c_e + b1) + W1b.p_s + W1c.p_r
+//       -> A_e = W1a.c_e + b1 once per edge, S_i = W1b.p_i and R_i = W1c.p_i once per NODE per step;
+//   (2) its last layer is linear and is followed by the sum over incoming edges
+//       (Networks.py:87-88):  sum_e (W3.h2_e + b3) = W3.(sum_e h2_e) + deg_i.b3
+//       -> the receiver-segmented sum runs on the 150-wide hidden state, W3 runs once per node.
+// Per edge and step only h2 = relu(W2.relu(A_e + S_s + R_r) + b2) remains (one 150x150 layer).
+//
+// Tiles: 128 rows (edges in receiver-major order, or nodes) x <=160 columns per CTA, 256 threads,
+// thread tile 16x5 (or 16x4), activations chained through shared memory, weights streamed
+// from L2 (spw_common.cuh).  All reductions run in a fixed order: results are bit-reproducible.
+#pragma once
+#include "spw_common.cuh"
+
+namespace spw {
+
+// =================================================================================================
+// weight packing: Keras [in][out] tensors -> zero-padded [Kp][ldw] matrices (optionally transposed)
+// =================================================================================================
+struct PackDesc {
+  const float* src; int src_ld, row0, col0, K, N, transpose;
+  float* dst; int Kp, ldw;
+};
+constexpr int kMaxPack = 28;
+struct PackArgs { PackDesc d[kMaxPack]; int n; };
+
+__global__ void __launch_bounds__(256) k_pack_weights(PackArgs a) {
+  const PackDesc d = a.d[blockIdx.y];
+  const int total = d.Kp * d.ldw;
+  for (int idx = blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += gridDim.x * blockDim.x) {
+    const int k = idx / d.ldw, n = idx - k * d.ldw;
+    float v = 0.f;
+    if (k < d.K && n < d.N)
+      v = d.transpose ? d.src[(size_t)(d.row0 + n) * d.src_ld + d.col0 + k]
+                      : d.src[(size_t)(d.row0 + k) * d.src_ld + d.col0 + n];
+    d.dst[idx] = v;
+  }
+}
+
+// =================================================================================================
+// small elementwise / per-node kernels
+// =================================================================================================
+// object-encoder layer 0 (Networks.py:65-66,71,76; K = 2): out[i][c] = relu(y*W[0][c] + w*W[1][c] + b[c])
+__global__ void __launch_bounds__(256) k_obj_enc0(const float* __restrict__ obj, int n, const float* __restrict__ W,
+                                                  const float* __restrict__ b, float* __restrict__ out) {
+  const int total = n * kDP;
+  for (int idx = blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += gridDim.x * blockDim.x) {
+    const int i = idx / kDP, c = idx - i * kDP;
+    const float y = obj[3 * (size_t)i + 1], w = obj[3 * (size_t)i + 2];
+    out[idx] = relu_f(fmaf(w, W[kDP + c], fmaf(y, W[c], b[c])));
+  }
+}
+
+__global__ void __launch_bounds__(256) k_deg_to_float(const int32_t* __restrict__ in_off, int n, float* __restrict__ degf) {
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x)
+    degf[i] = (float)(in_off[i + 1] - in_off[i]);
+}
+
+// head (Networks.py:93-96): logit_i = U5_i . V2[:,0] + c2[0]; one warp per node
+__global__ void __launch_bounds__(256) k_logit(const float* __restrict__ U, int n, const float* __restrict__ V2raw,
+                                               const float* __restrict__ c2raw, float* __restrict__ logits,
+                                               float* __restrict__ probs) {
+  const int lane = threadIdx.x & 31;
+  const int wpb = blockDim.x >> 5;
+  for (int i = blockIdx.x * wpb + (threadIdx.x >> 5); i < n; i += gridDim.x * wpb) {
+    float s = 0.f;
+    for (int c = lane; c < kDP; c += 32) s = fmaf(U[(size_t)i * kDP + c], V2raw[(size_t)c * (kDP + 1)], s);
+#pragma unroll
+    for (int m = 16; m >= 1; m >>= 1) s += __shfl_xor_sync(0xffffffffu, s, m);
+    if (lane == 0) {
+      const float z = s + c2raw[0];
+      logits[i] = z;
+      if (probs) probs[i] = 1.f / (1.f + expf(-z));
+    }
+  }
+}
+
+// dUpre5[i][c] = dlogit_i * V2[c][0] * [U5[i][c] > 0]
+__global__ void __launch_bounds__(256) k_logit_bwd(const float* __restrict__ dlogits, const float* __restrict__ U, int n,
+                                                   const float* __restrict__ V2raw, float* __restrict__ dU) {
+  const int total = n * kDP;
+  for (int idx = blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += gridDim.x * blockDim.x) {
+    const int i = idx / kDP, c = idx - i * kDP;
+    dU[idx] = U[idx] > 0.f ? dlogits[i] * V2raw[(size_t)c * (kDP + 1)] : 0.f;
+  }
+}
+
+// Keras binary_crossentropy on clipped probabilities + d(mean loss)/d(logit) (Networks.py:102)
+__global__ void __launch_bounds__(256) k_bce_grad(const float* __restrict__ logits, const float* __restrict__ target,
+                                                  int n, double inv_count, float* __restrict__ dlogits,
+                                                  double* __restrict__ stats) {
+  __shared__ double s_loss[256];
+  __shared__ double s_acc[256];
+  double loss = 0.0, correct = 0.0;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    const float z = logits[i], y = target[i];
+    const float p = 1.f / (1.f + expf(-z));
+    const float eps = 1e-7f;
+    const float pc = fminf(fmaxf(p, eps), 1.f - eps);
+    loss += -((double)y * (double)logf(pc) + (1.0 - (double)y) * (double)logf(1.f - pc));
+    correct += ((p > 0.5f) == (y > 0.5f)) ? 1.0 : 0.0;
+    // d/dz: clip passes gradient only strictly inside (eps, 1-eps); dL/dpc * dp/dz = (pc - y)
+    const bool inside = (p > eps) && (p < 1.f - eps);
+    dlogits[i] = inside ? (float)((double)(pc - y) * inv_count) : 0.f;
+  }
+  s_loss[threadIdx.x] = loss; s_acc[threadIdx.x] = correct;
+  __syncthreads();
+  for (int off = 128; off >= 1; off >>= 1) {
+    if ((int)threadIdx.x < off) { s_loss[threadIdx.x] += s_loss[threadIdx.x + off]; s_acc[threadIdx.x] += s_acc[threadIdx.x + off]; }
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) { atomicAdd(&stats[0], s_loss[0]); atomicAdd(&stats[1], s_acc[0]); }
+}
+
+// =================================================================================================
+// generic fused linear layer on node rows:  Y = post( act( sum_s X_s.W_s + rowscale*bias + addend ) )
+// =================================================================================================
+struct LinSeg { const float* X; const float* W; int ldx; int K; int Kp; };
+struct LinArgs {
+  int M, nseg, N;
+  LinSeg seg[3];
+  const float* bias;       // [N] or null
+  const float* rowscale;   // [M] per-row multiplier of the bias (in-degree) or null
+  const float* addend;     // [M][ld_add] pre-activation addend or null
+  int ld_add;
+  int act;                 // 0 none, 1 relu, 2 tanh
+  const float* mulsrc;     // post-activation factor source or null
+  int ld_mul;
+  int mulmode;             // 1: *= [mulsrc > 0]   2: *= (1 - mulsrc^2)
+  float* Y; int ldy;       // columns N..ldy-1 are written as 0
+  int accumulate;          // Y += result
+};
+
+template <int CN>
+__global__ void __launch_bounds__(kThreads, 1) k_linear(LinArgs a) {
+  SPW_DYN_SMEM(smem_raw);
+  float* smem = reinterpret_cast<float*>(smem_raw);
+  constexpr int LDW = CN * 32;
+  float* Xs[3];
+  int off = 0;
+  for (int s = 0; s < a.nseg; ++s) { Xs[s] = smem + off; off += kTM * a.seg[s].Kp; }
+  float* Wst = smem + off;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int ntiles = (a.M + kTM - 1) / kTM;
+  for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+    const int r0 = tile * kTM;
+    const int rows = imin(kTM, a.M - r0);
+    for (int s = 0; s < a.nseg; ++s) {
+      const LinSeg sg = a.seg[s];
+      const int k4 = sg.Kp >> 2;
+      for (int idx = tid; idx < kTM * k4; idx += kThreads) {
+        const int r = idx / k4, c = (idx - r * k4) << 2;
+        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (r < rows) {
+          const float* p = sg.X + (size_t)(r0 + r) * sg.ldx + c;
+          if (c + 3 < sg.K) {
+            v = *reinterpret_cast<const float4*>(p);
+          } else {
+            if (c < sg.K) v.x = p[0];
+            if (c + 1 < sg.K) v.y = p[1];
+            if (c + 2 < sg.K) v.z = p[2];
+          }
+        }
+        *reinterpret_cast<float4*>(Xs[s] + (size_t)r * sg.Kp + c) = v;
+      }
+    }
+    __syncthreads();
+    float acc[16][CN];
+    zero_acc<16, CN>(acc);
+    for (int s = 0; s < a.nseg; ++s) gemm_tile_acc<16, CN>(acc, Xs[s], a.seg[s].Kp, warp * 16, a.seg[s].W, a.seg[s].Kp, Wst);
+    // epilogue (registers -> global)
+#pragma unroll
+    for (int r = 0; r < 16; ++r) {
+      const int row = warp * 16 + r;
+      if (row >= rows) continue;
+      const size_t grow = (size_t)(r0 + row);
+      const float rs = a.rowscale ? a.rowscale[grow] : 1.f;
+#pragma unroll
+      for (int i = 0; i < CN; ++i) {
+        const int col = lane * CN + i;
+        if (col >= a.ldy) continue;
+        float v = 0.f;
+        if (col < a.N) {
+          v = acc[r][i];
+          if (a.bias) v = fmaf(rs, a.bias[col], v);
+          if (a.addend) v += a.addend[grow * a.ld_add + col];
+          if (a.act == 1) v = relu_f(v);
+          else if (a.act == 2) v = tanhf(v);
+          if (a.mulmode == 1) v = a.mulsrc[grow * a.ld_mul + col] > 0.f ? v : 0.f;
+          else if (a.mulmode == 2) { const float m = a.mulsrc[grow * a.ld_mul + col]; v *= (1.f - m * m); }
+          if (a.accumulate) v += a.Y[grow * a.ldy + col];
+        }
+        a.Y[grow * a.ldy + col] = v;
+      }
+    }
+    __syncthreads();
+  }
+}
+
+// =================================================================================================
+// generic weight gradient on node rows: part[cta] = X^T . dY (+ bias row from a ones / rowscale column)
+// =================================================================================================
+struct WgArgs {
+  int M;                   // rows to contract over
+  const float* X; int ldx; int Kin; int xmod;   // X row = r % xmod (xmod = 0: r)
+  const float* rowscale;   // value of the virtual column Kin (null: 1.0)
+  int rsmod;               // rowscale row = r % rsmod (rsmod = 0: r)
+  const float* dY; int ldy; int N;
+  float* part;             // [gridDim.x][16*TA * 16*TB]
+};
+
+template <int TA, int TB>
+__global__ void __launch_bounds__(kThreads, 1) k_wgrad(WgArgs a) {
+  SPW_DYN_SMEM(smem_raw);
+  float* Xs = reinterpret_cast<float*>(smem_raw);
+  constexpr int LX = 16 * TA, LY = 16 * TB;
+  float* Ys = Xs + kTM * LX;
+  const int tid = threadIdx.x;
+  float acc[TA][TB];
+#pragma unroll
+  for (int i = 0; i < TA; ++i)
+#pragma unroll
+    for (int j = 0; j < TB; ++j) acc[i][j] = 0.f;
+  const int ntiles = (a.M + kTM - 1) / kTM;
+  for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+    const int r0 = tile * kTM;
+    const int rows = imin(kTM, a.M - r0);
+    for (int idx = tid; idx < kTM * LX; idx += kThreads) {
+      const int r = idx / LX, c = idx - r * LX;
+      float v = 0.f;
+      if (r < rows) {
+        const size_t xr = a.xmod ? (size_t)((r0 + r) % a.xmod) : (size_t)(r0 + r);
+        if (c < a.Kin) v = a.X[xr * a.ldx + c];
+        else if (c == a.Kin) v = a.rowscale ? a.rowscale[a.rsmod ? (size_t)((r0 + r) % a.rsmod) : (size_t)(r0 + r)] : 1.f;
+      }
+      Xs[idx] = v;
+    }
+    for (int idx = tid; idx < kTM * LY; idx += kThreads) {
+      const int r = idx / LY, c = idx - r * LY;
+      Ys[idx] = (r < rows && c < a.N) ? a.dY[(size_t)(r0 + r) * a.ldy + c] : 0.f;
+    }
+    __syncthreads();
+    wgrad_tile_acc<TA, TB>(acc, Xs, LX, Ys, LY, kTM);
+    __syncthreads();
+  }
+  wgrad_flush<TA, TB>(acc, a.part + (size_t)blockIdx.x * (LX * LY), false);
+}
+
+// fixed-order sum over per-CTA partials -> compact Keras-layout gradient (+ bias from row Kin)
+struct RedArgs {
+  const float* part; int nparts; int part_stride; int src_ld;
+  int Kin, N;
+  float* dW; int dst_ld, dst_row0, dst_col0;   // null: skip the matrix
+  float* db; int db_off;                       // null: skip the bias row
+};
+__global__ void __launch_bounds__(256) k_reduce_parts(RedArgs a) {
+  const int total = (a.Kin + 1) * a.N;
+  for (int idx = blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += gridDim.x * blockDim.x) {
+    const int k = idx / a.N, n = idx - k * a.N;
+    if (k == a.Kin && !a.db) continue;
+    if (k < a.Kin && !a.dW) continue;
+    float s = 0.f;
+    const float* p = a.part + (size_t)k * a.src_ld + n;
+    for (int c = 0; c < a.nparts; ++c) s += p[(size_t)c * a.part_stride];
+    if (k < a.Kin) a.dW[(size_t)(a.dst_row0 + k) * a.dst_ld + a.dst_col0 + n] = s;
+    else a.db[a.db_off + n] = s;
+  }
+}
+
+// =================================================================================================
+// edge kernels
+// =================================================================================================
+// shared helper: activation tile epilogue  dst[row][col] = f(acc) with the bias "ones" column at kDE
+//   (col 150 = 1 for valid rows so that a later X^T.dY also yields the bias gradient, col 151 = 0)
+template <int ROWS, class F>
+__device__ __forceinline__ void store_act_tile(const float (&acc)[ROWS][5], float* dst, int warp, int lane, int rows, F f) {
+#pragma unroll
+  for (int r = 0; r < ROWS; ++r) {
+    const int row = warp * ROWS + r;
+#pragma unroll
+    for (int i = 0; i < 5; ++i) {
+      const int col = lane * 5 + i;
+      if (col >= kDEP) continue;
+      float v = 0.f;
+      if (row < rows) {
+        if (col < kDE) v = f(acc[r][i], row, col);
+        else if (col == kDE) v = 1.f;
+      }
+      dst[(size_t)row * kDEP + col] = v;
+    }
+  }
+}
+
+// relation-encoder layer 0 into a shared tile (Networks.py:58-62,69,75; K = 2):
+//   X0[r][k] = relu(dx*W0[0][k] + dy*W0[1][k] + b0[k]),   [dx,dy] = pos_receiver - pos_sender
+template <int TMR>
+__device__ __forceinline__ void build_x0(float* X0, float* sdx, float* sdy, const float* __restrict__ obj,
+                                         const int32_t* __restrict__ in_snd, const int32_t* __restrict__ in_rcv, int e0,
+                                         int rows, const float* __restrict__ W0, const float* __restrict__ b0) {
+  const int tid = threadIdx.x;
+  if (tid < TMR) {
+    float dx = 0.f, dy = 0.f;
+    if (tid < rows) {
+      const int s = in_snd[e0 + tid], rc = in_rcv[e0 + tid];
+      dx = obj[3 * (size_t)rc] - obj[3 * (size_t)s];
+      dy = obj[3 * (size_t)rc + 1] - obj[3 * (size_t)s + 1];
+    }
+    sdx[tid] = dx; sdy[tid] = dy;
+  }
+  __syncthreads();
+  for (int idx = tid; idx < TMR * kDEP; idx += kThreads) {
+    const int r = idx / kDEP, k = idx - r * kDEP;
+    float v = 0.f;
+    if (r < rows) {
+      if (k < kDE) v = relu_f(fmaf(sdy[r], W0[kDE + k], fmaf(sdx[r], W0[k], b0[k])));
+      else if (k == kDE) v = 1.f;
+    }
+    X0[idx] = v;
+  }
+}
+
+struct EdgeEncArgs {
+  int E;
+  const int32_t* in_snd; const int32_t* in_rcv;
+  const float* obj;
+  const float* W0; const float* b0;                       // raw rm.w0 [2][150], rm.b0
+  const float* RM1; const float* RM2; const float* RM3;   // packed [152][160]
+  const float* b1; const float* b2; const float* b3;      // raw biases [150]
+  const float* W1A; const float* bA;                      // packed rmp.w0[0:150], raw rmp.b0
+  float* A;                                               // [E][152]
+};
+
+// K2a: c_e = relu(rm(diff))  (4 layers) and A_e = W1a.c_e + b1, all inside one CTA tile
+__global__ void __launch_bounds__(kThreads, 1) k_edge_encode(EdgeEncArgs a) {
+  SPW_DYN_SMEM(smem_raw);
+  float* Xa = reinterpret_cast<float*>(smem_raw);
+  float* Xb = Xa + kTM * kDEP + 8;
+  float* Wst = Xb + kTM * kDEP + 8;
+  float* sdx = Wst + 2 * kKT * kLdwE;
+  float* sdy = sdx + kTM;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int ntiles = (a.E + kTM - 1) / kTM;
+  for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+    const int e0 = tile * kTM;
+    const int rows = imin(kTM, a.E - e0);
+    build_x0<kTM>(Xa, sdx, sdy, a.obj, a.in_snd, a.in_rcv, e0, rows, a.W0, a.b0);
+    __syncthreads();
+    float acc[16][5];
+    zero_acc<16, 5>(acc);
+    gemm_tile_acc<16, 5>(acc, Xa, kDEP, warp * 16, a.RM1, kDEP, Wst);
+    store_act_tile<16>(acc, Xb, warp, lane, rows, [&](float v, int, int c) { return relu_f(v + a.b1[c]); });
+    __syncthreads();
+    zero_acc<16, 5>(acc);
+    gemm_tile_acc<16, 5>(acc, Xb, kDEP, warp * 16, a.RM2, kDEP, Wst);
+    store_act_tile<16>(acc, Xa, warp, lane, rows, [&](float v, int, int c) { return relu_f(v + a.b2[c]); });
+    __syncthreads();
+    zero_acc<16, 5>(acc);
+    gemm_tile_acc<16, 5>(acc, Xa, kDEP, warp * 16, a.RM3, kDEP, Wst);
+    store_act_tile<16>(acc, Xb, warp, lane, rows, [&](float v, int, int c) { return relu_f(v + a.b3[c]); });
+    __syncthreads();
+    zero_acc<16, 5>(acc);
+    gemm_tile_acc<16, 5>(acc, Xb, kDEP, warp * 16, a.W1A, kDEP, Wst);
+#pragma unroll
+    for (int r = 0; r < 16; ++r) {
+      const int row = warp * 16 + r;
+      if (row >= rows) continue;
+#pragma unroll
+      for (int i = 0; i < 5; ++i) {
+        const int col = lane * 5 + i;
+        if (col >= kDEP) continue;
+        a.A[(size_t)(e0 + row) * kDEP + col] = col < kDE ? acc[r][i] + a.bA[col] : 0.f;
+      }
+    }
+    __syncthreads();
+  }
+}
+
+// H1 tile: relu(A_e + S_sender + R_receiver), 128-bit coalesced row gathers, one warp per row
+__device__ __forceinline__ void build_h1(float* H1, int* srcv, const float* __restrict__ A, const float* __restrict__ S,
+                                         const float* __restrict__ R, const int32_t* __restrict__ in_snd,
+                                         const int32_t* __restrict__ in_rcv, int e0, int rows) {
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  constexpr int C4 = kDEP / 4;   // 38 float4 per row
+  for (int r = warp; r < kTM; r += kThreads / 32) {
+    float4* dst = reinterpret_cast<float4*>(H1 + (size_t)r * kDEP);
+    if (r < rows) {
+      const int e = e0 + r;
+      const int s = in_snd[e], rc = in_rcv[e];
+      if (lane == 0) srcv[r] = rc;
+      const float4* a4 = reinterpret_cast<const float4*>(A + (size_t)e * kDEP);
+      const float4* s4 = reinterpret_cast<const float4*>(S + (size_t)s * kDEP);
+      const float4* r4 = reinterpret_cast<const float4*>(R + (size_t)rc * kDEP);
+      for (int c = lane; c < C4; c += 32) {
+        const float4 x = a4[c], y = s4[c], z = r4[c];
+        float4 h;
+        h.x = relu_f(x.x + y.x + z.x); h.y = relu_f(x.y + y.y + z.y);
+        h.z = relu_f(x.z + y.z + z.z); h.w = relu_f(x.w + y.w + z.w);
+        if (c == C4 - 1) { h.z = 1.f; h.w = 0.f; }   // columns 150 (bias ones) and 151 (pad)
+        dst[c] = h;
+      }
+    } else {
+      if (lane == 0) srcv[r] = -1;
+      for (int c = lane; c < C4; c += 32) dst[c] = make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+  }
+}
+
+struct EdgeStepArgs {
+  int E;
+  const int32_t* in_snd; const int32_t* in_rcv; const int32_t* in_off;
+  const float* A; const float* S; const float* R;     // [E][152], [n][152], [n][152]
+  const float* W2; const float* b2;                   // packed rmp.w1, raw rmp.b1
+  float* H2S;                                         // [n][152] sum over in-edges of h2
+  float* part_first; float* part_last;                // [ntiles][152] segments cut by a tile boundary
+};
+
+// K2b: per step -- gather, hidden layer 2, relu, deterministic receiver-segmented sum
+__global__ void __launch_bounds__(kThreads, 1) k_edge_step(EdgeStepArgs a) {
+  SPW_DYN_SMEM(smem_raw);
+  float* Xa = reinterpret_cast<float*>(smem_raw);
+  float* Xb = Xa + kTM * kDEP + 8;
+  float* Wst = Xb + kTM * kDEP + 8;
+  int* srcv = reinterpret_cast<int*>(Wst + 2 * kKT * kLdwE);
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int ntiles = (a.E + kTM - 1) / kTM;
+  for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+    const int e0 = tile * kTM;
+    const int rows = imin(kTM, a.E - e0);
+    build_h1(Xa, srcv, a.A, a.S, a.R, a.in_snd, a.in_rcv, e0, rows);
+    __syncthreads();
+    float acc[16][5];
+    zero_acc<16, 5>(acc);
+    gemm_tile_acc<16, 5>(acc, Xa, kDEP, warp * 16, a.W2, kDEP, Wst);
+    store_act_tile<16>(acc, Xb, warp, lane, rows, [&](float v, int, int c) { return relu_f(v + a.b2[c]); });
+    __syncthreads();
+    // receiver-segmented sum in row (= ascending sender = slot) order; one warp per node
+    const int n_first = srcv[0], n_last = srcv[rows - 1];
+    for (int node = n_first + warp; node <= n_last; node += kThreads / 32) {
+      const int s0 = a.in_off[node], s1 = a.in_off[node + 1];
+      const int lo = imax(s0, e0) - e0, hi = imin(s1, e0 + rows) - e0;
+      if (hi <= lo) continue;
+      float* dst;
+      if (s0 >= e0 && s1 <= e0 + rows) dst = a.H2S + (size_t)node * kDEP;
+      else if (s0 < e0) dst = a.part_first + (size_t)tile * kDEP;
+      else dst = a.part_last + (size_t)tile * kDEP;
+      for (int c = lane; c < kDEP; c += 32) {
+        float s = 0.f;
+        if (c < kDE)
+          for (int r = lo; r < hi; ++r) s += Xb[(size_t)r * kDEP + c];
+        dst[c] = s;
+      }
+    }
+    __syncthreads();
+  }
+}
+
+// segments cut by a tile boundary: H2S[node] = last-part of tile b + first-part of tile b+1
+__global__ void __launch_bounds__(256) k_fix_boundaries(int E, const int32_t* __restrict__ in_rcv,
+                                                        const float* __restrict__ part_first,
+                                                        const float* __restrict__ part_last, float* __restrict__ H2S) {
+  const int lane = threadIdx.x & 31, wpb = blockDim.x >> 5;
+  const int ntiles = (E + kTM - 1) / kTM;
+  for (int b = blockIdx.x * wpb + (threadIdx.x >> 5); b + 1 < ntiles; b += gridDim.x * wpb) {
+    const int e = (b + 1) * kTM;
+    const int node = in_rcv[e - 1];
+    if (in_rcv[e] != node) continue;
+    for (int c = lane; c < kDEP; c += 32)
+      H2S[(size_t)node * kDEP + c] = part_last[(size_t)b * kDEP + c] + part_first[(size_t)(b + 1) * kDEP + c];
+  }
+}
+
+struct EdgeStepBwdArgs {
+  int E;
+  const int32_t* in_snd; const int32_t* in_rcv;
+  const float* A; const float* S; const float* R;
+  const float* W2; const float* b2; const float* W2T;
+  const float* dH2S;        // [n][152]
+  float* dA;                // [E][152] accumulated over the 5 steps
+  float* DH1;               // [E][152] d(pre-activation of h1) of this step
+  float* partW2;            // [gridDim.x][160*160]
+  int first;                // first step processed (l = 5): dA is written, not accumulated
+};
+
+// K4b: per step backward of K2b -- recompute h1/h2, dW2 partials, d(h1 pre-activation)
+__global__ void __launch_bounds__(kThreads, 1) k_edge_step_bwd(EdgeStepBwdArgs a) {
+  SPW_DYN_SMEM(smem_raw);
+  float* Xa = reinterpret_cast<float*>(smem_raw);
+  float* Xb = Xa + kTM * kDEP + 8;
+  float* Wst = Xb + kTM * kDEP + 8;
+  int* srcv = reinterpret_cast<int*>(Wst + 2 * kKT * kLdwE);
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int ntiles = (a.E + kTM - 1) / kTM;
+  float* part = a.partW2 + (size_t)blockIdx.x * (160 * 160);
+  for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+    const int e0 = tile * kTM;
+    const int rows = imin(kTM, a.E - e0);
+    build_h1(Xa, srcv, a.A, a.S, a.R, a.in_snd, a.in_rcv, e0, rows);
+    __syncthreads();
+    float acc[16][5];
+    zero_acc<16, 5>(acc);
+    gemm_tile_acc<16, 5>(acc, Xa, kDEP, warp * 16, a.W2, kDEP, Wst);
+    // dH2pre = dH2S[receiver] * [h2pre > 0]   (no ones column: this tile is a dY operand)
+#pragma unroll
+    for (int r = 0; r < 16; ++r) {
+      const int row = warp * 16 + r;
+      const int rc = row < rows ? srcv[row] : -1;
+#pragma unroll
+      for (int i = 0; i < 5; ++i) {
+        const int col = lane * 5 + i;
+        if (col >= kDEP) continue;
+        float v = 0.f;
+        if (rc >= 0 && col < kDE && acc[r][i] + a.b2[col] > 0.f) v = a.dH2S[(size_t)rc * kDEP + col];
+        Xb[(size_t)row * kDEP + col] = v;
+      }
+    }
+    __syncthreads();
+    {
+      float wacc[10][10];
+#pragma unroll
+      for (int i = 0; i < 10; ++i)
+#pragma unroll
+        for (int j = 0; j < 10; ++j) wacc[i][j] = 0.f;
+      wgrad_tile_acc<10, 10>(wacc, Xa, kDEP, Xb, kDEP, kTM);
+      wgrad_flush<10, 10>(wacc, part, !(a.first && tile == (int)blockIdx.x));
+    }
+    zero_acc<16, 5>(acc);
+    gemm_tile_acc<16, 5>(acc, Xb, kDEP, warp * 16, a.W2T, kDEP, Wst);
+#pragma unroll
+    for (int r = 0; r < 16; ++r) {
+      const int row = warp * 16 + r;
+      if (row >= rows) continue;
+      const size_t g = (size_t)(e0 + row) * kDEP;
+#pragma unroll
+      for (int i = 0; i < 5; ++i) {
+        const int col = lane * 5 + i;
+        if (col >= kDEP) continue;
+        float v = 0.f;
+        if (col < kDE && Xa[(size_t)row * kDEP + col] > 0.f) v = acc[r][i];
+        a.DH1[g + col] = v;
+        a.dA[g + col] = a.first ? v : a.dA[g + col] + v;
+      }
+    }
+    __syncthreads();
+  }
+}
+
+// dS_i = sum over out-edges, dR_i = sum over in-edges of DH1 (fixed order); one warp per node
+__global__ void __launch_bounds__(256) k_gather_dsr(int n, const int32_t* __restrict__ in_off,
+                                                    const int32_t* __restrict__ out_off,
+                                                    const int32_t* __restrict__ out_pos, const float* __restrict__ DH1,
+                                                    float* __restrict__ dS, float* __restrict__ dR) {
+  const int lane = threadIdx.x & 31, wpb = blockDim.x >> 5;
+  constexpr int C4 = kDEP / 4;
+  for (int i = blockIdx.x * wpb + (threadIdx.x >> 5); i < n; i += gridDim.x * wpb) {
+    const int i0 = in_off[i], i1 = in_off[i + 1], o0 = out_off[i], o1 = out_off[i + 1];
+    for (int c = lane; c < C4; c += 32) {
+      float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
+      for (int e = i0; e < i1; ++e) {
+        const float4 v = reinterpret_cast<const float4*>(DH1 + (size_t)e * kDEP)[c];
+        s.x += v.x; s.y += v.y; s.z += v.z; s.w += v.w;
+      }
+      reinterpret_cast<float4*>(dR + (size_t)i * kDEP)[c] = s;
+      s = make_float4(0.f, 0.f, 0.f, 0.f);
+      for (int e = o0; e < o1; ++e) {
+        const float4 v = reinterpret_cast<const float4*>(DH1 + (size_t)out_pos[e] * kDEP)[c];
+        s.x += v.x; s.y += v.y; s.z += v.z; s.w += v.w;
+      }
+      reinterpret_cast<float4*>(dS + (size_t)i * kDEP)[c] = s;
+    }
+  }
+}
+
+struct EdgeEncBwdArgs {
+  int E;
+  const int32_t* in_snd; const int32_t* in_rcv;
+  const float* obj;
+  const float* W0; const float* b0;
+  const float* RM1; const float* RM2; const float* RM3;
+  const float* b1; const float* b2; const float* b3;
+  const float* RM1T; const float* RM2T; const float* RM3T; const float* W1AT;
+  const float* dA;          // [E][152] total gradient w.r.t. A_e
+  float* partM;             // [gridDim.x][4][160*160]: W1A, RM3, RM2, RM1
+  float* part0;             // [gridDim.x][3][152]: d rm.w0 row 0, row 1, d rm.b0
+};
+
+constexpr int kTMB = 64;    // rows per tile in the encoder backward (5 resident activation tiles)
+
+// K4a: backward of K2a -- recompute the 4 encoder layers per 64-edge tile, then walk back
+__global__ void __launch_bounds__(kThreads, 1) k_edge_encode_bwd(EdgeEncBwdArgs a) {
+  SPW_DYN_SMEM(smem_raw);
+  constexpr int TILE = kTMB * kDEP + 8;
+  float* Ba = reinterpret_cast<float*>(smem_raw);
+  float* Bb = Ba + TILE;
+  float* Bc = Bb + TILE;
+  float* Bd = Bc + TILE;
+  float* Be = Bd + TILE;
+  float* Wst = Be + TILE;
+  float* sdx = Wst + 2 * kKT * kLdwE;
+  float* sdy = sdx + kTMB;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int ntiles = (a.E + kTMB - 1) / kTMB;
+  float* partM = a.partM + (size_t)blockIdx.x * (4 * 160 * 160);
+  float* part0 = a.part0 + (size_t)blockIdx.x * (3 * kDEP);
+  bool first = true;
+  for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+    const int e0 = tile * kTMB;
+    const int rows = imin(kTMB, a.E - e0);
+    // ---- forward recompute: X0 (Ba) -> X1 (Bb) -> X2 (Bc) -> C (Bd)
+    build_x0<kTMB>(Ba, sdx, sdy, a.obj, a.in_snd, a.in_rcv, e0, rows, a.W0, a.b0);
+    // dA tile -> Be (a dY operand: no ones column)
+    for (int idx = tid; idx < kTMB * (kDEP / 4); idx += kThreads) {
+      const int r = idx / (kDEP / 4), c = idx - r * (kDEP / 4);
+      float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (r < rows) v = reinterpret_cast<const float4*>(a.dA + (size_t)(e0 + r) * kDEP)[c];
+      reinterpret_cast<float4*>(Be + (size_t)r * kDEP)[c] = v;
+    }
+    __syncthreads();
+    float acc[8][5];
+    zero_acc<8, 5>(acc);
+    gemm_tile_acc<8, 5>(acc, Ba, kDEP, warp * 8, a.RM1, kDEP, Wst);
+    store_act_tile<8>(acc, Bb, warp, lane, rows, [&](float v, int, int c) { return relu_f(v + a.b1[c]); });
+    __syncthreads();
+    zero_acc<8, 5>(acc);
+    gemm_tile_acc<8, 5>(acc, Bb, kDEP, warp * 8, a.RM2, kDEP, Wst);
+    store_act_tile<8>(acc, Bc, warp, lane, rows, [&](float v, int, int c) { return relu_f(v + a.b2[c]); });
+    __syncthreads();
+    zero_acc<8, 5>(acc);
+    gemm_tile_acc<8, 5>(acc, Bc, kDEP, warp * 8, a.RM3, kDEP, Wst);
+    store_act_tile<8>(acc, Bd, warp, lane, rows, [&](float v, int, int c) { return relu_f(v + a.b3[c]); });
+    __syncthreads();
+    // ---- backward.  Each stage: dW += X^T.dY (bias via the ones column), dX = (dY.W^T) * relu'
+    auto stage = [&](const float* X, float* dY, const float* WT, float* dXout, float* part) {
+      float wacc[10][10];
+#pragma unroll
+      for (int i = 0; i < 10; ++i)
+#pragma unroll
+        for (int j = 0; j < 10; ++j) wacc[i][j] = 0.f;
+      wgrad_tile_acc<10, 10>(wacc, X, kDEP, dY, kDEP, kTMB);
+      wgrad_flush<10, 10>(wacc, part, !first);
+      zero_acc<8, 5>(acc);
+      gemm_tile_acc<8, 5>(acc, dY, kDEP, warp * 8, WT, kDEP, Wst);
+      // mask with the layer input's relu (X holds post-relu values; X > 0 <=> pre-activation > 0)
+#pragma unroll
+      for (int r = 0; r < 8; ++r) {
+        const int row = warp * 8 + r;
+#pragma unroll
+        for (int i = 0; i < 5; ++i) {
+          const int col = lane * 5 + i;
+          if (col >= kDEP) continue;
+          float v = 0.f;
+          if (row < rows && col < kDE && X[(size_t)row * kDEP + col] > 0.f) v = acc[r][i];
+          dXout[(size_t)row * kDEP + col] = v;
+        }
+      }
+      __syncthreads();
+    };
+    stage(Bd, Be, a.W1AT, Be, partM);                    // A = C.W1a + b   : dC  -> Be (in place)
+    stage(Bc, Be, a.RM3T, Bd, partM + 1 * 160 * 160);    // C = relu(X2.W3) : dX2 -> Bd
+    stage(Bb, Bd, a.RM2T, Be, partM + 2 * 160 * 160);    // X2              : dX1 -> Be
+    stage(Ba, Be, a.RM1T, Bd, partM + 3 * 160 * 160);    // X1              : dX0 -> Bd
+    // layer 0 (K = 2): d rm.w0[0][k] = sum_r dx_r dX0[r][k], [1][k] with dy, d rm.b0[k] = sum_r dX0[r][k]
+    for (int k = tid; k < kDE; k += kThreads) {
+      float g0 = 0.f, g1 = 0.f, gb = 0.f;
+      for (int r = 0; r < rows; ++r) {
+        const float d = Bd[(size_t)r * kDEP + k];
+        g0 = fmaf(sdx[r], d, g0); g1 = fmaf(sdy[r], d, g1); gb += d;
+      }
+      if (first) { part0[k] = g0; part0[kDEP + k] = g1; part0[2 * kDEP + k] = gb; }
+      else { part0[k] += g0; part0[kDEP + k] += g1; part0[2 * kDEP + k] += gb; }
+    }
+    first = false;
+    __syncthreads();
+  }
+}
+
+}  // namespace spw

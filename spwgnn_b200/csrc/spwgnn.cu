@@ -1,0 +1,560 @@
+// spwgnn.cu -- C ABI (include/spwgnn.h) and launch sequences of the SPWGNN B200 hot path.
+// Build: nvcc -gencode arch=compute_100a,code=sm_100a -lineinfo -O3 --shared -Xcompiler -fPIC
+#include "../../include/spwgnn.h"
+#include "spw_common.cuh"
+#include "spw_edges.cuh"
+#include "spw_kernels.cuh"
+
+#include <stdarg.h>
+#include <stdio.h>
+#include <string.h>
+
+using namespace spw;
+
+namespace {
+
+thread_local char g_err[512] = "";
+
+int fail(int code, const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+  return code;
+}
+
+bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
+
+int check_launch(const char* what) {
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return fail(SPW_ERR_LAUNCH, "%s: %s", what, cudaGetErrorString(e));
+  return SPW_OK;
+}
+
+int num_sms() {
+  static int sms = 0;
+  if (sms == 0) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    if (sms <= 0) sms = 148;
+  }
+  return sms;
+}
+
+constexpr int kMaxCtas = 160;   // upper bound on persistent-grid size used to size partial buffers
+
+// ---- packed weight buffer -----------------------------------------------------------------------
+enum PackId {
+  P_RM1, P_RM2, P_RM3, P_W1A, P_W1B, P_W1C, P_W2, P_W3, P_V1A, P_V1B, P_V1C, P_V2P, P_OM1,
+  P_RM1T, P_RM2T, P_RM3T, P_W1AT, P_W1BT, P_W1CT, P_W2T, P_W3T, P_V1AT, P_V1BT, P_V1CT, P_V2PT, P_OM1T,
+  P_COUNT
+};
+struct PackShape { int Kp, ldw; };
+// forward matrices [in][out]; transposed ones [out][in]
+const PackShape kPackShape[P_COUNT] = {
+    {152, 160}, {152, 160}, {152, 160}, {152, 160}, {100, 160}, {100, 160}, {152, 160}, {152, 128},
+    {100, 128}, {100, 128}, {100, 128}, {100, 128}, {100, 128},
+    {152, 160}, {152, 160}, {152, 160}, {152, 160}, {152, 128}, {152, 128}, {152, 160}, {100, 160},
+    {100, 128}, {100, 128}, {100, 128}, {100, 128}, {100, 128}};
+
+size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
+
+struct Layout {
+  size_t pack[P_COUNT];
+  size_t Q1, Q, degf, A, PF, PL;
+  size_t P, S, R, H2S, G, U;     // per-step arrays (training: 5 slots; inference: fewer)
+  int slotsP, slotsSR, slotsN;   // number of step slots for P / (S,R) / (H2S,G,U)
+  // backward
+  size_t dU, dG, T, dS, dR, dH2S, DP, dQ, dQ1, dA, DH1, partE, partM, part0, partN;
+  size_t total;   // floats
+};
+
+constexpr size_t kPartNodeElems = 160 * 160;   // >= (16*TA)*(16*TB) for every node-level wgrad config
+
+Layout make_layout(int64_t n, int64_t E, int training) {
+  Layout L;
+  size_t off = 0;
+  auto take = [&](size_t floats) { size_t o = off; off = align_up(off + floats, 64); return o; };
+  for (int i = 0; i < P_COUNT; ++i) L.pack[i] = take((size_t)kPackShape[i].Kp * kPackShape[i].ldw);
+  const size_t nt = (size_t)((E + kTM - 1) / kTM) + 1;
+  L.Q1 = take(n * kDP);
+  L.Q = take(n * kDP);
+  L.degf = take(n);
+  L.A = take((size_t)E * kDEP + 8);
+  L.PF = take(nt * kDEP);
+  L.PL = take(nt * kDEP);
+  L.slotsP = training ? 5 : 2;
+  L.slotsSR = training ? 5 : 1;
+  L.slotsN = training ? 5 : 1;
+  L.P = take((size_t)L.slotsP * n * kDP);
+  L.S = take((size_t)L.slotsSR * n * kDEP);
+  L.R = take((size_t)L.slotsSR * n * kDEP);
+  L.H2S = take((size_t)L.slotsN * n * kDEP);
+  L.G = take((size_t)L.slotsN * n * kDP);
+  L.U = take((size_t)L.slotsN * n * kDP);
+  if (training) {
+    L.dU = take((size_t)5 * n * kDP);
+    L.dG = take((size_t)5 * n * kDP);
+    L.T = take((size_t)4 * n * kDP);
+    L.dS = take((size_t)4 * n * kDEP);
+    L.dR = take((size_t)4 * n * kDEP);
+    L.dH2S = take((size_t)n * kDEP);
+    L.DP = take((size_t)n * kDP);
+    L.dQ = take((size_t)n * kDP);
+    L.dQ1 = take((size_t)n * kDP);
+    L.dA = take((size_t)E * kDEP + 8);
+    L.DH1 = take((size_t)E * kDEP + 8);
+    L.partE = take((size_t)kMaxCtas * 160 * 160);
+    L.partM = take((size_t)kMaxCtas * 4 * 160 * 160);
+    L.part0 = take((size_t)kMaxCtas * 3 * kDEP);
+    L.partN = take((size_t)kMaxCtas * kPartNodeElems);
+  } else {
+    L.dU = L.dG = L.T = L.dS = L.dR = L.dH2S = L.DP = L.dQ = L.dQ1 = L.dA = L.DH1 = 0;
+    L.partE = L.partM = L.part0 = L.partN = 0;
+  }
+  L.total = off;
+  return L;
+}
+
+int check_params(const SpwParams* w, const char* what) {
+  if (!w) return fail(SPW_ERR_BAD_ARG, "%s: null parameter struct", what);
+  const float* const* p = reinterpret_cast<const float* const*>(w);
+  for (int i = 0; i < 22; ++i)
+    if (!p[i] || !aligned16(p[i])) return fail(SPW_ERR_BAD_ARG, "%s: tensor %d null or not 16-byte aligned", what, i);
+  return SPW_OK;
+}
+
+int check_graph(const SpwGraph* g) {
+  if (!g) return fail(SPW_ERR_BAD_ARG, "null graph");
+  if (g->n_towers < 0 || g->n_nodes < 0 || g->n_edges < 0) return fail(SPW_ERR_BAD_ARG, "negative graph size");
+  if (g->n_nodes > 0 && (!g->node_off || !g->in_off || !g->out_off)) return fail(SPW_ERR_BAD_ARG, "null graph offsets");
+  if (g->n_edges > 0 && (!g->in_snd || !g->in_rcv || !g->out_pos)) return fail(SPW_ERR_BAD_ARG, "null graph edge arrays");
+  return SPW_OK;
+}
+
+template <class K>
+void set_smem(K kern, size_t bytes) {
+  cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+}
+
+// ---- launch helpers -----------------------------------------------------------------------------
+int grid_for(int64_t items, int per_block) {
+  int64_t b = (items + per_block - 1) / per_block;
+  if (b < 1) b = 1;
+  const int64_t cap = (int64_t)num_sms() * 8;
+  return (int)(b < cap ? b : cap);
+}
+
+LinSeg seg(const float* X, int ldx, int K, const float* W) {
+  LinSeg s; s.X = X; s.W = W; s.ldx = ldx; s.K = K; s.Kp = (K + 3) / 4 * 4; return s;
+}
+
+struct LinOpt {
+  const float* bias = nullptr; const float* rowscale = nullptr; const float* addend = nullptr; int ld_add = 0;
+  int act = 0; const float* mulsrc = nullptr; int ld_mul = 0; int mulmode = 0; int accumulate = 0;
+};
+
+// Y[M][ldy] (N valid columns) from up to 3 (X, W) segments; wide = 150-column output (CN = 5)
+void launch_linear(cudaStream_t st, int M, int N, bool wide, int nseg, const LinSeg* segs, float* Y, int ldy,
+                   const LinOpt& o) {
+  if (M <= 0) return;
+  LinArgs a;
+  memset(&a, 0, sizeof(a));
+  a.M = M; a.nseg = nseg; a.N = N;
+  size_t xfloats = 0;
+  for (int s = 0; s < nseg; ++s) { a.seg[s] = segs[s]; xfloats += (size_t)kTM * segs[s].Kp; }
+  a.bias = o.bias; a.rowscale = o.rowscale; a.addend = o.addend; a.ld_add = o.ld_add; a.act = o.act;
+  a.mulsrc = o.mulsrc; a.ld_mul = o.ld_mul; a.mulmode = o.mulmode; a.Y = Y; a.ldy = ldy; a.accumulate = o.accumulate;
+  const int ntiles = (M + kTM - 1) / kTM;
+  const int grid = ntiles < num_sms() ? ntiles : num_sms();
+  if (wide) {
+    const size_t smem = (xfloats + 2 * kKT * kLdwE) * sizeof(float);
+    auto kern = k_linear<5>;
+    set_smem(kern, smem);
+    SPW_LAUNCH(kern, dim3(grid), dim3(kThreads), smem, st, a);
+  } else {
+    const size_t smem = (xfloats + 2 * kKT * kLdwP) * sizeof(float);
+    auto kern = k_linear<4>;
+    set_smem(kern, smem);
+    SPW_LAUNCH(kern, dim3(grid), dim3(kThreads), smem, st, a);
+  }
+}
+
+// dW[Kin][N] (+ bias row) = X^T dY over M rows, reduced in fixed order into the Keras-layout gradient
+struct WgOut { float* dW; int dst_ld, dst_row0, dst_col0; float* db; int db_off; };
+
+void launch_wgrad(cudaStream_t st, int M, const float* X, int ldx, int Kin, int xmod, const float* rowscale, int rsmod,
+                  const float* dY, int ldy, int N, float* part, const WgOut& out) {
+  WgArgs a;
+  a.M = M; a.X = X; a.ldx = ldx; a.Kin = Kin; a.xmod = xmod; a.rowscale = rowscale; a.rsmod = rsmod; a.dY = dY; a.ldy = ldy; a.N = N;
+  a.part = part;
+  const int ntiles = (M + kTM - 1) / kTM;
+  int grid = ntiles < num_sms() ? ntiles : num_sms();
+  if (grid < 1) grid = 1;
+  const bool wa = Kin + 1 > 112, wb = N > 112;
+  int LX = wa ? 160 : 112, LY = wb ? 160 : 112;
+  const size_t smem = (size_t)kTM * (LX + LY) * sizeof(float);
+  if (wa && wb) { auto k = k_wgrad<10, 10>; set_smem(k, smem); SPW_LAUNCH(k, dim3(grid), dim3(kThreads), smem, st, a); }
+  else if (wa) { auto k = k_wgrad<10, 7>; set_smem(k, smem); SPW_LAUNCH(k, dim3(grid), dim3(kThreads), smem, st, a); }
+  else if (wb) { auto k = k_wgrad<7, 10>; set_smem(k, smem); SPW_LAUNCH(k, dim3(grid), dim3(kThreads), smem, st, a); }
+  else { auto k = k_wgrad<7, 7>; set_smem(k, smem); SPW_LAUNCH(k, dim3(grid), dim3(kThreads), smem, st, a); }
+  RedArgs r;
+  r.part = part; r.nparts = grid; r.part_stride = LX * LY; r.src_ld = LY; r.Kin = Kin; r.N = N;
+  r.dW = out.dW; r.dst_ld = out.dst_ld; r.dst_row0 = out.dst_row0; r.dst_col0 = out.dst_col0;
+  r.db = out.db; r.db_off = out.db_off;
+  SPW_LAUNCH(k_reduce_parts, dim3(grid_for((int64_t)(Kin + 1) * N, 256)), dim3(256), 0, st, r);
+}
+
+void launch_reduce(cudaStream_t st, const float* part, int nparts, int part_stride, int src_ld, int Kin, int N,
+                   const WgOut& out) {
+  RedArgs r;
+  r.part = part; r.nparts = nparts; r.part_stride = part_stride; r.src_ld = src_ld; r.Kin = Kin; r.N = N;
+  r.dW = out.dW; r.dst_ld = out.dst_ld; r.dst_row0 = out.dst_row0; r.dst_col0 = out.dst_col0;
+  r.db = out.db; r.db_off = out.db_off;
+  SPW_LAUNCH(k_reduce_parts, dim3(grid_for((int64_t)(Kin + 1) * N, 256)), dim3(256), 0, st, r);
+}
+
+void pack_weights(cudaStream_t st, const SpwParams* w, float* ws, const Layout& L, bool with_transposes) {
+  PackArgs pa;
+  memset(&pa, 0, sizeof(pa));
+  int n = 0;
+  auto add = [&](int id, const float* src, int src_ld, int row0, int col0, int K, int N, int transpose) {
+    PackDesc& d = pa.d[n++];
+    d.src = src; d.src_ld = src_ld; d.row0 = row0; d.col0 = col0; d.K = K; d.N = N; d.transpose = transpose;
+    d.dst = ws + L.pack[id]; d.Kp = kPackShape[id].Kp; d.ldw = kPackShape[id].ldw;
+  };
+  add(P_RM1, w->rm_w[1], 150, 0, 0, 150, 150, 0);
+  add(P_RM2, w->rm_w[2], 150, 0, 0, 150, 150, 0);
+  add(P_RM3, w->rm_w[3], 150, 0, 0, 150, 150, 0);
+  add(P_W1A, w->rmp_w[0], 150, 0, 0, 150, 150, 0);     // Networks.py:86 concat order: [rel_enc | sender | receiver]
+  add(P_W1B, w->rmp_w[0], 150, 150, 0, 100, 150, 0);
+  add(P_W1C, w->rmp_w[0], 150, 250, 0, 100, 150, 0);
+  add(P_W2, w->rmp_w[1], 150, 0, 0, 150, 150, 0);
+  add(P_W3, w->rmp_w[2], 100, 0, 0, 150, 100, 0);
+  add(P_V1A, w->omp_w[0], 100, 0, 0, 100, 100, 0);     // Networks.py:89 concat order: [obj_enc | effect | prop]
+  add(P_V1B, w->omp_w[0], 100, 100, 0, 100, 100, 0);
+  add(P_V1C, w->omp_w[0], 100, 200, 0, 100, 100, 0);
+  add(P_V2P, w->omp_w[1], 101, 0, 1, 100, 100, 0);     // channels 1..100 (Networks.py:80)
+  add(P_OM1, w->om_w[1], 100, 0, 0, 100, 100, 0);
+  if (with_transposes) {
+    // transposed: dst[k][n] = src[row0 + n][col0 + k];  K = #cols of the source block, N = #rows
+    add(P_RM1T, w->rm_w[1], 150, 0, 0, 150, 150, 1);
+    add(P_RM2T, w->rm_w[2], 150, 0, 0, 150, 150, 1);
+    add(P_RM3T, w->rm_w[3], 150, 0, 0, 150, 150, 1);
+    add(P_W1AT, w->rmp_w[0], 150, 0, 0, 150, 150, 1);
+    add(P_W1BT, w->rmp_w[0], 150, 150, 0, 150, 100, 1);
+    add(P_W1CT, w->rmp_w[0], 150, 250, 0, 150, 100, 1);
+    add(P_W2T, w->rmp_w[1], 150, 0, 0, 150, 150, 1);
+    add(P_W3T, w->rmp_w[2], 100, 0, 0, 100, 150, 1);
+    add(P_V1AT, w->omp_w[0], 100, 0, 0, 100, 100, 1);
+    add(P_V1BT, w->omp_w[0], 100, 100, 0, 100, 100, 1);
+    add(P_V1CT, w->omp_w[0], 100, 200, 0, 100, 100, 1);
+    add(P_V2PT, w->omp_w[1], 101, 0, 1, 100, 100, 1);
+    add(P_OM1T, w->om_w[1], 100, 0, 0, 100, 100, 1);
+  }
+  pa.n = n;
+  SPW_LAUNCH(k_pack_weights, dim3(24, n), dim3(256), 0, st, pa);
+}
+
+size_t edge_tile_smem() { return (size_t)(2 * (kTM * kDEP + 8) + 2 * kKT * kLdwE + 2 * kTM) * sizeof(float); }
+size_t edge_encb_smem() { return (size_t)(5 * (kTMB * kDEP + 8) + 2 * kKT * kLdwE + 2 * kTMB) * sizeof(float); }
+
+}  // namespace
+
+// =================================================================================================
+extern "C" {
+
+int spw_version(void) { return SPW_VERSION; }
+const char* spw_last_error(void) { return g_err; }
+
+int spw_edges_count(const double* pos_xy, const int32_t* node_off, int32_t n_towers, int32_t n_nodes,
+                    int32_t max_nodes_per_tower, double thr, int fully_connected, int32_t* deg_out, int32_t* deg_in,
+                    int32_t* edge_off, void* stream) {
+  if (n_towers < 0 || n_nodes < 0) return fail(SPW_ERR_BAD_ARG, "spw_edges_count: negative size");
+  if (max_nodes_per_tower > SPW_MAX_NODES)
+    return fail(SPW_ERR_UNSUPPORTED, "spw_edges_count: %d blocks in a tower, limit is %d", max_nodes_per_tower, SPW_MAX_NODES);
+  if (!edge_off || (n_towers > 0 && !node_off) || (n_nodes > 0 && (!pos_xy || !deg_out || !deg_in)))
+    return fail(SPW_ERR_BAD_ARG, "spw_edges_count: null pointer");
+  cudaStream_t st = (cudaStream_t)stream;
+  if (n_towers == 0) { cudaMemsetAsync(edge_off, 0, sizeof(int32_t), st); return check_launch("spw_edges_count"); }
+  SPW_LAUNCH(k_edges_count, dim3(n_towers), dim3(kMaxNodes), 0, st, pos_xy, node_off, thr, fully_connected, deg_out,
+             deg_in, edge_off);
+  SPW_LAUNCH(k_scan_inplace, dim3(1), dim3(1024), 0, st, edge_off, (int)n_towers);
+  return check_launch("spw_edges_count");
+}
+
+int spw_edges_fill(const double* pos_xy, const int32_t* node_off, int32_t n_towers, int32_t n_nodes,
+                   int32_t max_nodes_per_tower, double thr, int fully_connected, const int32_t* edge_off, int32_t* snd,
+                   int32_t* rcv, int32_t* slot, int32_t* in_off, int32_t* in_snd, int32_t* in_rcv, int32_t* out_off,
+                   int32_t* out_pos, void* stream) {
+  if (n_towers < 0 || n_nodes < 0) return fail(SPW_ERR_BAD_ARG, "spw_edges_fill: negative size");
+  if (max_nodes_per_tower > SPW_MAX_NODES)
+    return fail(SPW_ERR_UNSUPPORTED, "spw_edges_fill: %d blocks in a tower, limit is %d", max_nodes_per_tower, SPW_MAX_NODES);
+  if (!edge_off || !in_off || !out_off) return fail(SPW_ERR_BAD_ARG, "spw_edges_fill: null offsets");
+  cudaStream_t st = (cudaStream_t)stream;
+  if (n_towers == 0) {
+    cudaMemsetAsync(in_off, 0, sizeof(int32_t), st);
+    cudaMemsetAsync(out_off, 0, sizeof(int32_t), st);
+    return check_launch("spw_edges_fill");
+  }
+  if (!pos_xy || !node_off || !in_snd || !in_rcv || !out_pos) return fail(SPW_ERR_BAD_ARG, "spw_edges_fill: null pointer");
+  SPW_LAUNCH(k_edges_fill, dim3(n_towers), dim3(kMaxNodes), 0, st, pos_xy, node_off, (int)n_towers, (int)n_nodes, thr,
+             fully_connected, edge_off, snd, rcv, slot, in_off, in_snd, in_rcv, out_off, out_pos);
+  return check_launch("spw_edges_fill");
+}
+
+size_t spw_workspace_bytes(int32_t n_nodes, int32_t n_edges, int training) {
+  if (n_nodes < 0 || n_edges < 0) return 0;
+  return make_layout(n_nodes, n_edges, training).total * sizeof(float);
+}
+
+int spw_forward(const SpwParams* w, const SpwGraph* g, const float* obj, float* logits, float* probs, void* workspace,
+                size_t workspace_bytes, int training, void* stream) {
+  int rc;
+  if ((rc = check_params(w, "spw_forward")) != SPW_OK) return rc;
+  if ((rc = check_graph(g)) != SPW_OK) return rc;
+  const int n = g->n_nodes, E = g->n_edges;
+  if (n == 0) return SPW_OK;
+  if (!obj || !logits || !workspace) return fail(SPW_ERR_BAD_ARG, "spw_forward: null pointer");
+  if (!aligned16(workspace)) return fail(SPW_ERR_BAD_ARG, "spw_forward: workspace not 16-byte aligned");
+  const Layout L = make_layout(n, E, training);
+  if (workspace_bytes < L.total * sizeof(float))
+    return fail(SPW_ERR_WORKSPACE, "spw_forward: workspace %zu < %zu bytes", workspace_bytes, L.total * sizeof(float));
+  cudaStream_t st = (cudaStream_t)stream;
+  float* ws = reinterpret_cast<float*>(workspace);
+  auto PK = [&](int id) { return ws + L.pack[id]; };
+  const size_t nP = (size_t)n * kDP, nE = (size_t)n * kDEP;
+
+  pack_weights(st, w, ws, L, training != 0);
+  SPW_LAUNCH(k_deg_to_float, dim3(grid_for(n, 256)), dim3(256), 0, st, g->in_off, n, ws + L.degf);
+
+  // object encoder (Networks.py:47,76): q1 = relu(om0([y,w])), q = relu(om1(q1))
+  SPW_LAUNCH(k_obj_enc0, dim3(grid_for((int64_t)n * kDP, 256)), dim3(256), 0, st, obj, n, w->om_w[0], w->om_b[0], ws + L.Q1);
+  {
+    LinSeg s = seg(ws + L.Q1, kDP, kDP, PK(P_OM1));
+    LinOpt o; o.bias = w->om_b[1]; o.act = 1;
+    launch_linear(st, n, kDP, false, 1, &s, ws + L.Q, kDP, o);
+  }
+  // relation encoder + A_e (Networks.py:46,75 and the c_e part of :86-87)
+  const int etiles = (E + kTM - 1) / kTM;
+  const int egrid = etiles < num_sms() ? etiles : num_sms();
+  if (E > 0) {
+    EdgeEncArgs a;
+    a.E = E; a.in_snd = g->in_snd; a.in_rcv = g->in_rcv; a.obj = obj; a.W0 = w->rm_w[0]; a.b0 = w->rm_b[0];
+    a.RM1 = PK(P_RM1); a.RM2 = PK(P_RM2); a.RM3 = PK(P_RM3); a.b1 = w->rm_b[1]; a.b2 = w->rm_b[2]; a.b3 = w->rm_b[3];
+    a.W1A = PK(P_W1A); a.bA = w->rmp_b[0]; a.A = ws + L.A;
+    set_smem(k_edge_encode, edge_tile_smem());
+    SPW_LAUNCH(k_edge_encode, dim3(egrid), dim3(kThreads), edge_tile_smem(), st, a);
+  }
+  // nodes without in-edges keep an all-zero aggregate
+  cudaMemsetAsync(ws + L.H2S, 0, (size_t)L.slotsN * nE * sizeof(float), st);
+  cudaMemsetAsync(ws + L.P, 0, nP * sizeof(float), st);          // propagation input is zeros (main.py:68)
+  cudaMemsetAsync(ws + L.S, 0, nE * sizeof(float), st);          // S^1 = R^1 = W1b.0 = 0
+  cudaMemsetAsync(ws + L.R, 0, nE * sizeof(float), st);
+
+  for (int l = 0; l < SPW_N_STEPS; ++l) {                        // Networks.py:83
+    const float* Pin = ws + L.P + (size_t)(training ? l : (l & 1)) * nP;
+    float* Pout = ws + L.P + (size_t)(training ? l + 1 : ((l + 1) & 1)) * nP;   // unused when l == 4
+    float* S = ws + L.S + (size_t)(training ? l : 0) * nE;
+    float* R = ws + L.R + (size_t)(training ? l : 0) * nE;
+    float* H2S = ws + L.H2S + (size_t)(training ? l : 0) * nE;
+    float* G = ws + L.G + (size_t)(training ? l : 0) * nP;
+    float* U = ws + L.U + (size_t)(training ? l : 0) * nP;
+    if (l > 0) {   // S = P.W1b, R = P.W1c   (sender / receiver parts of rmp layer 0, Networks.py:84-87)
+      LinSeg s1 = seg(Pin, kDP, kDP, PK(P_W1B));
+      LinSeg s2 = seg(Pin, kDP, kDP, PK(P_W1C));
+      LinOpt o;
+      launch_linear(st, n, kDE, true, 1, &s1, S, kDEP, o);
+      launch_linear(st, n, kDE, true, 1, &s2, R, kDEP, o);
+    }
+    if (E > 0) {
+      if (!training && l > 0) cudaMemsetAsync(H2S, 0, nE * sizeof(float), st);
+      EdgeStepArgs a;
+      a.E = E; a.in_snd = g->in_snd; a.in_rcv = g->in_rcv; a.in_off = g->in_off; a.A = ws + L.A; a.S = S; a.R = R;
+      a.W2 = PK(P_W2); a.b2 = w->rmp_b[1]; a.H2S = H2S; a.part_first = ws + L.PF; a.part_last = ws + L.PL;
+      set_smem(k_edge_step, edge_tile_smem());
+      SPW_LAUNCH(k_edge_step, dim3(egrid), dim3(kThreads), edge_tile_smem(), st, a);
+      if (etiles > 1)
+        SPW_LAUNCH(k_fix_boundaries, dim3(grid_for(etiles - 1, 8)), dim3(256), 0, st, E, g->in_rcv, ws + L.PF, ws + L.PL, H2S);
+    }
+    {   // g = tanh(W3.sum h2 + deg.b3)   (Networks.py:87-88)
+      LinSeg s = seg(H2S, kDEP, kDE, PK(P_W3));
+      LinOpt o; o.bias = w->rmp_b[2]; o.rowscale = ws + L.degf; o.act = 2;
+      launch_linear(st, n, kDP, false, 1, &s, G, kDP, o);
+    }
+    {   // u = relu(V1.[q, g, p] + c1)    (Networks.py:89-90, hidden layer of omp)
+      LinSeg s[3] = {seg(ws + L.Q, kDP, kDP, PK(P_V1A)), seg(G, kDP, kDP, PK(P_V1B)), seg(Pin, kDP, kDP, PK(P_V1C))};
+      LinOpt o; o.bias = w->omp_b[0]; o.act = 1;
+      launch_linear(st, n, kDP, false, l == 0 ? 2 : 3, s, U, kDP, o);   // p^0 = 0: skip its segment
+    }
+    if (l < SPW_N_STEPS - 1) {   // p = tanh(z[1:] + p)   (Networks.py:80,91)
+      LinSeg s = seg(U, kDP, kDP, PK(P_V2P));
+      LinOpt o; o.bias = w->omp_b[1] + 1; o.addend = Pin; o.ld_add = kDP; o.act = 2;
+      launch_linear(st, n, kDP, false, 1, &s, Pout, kDP, o);
+    } else {                     // head: channel 0 of the last z (Networks.py:93-96)
+      SPW_LAUNCH(k_logit, dim3(grid_for(n, 8)), dim3(256), 0, st, U, n, w->omp_w[1], w->omp_b[1], logits, probs);
+    }
+  }
+  return check_launch("spw_forward");
+}
+
+int spw_bce_grad(const float* logits, const float* target, int32_t n_nodes, double count, float* dlogits, double* stats,
+                 void* stream) {
+  if (n_nodes < 0 || count <= 0) return fail(SPW_ERR_BAD_ARG, "spw_bce_grad: bad size");
+  if (n_nodes == 0) return SPW_OK;
+  if (!logits || !target || !dlogits || !stats) return fail(SPW_ERR_BAD_ARG, "spw_bce_grad: null pointer");
+  SPW_LAUNCH(k_bce_grad, dim3(grid_for(n_nodes, 256)), dim3(256), 0, (cudaStream_t)stream, logits, target, (int)n_nodes,
+             1.0 / count, dlogits, stats);
+  return check_launch("spw_bce_grad");
+}
+
+int spw_backward(const SpwParams* w, const SpwGraph* g, const float* obj, const float* dlogits, void* workspace,
+                 size_t workspace_bytes, const SpwParams* grads, void* stream) {
+  int rc;
+  if ((rc = check_params(w, "spw_backward(weights)")) != SPW_OK) return rc;
+  if ((rc = check_params(grads, "spw_backward(grads)")) != SPW_OK) return rc;
+  if ((rc = check_graph(g)) != SPW_OK) return rc;
+  const int n = g->n_nodes, E = g->n_edges;
+  if (!workspace || !aligned16(workspace)) return fail(SPW_ERR_BAD_ARG, "spw_backward: bad workspace");
+  const Layout L = make_layout(n, E, 1);
+  if (workspace_bytes < L.total * sizeof(float))
+    return fail(SPW_ERR_WORKSPACE, "spw_backward: workspace %zu < %zu bytes", workspace_bytes, L.total * sizeof(float));
+  cudaStream_t st = (cudaStream_t)stream;
+  float* ws = reinterpret_cast<float*>(workspace);
+  auto PK = [&](int id) { return ws + L.pack[id]; };
+  const size_t nP = (size_t)n * kDP, nE = (size_t)n * kDEP;
+  if (n == 0) {
+    // no data: all gradients are zero
+    static const int sizes[22] = {300, 22500, 22500, 22500, 150, 150, 150, 150, 200, 10000, 100, 100,
+                                  52500, 22500, 15000, 150, 150, 100, 30000, 10100, 100, 101};
+    float* const* p = reinterpret_cast<float* const*>(grads);
+    for (int i = 0; i < 22; ++i) cudaMemsetAsync(p[i], 0, sizes[i] * sizeof(float), st);
+    return check_launch("spw_backward");
+  }
+  if (!obj || !dlogits) return fail(SPW_ERR_BAD_ARG, "spw_backward: null pointer");
+  const int etiles = (E + kTM - 1) / kTM;
+  const int egrid = etiles < num_sms() ? etiles : num_sms();
+  float* partN = ws + L.partN;
+
+  // head: dUpre^5 = dlogit (x) V2[:,0] * relu'
+  float* dU5 = ws + L.dU + 4 * nP;
+  const float* U5 = ws + L.U + 4 * nP;
+  SPW_LAUNCH(k_logit_bwd, dim3(grid_for((int64_t)n * kDP, 256)), dim3(256), 0, st, dlogits, U5, n, w->omp_w[1], dU5);
+
+  for (int l = SPW_N_STEPS - 1; l >= 0; --l) {   // step l+1 of the forward loop
+    const float* Pin = ws + L.P + (size_t)l * nP;
+    const float* S = ws + L.S + (size_t)l * nE;
+    const float* R = ws + L.R + (size_t)l * nE;
+    const float* G = ws + L.G + (size_t)l * nP;
+    const float* U = ws + L.U + (size_t)l * nP;
+    float* dU = ws + L.dU + (size_t)l * nP;
+    float* dG = ws + L.dG + (size_t)l * nP;
+    const float* Tl = l < 4 ? ws + L.T + (size_t)l * nP : nullptr;   // d(pre-tanh of p^{l+1})
+    if (l < SPW_N_STEPS - 1) {   // dUpre = (T.V2p^T) * relu'(u)
+      LinSeg s = seg(Tl, kDP, kDP, PK(P_V2PT));
+      LinOpt o; o.mulsrc = U; o.ld_mul = kDP; o.mulmode = 1;
+      launch_linear(st, n, kDP, false, 1, &s, dU, kDP, o);
+    }
+    {   // dq_pre += (dUpre.V1a^T) * relu'(q)
+      LinSeg s = seg(dU, kDP, kDP, PK(P_V1AT));
+      LinOpt o; o.mulsrc = ws + L.Q; o.ld_mul = kDP; o.mulmode = 1; o.accumulate = l < SPW_N_STEPS - 1;
+      launch_linear(st, n, kDP, false, 1, &s, ws + L.dQ, kDP, o);
+    }
+    {   // dg_pre = (dUpre.V1b^T) * (1 - g^2)
+      LinSeg s = seg(dU, kDP, kDP, PK(P_V1BT));
+      LinOpt o; o.mulsrc = G; o.ld_mul = kDP; o.mulmode = 2;
+      launch_linear(st, n, kDP, false, 1, &s, dG, kDP, o);
+    }
+    if (l > 0) {   // DP = dUpre.V1c^T (+ residual T)
+      LinSeg s = seg(dU, kDP, kDP, PK(P_V1CT));
+      LinOpt o; o.addend = Tl; o.ld_add = kDP;
+      launch_linear(st, n, kDP, false, 1, &s, ws + L.DP, kDP, o);
+    }
+    {   // d(sum h2) = dg_pre.W3^T
+      LinSeg s = seg(dG, kDP, kDP, PK(P_W3T));
+      LinOpt o;
+      launch_linear(st, n, kDE, true, 1, &s, ws + L.dH2S, kDEP, o);
+    }
+    if (E > 0) {
+      EdgeStepBwdArgs a;
+      a.E = E; a.in_snd = g->in_snd; a.in_rcv = g->in_rcv; a.A = ws + L.A; a.S = S; a.R = R; a.W2 = PK(P_W2);
+      a.b2 = w->rmp_b[1]; a.W2T = PK(P_W2T); a.dH2S = ws + L.dH2S; a.dA = ws + L.dA; a.DH1 = ws + L.DH1;
+      a.partW2 = ws + L.partE; a.first = (l == SPW_N_STEPS - 1);
+      set_smem(k_edge_step_bwd, edge_tile_smem());
+      SPW_LAUNCH(k_edge_step_bwd, dim3(egrid), dim3(kThreads), edge_tile_smem(), st, a);
+    }
+    if (l > 0) {
+      float* dS = ws + L.dS + (size_t)(l - 1) * nE;
+      float* dR = ws + L.dR + (size_t)(l - 1) * nE;
+      if (E > 0) {
+        SPW_LAUNCH(k_gather_dsr, dim3(grid_for(n, 8)), dim3(256), 0, st, n, g->in_off, g->out_off, g->out_pos,
+                   ws + L.DH1, dS, dR);
+      } else {
+        cudaMemsetAsync(dS, 0, nE * sizeof(float), st);
+        cudaMemsetAsync(dR, 0, nE * sizeof(float), st);
+      }
+      // T^{l} = (dS.W1b^T + dR.W1c^T + DP) * (1 - (p^l)^2)       (p^l = Pin of this step)
+      LinSeg s[2] = {seg(dS, kDEP, kDE, PK(P_W1BT)), seg(dR, kDEP, kDE, PK(P_W1CT))};
+      LinOpt o; o.addend = ws + L.DP; o.ld_add = kDP; o.mulsrc = Pin; o.ld_mul = kDP; o.mulmode = 2;
+      launch_linear(st, n, kDP, false, 2, s, ws + L.T + (size_t)(l - 1) * nP, kDP, o);
+    }
+  }
+
+  // ---- node-level weight gradients, each one contraction over all steps' rows -------------------
+  const float* degf = ws + L.degf;
+  // omp layer 0 = [V1a; V1b; V1c], bias c1
+  launch_wgrad(st, 5 * n, ws + L.Q, kDP, kDP, n, nullptr, 0, ws + L.dU, kDP, kDP, partN, {grads->omp_w[0], 100, 0, 0, grads->omp_b[0], 0});
+  launch_wgrad(st, 5 * n, ws + L.G, kDP, kDP, 0, nullptr, 0, ws + L.dU, kDP, kDP, partN, {grads->omp_w[0], 100, 100, 0, nullptr, 0});
+  launch_wgrad(st, 5 * n, ws + L.P, kDP, kDP, 0, nullptr, 0, ws + L.dU, kDP, kDP, partN, {grads->omp_w[0], 100, 200, 0, nullptr, 0});
+  // omp layer 1: channels 1..100 from T (steps 1..4), channel 0 from the head
+  launch_wgrad(st, 4 * n, ws + L.U, kDP, kDP, 0, nullptr, 0, ws + L.T, kDP, kDP, partN, {grads->omp_w[1], 101, 0, 1, grads->omp_b[1], 1});
+  launch_wgrad(st, n, U5, kDP, kDP, 0, nullptr, 0, dlogits, 1, 1, partN, {grads->omp_w[1], 101, 0, 0, grads->omp_b[1], 0});
+  // rmp layer 2 (W3, b3 scaled by in-degree)
+  launch_wgrad(st, 5 * n, ws + L.H2S, kDEP, kDE, 0, degf, n, ws + L.dG, kDP, kDP, partN, {grads->rmp_w[2], 100, 0, 0, grads->rmp_b[2], 0});
+  // rmp layer 0 rows 150..349 (W1b, W1c): X = p^{l} for steps 2..5
+  launch_wgrad(st, 4 * n, ws + L.P + nP, kDP, kDP, 0, nullptr, 0, ws + L.dS, kDEP, kDE, partN, {grads->rmp_w[0], 150, 150, 0, nullptr, 0});
+  launch_wgrad(st, 4 * n, ws + L.P + nP, kDP, kDP, 0, nullptr, 0, ws + L.dR, kDEP, kDE, partN, {grads->rmp_w[0], 150, 250, 0, nullptr, 0});
+  // object encoder
+  launch_wgrad(st, n, ws + L.Q1, kDP, kDP, 0, nullptr, 0, ws + L.dQ, kDP, kDP, partN, {grads->om_w[1], 100, 0, 0, grads->om_b[1], 0});
+  {
+    LinSeg s = seg(ws + L.dQ, kDP, kDP, PK(P_OM1T));
+    LinOpt o; o.mulsrc = ws + L.Q1; o.ld_mul = kDP; o.mulmode = 1;
+    launch_linear(st, n, kDP, false, 1, &s, ws + L.dQ1, kDP, o);
+  }
+  launch_wgrad(st, n, obj + 1, 3, 2, 0, nullptr, 0, ws + L.dQ1, kDP, kDP, partN, {grads->om_w[0], 100, 0, 0, grads->om_b[0], 0});
+
+  // ---- edge-level weight gradients --------------------------------------------------------------
+  if (E > 0) {
+    // rmp layer 1 (W2, b2) from the per-step kernel's per-CTA partials
+    launch_reduce(st, ws + L.partE, egrid, 160 * 160, 160, kDE, kDE, {grads->rmp_w[1], 150, 0, 0, grads->rmp_b[1], 0});
+    const int btiles = (E + kTMB - 1) / kTMB;
+    const int bgrid = btiles < num_sms() ? btiles : num_sms();
+    EdgeEncBwdArgs a;
+    a.E = E; a.in_snd = g->in_snd; a.in_rcv = g->in_rcv; a.obj = obj; a.W0 = w->rm_w[0]; a.b0 = w->rm_b[0];
+    a.RM1 = PK(P_RM1); a.RM2 = PK(P_RM2); a.RM3 = PK(P_RM3); a.b1 = w->rm_b[1]; a.b2 = w->rm_b[2]; a.b3 = w->rm_b[3];
+    a.RM1T = PK(P_RM1T); a.RM2T = PK(P_RM2T); a.RM3T = PK(P_RM3T); a.W1AT = PK(P_W1AT); a.dA = ws + L.dA;
+    a.partM = ws + L.partM; a.part0 = ws + L.part0;
+    set_smem(k_edge_encode_bwd, edge_encb_smem());
+    SPW_LAUNCH(k_edge_encode_bwd, dim3(bgrid), dim3(kThreads), edge_encb_smem(), st, a);
+    const int ps = 4 * 160 * 160;
+    launch_reduce(st, ws + L.partM, bgrid, ps, 160, kDE, kDE, {grads->rmp_w[0], 150, 0, 0, grads->rmp_b[0], 0});
+    launch_reduce(st, ws + L.partM + 160 * 160, bgrid, ps, 160, kDE, kDE, {grads->rm_w[3], 150, 0, 0, grads->rm_b[3], 0});
+    launch_reduce(st, ws + L.partM + 2 * 160 * 160, bgrid, ps, 160, kDE, kDE, {grads->rm_w[2], 150, 0, 0, grads->rm_b[2], 0});
+    launch_reduce(st, ws + L.partM + 3 * 160 * 160, bgrid, ps, 160, kDE, kDE, {grads->rm_w[1], 150, 0, 0, grads->rm_b[1], 0});
+    // layer 0: part0 rows [w0 row 0 | w0 row 1 | b0], each kDEP long  ->  treat as Kin = 2 (+ bias row)
+    launch_reduce(st, ws + L.part0, bgrid, 3 * kDEP, kDEP, 2, kDE, {grads->rm_w[0], 150, 0, 0, grads->rm_b[0], 0});
+  } else {
+    cudaMemsetAsync(grads->rmp_w[1], 0, 22500 * sizeof(float), st);
+    cudaMemsetAsync(grads->rmp_b[1], 0, 150 * sizeof(float), st);
+    cudaMemsetAsync(grads->rmp_w[0], 0, 150 * 150 * sizeof(float), st);   // rows 0..149 (rows 150.. written above)
+    cudaMemsetAsync(grads->rmp_b[0], 0, 150 * sizeof(float), st);
+    for (int i = 0; i < 4; ++i) {
+      cudaMemsetAsync(grads->rm_w[i], 0, (i == 0 ? 300 : 22500) * sizeof(float), st);
+      cudaMemsetAsync(grads->rm_b[i], 0, 150 * sizeof(float), st);
+    }
+  }
+  return check_launch("spw_backward");
+}
+
+}  // extern "C"
