@@ -67,6 +67,16 @@ typedef struct {
 int spw_version(void);
 const char* spw_last_error(void);
 
+/* ---- measurement hooks (bench.py) --------------------------------------------------------
+ * spw_launch_count: kernels launched by this library since it was loaded.
+ * spw_profile(1/0): bracket every kernel launch with CUDA events on its stream.
+ * spw_profile_report: synchronise those events and write "name launches total_ms" lines.
+ * spw_ffma_peak: FP32-pipe micro-benchmark, 2*16*iters flops per thread, grid x 256 threads. */
+long long spw_launch_count(void);
+int spw_profile(int enable);
+int spw_profile_report(char* buf, size_t cap);
+int spw_ffma_peak(float* out, int grid, int iters, void* stream);
+
 /* ---- edge-index construction (replaces main.py:66-81) ------------------------------------
  * Edge m->j (m != j, same tower) is active iff sqrt(dx*dx + dy*dy) < thr evaluated in IEEE
  * double with separately rounded multiplies/add/sqrt -- numpy's np.linalg.norm(...,axis=1) --

@@ -1,0 +1,182 @@
+"""Drop-in for /root/reference/src/Networks.py: `PropagationNetwork().getModel(n_objects, object_dim)`
+returns an object with the Keras calls the reference's callers make -- `.fit(x_dict, y_dict,
+batch_size=, epochs=, validation_split=, shuffle=, verbose=)` (main.py:92-98) and `.predict(x_dict)`
+-> ndarray (B, N, 1) (TowerCreator.py:430-431, JengaBuilder.py:328-329) -- backed by the sm_100a
+kernels in libspwgnn.so.  Differences by design:
+  * one set of weights serves every n_objects (the reference re-wires shared MLPs per N,
+    Networks.py:17-18,40-56); `getModel` still caches one facade per N like `self.Nets`;
+  * besides the dense one-hot dict, `predict_towers` / `fit_towers` take ragged raw poses and build
+    the relations on the GPU (no O(N^3) tensors);
+  * logits are exposed (`predict_logits`), and `predict_tower_sums` returns the per-tower sum of
+    block probabilities the demolish searches use (JengaBuilder.py:254-256, TowerCreator.py:299-300).
+"""
+import os
+import sys
+
+import numpy as np
+import torch
+
+try:
+    from .engine import Engine
+    from .graph import TowerBatch, REL_THRESHOLD
+    from ._lib import SpwError
+except ImportError:      # imported as top-level `Networks` (reference style: `from Networks import *`)
+    sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+    from spwgnn_b200.engine import Engine
+    from spwgnn_b200.graph import TowerBatch, REL_THRESHOLD
+    from spwgnn_b200._lib import SpwError
+
+__all__ = ['PropagationNetwork', 'PropagationModel', 'History']
+
+
+class History:
+    def __init__(self):
+        self.history = {}
+        self.epoch = []
+
+    def _add(self, epoch, **kv):
+        self.epoch.append(epoch)
+        for k, v in kv.items():
+            self.history.setdefault(k, []).append(v)
+
+
+class PropagationNetwork:
+    """Networks.py:12-104.  Holds the shared weights (one Engine) and a per-N facade cache."""
+
+    def __init__(self, device='cuda', seed=0):
+        self.Nets = {}
+        self.set_weights = False
+        self._device, self._seed = device, seed
+        self.engine = None
+
+    def getModel(self, n_objects, object_dim=3, relation_dim=1):
+        if n_objects in self.Nets:                      # Networks.py:17-18
+            return self.Nets[n_objects]
+        if object_dim != 3:
+            raise SpwError('object_dim=%d: only object_dim=3 is well defined in the reference (with 2 the object '
+                           'encoder is declared 2-wide but fed 1 feature, Networks.py:42,47,70-73)' % object_dim)
+        if self.engine is None:
+            self.engine = Engine(self._device, self._seed)
+            self.set_weights = True
+        model = PropagationModel(self.engine, n_objects)
+        self.Nets[n_objects] = model
+        return model
+
+
+class PropagationModel:
+    """The compiled-model facade: Adam(lr=5e-4) + binary_crossentropy + binary_accuracy (Networks.py:101-102)."""
+
+    def __init__(self, engine, n_objects):
+        self.engine = engine
+        self.n_objects = n_objects
+        self.lr = 5e-4
+
+    # ---- inference -----------------------------------------------------------------------------
+    def _batch_from_dict(self, x, sel=None):
+        obj = np.asarray(x['objects'])
+        rs, rr = np.asarray(x['sender_relations']), np.asarray(x['receiver_relations'])
+        if sel is not None:
+            obj, rs, rr = obj[sel], rs[sel], rr[sel]
+        if obj.shape[1] != self.n_objects:
+            raise SpwError('model built for %d objects, got %d' % (self.n_objects, obj.shape[1]))
+        return TowerBatch.from_dense_relations(obj, rs, rr, device=self.engine.device)
+
+    def predict(self, x, batch_size=None, verbose=0):
+        """x: the reference's dict ('objects', 'sender_relations', 'receiver_relations', 'propagation';
+        the all-zero 'propagation' seed is implied and ignored).  Returns float32 (B, N, 1)."""
+        B, N = np.asarray(x['objects']).shape[:2]
+        batch = self._batch_from_dict(x)
+        _, probs = self.engine.forward(batch, training=False)
+        return probs.reshape(B, N, 1).cpu().numpy()
+
+    def predict_logits(self, x):
+        B, N = np.asarray(x['objects']).shape[:2]
+        logits, _ = self.engine.forward(self._batch_from_dict(x), training=False)
+        return logits.reshape(B, N, 1).cpu().numpy()
+
+    def predict_towers(self, towers, inference_glue=True, thr=REL_THRESHOLD, fully_connected=False):
+        """Fast path: list of (N_t, 3) RAW [x, y, width] arrays (mixed sizes allowed).  With
+        inference_glue=True the relations are built as the reference's predict_stabilities does
+        (positions/170 thresholded against 170, i.e. fully connected).  Returns a list of (N_t,) arrays."""
+        batch = TowerBatch.from_towers(towers, thr=thr, fully_connected=fully_connected,
+                                       inference_glue=inference_glue, device=self.engine.device)
+        _, probs = self.engine.forward(batch, training=False)
+        p = probs.cpu().numpy()
+        off = batch.node_off_host
+        return [p[off[t]:off[t + 1]] for t in range(batch.n_towers)]
+
+    def predict_tower_sums(self, towers, **kw):
+        """Per-tower sum of block probabilities (the demolish searches' score), computed on the GPU."""
+        batch = TowerBatch.from_towers(towers, device=self.engine.device, **kw)
+        _, probs = self.engine.forward(batch, training=False)
+        seg = torch.repeat_interleave(torch.arange(batch.n_towers, device=probs.device),
+                                      torch.as_tensor(np.diff(batch.node_off_host), device=probs.device))
+        return torch.zeros(batch.n_towers, device=probs.device).index_add_(0, seg, probs).cpu().numpy()
+
+    # ---- training ------------------------------------------------------------------------------
+    def train_on_batch(self, batch, target):
+        """One optimiser step on a packed batch; returns (mean loss, binary accuracy)."""
+        eng = self.engine
+        stats = eng.loss_and_grads(batch, target)
+        eng.adam_step(lr=self.lr)
+        s = stats.cpu().numpy() / max(batch.n_nodes, 1)
+        return float(s[0]), float(s[1])
+
+    def test_on_batch(self, batch, target):
+        eng = self.engine
+        logits, _ = eng.forward(batch, training=False, want_probs=False)
+        _, stats = eng.bce_seed(logits, target, max(batch.n_nodes, 1))
+        s = stats.cpu().numpy() / max(batch.n_nodes, 1)
+        return float(s[0]), float(s[1])
+
+    def fit(self, x, y, batch_size=32, epochs=1, validation_split=0.0, shuffle=True, verbose=1, seed=None):
+        """Keras semantics: the LAST `validation_split` fraction is held out before shuffling; each epoch
+        shuffles the rest and steps once per mini-batch; epoch metrics are sample-weighted means."""
+        tgt_all = np.asarray(y['target'] if isinstance(y, dict) else y, dtype=np.float32)
+        B = tgt_all.shape[0]
+        n_val = int(B * validation_split) if validation_split else 0
+        n_tr = B - n_val
+        rng = np.random.default_rng(seed)
+        dev = self.engine.device
+        hist = History()
+        for ep in range(epochs):
+            order = rng.permutation(n_tr) if shuffle else np.arange(n_tr)
+            tl = ta = 0.0
+            for s0 in range(0, n_tr, batch_size):
+                sel = np.sort(order[s0:s0 + batch_size]) if not shuffle else order[s0:s0 + batch_size]
+                batch = self._batch_from_dict(x, sel)
+                tgt = torch.as_tensor(tgt_all[sel].reshape(-1)).to(dev)
+                l, a = self.train_on_batch(batch, tgt)
+                tl += l * len(sel); ta += a * len(sel)
+            rec = dict(loss=tl / max(n_tr, 1), binary_accuracy=ta / max(n_tr, 1))
+            if n_val:
+                vl = va = 0.0
+                for s0 in range(n_tr, B, batch_size):
+                    sel = np.arange(s0, min(s0 + batch_size, B))
+                    batch = self._batch_from_dict(x, sel)
+                    tgt = torch.as_tensor(tgt_all[sel].reshape(-1)).to(dev)
+                    l, a = self.test_on_batch(batch, tgt)
+                    vl += l * len(sel); va += a * len(sel)
+                rec.update(val_loss=vl / n_val, val_binary_accuracy=va / n_val)
+            hist._add(ep, **rec)
+            if verbose:
+                print('Epoch %d/%d - ' % (ep + 1, epochs) + ' - '.join('%s: %.4f' % kv for kv in rec.items()))
+        return hist
+
+    def evaluate(self, x, y, batch_size=32, verbose=0):
+        tgt_all = np.asarray(y['target'] if isinstance(y, dict) else y, dtype=np.float32)
+        B = tgt_all.shape[0]
+        tl = ta = 0.0
+        for s0 in range(0, B, batch_size):
+            sel = np.arange(s0, min(s0 + batch_size, B))
+            batch = self._batch_from_dict(x, sel)
+            l, a = self.test_on_batch(batch, torch.as_tensor(tgt_all[sel].reshape(-1)).to(self.engine.device))
+            tl += l * len(sel); ta += a * len(sel)
+        return [tl / max(B, 1), ta / max(B, 1)]
+
+    # ---- weights -------------------------------------------------------------------------------
+    def get_weights(self):
+        return [v.cpu().numpy() for v in self.engine.params.to_dict().values()]
+
+    def set_weights_dict(self, d):
+        self.engine.params.load_dict(d)

@@ -41,6 +41,22 @@ __global__ void __launch_bounds__(256) k_pack_weights(PackArgs a) {
   }
 }
 
+// FP32 pipe micro-benchmark (roofline denominator for the FFMA kernels; bench.py)
+__global__ void __launch_bounds__(256) k_ffma_peak(float* __restrict__ out, int iters) {
+  float a[16];
+  const float x = 1.0f + 1e-7f * threadIdx.x, y = 1e-9f * blockIdx.x;
+#pragma unroll
+  for (int i = 0; i < 16; ++i) a[i] = (float)i;
+  for (int it = 0; it < iters; ++it) {
+#pragma unroll
+    for (int i = 0; i < 16; ++i) a[i] = fmaf(a[i], x, y);
+  }
+  float s = 0.f;
+#pragma unroll
+  for (int i = 0; i < 16; ++i) s += a[i];
+  out[blockIdx.x * blockDim.x + threadIdx.x] = s;
+}
+
 // =================================================================================================
 // small elementwise / per-node kernels
 // =================================================================================================

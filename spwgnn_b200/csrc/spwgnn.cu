@@ -9,9 +9,51 @@
 #include <stdio.h>
 #include <string.h>
 
+#include <atomic>
+#include <map>
+#include <string>
+#include <vector>
+
 using namespace spw;
 
 namespace {
+
+// ---- launch accounting / per-kernel CUDA-event timing (bench.py: gpu_launches, roofline) -------
+namespace prof {
+std::atomic<long long> launches{0};
+bool enabled = false;
+#ifndef SPW_EMU
+struct Rec { const char* name; cudaEvent_t a, b; };
+std::vector<Rec> recs;
+#endif
+struct Scope {
+  cudaStream_t st; bool on;
+#ifndef SPW_EMU
+  cudaEvent_t b;
+#endif
+  Scope(const char* name, cudaStream_t s) : st(s), on(enabled) {
+    launches.fetch_add(1, std::memory_order_relaxed);
+#ifndef SPW_EMU
+    if (on) {
+      Rec r; r.name = name;
+      cudaEventCreate(&r.a); cudaEventCreate(&r.b);
+      cudaEventRecord(r.a, st);
+      b = r.b;
+      recs.push_back(r);
+    }
+#else
+    (void)name;
+#endif
+  }
+  ~Scope() {
+#ifndef SPW_EMU
+    if (on) cudaEventRecord(b, st);
+#endif
+  }
+};
+}  // namespace prof
+#define SPW_KLAUNCH(name, kern, grid, block, smem, st, ...) \
+  do { prof::Scope _scope(name, st); SPW_LAUNCH(kern, grid, block, smem, st, __VA_ARGS__); } while (0)
 
 thread_local char g_err[512] = "";
 
@@ -172,12 +214,12 @@ void launch_linear(cudaStream_t st, int M, int N, bool wide, int nseg, const Lin
     const size_t smem = (xfloats + 2 * kKT * kLdwE) * sizeof(float);
     auto kern = k_linear<5>;
     set_smem(kern, smem);
-    SPW_LAUNCH(kern, dim3(grid), dim3(kThreads), smem, st, a);
+    SPW_KLAUNCH("k_linear<5>", kern, dim3(grid), dim3(kThreads), smem, st, a);
   } else {
     const size_t smem = (xfloats + 2 * kKT * kLdwP) * sizeof(float);
     auto kern = k_linear<4>;
     set_smem(kern, smem);
-    SPW_LAUNCH(kern, dim3(grid), dim3(kThreads), smem, st, a);
+    SPW_KLAUNCH("k_linear<4>", kern, dim3(grid), dim3(kThreads), smem, st, a);
   }
 }
 
@@ -195,15 +237,15 @@ void launch_wgrad(cudaStream_t st, int M, const float* X, int ldx, int Kin, int 
   const bool wa = Kin + 1 > 112, wb = N > 112;
   int LX = wa ? 160 : 112, LY = wb ? 160 : 112;
   const size_t smem = (size_t)kTM * (LX + LY) * sizeof(float);
-  if (wa && wb) { auto k = k_wgrad<10, 10>; set_smem(k, smem); SPW_LAUNCH(k, dim3(grid), dim3(kThreads), smem, st, a); }
-  else if (wa) { auto k = k_wgrad<10, 7>; set_smem(k, smem); SPW_LAUNCH(k, dim3(grid), dim3(kThreads), smem, st, a); }
-  else if (wb) { auto k = k_wgrad<7, 10>; set_smem(k, smem); SPW_LAUNCH(k, dim3(grid), dim3(kThreads), smem, st, a); }
-  else { auto k = k_wgrad<7, 7>; set_smem(k, smem); SPW_LAUNCH(k, dim3(grid), dim3(kThreads), smem, st, a); }
+  if (wa && wb) { auto k = k_wgrad<10, 10>; set_smem(k, smem); SPW_KLAUNCH("k_wgrad", k, dim3(grid), dim3(kThreads), smem, st, a); }
+  else if (wa) { auto k = k_wgrad<10, 7>; set_smem(k, smem); SPW_KLAUNCH("k_wgrad", k, dim3(grid), dim3(kThreads), smem, st, a); }
+  else if (wb) { auto k = k_wgrad<7, 10>; set_smem(k, smem); SPW_KLAUNCH("k_wgrad", k, dim3(grid), dim3(kThreads), smem, st, a); }
+  else { auto k = k_wgrad<7, 7>; set_smem(k, smem); SPW_KLAUNCH("k_wgrad", k, dim3(grid), dim3(kThreads), smem, st, a); }
   RedArgs r;
   r.part = part; r.nparts = grid; r.part_stride = LX * LY; r.src_ld = LY; r.Kin = Kin; r.N = N;
   r.dW = out.dW; r.dst_ld = out.dst_ld; r.dst_row0 = out.dst_row0; r.dst_col0 = out.dst_col0;
   r.db = out.db; r.db_off = out.db_off;
-  SPW_LAUNCH(k_reduce_parts, dim3(grid_for((int64_t)(Kin + 1) * N, 256)), dim3(256), 0, st, r);
+  SPW_KLAUNCH("k_reduce_parts", k_reduce_parts, dim3(grid_for((int64_t)(Kin + 1) * N, 256)), dim3(256), 0, st, r);
 }
 
 void launch_reduce(cudaStream_t st, const float* part, int nparts, int part_stride, int src_ld, int Kin, int N,
@@ -212,7 +254,7 @@ void launch_reduce(cudaStream_t st, const float* part, int nparts, int part_stri
   r.part = part; r.nparts = nparts; r.part_stride = part_stride; r.src_ld = src_ld; r.Kin = Kin; r.N = N;
   r.dW = out.dW; r.dst_ld = out.dst_ld; r.dst_row0 = out.dst_row0; r.dst_col0 = out.dst_col0;
   r.db = out.db; r.db_off = out.db_off;
-  SPW_LAUNCH(k_reduce_parts, dim3(grid_for((int64_t)(Kin + 1) * N, 256)), dim3(256), 0, st, r);
+  SPW_KLAUNCH("k_reduce_parts", k_reduce_parts, dim3(grid_for((int64_t)(Kin + 1) * N, 256)), dim3(256), 0, st, r);
 }
 
 void pack_weights(cudaStream_t st, const SpwParams* w, float* ws, const Layout& L, bool with_transposes) {
@@ -254,7 +296,7 @@ void pack_weights(cudaStream_t st, const SpwParams* w, float* ws, const Layout& 
     add(P_OM1T, w->om_w[1], 100, 0, 0, 100, 100, 1);
   }
   pa.n = n;
-  SPW_LAUNCH(k_pack_weights, dim3(24, n), dim3(256), 0, st, pa);
+  SPW_KLAUNCH("k_pack_weights", k_pack_weights, dim3(24, n), dim3(256), 0, st, pa);
 }
 
 size_t edge_tile_smem() { return (size_t)(2 * (kTM * kDEP + 8) + 2 * kKT * kLdwE + 2 * kTM) * sizeof(float); }
@@ -266,6 +308,45 @@ size_t edge_encb_smem() { return (size_t)(5 * (kTMB * kDEP + 8) + 2 * kKT * kLdw
 extern "C" {
 
 int spw_version(void) { return SPW_VERSION; }
+
+long long spw_launch_count(void) { return prof::launches.load(); }
+
+int spw_profile(int enable) {
+  prof::enabled = enable != 0;
+  return SPW_OK;
+}
+
+// "name launches total_ms\n" per kernel, after synchronising the recorded events; clears the log
+int spw_profile_report(char* buf, size_t cap) {
+  if (!buf || cap == 0) return fail(SPW_ERR_BAD_ARG, "spw_profile_report: null buffer");
+  buf[0] = 0;
+#ifndef SPW_EMU
+  std::map<std::string, std::pair<long long, double>> acc;
+  for (auto& r : prof::recs) {
+    cudaEventSynchronize(r.b);
+    float ms = 0.f;
+    cudaEventElapsedTime(&ms, r.a, r.b);
+    auto& e = acc[r.name];
+    e.first += 1; e.second += ms;
+    cudaEventDestroy(r.a); cudaEventDestroy(r.b);
+  }
+  prof::recs.clear();
+  size_t off = 0;
+  for (auto& kv : acc) {
+    int w = snprintf(buf + off, cap - off, "%s %lld %.6f\n", kv.first.c_str(), kv.second.first, kv.second.second);
+    if (w < 0 || (size_t)w >= cap - off) break;
+    off += (size_t)w;
+  }
+#endif
+  return SPW_OK;
+}
+
+// FP32 FFMA pipe peak: `iters` dependent-chain-free FMAs x 16 accumulators per thread; flops = 2*16*iters*threads
+int spw_ffma_peak(float* out /*[grid*256]*/, int grid, int iters, void* stream) {
+  if (!out || grid <= 0 || iters <= 0) return fail(SPW_ERR_BAD_ARG, "spw_ffma_peak: bad argument");
+  SPW_KLAUNCH("k_ffma_peak", k_ffma_peak, dim3(grid), dim3(256), 0, (cudaStream_t)stream, out, iters);
+  return check_launch("spw_ffma_peak");
+}
 const char* spw_last_error(void) { return g_err; }
 
 int spw_edges_count(const double* pos_xy, const int32_t* node_off, int32_t n_towers, int32_t n_nodes,
@@ -278,9 +359,9 @@ int spw_edges_count(const double* pos_xy, const int32_t* node_off, int32_t n_tow
     return fail(SPW_ERR_BAD_ARG, "spw_edges_count: null pointer");
   cudaStream_t st = (cudaStream_t)stream;
   if (n_towers == 0) { cudaMemsetAsync(edge_off, 0, sizeof(int32_t), st); return check_launch("spw_edges_count"); }
-  SPW_LAUNCH(k_edges_count, dim3(n_towers), dim3(kMaxNodes), 0, st, pos_xy, node_off, thr, fully_connected, deg_out,
+  SPW_KLAUNCH("k_edges_count", k_edges_count, dim3(n_towers), dim3(kMaxNodes), 0, st, pos_xy, node_off, thr, fully_connected, deg_out,
              deg_in, edge_off);
-  SPW_LAUNCH(k_scan_inplace, dim3(1), dim3(1024), 0, st, edge_off, (int)n_towers);
+  SPW_KLAUNCH("k_scan_inplace", k_scan_inplace, dim3(1), dim3(1024), 0, st, edge_off, (int)n_towers);
   return check_launch("spw_edges_count");
 }
 
@@ -299,7 +380,7 @@ int spw_edges_fill(const double* pos_xy, const int32_t* node_off, int32_t n_towe
     return check_launch("spw_edges_fill");
   }
   if (!pos_xy || !node_off || !in_snd || !in_rcv || !out_pos) return fail(SPW_ERR_BAD_ARG, "spw_edges_fill: null pointer");
-  SPW_LAUNCH(k_edges_fill, dim3(n_towers), dim3(kMaxNodes), 0, st, pos_xy, node_off, (int)n_towers, (int)n_nodes, thr,
+  SPW_KLAUNCH("k_edges_fill", k_edges_fill, dim3(n_towers), dim3(kMaxNodes), 0, st, pos_xy, node_off, (int)n_towers, (int)n_nodes, thr,
              fully_connected, edge_off, snd, rcv, slot, in_off, in_snd, in_rcv, out_off, out_pos);
   return check_launch("spw_edges_fill");
 }
@@ -327,10 +408,10 @@ int spw_forward(const SpwParams* w, const SpwGraph* g, const float* obj, float* 
   const size_t nP = (size_t)n * kDP, nE = (size_t)n * kDEP;
 
   pack_weights(st, w, ws, L, training != 0);
-  SPW_LAUNCH(k_deg_to_float, dim3(grid_for(n, 256)), dim3(256), 0, st, g->in_off, n, ws + L.degf);
+  SPW_KLAUNCH("k_deg_to_float", k_deg_to_float, dim3(grid_for(n, 256)), dim3(256), 0, st, g->in_off, n, ws + L.degf);
 
   // object encoder (Networks.py:47,76): q1 = relu(om0([y,w])), q = relu(om1(q1))
-  SPW_LAUNCH(k_obj_enc0, dim3(grid_for((int64_t)n * kDP, 256)), dim3(256), 0, st, obj, n, w->om_w[0], w->om_b[0], ws + L.Q1);
+  SPW_KLAUNCH("k_obj_enc0", k_obj_enc0, dim3(grid_for((int64_t)n * kDP, 256)), dim3(256), 0, st, obj, n, w->om_w[0], w->om_b[0], ws + L.Q1);
   {
     LinSeg s = seg(ws + L.Q1, kDP, kDP, PK(P_OM1));
     LinOpt o; o.bias = w->om_b[1]; o.act = 1;
@@ -345,7 +426,7 @@ int spw_forward(const SpwParams* w, const SpwGraph* g, const float* obj, float* 
     a.RM1 = PK(P_RM1); a.RM2 = PK(P_RM2); a.RM3 = PK(P_RM3); a.b1 = w->rm_b[1]; a.b2 = w->rm_b[2]; a.b3 = w->rm_b[3];
     a.W1A = PK(P_W1A); a.bA = w->rmp_b[0]; a.A = ws + L.A;
     set_smem(k_edge_encode, edge_tile_smem());
-    SPW_LAUNCH(k_edge_encode, dim3(egrid), dim3(kThreads), edge_tile_smem(), st, a);
+    SPW_KLAUNCH("k_edge_encode", k_edge_encode, dim3(egrid), dim3(kThreads), edge_tile_smem(), st, a);
   }
   // nodes without in-edges keep an all-zero aggregate
   cudaMemsetAsync(ws + L.H2S, 0, (size_t)L.slotsN * nE * sizeof(float), st);
@@ -374,9 +455,9 @@ int spw_forward(const SpwParams* w, const SpwGraph* g, const float* obj, float* 
       a.E = E; a.in_snd = g->in_snd; a.in_rcv = g->in_rcv; a.in_off = g->in_off; a.A = ws + L.A; a.S = S; a.R = R;
       a.W2 = PK(P_W2); a.b2 = w->rmp_b[1]; a.H2S = H2S; a.part_first = ws + L.PF; a.part_last = ws + L.PL;
       set_smem(k_edge_step, edge_tile_smem());
-      SPW_LAUNCH(k_edge_step, dim3(egrid), dim3(kThreads), edge_tile_smem(), st, a);
+      SPW_KLAUNCH("k_edge_step", k_edge_step, dim3(egrid), dim3(kThreads), edge_tile_smem(), st, a);
       if (etiles > 1)
-        SPW_LAUNCH(k_fix_boundaries, dim3(grid_for(etiles - 1, 8)), dim3(256), 0, st, E, g->in_rcv, ws + L.PF, ws + L.PL, H2S);
+        SPW_KLAUNCH("k_fix_boundaries", k_fix_boundaries, dim3(grid_for(etiles - 1, 8)), dim3(256), 0, st, E, g->in_rcv, ws + L.PF, ws + L.PL, H2S);
     }
     {   // g = tanh(W3.sum h2 + deg.b3)   (Networks.py:87-88)
       LinSeg s = seg(H2S, kDEP, kDE, PK(P_W3));
@@ -393,7 +474,7 @@ int spw_forward(const SpwParams* w, const SpwGraph* g, const float* obj, float* 
       LinOpt o; o.bias = w->omp_b[1] + 1; o.addend = Pin; o.ld_add = kDP; o.act = 2;
       launch_linear(st, n, kDP, false, 1, &s, Pout, kDP, o);
     } else {                     // head: channel 0 of the last z (Networks.py:93-96)
-      SPW_LAUNCH(k_logit, dim3(grid_for(n, 8)), dim3(256), 0, st, U, n, w->omp_w[1], w->omp_b[1], logits, probs);
+      SPW_KLAUNCH("k_logit", k_logit, dim3(grid_for(n, 8)), dim3(256), 0, st, U, n, w->omp_w[1], w->omp_b[1], logits, probs);
     }
   }
   return check_launch("spw_forward");
@@ -404,7 +485,7 @@ int spw_bce_grad(const float* logits, const float* target, int32_t n_nodes, doub
   if (n_nodes < 0 || count <= 0) return fail(SPW_ERR_BAD_ARG, "spw_bce_grad: bad size");
   if (n_nodes == 0) return SPW_OK;
   if (!logits || !target || !dlogits || !stats) return fail(SPW_ERR_BAD_ARG, "spw_bce_grad: null pointer");
-  SPW_LAUNCH(k_bce_grad, dim3(grid_for(n_nodes, 256)), dim3(256), 0, (cudaStream_t)stream, logits, target, (int)n_nodes,
+  SPW_KLAUNCH("k_bce_grad", k_bce_grad, dim3(grid_for(n_nodes, 256)), dim3(256), 0, (cudaStream_t)stream, logits, target, (int)n_nodes,
              1.0 / count, dlogits, stats);
   return check_launch("spw_bce_grad");
 }
@@ -440,7 +521,7 @@ int spw_backward(const SpwParams* w, const SpwGraph* g, const float* obj, const 
   // head: dUpre^5 = dlogit (x) V2[:,0] * relu'
   float* dU5 = ws + L.dU + 4 * nP;
   const float* U5 = ws + L.U + 4 * nP;
-  SPW_LAUNCH(k_logit_bwd, dim3(grid_for((int64_t)n * kDP, 256)), dim3(256), 0, st, dlogits, U5, n, w->omp_w[1], dU5);
+  SPW_KLAUNCH("k_logit_bwd", k_logit_bwd, dim3(grid_for((int64_t)n * kDP, 256)), dim3(256), 0, st, dlogits, U5, n, w->omp_w[1], dU5);
 
   for (int l = SPW_N_STEPS - 1; l >= 0; --l) {   // step l+1 of the forward loop
     const float* Pin = ws + L.P + (size_t)l * nP;
@@ -482,13 +563,13 @@ int spw_backward(const SpwParams* w, const SpwGraph* g, const float* obj, const 
       a.b2 = w->rmp_b[1]; a.W2T = PK(P_W2T); a.dH2S = ws + L.dH2S; a.dA = ws + L.dA; a.DH1 = ws + L.DH1;
       a.partW2 = ws + L.partE; a.first = (l == SPW_N_STEPS - 1);
       set_smem(k_edge_step_bwd, edge_tile_smem());
-      SPW_LAUNCH(k_edge_step_bwd, dim3(egrid), dim3(kThreads), edge_tile_smem(), st, a);
+      SPW_KLAUNCH("k_edge_step_bwd", k_edge_step_bwd, dim3(egrid), dim3(kThreads), edge_tile_smem(), st, a);
     }
     if (l > 0) {
       float* dS = ws + L.dS + (size_t)(l - 1) * nE;
       float* dR = ws + L.dR + (size_t)(l - 1) * nE;
       if (E > 0) {
-        SPW_LAUNCH(k_gather_dsr, dim3(grid_for(n, 8)), dim3(256), 0, st, n, g->in_off, g->out_off, g->out_pos,
+        SPW_KLAUNCH("k_gather_dsr", k_gather_dsr, dim3(grid_for(n, 8)), dim3(256), 0, st, n, g->in_off, g->out_off, g->out_pos,
                    ws + L.DH1, dS, dR);
       } else {
         cudaMemsetAsync(dS, 0, nE * sizeof(float), st);
@@ -536,7 +617,7 @@ int spw_backward(const SpwParams* w, const SpwGraph* g, const float* obj, const 
     a.RM1T = PK(P_RM1T); a.RM2T = PK(P_RM2T); a.RM3T = PK(P_RM3T); a.W1AT = PK(P_W1AT); a.dA = ws + L.dA;
     a.partM = ws + L.partM; a.part0 = ws + L.part0;
     set_smem(k_edge_encode_bwd, edge_encb_smem());
-    SPW_LAUNCH(k_edge_encode_bwd, dim3(bgrid), dim3(kThreads), edge_encb_smem(), st, a);
+    SPW_KLAUNCH("k_edge_encode_bwd", k_edge_encode_bwd, dim3(bgrid), dim3(kThreads), edge_encb_smem(), st, a);
     const int ps = 4 * 160 * 160;
     launch_reduce(st, ws + L.partM, bgrid, ps, 160, kDE, kDE, {grads->rmp_w[0], 150, 0, 0, grads->rmp_b[0], 0});
     launch_reduce(st, ws + L.partM + 160 * 160, bgrid, ps, 160, kDE, kDE, {grads->rm_w[3], 150, 0, 0, grads->rm_b[3], 0});

@@ -1,0 +1,117 @@
+"""Host-side driver of the CUDA hot path: forward, loss seed, backward, Keras-form Adam.
+
+Everything numerical happens inside libspwgnn.so (include/spwgnn.h); torch supplies device
+memory, streams and (for data parallelism) torch.distributed.  No CPU fallback exists.
+"""
+import ctypes
+
+import torch
+
+from ._lib import lib, require_cuda
+from .graph import TowerBatch, _stream_ptr
+from .params import ParamBuffer, FLAT_SIZE
+
+
+class Workspace:
+    """Grow-only device scratch shared by forward and backward (caller-owned, see spwgnn.h)."""
+
+    def __init__(self, device):
+        self.device = device
+        self.buf = None
+
+    def get(self, nbytes):
+        if self.buf is None or self.buf.numel() < nbytes:
+            self.buf = None
+            self.buf = torch.empty(int(nbytes * 1.1) + 256, dtype=torch.uint8, device=self.device)
+        return self.buf
+
+
+class Engine:
+    """One replica of the network on one GPU."""
+
+    def __init__(self, device='cuda', seed=0):
+        require_cuda()
+        self.api = lib()
+        self.device = torch.device(device)
+        self.params = ParamBuffer(self.device).glorot_init(seed)
+        self.grads = ParamBuffer(self.device)
+        self.ws = Workspace(self.device)        # training: must survive until backward
+        self.ws_inf = Workspace(self.device)    # inference: separate, so a predict() between forward and
+                                                # backward of a training step cannot clobber saved state
+        self._adam = None
+        self._fwd = None
+
+    # ---- forward ------------------------------------------------------------------------------
+    def forward(self, batch: TowerBatch, training=False, want_probs=True):
+        """Per-block logits (and sigmoid probabilities) for a packed batch (Networks.py:58-96)."""
+        api, n = self.api, batch.n_nodes
+        logits = torch.empty(max(n, 1), dtype=torch.float32, device=self.device)
+        probs = torch.empty(max(n, 1), dtype=torch.float32, device=self.device) if want_probs else None
+        nbytes = api.dll.spw_workspace_bytes(n, batch.n_edges, int(training))
+        ws = (self.ws if training else self.ws_inf).get(nbytes)
+        wp = self.params.c_struct()
+        api.check(api.dll.spw_forward(ctypes.byref(wp), ctypes.byref(batch.c_graph), batch.obj.data_ptr(),
+                                      logits.data_ptr(), probs.data_ptr() if want_probs else None, ws.data_ptr(),
+                                      ws.numel(), int(training), _stream_ptr(self.device)))
+        if training:
+            self._fwd = (batch, ws, logits)
+        return logits[:n], (probs[:n] if want_probs else None)
+
+    # ---- loss seed + backward -------------------------------------------------------------------
+    def bce_seed(self, logits, target, count):
+        """Keras binary_crossentropy (Networks.py:102).  Returns (dlogits, stats) with stats a device
+        double[2] = [sum of per-block losses, number of correct predictions]."""
+        api, n = self.api, logits.numel()
+        dlogits = torch.empty(max(n, 1), dtype=torch.float32, device=self.device)
+        stats = torch.zeros(2, dtype=torch.float64, device=self.device)
+        api.check(api.dll.spw_bce_grad(logits.data_ptr(), target.data_ptr(), n, float(count), dlogits.data_ptr(),
+                                       stats.data_ptr(), _stream_ptr(self.device)))
+        return dlogits[:n], stats
+
+    def backward(self, dlogits):
+        """Gradients of sum(dlogits*logits) w.r.t. all 22 tensors -> self.grads (overwritten)."""
+        batch, ws, _ = self._fwd
+        api = self.api
+        wp, gp = self.params.c_struct(), self.grads.c_struct()
+        dl = dlogits.contiguous()
+        api.check(api.dll.spw_backward(ctypes.byref(wp), ctypes.byref(batch.c_graph), batch.obj.data_ptr(),
+                                       dl.data_ptr(), ws.data_ptr(), ws.numel(), ctypes.byref(gp),
+                                       _stream_ptr(self.device)))
+        return self.grads
+
+    def loss_and_grads(self, batch, target, count=None):
+        """forward(training) + BCE + backward.  `count` = number of blocks the mean runs over
+        (global count under data parallelism).  Returns stats (device double[2])."""
+        logits, _ = self.forward(batch, training=True, want_probs=False)
+        dl, stats = self.bce_seed(logits, target, count if count is not None else max(batch.n_nodes, 1))
+        self.backward(dl)
+        return stats
+
+    # ---- optimiser (host-side torch on the flat buffers) ----------------------------------------
+    def adam_step(self, lr=5e-4, beta1=0.9, beta2=0.999, eps=1e-7):
+        """Keras 2.2 Adam (Networks.py:101): lr_t = lr*sqrt(1-b2^t)/(1-b1^t); p -= lr_t*m/(sqrt(v)+eps)."""
+        if self._adam is None:
+            self._adam = dict(t=0, m=torch.zeros(FLAT_SIZE, device=self.device), v=torch.zeros(FLAT_SIZE, device=self.device))
+        a = self._adam
+        a['t'] += 1
+        t, g = a['t'], self.grads.flat
+        a['m'].mul_(beta1).add_(g, alpha=1 - beta1)
+        a['v'].mul_(beta2).addcmul_(g, g, value=1 - beta2)
+        lr_t = lr * (1 - beta2 ** t) ** 0.5 / (1 - beta1 ** t)
+        self.params.flat.addcdiv_(a['m'], a['v'].sqrt().add_(eps), value=-lr_t)
+
+
+class PropNetFunction(torch.autograd.Function):
+    """torch.autograd bridge: logits = PropNetFunction.apply(flat_params, engine, batch)."""
+
+    @staticmethod
+    def forward(ctx, flat_params, engine, batch):
+        assert flat_params.data_ptr() == engine.params.flat.data_ptr(), 'pass engine.params.flat'
+        logits, _ = engine.forward(batch, training=True, want_probs=False)
+        ctx.engine = engine
+        return logits.clone()
+
+    @staticmethod
+    def backward(ctx, dlogits):
+        g = ctx.engine.backward(dlogits)
+        return g.flat.clone(), None, None

@@ -1,0 +1,261 @@
+"""Parity tests proper (run on the B200 box: pytest -m gpu).  The CUDA path is reached through the
+C ABI of libspwgnn.so; the oracle (oracle/propnet.py, fp64) is only the checker.
+
+Bars (BASELINE.json north_star): edge indices and packing bit-exact; logits and gradients within
+1e-5 relative (max|delta| / max|ref| per tensor) of the fp64 oracle evaluated on the same fp32
+weights and inputs.
+"""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import propnet as O
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-5
+
+
+@pytest.fixture(scope='module')
+def eng():
+    from spwgnn_b200.engine import Engine
+    assert torch.cuda.is_available()
+    e = Engine('cuda:0', seed=3)
+    e.w64 = O.init_weights(3, nonzero_bias=True)
+    e.params.load_dict(e.w64)
+    return e
+
+
+def _oracle_edges(raw, node_off, fc=False, pos=None, thr=170.0):
+    return O.edge_list(raw[:, :2] if pos is None else pos, node_off, thr=thr, fully_connected=fc)
+
+
+def _check_edges(batch, eo, snd, rcv, slot):
+    E = batch.n_edges
+    assert E == int(eo[-1])
+    if batch.edge_off is not None:
+        assert np.array_equal(batch.edge_off.cpu().numpy(), eo)
+    s, r, sl = [t.cpu().numpy()[:E] for t in batch.slot_list]
+    assert np.array_equal(s, snd) and np.array_equal(r, rcv) and np.array_equal(sl, slot)
+    # CSR views: receiver-major order = stable sort by receiver of the slot-order list
+    order = np.lexsort((np.arange(E), rcv))
+    assert np.array_equal(batch.in_snd.cpu().numpy()[:E], snd[order])
+    assert np.array_equal(batch.in_rcv.cpu().numpy()[:E], rcv[order])
+    assert np.array_equal(batch.out_pos.cpu().numpy()[:E][order], np.arange(E))
+    n = batch.n_nodes
+    assert np.array_equal(np.diff(batch.in_off.cpu().numpy()[:n + 1]), np.bincount(rcv, minlength=n))
+    assert np.array_equal(np.diff(batch.out_off.cpu().numpy()[:n + 1]), np.bincount(snd, minlength=n))
+
+
+def _rel(got, ref):
+    ref = np.asarray(ref, dtype=np.float64)
+    return float(np.abs(np.asarray(got, dtype=np.float64) - ref).max() / max(np.abs(ref).max(), 1e-30))
+
+
+def _oracle_all(w64, raw, snd, rcv, tgt):
+    obj64 = torch.as_tensor((raw / 170.0).astype(np.float32).astype(np.float64))
+    return O.loss_and_grads_sparse(w64, obj64, torch.as_tensor(snd), torch.as_tensor(rcv),
+                                   torch.as_tensor(np.asarray(tgt, dtype=np.float64)))
+
+
+# ------------------------------------------------------------------------------------------------
+def test_edges_bit_exact_random_and_adversarial():
+    from spwgnn_b200.graph import TowerBatch
+    from spwgnn_b200 import synth
+    towers = synth.make_towers('uniform', 300, 11, lo=2, hi=40) + synth.make_towers('tower', 50, 12, n=6)
+    # adversarial: distance exactly 170, one ulp either side, coincident blocks, N = 0 / 1 / 2 / 64
+    a = np.array([[100.0, 110.0, 150.0], [270.0, 110.0, 150.0], [100.0, 280.0, 80.0]])              # exactly 170
+    b = np.array([[100.0, 110.0, 150.0], [np.nextafter(270.0, 0), 110.0, 90.0], [np.nextafter(270.0, 1e9), 110.0, 70.0]])
+    c = np.array([[500.0, 110.0, 60.0]] * 4)                                                           # coincident
+    d = np.array([[0.0, 0.0, 50.0], [102.0, 136.0, 50.0], [119.99999999999999, 120.41594578792295, 60.0]])  # 3-4-5 triangle *34 = 170
+    e64 = np.stack([400.0 + 13.0 * np.arange(64), 110.0 + 80.0 * (np.arange(64) % 5), 50.0 + np.arange(64)], 1)
+    towers += [a, b, c, d, e64, np.zeros((0, 3)), np.array([[1.0, 2.0, 3.0]]), np.array([[1.0, 2.0, 3.0], [400.0, 2.0, 3.0]])]
+    raw, node_off = synth.pack_towers(towers)
+    for fc in (False, True):
+        batch = TowerBatch.from_towers(towers, fully_connected=fc, want_slot_list=True)
+        _check_edges(batch, *_oracle_edges(raw, node_off, fc))
+    # inference glue: normalised positions against 170 -> fully connected (reference quirk F5)
+    batch = TowerBatch.from_towers(towers, inference_glue=True, want_slot_list=True)
+    eo, snd, rcv, slot = _oracle_edges(raw, node_off, pos=raw[:, :2] / 170.0)
+    _check_edges(batch, eo, snd, rcv, slot)
+    assert batch.n_edges == int(sum(len(t) * (len(t) - 1) for t in towers))
+
+
+def test_too_many_blocks_raises():
+    from spwgnn_b200.graph import TowerBatch
+    from spwgnn_b200 import SpwError
+    with pytest.raises(SpwError):
+        TowerBatch.from_towers([np.zeros((65, 3))])
+
+
+@pytest.mark.parametrize('kind,kw,count,fc', [
+    ('uniform', dict(lo=2, hi=20), 48, False),
+    ('uniform', dict(lo=2, hi=16), 40, True),
+    ('jenga18', {}, 6, False),
+    ('tower', dict(n=6), 64, False),
+])
+def test_forward_backward_match_oracle(eng, kind, kw, count, fc):
+    from spwgnn_b200.graph import TowerBatch
+    from spwgnn_b200 import synth
+    towers = synth.make_towers(kind, count, 21, **kw)
+    raw, node_off = synth.pack_towers(towers)
+    batch = TowerBatch.from_towers(towers, fully_connected=fc, want_slot_list=True)
+    eo, snd, rcv, slot = _oracle_edges(raw, node_off, fc)
+    _check_edges(batch, eo, snd, rcv, slot)
+    n = batch.n_nodes
+    tgt = (np.random.default_rng(1).random(n) > 0.5).astype(np.float32)
+    stats = eng.loss_and_grads(batch, torch.as_tensor(tgt).cuda())
+    loss, probs, logits, g64 = _oracle_all(eng.w64, raw, snd, rcv, tgt)
+    assert _rel(eng._fwd[2][:n].cpu().numpy(), logits.numpy()) < TOL
+    assert abs(float(stats[0]) / n - float(loss)) < 1e-5 * max(1.0, float(loss))
+    for k in O.tensor_names():
+        assert _rel(eng.grads.views[k].cpu().numpy(), g64[k].numpy()) < TOL, k
+    # inference path (rolling buffers) gives the same logits as the training path, bit for bit
+    li, pi = eng.forward(batch, training=False)
+    assert torch.equal(li, eng._fwd[2][:n])
+    assert _rel(pi.cpu().numpy(), probs.numpy()) < TOL
+
+
+def test_golden_fixtures_through_facade(golden_dir):
+    """Fixtures produced by running the reference's own Networks.py/main.py (oracle/make_golden.py)."""
+    from spwgnn_b200.Networks import PropagationNetwork
+    from spwgnn_b200.graph import TowerBatch
+    wz = np.load(os.path.join(golden_dir, 'weights.npz'))
+    pn = PropagationNetwork()
+    for name in ['train_n2', 'train_n4', 'train_n7', 'train_n9', 'predict_jenga_n5', 'predict_jenga_n9']:
+        g = np.load(os.path.join(golden_dir, name + '.npz'))
+        N = int(g['n_objects'])
+        model = pn.getModel(N, 3)
+        assert pn.getModel(N, 3) is model                       # cached per N like Networks.py:17-18
+        model.set_weights_dict({k: wz[k] for k in wz.files})
+        x = {'objects': g['objects'], 'sender_relations': g['sender_relations'],
+             'receiver_relations': g['receiver_relations'],
+             'propagation': np.zeros(g['objects'].shape[:2] + (100,))}
+        out = model.predict(x)
+        assert out.shape == g['probs'].shape and out.dtype == np.float32
+        assert _rel(out, g['probs']) < TOL, name
+        if 'raw_pos' in g.files:
+            # fast path on raw poses builds the same relations on the GPU
+            B = g['raw_pos'].shape[0]
+            raw = np.concatenate([g['raw_pos'], g['objects'][:, :, 2:3] * 170.0], axis=2)
+            res = model.predict_towers([raw[b] for b in range(B)], inference_glue=False)
+            assert _rel(np.stack(res)[:, :, None], g['probs']) < TOL, name
+        if 'g:rm.w0' in g.files:
+            eng = pn.engine
+            batch = TowerBatch.from_dense_relations(g['objects'], g['sender_relations'], g['receiver_relations'])
+            tgt = torch.as_tensor(g['target'].reshape(-1).astype(np.float32)).cuda()
+            stats = eng.loss_and_grads(batch, tgt)
+            assert abs(float(stats[0]) / batch.n_nodes - float(g['loss'])) < 1e-5
+            for k in O.tensor_names():
+                assert _rel(eng.grads.views[k].cpu().numpy(), g['g:' + k]) < TOL, (name, k)
+
+
+def test_mixed_sizes_equal_group_by_n(eng):
+    """One packed ragged batch == one reference-style model per N with shared weights."""
+    from spwgnn_b200.graph import TowerBatch
+    from spwgnn_b200 import synth
+    towers = synth.make_towers('uniform', 60, 31, lo=3, hi=12)
+    batch = TowerBatch.from_towers(towers)
+    logits, _ = eng.forward(batch, training=False)
+    logits = logits.cpu().numpy()
+    off = batch.node_off_host
+    for N in sorted({len(t) for t in towers}):
+        idx = [i for i, t in enumerate(towers) if len(t) == N]
+        sub = TowerBatch.from_towers([towers[i] for i in idx])
+        ls, _ = eng.forward(sub, training=False)
+        ls = ls.cpu().numpy().reshape(len(idx), N)
+        for k, i in enumerate(idx):
+            # same per-node summation order; only segments cut by a 128-edge tile boundary associate
+            # differently between the two packings
+            assert _rel(ls[k], logits[off[i]:off[i + 1]]) < 2e-6
+
+
+def test_deterministic_bitwise(eng):
+    from spwgnn_b200.graph import TowerBatch
+    from spwgnn_b200 import synth
+    towers = synth.make_towers('uniform', 200, 41, lo=4, hi=24)
+    batch = TowerBatch.from_towers(towers)
+    tgt = torch.as_tensor((np.random.default_rng(2).random(batch.n_nodes) > 0.5).astype(np.float32)).cuda()
+    eng.loss_and_grads(batch, tgt)
+    g1, l1 = eng.grads.flat.clone(), eng._fwd[2].clone()
+    eng.loss_and_grads(batch, tgt)
+    assert torch.equal(l1, eng._fwd[2]) and torch.equal(g1, eng.grads.flat)
+
+
+def test_full_size_properties_config2(eng):
+    """BASELINE config 2 at full size (4096 ten-block towers, fully connected): size-independent
+    properties + a subsample against the oracle."""
+    from spwgnn_b200.graph import TowerBatch
+    from spwgnn_b200 import synth
+    towers = synth.make_towers('jenga', 4096, 1235, n=10)
+    batch = TowerBatch.from_towers(towers, fully_connected=True)
+    assert batch.n_nodes == 40960 and batch.n_edges == 368640
+    tgt = torch.as_tensor((np.random.default_rng(3).random(batch.n_nodes) > 0.5).astype(np.float32)).cuda()
+    logits, _ = eng.forward(batch, training=True, want_probs=False)
+    logits = logits.clone()
+    dl, stats = eng.bce_seed(logits, tgt, batch.n_nodes)
+    g1 = eng.backward(dl).flat.clone()
+    assert torch.isfinite(logits).all() and torch.isfinite(g1).all()
+    # (1) tower-permutation equivariance (to rounding: tile boundaries cut different segments)
+    perm = np.random.default_rng(4).permutation(4096)
+    pb = TowerBatch.from_towers([towers[i] for i in perm], fully_connected=True)
+    lp, _ = eng.forward(pb, training=False)
+    ref = logits.view(4096, 10)[torch.as_tensor(perm).cuda()]
+    assert float((lp.view(4096, 10) - ref).abs().max() / ref.abs().max()) < 2e-6
+    # (2) backward is linear in the seed: scaling by 2 is exact in binary floating point
+    eng.forward(batch, training=True, want_probs=False)
+    g2 = eng.backward(dl * 2).flat.clone()
+    assert torch.equal(g2, g1 * 2)
+    # (3) a 6-tower subsample against the fp64 oracle
+    idx = [0, 17, 1000, 2048, 4000, 4095]
+    raw, node_off = synth.pack_towers([towers[i] for i in idx])
+    eo, snd, rcv, slot = _oracle_edges(raw, node_off, True)
+    _, _, l64, _ = _oracle_all(eng.w64, raw, snd, rcv, np.zeros(len(raw)))
+    got = logits.view(4096, 10)[torch.as_tensor(idx).cuda()].reshape(-1).cpu().numpy()
+    assert _rel(got, l64.numpy()) < TOL
+    # (4) the gradient of the whole batch equals the sum over two halves (fixed-order sums, so only
+    #     to rounding): checks the per-CTA partial reduction at scale
+    half = TowerBatch.from_towers(towers[:2048], fully_connected=True)
+    eng.forward(half, training=True, want_probs=False)
+    ga = eng.backward(dl[:20480].contiguous()).flat.clone()
+    half2 = TowerBatch.from_towers(towers[2048:], fully_connected=True)
+    eng.forward(half2, training=True, want_probs=False)
+    gb = eng.backward(dl[20480:].contiguous()).flat.clone()
+    assert float((ga + gb - g1).abs().max() / g1.abs().max()) < 2e-5
+
+
+def test_fit_predict_facade_runs_like_main_py():
+    """main.py:92-98 style call: dict in, History out, loss goes down on a learnable toy target."""
+    from spwgnn_b200.Networks import PropagationNetwork
+    from spwgnn_b200 import synth
+    towers = synth.make_towers('tower', 160, 51, n=6)
+    raw = np.stack(towers)                                   # (160, 7, 3)
+    rs, rr = O.build_relations_dense(raw[:, :, :2])
+    objects = raw / 170.0
+    y = (raw[:, :, 1:2] < 300).astype(np.float64)            # learnable: low blocks are "stable"
+    model = PropagationNetwork(seed=5).getModel(7, 3)
+    x = {'objects': objects, 'sender_relations': rs, 'receiver_relations': rr, 'propagation': np.zeros((160, 7, 100))}
+    h = model.fit(x, {'target': y}, batch_size=32, epochs=4, validation_split=0.2, shuffle=True, verbose=0, seed=0)
+    assert set(h.history) == {'loss', 'binary_accuracy', 'val_loss', 'val_binary_accuracy'}
+    assert h.history['loss'][-1] < h.history['loss'][0]
+    p = model.predict(x)
+    assert p.shape == (160, 7, 1) and np.all((p > 0) & (p < 1))
+    assert [float(s[0]) for s in p[0]] == [float(v) for v in p[0, :, 0]]   # the reference iterates `for s in out[0]: s[0]`
+
+
+def test_autograd_function_bridge(eng):
+    from spwgnn_b200.engine import PropNetFunction
+    from spwgnn_b200.graph import TowerBatch
+    from spwgnn_b200 import synth
+    towers = synth.make_towers('uniform', 10, 61, lo=3, hi=8)
+    batch = TowerBatch.from_towers(towers)
+    flat = eng.params.flat.requires_grad_(True)
+    try:
+        logits = PropNetFunction.apply(flat, eng, batch)
+        loss = (logits * logits).sum()
+        loss.backward()
+        assert flat.grad is not None and torch.isfinite(flat.grad).all() and float(flat.grad.abs().max()) > 0
+    finally:
+        flat.grad = None
+        flat.requires_grad_(False)
