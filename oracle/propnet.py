@@ -72,14 +72,52 @@ def init_weights(seed=0, dtype=torch.float64, nonzero_bias=False):
     return w
 
 
+_PROBE = None     # when a list: every relu records min|pre-activation| (distance to the kink)
+
+
+def _relu(x):
+    if _PROBE is not None and x.numel():
+        _PROBE.append(float(x.detach().abs().min()))
+    return torch.relu(x)
+
+
 def _mlp(w, net, x):
     """Blocks.py:20-28 / 60-68: Dense+relu for all but the last layer, last layer linear."""
     n = len(LAYER_DIMS[net])
     for li in range(n):
         x = x @ w['%s.w%d' % (net, li)] + w['%s.b%d' % (net, li)]
         if li < n - 1:
-            x = torch.relu(x)
+            x = _relu(x)
     return x
+
+
+def min_relu_margin(w, obj, snd, rcv):
+    """Smallest |pre-activation| over every relu unit of a forward pass.  Gradients of a relu network
+    are discontinuous at 0: an fp32 evaluation whose rounding error exceeds this margin can switch a
+    unit that the fp64 evaluation does not, and then differs by that unit's whole contribution."""
+    global _PROBE
+    _PROBE = []
+    try:
+        with torch.no_grad():
+            forward_sparse(w, obj, snd, rcv)
+        return min(_PROBE) if _PROBE else float('inf')
+    finally:
+        _PROBE = None
+
+
+def kinkfree_weights(seed=0, dtype=torch.float64, scale=0.1):
+    """Test weights that keep every relu unit far from its kink: glorot kernels scaled by `scale`,
+    hidden biases +-1 (random sign, so both relu states occur), output biases small."""
+    g = torch.Generator().manual_seed(seed + 1000)
+    w = init_weights(seed, dtype=torch.float64, nonzero_bias=True)
+    relu_biases = ['rm.b0', 'rm.b1', 'rm.b2', 'rm.b3', 'om.b0', 'om.b1', 'rmp.b0', 'rmp.b1', 'omp.b0']
+    for k in list(w):
+        if '.w' in k:
+            w[k] = (w[k] * scale).float().double()
+    for k in relu_biases:
+        sign = (torch.rand(w[k].shape, generator=g) > 0.5).double() * 2 - 1
+        w[k] = sign
+    return {k: v.float().to(dtype) for k, v in w.items()}
 
 
 # ----------------------------------------------------------------------------------------
@@ -171,8 +209,8 @@ def forward_dense(w, objects, sender_relations, receiver_relations, propagation=
     s_pos = senders[:, :, 0:2]                               # :59
     diff_rs = r_pos - s_pos                                  # :62
     obj_in = torch.cat([objects[:, :, 1:2], objects[:, :, 2:3]], dim=-1)   # :65-66,71
-    rel_enc = torch.relu(_mlp(w, 'rm', diff_rs))             # :75
-    obj_enc = torch.relu(_mlp(w, 'om', obj_in))              # :76   (dropout :77-78 = identity)
+    rel_enc = _relu(_mlp(w, 'rm', diff_rs))                  # :75
+    obj_enc = _relu(_mlp(w, 'om', obj_in))                   # :76   (dropout :77-78 = identity)
     prop = propagation                                       # :79
     x = None
     for _ in range(N_STEPS):                                 # :83
@@ -194,8 +232,8 @@ def forward_sparse(w, obj, snd, rcv, return_logits=False):
     n = obj.shape[0]
     snd = snd.long(); rcv = rcv.long()
     diff = obj[rcv, 0:2] - obj[snd, 0:2]
-    c = torch.relu(_mlp(w, 'rm', diff))
-    q = torch.relu(_mlp(w, 'om', obj[:, 1:3]))
+    c = _relu(_mlp(w, 'rm', diff))
+    q = _relu(_mlp(w, 'om', obj[:, 1:3]))
     p = torch.zeros(n, PROP_DIM, dtype=obj.dtype)
     z = None
     for _ in range(N_STEPS):
