@@ -35,7 +35,7 @@ def eng():
     assert torch.cuda.is_available()
     e = Engine('cuda:0', seed=3)
     e.w_glorot = O.init_weights(3, nonzero_bias=True)
-    e.w_kinkfree = O.kinkfree_weights(3, scale=0.3)
+    e.w_kinkfree = O.kinkfree_weights(3)
     e.w64 = e.w_glorot
     e.params.load_dict(e.w64)
     return e
