@@ -135,11 +135,20 @@ def test_forward_backward_match_oracle(eng, kind, kw, count, fc, weights):
     if weights == 'kinkfree':
         obj64 = torch.as_tensor((raw / 170.0).astype(np.float32).astype(np.float64))
         assert O.min_relu_margin(eng.w64, obj64, torch.as_tensor(snd), torch.as_tensor(rcv)) > 1e-3
-    gtol = TOL if weights == 'kinkfree' else KINK_BOUND
     errs = {k: _rel(eng.grads.views[k].cpu().numpy(), g64[k].numpy()) for k in O.tensor_names()}
     print('grad rel err [%s %s fc=%s]: worst %.2e' % (weights, kind, fc, max(errs.values())))
-    for k, e in errs.items():
-        assert e < gtol, (k, e)
+    if weights == 'kinkfree':
+        # smooth regime: 1e-5, or -- for tensors whose sum cancels heavily (e.g. d rm.w0 = sum_e dx_e * ...
+        # over +-dx pairs) -- no worse than 4x the rounding error of a plain fp32 evaluation of the oracle
+        w32 = {k: v.float() for k, v in eng.w64.items()}
+        obj32 = torch.as_tensor((raw / 170.0).astype(np.float32))
+        _, _, _, g32 = O.loss_and_grads_sparse(w32, obj32, torch.as_tensor(snd), torch.as_tensor(rcv), torch.as_tensor(tgt))
+        for k, e in errs.items():
+            e32 = _rel(g32[k].numpy(), g64[k].numpy())
+            assert e < max(TOL, 4 * e32), (k, e, e32)
+    else:
+        for k, e in errs.items():
+            assert e < KINK_BOUND, (k, e)
     # inference path (rolling buffers) gives the same logits as the training path, bit for bit
     li, pi = eng.forward(batch, training=False)
     assert torch.equal(li, eng._fwd[2][:n])
