@@ -149,15 +149,28 @@ __device__ __forceinline__ void wgrad_tile_acc(float (&acc)[TA][TB], const float
   }
 }
 
-// acc -> per-CTA partial matrix in global memory (row length 16*TB), read-modify-write.
-template <int TA, int TB>
-__device__ __forceinline__ void wgrad_flush(const float (&acc)[TA][TB], float* part, bool accumulate) {
+// acc -> per-CTA partial matrix in global memory (row length 16*TB).  ACC: read-modify-write, issued
+// as two batches of TA/2 rows so that all loads of a batch are in flight together.
+template <int TA, int TB, bool ACC>
+__device__ __forceinline__ void wgrad_flush(const float (&acc)[TA][TB], float* part) {
   const int ja = threadIdx.x >> 4, jb = threadIdx.x & 15;
+  float* base = part + (size_t)(TA * ja) * (16 * TB) + TB * jb;
+  constexpr int H = (TA + 1) / 2;
 #pragma unroll
-  for (int a = 0; a < TA; ++a) {
-    float* p = part + (size_t)(TA * ja + a) * (16 * TB) + TB * jb;
+  for (int h = 0; h < TA; h += H) {
+    float old[H][TB];
+    if (ACC) {
 #pragma unroll
-    for (int b = 0; b < TB; ++b) p[b] = accumulate ? p[b] + acc[a][b] : acc[a][b];
+      for (int a = 0; a < H; ++a)
+        if (h + a < TA) load_vec<TB>(base + (size_t)(h + a) * (16 * TB), old[a]);
+    }
+#pragma unroll
+    for (int a = 0; a < H; ++a) {
+      if (h + a >= TA) continue;
+      float* p = base + (size_t)(h + a) * (16 * TB);
+#pragma unroll
+      for (int b = 0; b < TB; ++b) p[b] = ACC ? old[a][b] + acc[h + a][b] : acc[h + a][b];
+    }
   }
 }
 

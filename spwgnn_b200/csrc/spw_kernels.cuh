@@ -151,24 +151,24 @@ struct LinArgs {
   int accumulate;          // Y += result
 };
 
-template <int CN>
-__global__ void __launch_bounds__(kThreads, 1) k_linear(LinArgs a) {
+template <int CN, int TMR>
+__global__ void __launch_bounds__(kThreads, (TMR == 64 ? 2 : 1)) k_linear(LinArgs a) {
   SPW_DYN_SMEM(smem_raw);
   float* smem = reinterpret_cast<float*>(smem_raw);
-  constexpr int LDW = CN * 32;
+  constexpr int ROWS = TMR / 8;
   float* Xs[3];
   int off = 0;
-  for (int s = 0; s < a.nseg; ++s) { Xs[s] = smem + off; off += kTM * a.seg[s].Kp; }
+  for (int s = 0; s < a.nseg; ++s) { Xs[s] = smem + off; off += TMR * a.seg[s].Kp; }
   float* Wst = smem + off;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int ntiles = (a.M + kTM - 1) / kTM;
+  const int ntiles = (a.M + TMR - 1) / TMR;
   for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
-    const int r0 = tile * kTM;
-    const int rows = imin(kTM, a.M - r0);
+    const int r0 = tile * TMR;
+    const int rows = imin(TMR, a.M - r0);
     for (int s = 0; s < a.nseg; ++s) {
       const LinSeg sg = a.seg[s];
       const int k4 = sg.Kp >> 2;
-      for (int idx = tid; idx < kTM * k4; idx += kThreads) {
+      for (int idx = tid; idx < TMR * k4; idx += kThreads) {
         const int r = idx / k4, c = (idx - r * k4) << 2;
         float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
         if (r < rows) {
@@ -185,32 +185,43 @@ __global__ void __launch_bounds__(kThreads, 1) k_linear(LinArgs a) {
       }
     }
     __syncthreads();
-    float acc[16][CN];
-    zero_acc<16, CN>(acc);
-    for (int s = 0; s < a.nseg; ++s) gemm_tile_acc<16, CN>(acc, Xs[s], a.seg[s].Kp, warp * 16, a.seg[s].W, a.seg[s].Kp, Wst);
+    float acc[ROWS][CN];
+    zero_acc<ROWS, CN>(acc);
+    for (int s = 0; s < a.nseg; ++s)
+      gemm_tile_acc<ROWS, CN>(acc, Xs[s], a.seg[s].Kp, warp * ROWS, a.seg[s].W, a.seg[s].Kp, Wst);
     // epilogue (registers -> global)
+    const bool vec4 = (CN == 4) && ((a.ldy & 3) == 0) && (lane * 4 + 3 < a.ldy);
 #pragma unroll
-    for (int r = 0; r < 16; ++r) {
-      const int row = warp * 16 + r;
+    for (int r = 0; r < ROWS; ++r) {
+      const int row = warp * ROWS + r;
       if (row >= rows) continue;
       const size_t grow = (size_t)(r0 + row);
       const float rs = a.rowscale ? a.rowscale[grow] : 1.f;
+      float v[CN];
 #pragma unroll
       for (int i = 0; i < CN; ++i) {
         const int col = lane * CN + i;
-        if (col >= a.ldy) continue;
-        float v = 0.f;
+        float t = 0.f;
         if (col < a.N) {
-          v = acc[r][i];
-          if (a.bias) v = fmaf(rs, a.bias[col], v);
-          if (a.addend) v += a.addend[grow * a.ld_add + col];
-          if (a.act == 1) v = relu_f(v);
-          else if (a.act == 2) v = tanhf(v);
-          if (a.mulmode == 1) v = a.mulsrc[grow * a.ld_mul + col] > 0.f ? v : 0.f;
-          else if (a.mulmode == 2) { const float m = a.mulsrc[grow * a.ld_mul + col]; v *= (1.f - m * m); }
-          if (a.accumulate) v += a.Y[grow * a.ldy + col];
+          t = acc[r][i];
+          if (a.bias) t = fmaf(rs, a.bias[col], t);
+          if (a.addend) t += a.addend[grow * a.ld_add + col];
+          if (a.act == 1) t = relu_f(t);
+          else if (a.act == 2) t = tanhf(t);
+          if (a.mulmode == 1) t = a.mulsrc[grow * a.ld_mul + col] > 0.f ? t : 0.f;
+          else if (a.mulmode == 2) { const float m = a.mulsrc[grow * a.ld_mul + col]; t *= (1.f - m * m); }
+          if (a.accumulate) t += a.Y[grow * a.ldy + col];
         }
-        a.Y[grow * a.ldy + col] = v;
+        v[i] = t;
+      }
+      if (vec4) {
+        *reinterpret_cast<float4*>(a.Y + grow * a.ldy + lane * 4) = make_float4(v[0], v[1], v[2], v[CN - 1]);
+      } else {
+#pragma unroll
+        for (int i = 0; i < CN; ++i) {
+          const int col = lane * CN + i;
+          if (col < a.ldy) a.Y[grow * a.ldy + col] = v[i];
+        }
       }
     }
     __syncthreads();
@@ -263,7 +274,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_wgrad(WgArgs a) {
     wgrad_tile_acc<TA, TB>(acc, Xs, LX, Ys, LY, kTM);
     __syncthreads();
   }
-  wgrad_flush<TA, TB>(acc, a.part + (size_t)blockIdx.x * (LX * LY), false);
+  wgrad_flush<TA, TB, false>(acc, a.part + (size_t)blockIdx.x * (LX * LY));
 }
 
 // fixed-order sum over per-CTA partials -> compact Keras-layout gradient (+ bias from row Kin)
@@ -350,77 +361,102 @@ struct EdgeEncArgs {
   float* A;                                               // [E][152]
 };
 
+constexpr int kTME = 64;    // edge-tile rows of the forward edge kernels (two CTAs per SM)
+
 // K2a: c_e = relu(rm(diff))  (4 layers) and A_e = W1a.c_e + b1, all inside one CTA tile
-__global__ void __launch_bounds__(kThreads, 1) k_edge_encode(EdgeEncArgs a) {
+__global__ void __launch_bounds__(kThreads, 2) k_edge_encode(EdgeEncArgs a) {
   SPW_DYN_SMEM(smem_raw);
+  constexpr int ROWS = kTME / 8;
   float* Xa = reinterpret_cast<float*>(smem_raw);
-  float* Xb = Xa + kTM * kDEP + 8;
-  float* Wst = Xb + kTM * kDEP + 8;
+  float* Xb = Xa + kTME * kDEP + 8;
+  float* Wst = Xb + kTME * kDEP + 8;
   float* sdx = Wst + 2 * kKT * kLdwE;
-  float* sdy = sdx + kTM;
+  float* sdy = sdx + kTME;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int ntiles = (a.E + kTM - 1) / kTM;
+  const int ntiles = (a.E + kTME - 1) / kTME;
   for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
-    const int e0 = tile * kTM;
-    const int rows = imin(kTM, a.E - e0);
-    build_x0<kTM>(Xa, sdx, sdy, a.obj, a.in_snd, a.in_rcv, e0, rows, a.W0, a.b0);
+    const int e0 = tile * kTME;
+    const int rows = imin(kTME, a.E - e0);
+    build_x0<kTME>(Xa, sdx, sdy, a.obj, a.in_snd, a.in_rcv, e0, rows, a.W0, a.b0);
     __syncthreads();
-    float acc[16][5];
-    zero_acc<16, 5>(acc);
-    gemm_tile_acc<16, 5>(acc, Xa, kDEP, warp * 16, a.RM1, kDEP, Wst);
-    store_act_tile<16>(acc, Xb, warp, lane, rows, [&](float v, int, int c) { return relu_f(v + a.b1[c]); });
+    float acc[ROWS][5];
+    zero_acc<ROWS, 5>(acc);
+    gemm_tile_acc<ROWS, 5>(acc, Xa, kDEP, warp * ROWS, a.RM1, kDEP, Wst);
+    store_act_tile<ROWS>(acc, Xb, warp, lane, rows, [&](float v, int, int c) { return relu_f(v + a.b1[c]); });
     __syncthreads();
-    zero_acc<16, 5>(acc);
-    gemm_tile_acc<16, 5>(acc, Xb, kDEP, warp * 16, a.RM2, kDEP, Wst);
-    store_act_tile<16>(acc, Xa, warp, lane, rows, [&](float v, int, int c) { return relu_f(v + a.b2[c]); });
+    zero_acc<ROWS, 5>(acc);
+    gemm_tile_acc<ROWS, 5>(acc, Xb, kDEP, warp * ROWS, a.RM2, kDEP, Wst);
+    store_act_tile<ROWS>(acc, Xa, warp, lane, rows, [&](float v, int, int c) { return relu_f(v + a.b2[c]); });
     __syncthreads();
-    zero_acc<16, 5>(acc);
-    gemm_tile_acc<16, 5>(acc, Xa, kDEP, warp * 16, a.RM3, kDEP, Wst);
-    store_act_tile<16>(acc, Xb, warp, lane, rows, [&](float v, int, int c) { return relu_f(v + a.b3[c]); });
+    zero_acc<ROWS, 5>(acc);
+    gemm_tile_acc<ROWS, 5>(acc, Xa, kDEP, warp * ROWS, a.RM3, kDEP, Wst);
+    store_act_tile<ROWS>(acc, Xb, warp, lane, rows, [&](float v, int, int c) { return relu_f(v + a.b3[c]); });
     __syncthreads();
-    zero_acc<16, 5>(acc);
-    gemm_tile_acc<16, 5>(acc, Xb, kDEP, warp * 16, a.W1A, kDEP, Wst);
+    zero_acc<ROWS, 5>(acc);
+    gemm_tile_acc<ROWS, 5>(acc, Xb, kDEP, warp * ROWS, a.W1A, kDEP, Wst);
+    // A tile -> Xa (free), then 128-bit coalesced rows to HBM
 #pragma unroll
-    for (int r = 0; r < 16; ++r) {
-      const int row = warp * 16 + r;
-      if (row >= rows) continue;
+    for (int r = 0; r < ROWS; ++r) {
+      const int row = warp * ROWS + r;
 #pragma unroll
       for (int i = 0; i < 5; ++i) {
         const int col = lane * 5 + i;
-        if (col >= kDEP) continue;
-        a.A[(size_t)(e0 + row) * kDEP + col] = col < kDE ? acc[r][i] + a.bA[col] : 0.f;
+        if (col < kDEP) Xa[(size_t)row * kDEP + col] = col < kDE ? acc[r][i] + a.bA[col] : 0.f;
       }
     }
+    __syncthreads();
+    for (int idx = tid; idx < rows * (kDEP / 4); idx += kThreads)
+      reinterpret_cast<float4*>(a.A + (size_t)e0 * kDEP)[idx] = reinterpret_cast<const float4*>(Xa)[idx];
     __syncthreads();
   }
 }
 
-// H1 tile: relu(A_e + S_sender + R_receiver), 128-bit coalesced row gathers, one warp per row
+// H1 tile: relu(A_e + S_sender + R_receiver).  One warp per row, 128-bit coalesced row gathers, four
+// rows (24 loads per lane) in flight at a time so the gather is bandwidth- not latency-bound.
+template <int TMR>
 __device__ __forceinline__ void build_h1(float* H1, int* srcv, const float* __restrict__ A, const float* __restrict__ S,
                                          const float* __restrict__ R, const int32_t* __restrict__ in_snd,
                                          const int32_t* __restrict__ in_rcv, int e0, int rows) {
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  constexpr int C4 = kDEP / 4;   // 38 float4 per row
-  for (int r = warp; r < kTM; r += kThreads / 32) {
-    float4* dst = reinterpret_cast<float4*>(H1 + (size_t)r * kDEP);
-    if (r < rows) {
-      const int e = e0 + r;
-      const int s = in_snd[e], rc = in_rcv[e];
-      if (lane == 0) srcv[r] = rc;
-      const float4* a4 = reinterpret_cast<const float4*>(A + (size_t)e * kDEP);
-      const float4* s4 = reinterpret_cast<const float4*>(S + (size_t)s * kDEP);
-      const float4* r4 = reinterpret_cast<const float4*>(R + (size_t)rc * kDEP);
-      for (int c = lane; c < C4; c += 32) {
-        const float4 x = a4[c], y = s4[c], z = r4[c];
+  constexpr int C4 = kDEP / 4;        // 38 float4 per row
+  constexpr int RPW = TMR / 8;        // rows per warp
+  const int r0 = warp * RPW;
+  int my_s = -1, my_r = -1;
+  if (lane < RPW && r0 + lane < rows) { my_s = in_snd[e0 + r0 + lane]; my_r = in_rcv[e0 + r0 + lane]; }
+  if (lane < RPW) srcv[r0 + lane] = my_r;
+  const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
+  for (int rb = 0; rb < RPW; rb += 4) {
+    float4 va[4][2], vs[4][2], vr[4][2];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int s = __shfl_sync(0xffffffffu, my_s, rb + j), rc = __shfl_sync(0xffffffffu, my_r, rb + j);
+      const size_t e = (size_t)(e0 + r0 + rb + j);
+#pragma unroll
+      for (int p = 0; p < 2; ++p) {
+        const int c = lane + 32 * p;
+        if (rc >= 0 && c < C4) {
+          va[j][p] = reinterpret_cast<const float4*>(A + e * kDEP)[c];
+          vs[j][p] = reinterpret_cast<const float4*>(S + (size_t)s * kDEP)[c];
+          vr[j][p] = reinterpret_cast<const float4*>(R + (size_t)rc * kDEP)[c];
+        } else {
+          va[j][p] = z4; vs[j][p] = z4; vr[j][p] = z4;
+        }
+      }
+    }
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int rc = __shfl_sync(0xffffffffu, my_r, rb + j);
+      float4* dst = reinterpret_cast<float4*>(H1 + (size_t)(r0 + rb + j) * kDEP);
+#pragma unroll
+      for (int p = 0; p < 2; ++p) {
+        const int c = lane + 32 * p;
+        if (c >= C4) continue;
         float4 h;
-        h.x = relu_f(x.x + y.x + z.x); h.y = relu_f(x.y + y.y + z.y);
-        h.z = relu_f(x.z + y.z + z.z); h.w = relu_f(x.w + y.w + z.w);
-        if (c == C4 - 1) { h.z = 1.f; h.w = 0.f; }   // columns 150 (bias ones) and 151 (pad)
+        h.x = relu_f(va[j][p].x + vs[j][p].x + vr[j][p].x); h.y = relu_f(va[j][p].y + vs[j][p].y + vr[j][p].y);
+        h.z = relu_f(va[j][p].z + vs[j][p].z + vr[j][p].z); h.w = relu_f(va[j][p].w + vs[j][p].w + vr[j][p].w);
+        if (c == C4 - 1) { h.z = rc >= 0 ? 1.f : 0.f; h.w = 0.f; }   // columns 150 (bias ones) and 151 (pad)
         dst[c] = h;
       }
-    } else {
-      if (lane == 0) srcv[r] = -1;
-      for (int c = lane; c < C4; c += 32) dst[c] = make_float4(0.f, 0.f, 0.f, 0.f);
     }
   }
 }
@@ -432,26 +468,41 @@ struct EdgeStepArgs {
   const float* W2; const float* b2;                   // packed rmp.w1, raw rmp.b1
   float* H2S;                                         // [n][152] sum over in-edges of h2
   float* part_first; float* part_last;                // [ntiles][152] segments cut by a tile boundary
+  uint32_t* maskbits;                                 // [E][8] relu mask of h2 (training) or null:
+                                                      //   word i (<5), bit j  <->  column 5*j + i
 };
 
 // K2b: per step -- gather, hidden layer 2, relu, deterministic receiver-segmented sum
-__global__ void __launch_bounds__(kThreads, 1) k_edge_step(EdgeStepArgs a) {
+__global__ void __launch_bounds__(kThreads, 2) k_edge_step(EdgeStepArgs a) {
   SPW_DYN_SMEM(smem_raw);
+  constexpr int ROWS = kTME / 8;
   float* Xa = reinterpret_cast<float*>(smem_raw);
-  float* Xb = Xa + kTM * kDEP + 8;
-  float* Wst = Xb + kTM * kDEP + 8;
+  float* Xb = Xa + kTME * kDEP + 8;
+  float* Wst = Xb + kTME * kDEP + 8;
   int* srcv = reinterpret_cast<int*>(Wst + 2 * kKT * kLdwE);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int ntiles = (a.E + kTM - 1) / kTM;
+  const int ntiles = (a.E + kTME - 1) / kTME;
   for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
-    const int e0 = tile * kTM;
-    const int rows = imin(kTM, a.E - e0);
-    build_h1(Xa, srcv, a.A, a.S, a.R, a.in_snd, a.in_rcv, e0, rows);
+    const int e0 = tile * kTME;
+    const int rows = imin(kTME, a.E - e0);
+    build_h1<kTME>(Xa, srcv, a.A, a.S, a.R, a.in_snd, a.in_rcv, e0, rows);
     __syncthreads();
-    float acc[16][5];
-    zero_acc<16, 5>(acc);
-    gemm_tile_acc<16, 5>(acc, Xa, kDEP, warp * 16, a.W2, kDEP, Wst);
-    store_act_tile<16>(acc, Xb, warp, lane, rows, [&](float v, int, int c) { return relu_f(v + a.b2[c]); });
+    float acc[ROWS][5];
+    zero_acc<ROWS, 5>(acc);
+    gemm_tile_acc<ROWS, 5>(acc, Xa, kDEP, warp * ROWS, a.W2, kDEP, Wst);
+#pragma unroll
+    for (int r = 0; r < ROWS; ++r) {
+      const int row = warp * ROWS + r;
+#pragma unroll
+      for (int i = 0; i < 5; ++i) {
+        const int col = lane * 5 + i;
+        const float pre = col < kDE ? acc[r][i] + a.b2[col] : 0.f;
+        const bool on = (row < rows) && (col < kDE) && (pre > 0.f);
+        const unsigned bal = __ballot_sync(0xffffffffu, on);
+        if (a.maskbits && lane == 0 && row < rows) a.maskbits[(size_t)(e0 + row) * 8 + i] = bal;
+        if (col < kDEP) Xb[(size_t)row * kDEP + col] = on ? pre : 0.f;
+      }
+    }
     __syncthreads();
     // receiver-segmented sum in row (= ascending sender = slot) order; one warp per node
     const int n_first = srcv[0], n_last = srcv[rows - 1];
@@ -475,13 +526,13 @@ __global__ void __launch_bounds__(kThreads, 1) k_edge_step(EdgeStepArgs a) {
 }
 
 // segments cut by a tile boundary: H2S[node] = last-part of tile b + first-part of tile b+1
-__global__ void __launch_bounds__(256) k_fix_boundaries(int E, const int32_t* __restrict__ in_rcv,
+__global__ void __launch_bounds__(256) k_fix_boundaries(int E, int tile_rows, const int32_t* __restrict__ in_rcv,
                                                         const float* __restrict__ part_first,
                                                         const float* __restrict__ part_last, float* __restrict__ H2S) {
   const int lane = threadIdx.x & 31, wpb = blockDim.x >> 5;
-  const int ntiles = (E + kTM - 1) / kTM;
+  const int ntiles = (E + tile_rows - 1) / tile_rows;
   for (int b = blockIdx.x * wpb + (threadIdx.x >> 5); b + 1 < ntiles; b += gridDim.x * wpb) {
-    const int e = (b + 1) * kTM;
+    const int e = (b + 1) * tile_rows;
     const int node = in_rcv[e - 1];
     if (in_rcv[e] != node) continue;
     for (int c = lane; c < kDEP; c += 32)
@@ -493,7 +544,8 @@ struct EdgeStepBwdArgs {
   int E;
   const int32_t* in_snd; const int32_t* in_rcv;
   const float* A; const float* S; const float* R;
-  const float* W2; const float* b2; const float* W2T;
+  const float* W2T;
+  const uint32_t* maskbits; // [E][8] relu mask of h2 written by k_edge_step in the forward pass
   const float* dH2S;        // [n][152]
   float* dA;                // [E][152] accumulated over the 5 steps
   float* DH1;               // [E][152] d(pre-activation of h1) of this step
@@ -501,36 +553,57 @@ struct EdgeStepBwdArgs {
   int first;                // first step processed (l = 5): dA is written, not accumulated
 };
 
-// K4b: per step backward of K2b -- recompute h1/h2, dW2 partials, d(h1 pre-activation)
+// K4b: per step backward of K2b -- rebuild h1 (gather), d h2 from the saved relu bits, dW2 partials,
+// d(h1 pre-activation) = (d h2 . W2^T) * relu'(h1)
 __global__ void __launch_bounds__(kThreads, 1) k_edge_step_bwd(EdgeStepBwdArgs a) {
   SPW_DYN_SMEM(smem_raw);
   float* Xa = reinterpret_cast<float*>(smem_raw);
   float* Xb = Xa + kTM * kDEP + 8;
   float* Wst = Xb + kTM * kDEP + 8;
   int* srcv = reinterpret_cast<int*>(Wst + 2 * kKT * kLdwE);
+  uint32_t* smask = reinterpret_cast<uint32_t*>(srcv + kTM);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int ntiles = (a.E + kTM - 1) / kTM;
   float* part = a.partW2 + (size_t)blockIdx.x * (160 * 160);
+  constexpr int C4 = kDEP / 4;
   for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
     const int e0 = tile * kTM;
     const int rows = imin(kTM, a.E - e0);
-    build_h1(Xa, srcv, a.A, a.S, a.R, a.in_snd, a.in_rcv, e0, rows);
+    build_h1<kTM>(Xa, srcv, a.A, a.S, a.R, a.in_snd, a.in_rcv, e0, rows);
+    for (int idx = tid; idx < kTM * 5; idx += kThreads) {
+      const int r = idx / 5, i = idx - r * 5;
+      smask[idx] = r < rows ? a.maskbits[(size_t)(e0 + r) * 8 + i] : 0u;
+    }
     __syncthreads();
-    float acc[16][5];
-    zero_acc<16, 5>(acc);
-    gemm_tile_acc<16, 5>(acc, Xa, kDEP, warp * 16, a.W2, kDEP, Wst);
-    // dH2pre = dH2S[receiver] * [h2pre > 0]   (no ones column: this tile is a dY operand)
+    // dH2pre[row][col] = mask ? dH2S[receiver][col] : 0   (a dY operand: no ones column)
+    for (int rb = warp * 16; rb < warp * 16 + 16; rb += 4) {
+      float4 d[4][2];
 #pragma unroll
-    for (int r = 0; r < 16; ++r) {
-      const int row = warp * 16 + r;
-      const int rc = row < rows ? srcv[row] : -1;
+      for (int j = 0; j < 4; ++j) {
+        const int rc = srcv[rb + j];
 #pragma unroll
-      for (int i = 0; i < 5; ++i) {
-        const int col = lane * 5 + i;
-        if (col >= kDEP) continue;
-        float v = 0.f;
-        if (rc >= 0 && col < kDE && acc[r][i] + a.b2[col] > 0.f) v = a.dH2S[(size_t)rc * kDEP + col];
-        Xb[(size_t)row * kDEP + col] = v;
+        for (int p = 0; p < 2; ++p) {
+          const int c = lane + 32 * p;
+          d[j][p] = (rc >= 0 && c < C4) ? reinterpret_cast<const float4*>(a.dH2S + (size_t)rc * kDEP)[c]
+                                        : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+      }
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const uint32_t* mw = smask + (rb + j) * 5;
+#pragma unroll
+        for (int p = 0; p < 2; ++p) {
+          const int c = lane + 32 * p;
+          if (c >= C4) continue;
+          const int col = 4 * c;
+          float4 v = d[j][p];
+          // column -> (word = col % 5, bit = col / 5)
+          v.x = (col < kDE && ((mw[col % 5] >> (col / 5)) & 1u)) ? v.x : 0.f;
+          v.y = (col + 1 < kDE && ((mw[(col + 1) % 5] >> ((col + 1) / 5)) & 1u)) ? v.y : 0.f;
+          v.z = (col + 2 < kDE && ((mw[(col + 2) % 5] >> ((col + 2) / 5)) & 1u)) ? v.z : 0.f;
+          v.w = (col + 3 < kDE && ((mw[(col + 3) % 5] >> ((col + 3) / 5)) & 1u)) ? v.w : 0.f;
+          reinterpret_cast<float4*>(Xb + (size_t)(rb + j) * kDEP)[c] = v;
+        }
       }
     }
     __syncthreads();
@@ -541,23 +614,33 @@ __global__ void __launch_bounds__(kThreads, 1) k_edge_step_bwd(EdgeStepBwdArgs a
 #pragma unroll
         for (int j = 0; j < 10; ++j) wacc[i][j] = 0.f;
       wgrad_tile_acc<10, 10>(wacc, Xa, kDEP, Xb, kDEP, kTM);
-      wgrad_flush<10, 10>(wacc, part, !(a.first && tile == (int)blockIdx.x));
+      if (a.first && tile == (int)blockIdx.x) wgrad_flush<10, 10, false>(wacc, part);
+      else wgrad_flush<10, 10, true>(wacc, part);
     }
+    float acc[16][5];
     zero_acc<16, 5>(acc);
     gemm_tile_acc<16, 5>(acc, Xb, kDEP, warp * 16, a.W2T, kDEP, Wst);
+    // masked result -> Xb (free after the GEMM), then 128-bit coalesced rows to HBM
 #pragma unroll
     for (int r = 0; r < 16; ++r) {
       const int row = warp * 16 + r;
-      if (row >= rows) continue;
-      const size_t g = (size_t)(e0 + row) * kDEP;
 #pragma unroll
       for (int i = 0; i < 5; ++i) {
         const int col = lane * 5 + i;
-        if (col >= kDEP) continue;
-        float v = 0.f;
-        if (col < kDE && Xa[(size_t)row * kDEP + col] > 0.f) v = acc[r][i];
-        a.DH1[g + col] = v;
-        a.dA[g + col] = a.first ? v : a.dA[g + col] + v;
+        if (col < kDEP) Xb[(size_t)row * kDEP + col] = (col < kDE && Xa[(size_t)row * kDEP + col] > 0.f) ? acc[r][i] : 0.f;
+      }
+    }
+    __syncthreads();
+    for (int idx = tid; idx < rows * C4; idx += kThreads) {
+      const float4 v = reinterpret_cast<const float4*>(Xb)[idx];
+      const size_t g = (size_t)e0 * C4 + idx;
+      reinterpret_cast<float4*>(a.DH1)[g] = v;
+      if (a.first) {
+        reinterpret_cast<float4*>(a.dA)[g] = v;
+      } else {
+        float4 o = reinterpret_cast<const float4*>(a.dA)[g];
+        o.x += v.x; o.y += v.y; o.z += v.z; o.w += v.w;
+        reinterpret_cast<float4*>(a.dA)[g] = o;
       }
     }
     __syncthreads();
@@ -656,7 +739,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_edge_encode_bwd(EdgeEncBwdArgs 
 #pragma unroll
         for (int j = 0; j < 10; ++j) wacc[i][j] = 0.f;
       wgrad_tile_acc<10, 10>(wacc, X, kDEP, dY, kDEP, kTMB);
-      wgrad_flush<10, 10>(wacc, part, !first);
+      if (first) wgrad_flush<10, 10, false>(wacc, part); else wgrad_flush<10, 10, true>(wacc, part);
       zero_acc<8, 5>(acc);
       gemm_tile_acc<8, 5>(acc, dY, kDEP, warp * 8, WT, kDEP, Wst);
       // mask with the layer input's relu (X holds post-relu values; X > 0 <=> pre-activation > 0)

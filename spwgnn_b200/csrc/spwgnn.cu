@@ -84,7 +84,8 @@ int num_sms() {
   return sms;
 }
 
-constexpr int kMaxCtas = 160;   // upper bound on persistent-grid size used to size partial buffers
+constexpr int kMaxCtas = 160;
+constexpr int kTN = 64;         // node-tile rows of k_linear (two CTAs per SM)   // upper bound on persistent-grid size used to size partial buffers
 
 // ---- packed weight buffer -----------------------------------------------------------------------
 enum PackId {
@@ -108,7 +109,7 @@ struct Layout {
   size_t P, S, R, H2S, G, U;     // per-step arrays (training: 5 slots; inference: fewer)
   int slotsP, slotsSR, slotsN;   // number of step slots for P / (S,R) / (H2S,G,U)
   // backward
-  size_t dU, dG, T, dS, dR, dH2S, DP, dQ, dQ1, dA, DH1, partE, partM, part0, partN;
+  size_t dU, dG, T, dS, dR, dH2S, DP, dQ, dQ1, dA, DH1, M2, partE, partM, part0, partN;
   size_t total;   // floats
 };
 
@@ -119,7 +120,7 @@ Layout make_layout(int64_t n, int64_t E, int training) {
   size_t off = 0;
   auto take = [&](size_t floats) { size_t o = off; off = align_up(off + floats, 64); return o; };
   for (int i = 0; i < P_COUNT; ++i) L.pack[i] = take((size_t)kPackShape[i].Kp * kPackShape[i].ldw);
-  const size_t nt = (size_t)((E + kTM - 1) / kTM) + 1;
+  const size_t nt = (size_t)((E + kTME - 1) / kTME) + 1;
   L.Q1 = take(n * kDP);
   L.Q = take(n * kDP);
   L.degf = take(n);
@@ -147,12 +148,13 @@ Layout make_layout(int64_t n, int64_t E, int training) {
     L.dQ1 = take((size_t)n * kDP);
     L.dA = take((size_t)E * kDEP + 8);
     L.DH1 = take((size_t)E * kDEP + 8);
+    L.M2 = take((size_t)SPW_N_STEPS * E * 8);      // relu bits of h2, 8 words per edge and step
     L.partE = take((size_t)kMaxCtas * 160 * 160);
     L.partM = take((size_t)kMaxCtas * 4 * 160 * 160);
     L.part0 = take((size_t)kMaxCtas * 3 * kDEP);
     L.partN = take((size_t)kMaxCtas * kPartNodeElems);
   } else {
-    L.dU = L.dG = L.T = L.dS = L.dR = L.dH2S = L.DP = L.dQ = L.dQ1 = L.dA = L.DH1 = 0;
+    L.dU = L.dG = L.T = L.dS = L.dR = L.dH2S = L.DP = L.dQ = L.dQ1 = L.dA = L.DH1 = L.M2 = 0;
     L.partE = L.partM = L.part0 = L.partN = 0;
   }
   L.total = off;
@@ -205,19 +207,19 @@ void launch_linear(cudaStream_t st, int M, int N, bool wide, int nseg, const Lin
   memset(&a, 0, sizeof(a));
   a.M = M; a.nseg = nseg; a.N = N;
   size_t xfloats = 0;
-  for (int s = 0; s < nseg; ++s) { a.seg[s] = segs[s]; xfloats += (size_t)kTM * segs[s].Kp; }
+  for (int s = 0; s < nseg; ++s) { a.seg[s] = segs[s]; xfloats += (size_t)kTN * segs[s].Kp; }
   a.bias = o.bias; a.rowscale = o.rowscale; a.addend = o.addend; a.ld_add = o.ld_add; a.act = o.act;
   a.mulsrc = o.mulsrc; a.ld_mul = o.ld_mul; a.mulmode = o.mulmode; a.Y = Y; a.ldy = ldy; a.accumulate = o.accumulate;
-  const int ntiles = (M + kTM - 1) / kTM;
-  const int grid = ntiles < num_sms() ? ntiles : num_sms();
+  const int ntiles = (M + kTN - 1) / kTN;
+  const int grid = ntiles < 2 * num_sms() ? ntiles : 2 * num_sms();
   if (wide) {
     const size_t smem = (xfloats + 2 * kKT * kLdwE) * sizeof(float);
-    auto kern = k_linear<5>;
+    auto kern = k_linear<5, kTN>;
     set_smem(kern, smem);
     SPW_KLAUNCH("k_linear<5>", kern, dim3(grid), dim3(kThreads), smem, st, a);
   } else {
     const size_t smem = (xfloats + 2 * kKT * kLdwP) * sizeof(float);
-    auto kern = k_linear<4>;
+    auto kern = k_linear<4, kTN>;
     set_smem(kern, smem);
     SPW_KLAUNCH("k_linear<4>", kern, dim3(grid), dim3(kThreads), smem, st, a);
   }
@@ -299,7 +301,8 @@ void pack_weights(cudaStream_t st, const SpwParams* w, float* ws, const Layout& 
   SPW_KLAUNCH("k_pack_weights", k_pack_weights, dim3(24, n), dim3(256), 0, st, pa);
 }
 
-size_t edge_tile_smem() { return (size_t)(2 * (kTM * kDEP + 8) + 2 * kKT * kLdwE + 2 * kTM) * sizeof(float); }
+size_t edge_fwd_smem() { return (size_t)(2 * (kTME * kDEP + 8) + 2 * kKT * kLdwE + 2 * kTME) * sizeof(float); }
+size_t edge_bwd_smem() { return (size_t)(2 * (kTM * kDEP + 8) + 2 * kKT * kLdwE + kTM + 5 * kTM) * sizeof(float); }
 size_t edge_encb_smem() { return (size_t)(5 * (kTMB * kDEP + 8) + 2 * kKT * kLdwE + 2 * kTMB) * sizeof(float); }
 
 }  // namespace
@@ -418,15 +421,15 @@ int spw_forward(const SpwParams* w, const SpwGraph* g, const float* obj, float* 
     launch_linear(st, n, kDP, false, 1, &s, ws + L.Q, kDP, o);
   }
   // relation encoder + A_e (Networks.py:46,75 and the c_e part of :86-87)
-  const int etiles = (E + kTM - 1) / kTM;
-  const int egrid = etiles < num_sms() ? etiles : num_sms();
+  const int etiles = (E + kTME - 1) / kTME;
+  const int egrid = etiles < 2 * num_sms() ? etiles : 2 * num_sms();
   if (E > 0) {
     EdgeEncArgs a;
     a.E = E; a.in_snd = g->in_snd; a.in_rcv = g->in_rcv; a.obj = obj; a.W0 = w->rm_w[0]; a.b0 = w->rm_b[0];
     a.RM1 = PK(P_RM1); a.RM2 = PK(P_RM2); a.RM3 = PK(P_RM3); a.b1 = w->rm_b[1]; a.b2 = w->rm_b[2]; a.b3 = w->rm_b[3];
     a.W1A = PK(P_W1A); a.bA = w->rmp_b[0]; a.A = ws + L.A;
-    set_smem(k_edge_encode, edge_tile_smem());
-    SPW_KLAUNCH("k_edge_encode", k_edge_encode, dim3(egrid), dim3(kThreads), edge_tile_smem(), st, a);
+    set_smem(k_edge_encode, edge_fwd_smem());
+    SPW_KLAUNCH("k_edge_encode", k_edge_encode, dim3(egrid), dim3(kThreads), edge_fwd_smem(), st, a);
   }
   // nodes without in-edges keep an all-zero aggregate
   cudaMemsetAsync(ws + L.H2S, 0, (size_t)L.slotsN * nE * sizeof(float), st);
@@ -454,10 +457,11 @@ int spw_forward(const SpwParams* w, const SpwGraph* g, const float* obj, float* 
       EdgeStepArgs a;
       a.E = E; a.in_snd = g->in_snd; a.in_rcv = g->in_rcv; a.in_off = g->in_off; a.A = ws + L.A; a.S = S; a.R = R;
       a.W2 = PK(P_W2); a.b2 = w->rmp_b[1]; a.H2S = H2S; a.part_first = ws + L.PF; a.part_last = ws + L.PL;
-      set_smem(k_edge_step, edge_tile_smem());
-      SPW_KLAUNCH("k_edge_step", k_edge_step, dim3(egrid), dim3(kThreads), edge_tile_smem(), st, a);
+      a.maskbits = training ? reinterpret_cast<uint32_t*>(ws + L.M2) + (size_t)l * E * 8 : nullptr;
+      set_smem(k_edge_step, edge_fwd_smem());
+      SPW_KLAUNCH("k_edge_step", k_edge_step, dim3(egrid), dim3(kThreads), edge_fwd_smem(), st, a);
       if (etiles > 1)
-        SPW_KLAUNCH("k_fix_boundaries", k_fix_boundaries, dim3(grid_for(etiles - 1, 8)), dim3(256), 0, st, E, g->in_rcv, ws + L.PF, ws + L.PL, H2S);
+        SPW_KLAUNCH("k_fix_boundaries", k_fix_boundaries, dim3(grid_for(etiles - 1, 8)), dim3(256), 0, st, E, (int)kTME, g->in_rcv, ws + L.PF, ws + L.PL, H2S);
     }
     {   // g = tanh(W3.sum h2 + deg.b3)   (Networks.py:87-88)
       LinSeg s = seg(H2S, kDEP, kDE, PK(P_W3));
@@ -559,11 +563,12 @@ int spw_backward(const SpwParams* w, const SpwGraph* g, const float* obj, const 
     }
     if (E > 0) {
       EdgeStepBwdArgs a;
-      a.E = E; a.in_snd = g->in_snd; a.in_rcv = g->in_rcv; a.A = ws + L.A; a.S = S; a.R = R; a.W2 = PK(P_W2);
-      a.b2 = w->rmp_b[1]; a.W2T = PK(P_W2T); a.dH2S = ws + L.dH2S; a.dA = ws + L.dA; a.DH1 = ws + L.DH1;
+      a.E = E; a.in_snd = g->in_snd; a.in_rcv = g->in_rcv; a.A = ws + L.A; a.S = S; a.R = R;
+      a.W2T = PK(P_W2T); a.dH2S = ws + L.dH2S; a.dA = ws + L.dA; a.DH1 = ws + L.DH1;
+      a.maskbits = reinterpret_cast<const uint32_t*>(ws + L.M2) + (size_t)l * E * 8;
       a.partW2 = ws + L.partE; a.first = (l == SPW_N_STEPS - 1);
-      set_smem(k_edge_step_bwd, edge_tile_smem());
-      SPW_KLAUNCH("k_edge_step_bwd", k_edge_step_bwd, dim3(egrid), dim3(kThreads), edge_tile_smem(), st, a);
+      set_smem(k_edge_step_bwd, edge_bwd_smem());
+      SPW_KLAUNCH("k_edge_step_bwd", k_edge_step_bwd, dim3(egrid), dim3(kThreads), edge_bwd_smem(), st, a);
     }
     if (l > 0) {
       float* dS = ws + L.dS + (size_t)(l - 1) * nE;

@@ -84,6 +84,15 @@ template <class T> static inline T __shfl_xor_sync(unsigned, T v, int m) { retur
 template <class T> static inline T __shfl_down_sync(unsigned, T v, int d) { int l = threadIdx.x % 32; return emu_shfl(v, l + d < 32 ? l + d : l); }
 template <class T> static inline T __shfl_up_sync(unsigned, T v, int d) { int l = threadIdx.x % 32; return emu_shfl(v, l - d >= 0 ? l - d : l); }
 
+static inline unsigned __ballot_sync(unsigned, int pred) {
+  int w = threadIdx.x / 32, l = threadIdx.x % 32;
+  emu::g_block->shfl_buf[w][l] = pred ? 1u : 0u;
+  pthread_barrier_wait(&emu::g_block->warp_bar[w]);
+  unsigned r = 0;
+  for (int i = 0; i < 32; ++i) r |= (emu::g_block->shfl_buf[w][i] & 1u) << i;
+  pthread_barrier_wait(&emu::g_block->warp_bar[w]);
+  return r;
+}
 static inline int atomicAdd(int* p, int v) { return __atomic_fetch_add(p, v, __ATOMIC_SEQ_CST); }
 static inline unsigned atomicAdd(unsigned* p, unsigned v) { return __atomic_fetch_add(p, v, __ATOMIC_SEQ_CST); }
 static inline unsigned long long atomicAdd(unsigned long long* p, unsigned long long v) { return __atomic_fetch_add(p, v, __ATOMIC_SEQ_CST); }
