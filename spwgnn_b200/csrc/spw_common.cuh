@@ -149,12 +149,12 @@ __device__ __forceinline__ void wgrad_tile_acc(float (&acc)[TA][TB], const float
   }
 }
 
-// acc -> per-CTA partial matrix in global memory (row length 16*TB).  ACC: read-modify-write, issued
-// as two batches of TA/2 rows so that all loads of a batch are in flight together.
+// acc -> per-CTA partial in global memory, THREAD-MAJOR layout: element (a, b) of thread t lives at
+// part[(a*TB + b)*kThreads + t], so every load/store of the read-modify-write is a fully coalesced
+// 128-byte warp access (k_reduce_parts undoes the mapping).  ACC = accumulate into the partial.
 template <int TA, int TB, bool ACC>
 __device__ __forceinline__ void wgrad_flush(const float (&acc)[TA][TB], float* part) {
-  const int ja = threadIdx.x >> 4, jb = threadIdx.x & 15;
-  float* base = part + (size_t)(TA * ja) * (16 * TB) + TB * jb;
+  float* base = part + threadIdx.x;
   constexpr int H = (TA + 1) / 2;
 #pragma unroll
   for (int h = 0; h < TA; h += H) {
@@ -162,14 +162,16 @@ __device__ __forceinline__ void wgrad_flush(const float (&acc)[TA][TB], float* p
     if (ACC) {
 #pragma unroll
       for (int a = 0; a < H; ++a)
-        if (h + a < TA) load_vec<TB>(base + (size_t)(h + a) * (16 * TB), old[a]);
+#pragma unroll
+        for (int b = 0; b < TB; ++b)
+          if (h + a < TA) old[a][b] = base[(size_t)((h + a) * TB + b) * kThreads];
     }
 #pragma unroll
     for (int a = 0; a < H; ++a) {
       if (h + a >= TA) continue;
-      float* p = base + (size_t)(h + a) * (16 * TB);
 #pragma unroll
-      for (int b = 0; b < TB; ++b) p[b] = ACC ? old[a][b] + acc[h + a][b] : acc[h + a][b];
+      for (int b = 0; b < TB; ++b)
+        base[(size_t)((h + a) * TB + b) * kThreads] = ACC ? old[a][b] + acc[h + a][b] : acc[h + a][b];
     }
   }
 }

@@ -240,38 +240,59 @@ struct WgArgs {
   float* part;             // [gridDim.x][16*TA * 16*TB]
 };
 
-template <int TA, int TB>
-__global__ void __launch_bounds__(kThreads, 1) k_wgrad(WgArgs a) {
+template <int TA, int TB, int TMR, int MINB>
+__global__ void __launch_bounds__(kThreads, MINB) k_wgrad(WgArgs a) {
   SPW_DYN_SMEM(smem_raw);
   float* Xs = reinterpret_cast<float*>(smem_raw);
   constexpr int LX = 16 * TA, LY = 16 * TB;
-  float* Ys = Xs + kTM * LX;
+  float* Ys = Xs + TMR * LX;
   const int tid = threadIdx.x;
   float acc[TA][TB];
 #pragma unroll
   for (int i = 0; i < TA; ++i)
 #pragma unroll
     for (int j = 0; j < TB; ++j) acc[i][j] = 0.f;
-  const int ntiles = (a.M + kTM - 1) / kTM;
+  const int ntiles = (a.M + TMR - 1) / TMR;
+  const bool xvec = (a.ldx & 3) == 0, yvec = (a.ldy & 3) == 0;
   for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
-    const int r0 = tile * kTM;
-    const int rows = imin(kTM, a.M - r0);
-    for (int idx = tid; idx < kTM * LX; idx += kThreads) {
-      const int r = idx / LX, c = idx - r * LX;
-      float v = 0.f;
+    const int r0 = tile * TMR;
+    const int rows = imin(TMR, a.M - r0);
+    for (int idx = tid; idx < TMR * (LX / 4); idx += kThreads) {
+      const int r = idx / (LX / 4), c = (idx - r * (LX / 4)) * 4;
+      float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
       if (r < rows) {
         const size_t xr = a.xmod ? (size_t)((r0 + r) % a.xmod) : (size_t)(r0 + r);
-        if (c < a.Kin) v = a.X[xr * a.ldx + c];
-        else if (c == a.Kin) v = a.rowscale ? a.rowscale[a.rsmod ? (size_t)((r0 + r) % a.rsmod) : (size_t)(r0 + r)] : 1.f;
+        const float* p = a.X + xr * a.ldx + c;
+        if (xvec && c + 3 < a.Kin) {
+          v = *reinterpret_cast<const float4*>(p);
+        } else {
+          const float one = a.rowscale ? a.rowscale[a.rsmod ? (size_t)((r0 + r) % a.rsmod) : (size_t)(r0 + r)] : 1.f;
+          v.x = c < a.Kin ? p[0] : (c == a.Kin ? one : 0.f);
+          v.y = c + 1 < a.Kin ? p[1] : (c + 1 == a.Kin ? one : 0.f);
+          v.z = c + 2 < a.Kin ? p[2] : (c + 2 == a.Kin ? one : 0.f);
+          v.w = c + 3 < a.Kin ? p[3] : (c + 3 == a.Kin ? one : 0.f);
+        }
       }
-      Xs[idx] = v;
+      *reinterpret_cast<float4*>(Xs + (size_t)r * LX + c) = v;
     }
-    for (int idx = tid; idx < kTM * LY; idx += kThreads) {
-      const int r = idx / LY, c = idx - r * LY;
-      Ys[idx] = (r < rows && c < a.N) ? a.dY[(size_t)(r0 + r) * a.ldy + c] : 0.f;
+    for (int idx = tid; idx < TMR * (LY / 4); idx += kThreads) {
+      const int r = idx / (LY / 4), c = (idx - r * (LY / 4)) * 4;
+      float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (r < rows) {
+        const float* p = a.dY + (size_t)(r0 + r) * a.ldy + c;
+        if (yvec && c + 3 < a.N) {
+          v = *reinterpret_cast<const float4*>(p);
+        } else {
+          if (c < a.N) v.x = p[0];
+          if (c + 1 < a.N) v.y = p[1];
+          if (c + 2 < a.N) v.z = p[2];
+          if (c + 3 < a.N) v.w = p[3];
+        }
+      }
+      *reinterpret_cast<float4*>(Ys + (size_t)r * LY + c) = v;
     }
     __syncthreads();
-    wgrad_tile_acc<TA, TB>(acc, Xs, LX, Ys, LY, kTM);
+    wgrad_tile_acc<TA, TB>(acc, Xs, LX, Ys, LY, TMR);
     __syncthreads();
   }
   wgrad_flush<TA, TB, false>(acc, a.part + (size_t)blockIdx.x * (LX * LY));
@@ -279,7 +300,8 @@ __global__ void __launch_bounds__(kThreads, 1) k_wgrad(WgArgs a) {
 
 // fixed-order sum over per-CTA partials -> compact Keras-layout gradient (+ bias from row Kin)
 struct RedArgs {
-  const float* part; int nparts; int part_stride; int src_ld;
+  const float* part; int nparts; int part_stride; int src_ld;   // src_ld: row length (linear layout only)
+  int TA, TB;                                                   // > 0: thread-major layout of wgrad_flush<TA,TB>
   int Kin, N;
   float* dW; int dst_ld, dst_row0, dst_col0;   // null: skip the matrix
   float* db; int db_off;                       // null: skip the bias row
@@ -291,7 +313,13 @@ __global__ void __launch_bounds__(256) k_reduce_parts(RedArgs a) {
     if (k == a.Kin && !a.db) continue;
     if (k < a.Kin && !a.dW) continue;
     float s = 0.f;
-    const float* p = a.part + (size_t)k * a.src_ld + n;
+    const float* p;
+    if (a.TA > 0) {
+      const int ja = k / a.TA, ea = k - ja * a.TA, jb = n / a.TB, eb = n - jb * a.TB;
+      p = a.part + (size_t)(ea * a.TB + eb) * kThreads + (ja * 16 + jb);
+    } else {
+      p = a.part + (size_t)k * a.src_ld + n;
+    }
     for (int c = 0; c < a.nparts; ++c) s += p[(size_t)c * a.part_stride];
     if (k < a.Kin) a.dW[(size_t)(a.dst_row0 + k) * a.dst_ld + a.dst_col0 + n] = s;
     else a.db[a.db_off + n] = s;

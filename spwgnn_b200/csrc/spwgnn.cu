@@ -152,7 +152,7 @@ Layout make_layout(int64_t n, int64_t E, int training) {
     L.partE = take((size_t)kMaxCtas * 160 * 160);
     L.partM = take((size_t)kMaxCtas * 4 * 160 * 160);
     L.part0 = take((size_t)kMaxCtas * 3 * kDEP);
-    L.partN = take((size_t)kMaxCtas * kPartNodeElems);
+    L.partN = take((size_t)2 * kMaxCtas * kPartNodeElems);
   } else {
     L.dU = L.dG = L.T = L.dS = L.dR = L.dH2S = L.DP = L.dQ = L.dQ1 = L.dA = L.DH1 = L.M2 = 0;
     L.partE = L.partM = L.part0 = L.partN = 0;
@@ -228,35 +228,35 @@ void launch_linear(cudaStream_t st, int M, int N, bool wide, int nseg, const Lin
 // dW[Kin][N] (+ bias row) = X^T dY over M rows, reduced in fixed order into the Keras-layout gradient
 struct WgOut { float* dW; int dst_ld, dst_row0, dst_col0; float* db; int db_off; };
 
-void launch_wgrad(cudaStream_t st, int M, const float* X, int ldx, int Kin, int xmod, const float* rowscale, int rsmod,
-                  const float* dY, int ldy, int N, float* part, const WgOut& out) {
-  WgArgs a;
-  a.M = M; a.X = X; a.ldx = ldx; a.Kin = Kin; a.xmod = xmod; a.rowscale = rowscale; a.rsmod = rsmod; a.dY = dY; a.ldy = ldy; a.N = N;
-  a.part = part;
-  const int ntiles = (M + kTM - 1) / kTM;
-  int grid = ntiles < num_sms() ? ntiles : num_sms();
-  if (grid < 1) grid = 1;
-  const bool wa = Kin + 1 > 112, wb = N > 112;
-  int LX = wa ? 160 : 112, LY = wb ? 160 : 112;
-  const size_t smem = (size_t)kTM * (LX + LY) * sizeof(float);
-  if (wa && wb) { auto k = k_wgrad<10, 10>; set_smem(k, smem); SPW_KLAUNCH("k_wgrad", k, dim3(grid), dim3(kThreads), smem, st, a); }
-  else if (wa) { auto k = k_wgrad<10, 7>; set_smem(k, smem); SPW_KLAUNCH("k_wgrad", k, dim3(grid), dim3(kThreads), smem, st, a); }
-  else if (wb) { auto k = k_wgrad<7, 10>; set_smem(k, smem); SPW_KLAUNCH("k_wgrad", k, dim3(grid), dim3(kThreads), smem, st, a); }
-  else { auto k = k_wgrad<7, 7>; set_smem(k, smem); SPW_KLAUNCH("k_wgrad", k, dim3(grid), dim3(kThreads), smem, st, a); }
+void launch_reduce(cudaStream_t st, const float* part, int nparts, int part_stride, int src_ld, int TA, int TB, int Kin,
+                   int N, const WgOut& out) {
   RedArgs r;
-  r.part = part; r.nparts = grid; r.part_stride = LX * LY; r.src_ld = LY; r.Kin = Kin; r.N = N;
+  r.part = part; r.nparts = nparts; r.part_stride = part_stride; r.src_ld = src_ld; r.TA = TA; r.TB = TB; r.Kin = Kin; r.N = N;
   r.dW = out.dW; r.dst_ld = out.dst_ld; r.dst_row0 = out.dst_row0; r.dst_col0 = out.dst_col0;
   r.db = out.db; r.db_off = out.db_off;
   SPW_KLAUNCH("k_reduce_parts", k_reduce_parts, dim3(grid_for((int64_t)(Kin + 1) * N, 256)), dim3(256), 0, st, r);
 }
 
-void launch_reduce(cudaStream_t st, const float* part, int nparts, int part_stride, int src_ld, int Kin, int N,
-                   const WgOut& out) {
-  RedArgs r;
-  r.part = part; r.nparts = nparts; r.part_stride = part_stride; r.src_ld = src_ld; r.Kin = Kin; r.N = N;
-  r.dW = out.dW; r.dst_ld = out.dst_ld; r.dst_row0 = out.dst_row0; r.dst_col0 = out.dst_col0;
-  r.db = out.db; r.db_off = out.db_off;
-  SPW_KLAUNCH("k_reduce_parts", k_reduce_parts, dim3(grid_for((int64_t)(Kin + 1) * N, 256)), dim3(256), 0, st, r);
+constexpr int kTW = 64;   // rows per tile of the node-level weight-gradient kernel
+
+void launch_wgrad(cudaStream_t st, int M, const float* X, int ldx, int Kin, int xmod, const float* rowscale, int rsmod,
+                  const float* dY, int ldy, int N, float* part, const WgOut& out) {
+  WgArgs a;
+  a.M = M; a.X = X; a.ldx = ldx; a.Kin = Kin; a.xmod = xmod; a.rowscale = rowscale; a.rsmod = rsmod; a.dY = dY; a.ldy = ldy; a.N = N;
+  a.part = part;
+  const int ntiles = (M + kTW - 1) / kTW;
+  const bool wa = Kin + 1 > 112, wb = N > 112;
+  const int LX = wa ? 160 : 112, LY = wb ? 160 : 112;
+  const int per_sm = (wa || wb) ? 1 : 2;
+  int grid = ntiles < per_sm * num_sms() ? ntiles : per_sm * num_sms();
+  if (grid < 1) grid = 1;
+  if (grid > kMaxCtas * 2) grid = kMaxCtas * 2;
+  const size_t smem = (size_t)kTW * (LX + LY) * sizeof(float);
+  if (wa && wb) { auto k = k_wgrad<10, 10, kTW, 1>; set_smem(k, smem); SPW_KLAUNCH("k_wgrad", k, dim3(grid), dim3(kThreads), smem, st, a); }
+  else if (wa) { auto k = k_wgrad<10, 7, kTW, 1>; set_smem(k, smem); SPW_KLAUNCH("k_wgrad", k, dim3(grid), dim3(kThreads), smem, st, a); }
+  else if (wb) { auto k = k_wgrad<7, 10, kTW, 1>; set_smem(k, smem); SPW_KLAUNCH("k_wgrad", k, dim3(grid), dim3(kThreads), smem, st, a); }
+  else { auto k = k_wgrad<7, 7, kTW, 2>; set_smem(k, smem); SPW_KLAUNCH("k_wgrad", k, dim3(grid), dim3(kThreads), smem, st, a); }
+  launch_reduce(st, part, grid, LX * LY, 0, wa ? 10 : 7, wb ? 10 : 7, Kin, N, out);
 }
 
 void pack_weights(cudaStream_t st, const SpwParams* w, float* ws, const Layout& L, bool with_transposes) {
@@ -613,7 +613,7 @@ int spw_backward(const SpwParams* w, const SpwGraph* g, const float* obj, const 
   // ---- edge-level weight gradients --------------------------------------------------------------
   if (E > 0) {
     // rmp layer 1 (W2, b2) from the per-step kernel's per-CTA partials
-    launch_reduce(st, ws + L.partE, egrid, 160 * 160, 160, kDE, kDE, {grads->rmp_w[1], 150, 0, 0, grads->rmp_b[1], 0});
+    launch_reduce(st, ws + L.partE, egrid, 160 * 160, 0, 10, 10, kDE, kDE, {grads->rmp_w[1], 150, 0, 0, grads->rmp_b[1], 0});
     const int btiles = (E + kTMB - 1) / kTMB;
     const int bgrid = btiles < num_sms() ? btiles : num_sms();
     EdgeEncBwdArgs a;
@@ -624,12 +624,12 @@ int spw_backward(const SpwParams* w, const SpwGraph* g, const float* obj, const 
     set_smem(k_edge_encode_bwd, edge_encb_smem());
     SPW_KLAUNCH("k_edge_encode_bwd", k_edge_encode_bwd, dim3(bgrid), dim3(kThreads), edge_encb_smem(), st, a);
     const int ps = 4 * 160 * 160;
-    launch_reduce(st, ws + L.partM, bgrid, ps, 160, kDE, kDE, {grads->rmp_w[0], 150, 0, 0, grads->rmp_b[0], 0});
-    launch_reduce(st, ws + L.partM + 160 * 160, bgrid, ps, 160, kDE, kDE, {grads->rm_w[3], 150, 0, 0, grads->rm_b[3], 0});
-    launch_reduce(st, ws + L.partM + 2 * 160 * 160, bgrid, ps, 160, kDE, kDE, {grads->rm_w[2], 150, 0, 0, grads->rm_b[2], 0});
-    launch_reduce(st, ws + L.partM + 3 * 160 * 160, bgrid, ps, 160, kDE, kDE, {grads->rm_w[1], 150, 0, 0, grads->rm_b[1], 0});
+    launch_reduce(st, ws + L.partM, bgrid, ps, 0, 10, 10, kDE, kDE, {grads->rmp_w[0], 150, 0, 0, grads->rmp_b[0], 0});
+    launch_reduce(st, ws + L.partM + 160 * 160, bgrid, ps, 0, 10, 10, kDE, kDE, {grads->rm_w[3], 150, 0, 0, grads->rm_b[3], 0});
+    launch_reduce(st, ws + L.partM + 2 * 160 * 160, bgrid, ps, 0, 10, 10, kDE, kDE, {grads->rm_w[2], 150, 0, 0, grads->rm_b[2], 0});
+    launch_reduce(st, ws + L.partM + 3 * 160 * 160, bgrid, ps, 0, 10, 10, kDE, kDE, {grads->rm_w[1], 150, 0, 0, grads->rm_b[1], 0});
     // layer 0: part0 rows [w0 row 0 | w0 row 1 | b0], each kDEP long  ->  treat as Kin = 2 (+ bias row)
-    launch_reduce(st, ws + L.part0, bgrid, 3 * kDEP, kDEP, 2, kDE, {grads->rm_w[0], 150, 0, 0, grads->rm_b[0], 0});
+    launch_reduce(st, ws + L.part0, bgrid, 3 * kDEP, kDEP, 0, 0, 2, kDE, {grads->rm_w[0], 150, 0, 0, grads->rm_b[0], 0});
   } else {
     cudaMemsetAsync(grads->rmp_w[1], 0, 22500 * sizeof(float), st);
     cudaMemsetAsync(grads->rmp_b[1], 0, 150 * sizeof(float), st);
