@@ -76,6 +76,9 @@ long long spw_launch_count(void);
 int spw_profile(int enable);
 int spw_profile_report(char* buf, size_t cap);
 int spw_ffma_peak(float* out, int grid, int iters, void* stream);
+/* tcgen05 / TMEM self test (3xTF32): D[128][160] = A[128][152] . W[K][N] (K<=152, N<=160); scratch: 48640 floats;
+ * status (device int): 1 = ok, -1 = the MMA completion barrier timed out. */
+int spw_tc_selftest(const float* A, const float* W, int K, int N, float* D, float* scratch, int* status, void* stream);
 
 /* ---- edge-index construction (replaces main.py:66-81) ------------------------------------
  * Edge m->j (m != j, same tower) is active iff sqrt(dx*dx + dy*dy) < thr evaluated in IEEE

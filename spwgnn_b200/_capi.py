@@ -32,7 +32,7 @@ class SpwGraph(C.Structure):
     ]
 
 
-EXPORTS = ['spw_version', 'spw_last_error', 'spw_launch_count', 'spw_profile', 'spw_profile_report', 'spw_ffma_peak', 'spw_edges_count', 'spw_edges_fill', 'spw_workspace_bytes',
+EXPORTS = ['spw_version', 'spw_last_error', 'spw_launch_count', 'spw_profile', 'spw_profile_report', 'spw_ffma_peak', 'spw_tc_selftest', 'spw_edges_count', 'spw_edges_fill', 'spw_workspace_bytes',
            'spw_forward', 'spw_bce_grad', 'spw_backward']
 
 
@@ -60,6 +60,8 @@ class CApi:
         d.spw_profile_report.argtypes = [C.c_char_p, C.c_size_t]
         d.spw_ffma_peak.restype = C.c_int
         d.spw_ffma_peak.argtypes = [vp, C.c_int, C.c_int, vp]
+        d.spw_tc_selftest.restype = C.c_int
+        d.spw_tc_selftest.argtypes = [vp, vp, C.c_int, C.c_int, vp, vp, vp, vp]
         d.spw_edges_count.restype = C.c_int
         d.spw_edges_count.argtypes = [vp, vp, i32, i32, i32, f64, C.c_int, vp, vp, vp, vp]
         d.spw_edges_fill.restype = C.c_int

@@ -1,0 +1,215 @@
+// spw_tc.cuh -- Blackwell tensor-core (tcgen05 / TMEM) building blocks, sm_100a only.
+//
+// fp32-accurate GEMM on the 5th-generation tensor cores by the 3xTF32 split:
+//     x = hi + lo,  hi = rna_tf32(x),  lo = rna_tf32(x - hi)       (|x - hi - lo| <= 2^-22 |x|)
+//     A.B ~= A_hi.B_hi + A_lo.B_hi + A_hi.B_lo                     (fp32 accumulate in TMEM)
+// Operand placement (tcgen05.mma kind::tf32, cta_group::1, M = 128, N = 160, K = 8 per instruction):
+//   A (activations, 128 rows = 128 TMEM lanes): in TENSOR MEMORY, one 32-bit column per k element;
+//       written straight from registers with tcgen05.st -- activations never touch shared memory;
+//   B (weights): in shared memory, K-major, no swizzle ("interleave" canonical layout): per k-step
+//       [chunk c = 0,1][n = 0..159][4 floats], i.e. core matrices of 8 rows x 16 bytes,
+//       leading-dimension (K) byte offset 2560, stride (N) byte offset 128;
+//   D (accumulator): TMEM, 160 columns.
+// TMEM map (512 columns): [0,160) A_hi, [160,320) A_lo, [320,480) D.
+#pragma once
+#ifndef SPW_EMU
+#include "spw_common.cuh"
+
+namespace spw {
+namespace tc {
+
+constexpr int kN = 160;                 // MMA N (150 valid columns)
+constexpr int kKS = 19;                 // k-steps of 8 (K = 152, rows 150/151 zero)
+constexpr int kBStepFloats = 2 * kN * 4;            // floats per k-step of a packed B matrix (1280)
+constexpr int kBFloats = kKS * kBStepFloats;        // 24320 floats = 97280 bytes per hi or lo matrix
+constexpr uint32_t kColAhi = 0, kColAlo = 160, kColD = 320;
+constexpr uint32_t kTmemCols = 512;
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+// ---- TMEM allocation (one warp) ------------------------------------------------------------------
+__device__ __forceinline__ void tmem_alloc(uint32_t* smem_dst, uint32_t ncols) {
+  asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(smem_dst)), "r"(ncols));
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::);
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols) {
+  asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols));
+}
+__device__ __forceinline__ void fence_before_sync() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void fence_after_sync() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
+// ---- TMEM <-> registers (thread = TMEM lane; warp w may touch lanes [32*(w%4), +32)) --------------
+__device__ __forceinline__ void tmem_st8(uint32_t taddr, const uint32_t (&v)[8]) {
+  asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"r"(taddr), "r"(v[0]),
+               "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7])
+               : "memory");
+}
+__device__ __forceinline__ void tmem_wait_st() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&v)[16]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
+        "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
+      : "r"(taddr)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+// ---- 3xTF32 split ---------------------------------------------------------------------------------
+__device__ __forceinline__ void split_tf32(float x, uint32_t& hi, uint32_t& lo) {
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(hi) : "f"(x));
+  const float r = x - __uint_as_float(hi);
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(lo) : "f"(r));
+}
+
+// ---- descriptors ----------------------------------------------------------------------------------
+// shared-memory matrix descriptor (cute::UMMA::SmemDescriptor): start>>4 [0,14), LBO>>4 [16,30),
+// SBO>>4 [32,46), version = 1 [46,48), layout type [61,64) = 0 (no swizzle)
+__device__ __forceinline__ uint64_t make_b_desc(uint32_t smem_addr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+  uint64_t d = 0;
+  d |= (uint64_t)((smem_addr >> 4) & 0x3fff);
+  d |= (uint64_t)((lbo_bytes >> 4) & 0x3fff) << 16;
+  d |= (uint64_t)((sbo_bytes >> 4) & 0x3fff) << 32;
+  d |= (uint64_t)1 << 46;
+  return d;
+}
+// instruction descriptor (cute::UMMA::InstrDescriptor): D = F32, A = B = TF32, both K-major
+__device__ __forceinline__ constexpr uint32_t make_idesc_tf32(int M, int N) {
+  return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+
+// D[tmem] (+)= A[tmem] . B[smem]   (issued by ONE thread)
+__device__ __forceinline__ void mma_tf32_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, {%5, %5, %5, %5}, p;\n\t"
+      "}\n" ::"r"(d_tmem),
+      "r"(a_tmem), "l"(b_desc), "r"(idesc), "r"(accumulate), "r"(0u)
+      : "memory");
+}
+// make the mbarrier track completion of all MMAs issued so far by this thread
+__device__ __forceinline__ void mma_commit(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+
+// ---- mbarrier --------------------------------------------------------------------------------------
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void fence_mbar_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+// bounded wait: returns false on timeout instead of hanging the GPU
+__device__ __forceinline__ bool mbar_wait(uint64_t* bar, uint32_t parity) {
+  const uint32_t a = smem_u32(bar);
+  for (int it = 0; it < (1 << 22); ++it) {
+    uint32_t ok;
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.b32 %0, 1, 0, p;\n\t"
+        "}\n"
+        : "=r"(ok)
+        : "r"(a), "r"(parity)
+        : "memory");
+    if (ok) return true;
+  }
+  return false;
+}
+
+// issue the 3 x kKS MMAs of one 128-row tile: D = A_hi.B_hi + A_lo.B_hi + A_hi.B_lo
+__device__ __forceinline__ void issue_tile_mmas(uint32_t tmem_base, const float* Bhi_s, const float* Blo_s) {
+  const uint32_t idesc = make_idesc_tf32(128, kN);
+  const uint32_t bhi = smem_u32(Bhi_s), blo = smem_u32(Blo_s);
+#pragma unroll 1
+  for (int ks = 0; ks < kKS; ++ks) {
+    const uint64_t dhi = make_b_desc(bhi + ks * (kBStepFloats * 4), kN * 16, 128);
+    const uint64_t dlo = make_b_desc(blo + ks * (kBStepFloats * 4), kN * 16, 128);
+    mma_tf32_ts(tmem_base + kColD, tmem_base + kColAlo + 8 * ks, dhi, idesc, ks > 0 ? 1u : 0u);
+    mma_tf32_ts(tmem_base + kColD, tmem_base + kColAhi + 8 * ks, dlo, idesc, 1u);
+    mma_tf32_ts(tmem_base + kColD, tmem_base + kColAhi + 8 * ks, dhi, idesc, 1u);
+  }
+}
+
+// ---- weight packing: Keras W[K][N] (row-major, ld) -> hi / lo B operands in the layout above -------
+__global__ void __launch_bounds__(256) k_pack_umma(const float* __restrict__ W, int ld, int row0, int col0, int K, int N,
+                                                   int transpose, float* __restrict__ hi, float* __restrict__ lo) {
+  for (int idx = blockIdx.x * blockDim.x + threadIdx.x; idx < kBFloats; idx += gridDim.x * blockDim.x) {
+    const int e = idx & 3, n = (idx >> 2) % kN, c = ((idx >> 2) / kN) & 1, ks = (idx >> 2) / (2 * kN);
+    const int k = 8 * ks + 4 * c + e;
+    float v = 0.f;
+    if (k < K && n < N) v = transpose ? W[(size_t)(row0 + n) * ld + col0 + k] : W[(size_t)(row0 + k) * ld + col0 + n];
+    uint32_t h, l;
+    split_tf32(v, h, l);
+    hi[idx] = __uint_as_float(h);
+    lo[idx] = __uint_as_float(l);
+  }
+}
+
+// ---- self test: D[128][160] = A[128][152] . B (packed hi/lo), one CTA of 128 threads ----------------
+__global__ void __launch_bounds__(128, 1) k_tc_selftest(const float* __restrict__ A, const float* __restrict__ Bhi,
+                                                        const float* __restrict__ Blo, float* __restrict__ D,
+                                                        int* __restrict__ status) {
+  SPW_DYN_SMEM(smem_raw);
+  float* Bhi_s = reinterpret_cast<float*>(smem_raw);
+  float* Blo_s = Bhi_s + kBFloats;
+  uint64_t* bar = reinterpret_cast<uint64_t*>(Blo_s + kBFloats);
+  uint32_t* tptr = reinterpret_cast<uint32_t*>(bar + 1);
+  const int tid = threadIdx.x, warp = tid >> 5;
+  if (warp == 0) tmem_alloc(tptr, kTmemCols);
+  if (tid == 32) { mbar_init(bar, 1); fence_mbar_init(); }
+  for (int i = tid; i < kBFloats / 4; i += 128) {
+    reinterpret_cast<float4*>(Bhi_s)[i] = reinterpret_cast<const float4*>(Bhi)[i];
+    reinterpret_cast<float4*>(Blo_s)[i] = reinterpret_cast<const float4*>(Blo)[i];
+  }
+  fence_async_smem();            // generic-proxy smem writes -> visible to the tensor core (async proxy)
+  fence_before_sync();
+  __syncthreads();
+  fence_after_sync();
+  const uint32_t tmem_base = *tptr;
+  const uint32_t lane_addr = tmem_base + ((uint32_t)(32 * (warp & 3)) << 16);
+  // A row -> hi / lo -> TMEM
+  const float* arow = A + (size_t)tid * kDEP;
+#pragma unroll 1
+  for (int c = 0; c < kDEP; c += 8) {
+    const float4 x0 = *reinterpret_cast<const float4*>(arow + c), x1 = *reinterpret_cast<const float4*>(arow + c + 4);
+    const float x[8] = {x0.x, x0.y, x0.z, x0.w, x1.x, x1.y, x1.z, x1.w};
+    uint32_t h[8], l[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) split_tf32(x[i], h[i], l[i]);
+    tmem_st8(lane_addr + kColAhi + c, h);
+    tmem_st8(lane_addr + kColAlo + c, l);
+  }
+  tmem_wait_st();
+  fence_before_sync();
+  __syncthreads();
+  if (tid == 0) {
+    fence_after_sync();
+    issue_tile_mmas(tmem_base, Bhi_s, Blo_s);
+    mma_commit(bar);
+  }
+  const bool ok = mbar_wait(bar, 0);
+  fence_after_sync();
+  if (!ok) {
+    if (tid == 0) *status = -1;
+  } else {
+#pragma unroll 1
+    for (int c = 0; c < kN; c += 16) {
+      uint32_t v[16];
+      tmem_ld16(lane_addr + kColD + c, v);
+      tmem_wait_ld();
+#pragma unroll
+      for (int i = 0; i < 16; ++i) D[(size_t)tid * kN + c + i] = __uint_as_float(v[i]);
+    }
+    if (tid == 0) *status = 1;
+  }
+  fence_before_sync();
+  __syncthreads();
+  if (warp == 0) tmem_dealloc(tmem_base, kTmemCols);
+}
+
+}  // namespace tc
+}  // namespace spw
+#endif  // SPW_EMU

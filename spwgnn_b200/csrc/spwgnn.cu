@@ -4,6 +4,7 @@
 #include "spw_common.cuh"
 #include "spw_edges.cuh"
 #include "spw_kernels.cuh"
+#include "spw_tc.cuh"
 
 #include <stdarg.h>
 #include <stdio.h>
@@ -351,6 +352,23 @@ int spw_ffma_peak(float* out /*[grid*256]*/, int grid, int iters, void* stream) 
   return check_launch("spw_ffma_peak");
 }
 const char* spw_last_error(void) { return g_err; }
+
+// tcgen05 self test: D[128][160] = A[128][152] . W, W given as a Keras [K][N] matrix (ld = N); scratch holds the
+// packed hi/lo B operands (2 * 24320 floats); status: 1 ok, -1 the MMA never signalled its mbarrier
+int spw_tc_selftest(const float* A, const float* W, int K, int N, float* D, float* scratch, int* status, void* stream) {
+#ifdef SPW_EMU
+  (void)A; (void)W; (void)K; (void)N; (void)D; (void)scratch; (void)status; (void)stream;
+  return fail(SPW_ERR_UNSUPPORTED, "spw_tc_selftest: tensor-core path is not emulated");
+#else
+  if (!A || !W || !D || !scratch || !status || K > 152 || N > 160) return fail(SPW_ERR_BAD_ARG, "spw_tc_selftest: bad argument");
+  cudaStream_t st = (cudaStream_t)stream;
+  SPW_KLAUNCH("k_pack_umma", tc::k_pack_umma, dim3(48), dim3(256), 0, st, W, N, 0, 0, K, N, 0, scratch, scratch + tc::kBFloats);
+  const size_t smem = (size_t)2 * tc::kBFloats * sizeof(float) + 64;
+  set_smem(tc::k_tc_selftest, smem);
+  SPW_KLAUNCH("k_tc_selftest", tc::k_tc_selftest, dim3(1), dim3(128), smem, st, A, scratch, scratch + tc::kBFloats, D, status);
+  return check_launch("spw_tc_selftest");
+#endif
+}
 
 int spw_edges_count(const double* pos_xy, const int32_t* node_off, int32_t n_towers, int32_t n_nodes,
                     int32_t max_nodes_per_tower, double thr, int fully_connected, int32_t* deg_out, int32_t* deg_in,
