@@ -210,6 +210,161 @@ __global__ void __launch_bounds__(128, 1) k_tc_selftest(const float* __restrict_
   if (warp == 0) tmem_dealloc(tmem_base, kTmemCols);
 }
 
+// =================================================================================================
+// K2b on the tensor cores: per step -- gather, hidden layer 2 (3xTF32 tcgen05), relu, relu bits,
+// deterministic receiver-segmented sum.  Persistent, one CTA per SM, 128-edge tiles.
+//   shared memory: W2 hi/lo resident for the whole kernel (190 KB) + a 128 x 64 column staging slab
+//   tensor memory: A_hi | A_lo | D as in the map above
+//   thread = (row = TMEM lane, column half); warps w and w+4 share a lane quarter
+// =================================================================================================
+constexpr int kStagePitch = 65;
+constexpr int kStageCols = 64;
+
+struct EdgeStepTcArgs {
+  int E;
+  const int32_t* in_snd; const int32_t* in_rcv; const int32_t* in_off;
+  const float* A; const float* S; const float* R;     // [E][152], [n][152], [n][152]
+  const float* W2hi; const float* W2lo;               // packed B operands (k_pack_umma)
+  const float* b2;                                    // raw rmp.b1 [150]
+  float* H2S;                                         // [n][152]
+  float* part_first; float* part_last;                // [ntiles][152] (tiles of 128 edges)
+  uint32_t* maskbits;                                 // [E][8] or null (layout as k_edge_step)
+};
+
+constexpr size_t kEdgeStepTcSmem = (size_t)(2 * kBFloats + kTM * kStagePitch + kTM + kTM * 5 + 160) * sizeof(float) + 64;
+
+__global__ void __launch_bounds__(kThreads, 1) k_edge_step_tc(EdgeStepTcArgs a) {
+  SPW_DYN_SMEM(smem_raw);
+  float* Bhi_s = reinterpret_cast<float*>(smem_raw);
+  float* Blo_s = Bhi_s + kBFloats;
+  float* stage = Blo_s + kBFloats;
+  int* srcv = reinterpret_cast<int*>(stage + kTM * kStagePitch);
+  uint32_t* smask = reinterpret_cast<uint32_t*>(srcv + kTM);
+  float* sb2 = reinterpret_cast<float*>(smask + kTM * 5);
+  uint64_t* bar = reinterpret_cast<uint64_t*>(sb2 + 160);
+  uint32_t* tptr = reinterpret_cast<uint32_t*>(bar + 1);
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int row = 32 * (warp & 3) + lane, half = warp >> 2;
+
+  if (warp == 0) tmem_alloc(tptr, kTmemCols);
+  if (tid == 32) { mbar_init(bar, 1); fence_mbar_init(); }
+  for (int i = tid; i < kBFloats / 4; i += kThreads) {
+    reinterpret_cast<float4*>(Bhi_s)[i] = reinterpret_cast<const float4*>(a.W2hi)[i];
+    reinterpret_cast<float4*>(Blo_s)[i] = reinterpret_cast<const float4*>(a.W2lo)[i];
+  }
+  if (tid < 160) sb2[tid] = tid < kDE ? a.b2[tid] : 0.f;
+  fence_async_smem();
+  fence_before_sync();
+  __syncthreads();
+  fence_after_sync();
+  const uint32_t tmem_base = *tptr;
+  const uint32_t lane_addr = tmem_base + ((uint32_t)(32 * (warp & 3)) << 16);
+  uint32_t parity = 0;
+  bool failed = false;
+  const int ntiles = (a.E + kTM - 1) / kTM;
+
+  for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+    const int e0 = tile * kTM;
+    const int rows = imin(kTM, a.E - e0);
+    // ---- build h1 = relu(A_e + S_s + R_r) for this thread's row / column half, split, store to TMEM
+    {
+      const bool valid = row < rows;
+      int s = 0, rc = -1;
+      if (valid) { s = a.in_snd[e0 + row]; rc = a.in_rcv[e0 + row]; }
+      if (half == 0) srcv[row] = rc;
+      for (int i = tid; i < kTM * 5; i += kThreads) smask[i] = 0u;
+      const float* pa = a.A + (size_t)(e0 + (valid ? row : 0)) * kDEP;
+      const float* ps = a.S + (size_t)s * kDEP;
+      const float* pr = a.R + (size_t)(valid ? rc : 0) * kDEP;
+      const int c_beg = half ? 80 : 0, c_end = half ? kDEP : 80;
+#pragma unroll 2
+      for (int c = c_beg; c < c_end; c += 8) {
+        uint32_t h[8], l[8];
+        if (valid) {
+          const float4 a0 = *reinterpret_cast<const float4*>(pa + c), a1 = *reinterpret_cast<const float4*>(pa + c + 4);
+          const float4 s0 = *reinterpret_cast<const float4*>(ps + c), s1 = *reinterpret_cast<const float4*>(ps + c + 4);
+          const float4 r0 = *reinterpret_cast<const float4*>(pr + c), r1 = *reinterpret_cast<const float4*>(pr + c + 4);
+          const float x[8] = {a0.x + s0.x + r0.x, a0.y + s0.y + r0.y, a0.z + s0.z + r0.z, a0.w + s0.w + r0.w,
+                              a1.x + s1.x + r1.x, a1.y + s1.y + r1.y, a1.z + s1.z + r1.z, a1.w + s1.w + r1.w};
+#pragma unroll
+          for (int i = 0; i < 8; ++i) split_tf32(relu_f(x[i]), h[i], l[i]);
+        } else {
+#pragma unroll
+          for (int i = 0; i < 8; ++i) { h[i] = 0u; l[i] = 0u; }
+        }
+        tmem_st8(lane_addr + kColAhi + c, h);
+        tmem_st8(lane_addr + kColAlo + c, l);
+      }
+    }
+    tmem_wait_st();
+    fence_before_sync();
+    __syncthreads();
+    if (tid == 0) {
+      fence_after_sync();
+      issue_tile_mmas(tmem_base, Bhi_s, Blo_s);
+      mma_commit(bar);
+    }
+    if (!mbar_wait(bar, parity)) failed = true;
+    parity ^= 1u;
+    fence_after_sync();
+    // ---- epilogue: D -> +b2, relu, relu bits -> staging slab -> receiver-segmented sum
+    const int n_first = srcv[0], n_last = srcv[rows - 1];
+    for (int c0 = 0; c0 < kN; c0 += kStageCols) {
+      const int ncols = imin(kStageCols, kN - c0);
+      for (int blk = half; blk * 16 < ncols; blk += 2) {
+        uint32_t v[16];
+        tmem_ld16(lane_addr + kColD + c0 + blk * 16, v);
+        tmem_wait_ld();
+        uint32_t mw[5] = {0u, 0u, 0u, 0u, 0u};
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {
+          const int col = c0 + blk * 16 + i;
+          const float pre = __uint_as_float(v[i]) + sb2[col];
+          const bool on = (col < kDE) && (pre > 0.f);
+          stage[row * kStagePitch + blk * 16 + i] = on ? pre : 0.f;
+          if (on) mw[col % 5] |= 1u << (col / 5);
+        }
+        if (a.maskbits && row < rows) {
+#pragma unroll
+          for (int w = 0; w < 5; ++w)
+            if (mw[w]) atomicOr(&smask[row * 5 + w], mw[w]);
+        }
+      }
+      __syncthreads();
+      const int nnodes = n_last - n_first + 1;
+      for (int item = tid; item < nnodes * ncols; item += kThreads) {
+        const int node = n_first + item / ncols, c = item - (item / ncols) * ncols;
+        const int s0 = a.in_off[node], s1 = a.in_off[node + 1];
+        const int lo = imax(s0, e0) - e0, hi = imin(s1, e0 + rows) - e0;
+        if (hi <= lo) continue;
+        const int col = c0 + c;
+        if (col >= kDEP) continue;
+        float sum = 0.f;
+        if (col < kDE)
+          for (int r = lo; r < hi; ++r) sum += stage[r * kStagePitch + c];
+        float* dst;
+        if (s0 >= e0 && s1 <= e0 + rows) dst = a.H2S + (size_t)node * kDEP;
+        else if (s0 < e0) dst = a.part_first + (size_t)tile * kDEP;
+        else dst = a.part_last + (size_t)tile * kDEP;
+        dst[col] = sum;
+      }
+      __syncthreads();
+    }
+    if (a.maskbits) {
+      for (int i = tid; i < rows * 5; i += kThreads) {
+        const int r = i / 5, w = i - r * 5;
+        a.maskbits[(size_t)(e0 + r) * 8 + w] = smask[i];
+      }
+    }
+    fence_before_sync();
+    __syncthreads();
+  }
+  if (failed && tid == 0) a.H2S[0] = __int_as_float(0x7fc00000);   // fail loudly: poison the output (MMA barrier timed out)
+  fence_before_sync();
+  __syncthreads();
+  if (warp == 0) tmem_dealloc(tmem_base, kTmemCols);
+}
+
 }  // namespace tc
 }  // namespace spw
 #endif  // SPW_EMU

@@ -17,6 +17,14 @@
 
 using namespace spw;
 
+// Tensor-core (tcgen05) kernels replace their FFMA counterparts in the GPU build; the host emulator
+// build (tools/cuemu, test infrastructure) always uses the FFMA kernels.
+#ifdef SPW_EMU
+#define SPW_USE_TC 0
+#elif !defined(SPW_USE_TC)
+#define SPW_USE_TC 1
+#endif
+
 namespace {
 
 // ---- launch accounting / per-kernel CUDA-event timing (bench.py: gpu_launches, roofline) -------
@@ -106,7 +114,7 @@ size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
 
 struct Layout {
   size_t pack[P_COUNT];
-  size_t Q1, Q, degf, A, PF, PL;
+  size_t Q1, Q, degf, A, PF, PL, W2hi, W2lo;
   size_t P, S, R, H2S, G, U;     // per-step arrays (training: 5 slots; inference: fewer)
   int slotsP, slotsSR, slotsN;   // number of step slots for P / (S,R) / (H2S,G,U)
   // backward
@@ -122,6 +130,8 @@ Layout make_layout(int64_t n, int64_t E, int training) {
   auto take = [&](size_t floats) { size_t o = off; off = align_up(off + floats, 64); return o; };
   for (int i = 0; i < P_COUNT; ++i) L.pack[i] = take((size_t)kPackShape[i].Kp * kPackShape[i].ldw);
   const size_t nt = (size_t)((E + kTME - 1) / kTME) + 1;
+  L.W2hi = take(24320);
+  L.W2lo = take(24320);
   L.Q1 = take(n * kDP);
   L.Q = take(n * kDP);
   L.degf = take(n);
@@ -429,6 +439,9 @@ int spw_forward(const SpwParams* w, const SpwGraph* g, const float* obj, float* 
   const size_t nP = (size_t)n * kDP, nE = (size_t)n * kDEP;
 
   pack_weights(st, w, ws, L, training != 0);
+#if SPW_USE_TC
+  SPW_KLAUNCH("k_pack_umma", tc::k_pack_umma, dim3(48), dim3(256), 0, st, (const float*)w->rmp_w[1], 150, 0, 0, 150, 150, 0, ws + L.W2hi, ws + L.W2lo);
+#endif
   SPW_KLAUNCH("k_deg_to_float", k_deg_to_float, dim3(grid_for(n, 256)), dim3(256), 0, st, g->in_off, n, ws + L.degf);
 
   // object encoder (Networks.py:47,76): q1 = relu(om0([y,w])), q = relu(om1(q1))
@@ -476,10 +489,25 @@ int spw_forward(const SpwParams* w, const SpwGraph* g, const float* obj, float* 
       a.E = E; a.in_snd = g->in_snd; a.in_rcv = g->in_rcv; a.in_off = g->in_off; a.A = ws + L.A; a.S = S; a.R = R;
       a.W2 = PK(P_W2); a.b2 = w->rmp_b[1]; a.H2S = H2S; a.part_first = ws + L.PF; a.part_last = ws + L.PL;
       a.maskbits = training ? reinterpret_cast<uint32_t*>(ws + L.M2) + (size_t)l * E * 8 : nullptr;
+#if SPW_USE_TC
+      {
+        tc::EdgeStepTcArgs t;
+        t.E = E; t.in_snd = g->in_snd; t.in_rcv = g->in_rcv; t.in_off = g->in_off; t.A = ws + L.A; t.S = S; t.R = R;
+        t.W2hi = ws + L.W2hi; t.W2lo = ws + L.W2lo; t.b2 = w->rmp_b[1]; t.H2S = H2S; t.part_first = ws + L.PF;
+        t.part_last = ws + L.PL; t.maskbits = a.maskbits;
+        const int ttiles = (E + kTM - 1) / kTM;
+        const int tgrid = ttiles < num_sms() ? ttiles : num_sms();
+        set_smem(tc::k_edge_step_tc, tc::kEdgeStepTcSmem);
+        SPW_KLAUNCH("k_edge_step_tc", tc::k_edge_step_tc, dim3(tgrid), dim3(kThreads), tc::kEdgeStepTcSmem, st, t);
+        if (ttiles > 1)
+          SPW_KLAUNCH("k_fix_boundaries", k_fix_boundaries, dim3(grid_for(ttiles - 1, 8)), dim3(256), 0, st, E, (int)kTM, g->in_rcv, ws + L.PF, ws + L.PL, H2S);
+      }
+#else
       set_smem(k_edge_step, edge_fwd_smem());
       SPW_KLAUNCH("k_edge_step", k_edge_step, dim3(egrid), dim3(kThreads), edge_fwd_smem(), st, a);
       if (etiles > 1)
         SPW_KLAUNCH("k_fix_boundaries", k_fix_boundaries, dim3(grid_for(etiles - 1, 8)), dim3(256), 0, st, E, (int)kTME, g->in_rcv, ws + L.PF, ws + L.PL, H2S);
+#endif
     }
     {   // g = tanh(W3.sum h2 + deg.b3)   (Networks.py:87-88)
       LinSeg s = seg(H2S, kDEP, kDE, PK(P_W3));
