@@ -119,7 +119,10 @@ __device__ __forceinline__ bool mbar_wait(uint64_t* bar, uint32_t parity) {
   return false;
 }
 
-// issue the 3 x kKS MMAs of one 128-row tile: D = A_hi.B_hi + A_lo.B_hi + A_hi.B_lo
+// issue the 3 x kKS MMAs of one 128-row tile: D = (A_lo.B_hi + A_hi.B_lo) + A_hi.B_hi.
+// The tensor core truncates when it adds into the fp32 accumulator, so the ORDER matters: the 38
+// correction products (2^-11 of the result) go first, while the accumulator is still tiny; only
+// the 19 main products accumulate at full magnitude (measured: 3x smaller error than interleaving).
 __device__ __forceinline__ void issue_tile_mmas(uint32_t tmem_base, const float* Bhi_s, const float* Blo_s) {
   const uint32_t idesc = make_idesc_tf32(128, kN);
   const uint32_t bhi = smem_u32(Bhi_s), blo = smem_u32(Blo_s);
@@ -129,6 +132,10 @@ __device__ __forceinline__ void issue_tile_mmas(uint32_t tmem_base, const float*
     const uint64_t dlo = make_b_desc(blo + ks * (kBStepFloats * 4), kN * 16, 128);
     mma_tf32_ts(tmem_base + kColD, tmem_base + kColAlo + 8 * ks, dhi, idesc, ks > 0 ? 1u : 0u);
     mma_tf32_ts(tmem_base + kColD, tmem_base + kColAhi + 8 * ks, dlo, idesc, 1u);
+  }
+#pragma unroll 1
+  for (int ks = 0; ks < kKS; ++ks) {
+    const uint64_t dhi = make_b_desc(bhi + ks * (kBStepFloats * 4), kN * 16, 128);
     mma_tf32_ts(tmem_base + kColD, tmem_base + kColAhi + 8 * ks, dhi, idesc, 1u);
   }
 }
