@@ -497,7 +497,7 @@ struct EdgeStepArgs {
   float* H2S;                                         // [n][152] sum over in-edges of h2
   float* part_first; float* part_last;                // [ntiles][152] segments cut by a tile boundary
   uint32_t* maskbits;                                 // [E][8] relu mask of h2 (training) or null:
-                                                      //   word i (<5), bit j  <->  column 5*j + i
+                                                      //   bit (col & 31) of word (col >> 5), 5 words used
 };
 
 // K2b: per step -- gather, hidden layer 2, relu, deterministic receiver-segmented sum
@@ -518,20 +518,19 @@ __global__ void __launch_bounds__(kThreads, 2) k_edge_step(EdgeStepArgs a) {
     float acc[ROWS][5];
     zero_acc<ROWS, 5>(acc);
     gemm_tile_acc<ROWS, 5>(acc, Xa, kDEP, warp * ROWS, a.W2, kDEP, Wst);
-#pragma unroll
-    for (int r = 0; r < ROWS; ++r) {
-      const int row = warp * ROWS + r;
-#pragma unroll
-      for (int i = 0; i < 5; ++i) {
-        const int col = lane * 5 + i;
-        const float pre = col < kDE ? acc[r][i] + a.b2[col] : 0.f;
-        const bool on = (row < rows) && (col < kDE) && (pre > 0.f);
-        const unsigned bal = __ballot_sync(0xffffffffu, on);
-        if (a.maskbits && lane == 0 && row < rows) a.maskbits[(size_t)(e0 + row) * 8 + i] = bal;
-        if (col < kDEP) Xb[(size_t)row * kDEP + col] = on ? pre : 0.f;
+    store_act_tile<ROWS>(acc, Xb, warp, lane, rows, [&](float v, int, int c) { return relu_f(v + a.b2[c]); });
+    __syncthreads();
+    if (a.maskbits) {   // relu bits of h2 for the backward pass (h2 > 0 <=> pre-activation > 0)
+      for (int idx = tid; idx < rows * 5; idx += kThreads) {
+        const int r = idx / 5, w = idx - r * 5;
+        uint32_t m = 0u;
+        for (int b = 0; b < 32; ++b) {
+          const int col = 32 * w + b;
+          if (col < kDE && Xb[(size_t)r * kDEP + col] > 0.f) m |= 1u << b;
+        }
+        a.maskbits[(size_t)(e0 + r) * 8 + w] = m;
       }
     }
-    __syncthreads();
     // receiver-segmented sum in row (= ascending sender = slot) order; one warp per node
     const int n_first = srcv[0], n_last = srcv[rows - 1];
     for (int node = n_first + warp; node <= n_last; node += kThreads / 32) {
@@ -625,11 +624,11 @@ __global__ void __launch_bounds__(kThreads, 1) k_edge_step_bwd(EdgeStepBwdArgs a
           if (c >= C4) continue;
           const int col = 4 * c;
           float4 v = d[j][p];
-          // column -> (word = col % 5, bit = col / 5)
-          v.x = (col < kDE && ((mw[col % 5] >> (col / 5)) & 1u)) ? v.x : 0.f;
-          v.y = (col + 1 < kDE && ((mw[(col + 1) % 5] >> ((col + 1) / 5)) & 1u)) ? v.y : 0.f;
-          v.z = (col + 2 < kDE && ((mw[(col + 2) % 5] >> ((col + 2) / 5)) & 1u)) ? v.z : 0.f;
-          v.w = (col + 3 < kDE && ((mw[(col + 3) % 5] >> ((col + 3) / 5)) & 1u)) ? v.w : 0.f;
+          const uint32_t bits = mw[col >> 5] >> (col & 31);     // 4 consecutive columns never straddle a word
+          v.x = (col < kDE && (bits & 1u)) ? v.x : 0.f;
+          v.y = (col + 1 < kDE && (bits & 2u)) ? v.y : 0.f;
+          v.z = (col + 2 < kDE && (bits & 4u)) ? v.z : 0.f;
+          v.w = (col + 3 < kDE && (bits & 8u)) ? v.w : 0.f;
           reinterpret_cast<float4*>(Xb + (size_t)(rb + j) * kDEP)[c] = v;
         }
       }

@@ -141,13 +141,16 @@ __device__ __forceinline__ void issue_tile_mmas(uint32_t tmem_base, const float*
 }
 
 // ---- weight packing: Keras W[K][N] (row-major, ld) -> hi / lo B operands in the layout above -------
+// bias (may be null): stored as row k == K of the operand, picked up by a ones column in A.
 __global__ void __launch_bounds__(256) k_pack_umma(const float* __restrict__ W, int ld, int row0, int col0, int K, int N,
-                                                   int transpose, float* __restrict__ hi, float* __restrict__ lo) {
+                                                   int transpose, const float* __restrict__ bias, float* __restrict__ hi,
+                                                   float* __restrict__ lo) {
   for (int idx = blockIdx.x * blockDim.x + threadIdx.x; idx < kBFloats; idx += gridDim.x * blockDim.x) {
     const int e = idx & 3, n = (idx >> 2) % kN, c = ((idx >> 2) / kN) & 1, ks = (idx >> 2) / (2 * kN);
     const int k = 8 * ks + 4 * c + e;
     float v = 0.f;
     if (k < K && n < N) v = transpose ? W[(size_t)(row0 + n) * ld + col0 + k] : W[(size_t)(row0 + k) * ld + col0 + n];
+    else if (bias && k == K && n < N) v = bias[n];
     uint32_t h, l;
     split_tf32(v, h, l);
     hi[idx] = __uint_as_float(h);
@@ -224,7 +227,7 @@ __global__ void __launch_bounds__(128, 1) k_tc_selftest(const float* __restrict_
 //   tensor memory: A_hi | A_lo | D as in the map above
 //   thread = (row = TMEM lane, column half); warps w and w+4 share a lane quarter
 // =================================================================================================
-constexpr int kStagePitch = 65;
+constexpr int kStagePitch = 66;      // 8-byte aligned rows; row-thread 64-bit accesses are conflict-free
 constexpr int kStageCols = 64;
 
 struct EdgeStepTcArgs {
@@ -232,13 +235,51 @@ struct EdgeStepTcArgs {
   const int32_t* in_snd; const int32_t* in_rcv; const int32_t* in_off;
   const float* A; const float* S; const float* R;     // [E][152], [n][152], [n][152]
   const float* W2hi; const float* W2lo;               // packed B operands (k_pack_umma)
-  const float* b2;                                    // raw rmp.b1 [150]
   float* H2S;                                         // [n][152]
   float* part_first; float* part_last;                // [ntiles][152] (tiles of 128 edges)
-  uint32_t* maskbits;                                 // [E][8] or null (layout as k_edge_step)
+  uint32_t* maskbits;                                 // [E][8] or null: bit (col & 31) of word (col >> 5)
 };
 
-constexpr size_t kEdgeStepTcSmem = (size_t)(2 * kBFloats + kTM * kStagePitch + kTM + kTM * 5 + 160) * sizeof(float) + 64;
+constexpr size_t kEdgeStepTcSmem = (size_t)(2 * kBFloats + kTM * kStagePitch + 2 * kTM + (kTM + 8) / 2 + kTM * 5) * sizeof(float) + 16;
+static_assert(kEdgeStepTcSmem <= 232448, "k_edge_step_tc shared memory exceeds the 227 KB per-CTA limit");
+
+// coalesced gather of one 64-column slab of h1 = relu(A_e + S_s + R_r): half a warp per row,
+// 128-bit loads along the row, four row-pairs (12 loads per lane) in flight
+__device__ __forceinline__ void build_h1_slab(float* stage, const int* ssnd, const int* srcv, const float* __restrict__ A,
+                                              const float* __restrict__ S, const float* __restrict__ R, int e0, int c0,
+                                              int ncols) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int sub = lane >> 4, c4 = lane & 15;
+  const bool col_ok = 4 * c4 < ncols;
+  const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll 1
+  for (int it = 0; it < 8; it += 4) {
+    float4 va[4], vs[4], vr[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int r = warp * 16 + 2 * (it + j) + sub;
+      const int rc = srcv[r];
+      if (rc >= 0 && col_ok) {
+        va[j] = *reinterpret_cast<const float4*>(A + (size_t)(e0 + r) * kDEP + c0 + 4 * c4);
+        vs[j] = *reinterpret_cast<const float4*>(S + (size_t)ssnd[r] * kDEP + c0 + 4 * c4);
+        vr[j] = *reinterpret_cast<const float4*>(R + (size_t)rc * kDEP + c0 + 4 * c4);
+      } else {
+        va[j] = z4; vs[j] = z4; vr[j] = z4;
+      }
+    }
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int r = warp * 16 + 2 * (it + j) + sub;
+      if (!col_ok) continue;
+      float2* dst = reinterpret_cast<float2*>(stage + r * kStagePitch + 4 * c4);
+      dst[0] = make_float2(relu_f(va[j].x + vs[j].x + vr[j].x), relu_f(va[j].y + vs[j].y + vr[j].y));
+      if (c0 + 4 * c4 == kDE - 2)     // columns 150 / 151: the ones column that picks up the bias row, and the pad
+        dst[1] = make_float2(srcv[r] >= 0 ? 1.f : 0.f, 0.f);
+      else
+        dst[1] = make_float2(relu_f(va[j].z + vs[j].z + vr[j].z), relu_f(va[j].w + vs[j].w + vr[j].w));
+    }
+  }
+}
 
 __global__ void __launch_bounds__(kThreads, 1) k_edge_step_tc(EdgeStepTcArgs a) {
   SPW_DYN_SMEM(smem_raw);
@@ -246,9 +287,10 @@ __global__ void __launch_bounds__(kThreads, 1) k_edge_step_tc(EdgeStepTcArgs a) 
   float* Blo_s = Bhi_s + kBFloats;
   float* stage = Blo_s + kBFloats;
   int* srcv = reinterpret_cast<int*>(stage + kTM * kStagePitch);
-  uint32_t* smask = reinterpret_cast<uint32_t*>(srcv + kTM);
-  float* sb2 = reinterpret_cast<float*>(smask + kTM * 5);
-  uint64_t* bar = reinterpret_cast<uint64_t*>(sb2 + 160);
+  int* ssnd = srcv + kTM;
+  short* snoff = reinterpret_cast<short*>(ssnd + kTM);   // in_off - e0 of the tile's nodes, clamped (kTM + 8 entries)
+  uint16_t* smask = reinterpret_cast<uint16_t*>(snoff + kTM + 8);   // relu bits, 10 half-words per row
+  uint64_t* bar = reinterpret_cast<uint64_t*>(smask + kTM * 10);
   uint32_t* tptr = reinterpret_cast<uint32_t*>(bar + 1);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int row = 32 * (warp & 3) + lane, half = warp >> 2;
@@ -259,7 +301,6 @@ __global__ void __launch_bounds__(kThreads, 1) k_edge_step_tc(EdgeStepTcArgs a) 
     reinterpret_cast<float4*>(Bhi_s)[i] = reinterpret_cast<const float4*>(a.W2hi)[i];
     reinterpret_cast<float4*>(Blo_s)[i] = reinterpret_cast<const float4*>(a.W2lo)[i];
   }
-  if (tid < 160) sb2[tid] = tid < kDE ? a.b2[tid] : 0.f;
   fence_async_smem();
   fence_before_sync();
   __syncthreads();
@@ -273,35 +314,39 @@ __global__ void __launch_bounds__(kThreads, 1) k_edge_step_tc(EdgeStepTcArgs a) 
   for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
     const int e0 = tile * kTM;
     const int rows = imin(kTM, a.E - e0);
-    // ---- build h1 = relu(A_e + S_s + R_r) for this thread's row / column half, split, store to TMEM
-    {
-      const bool valid = row < rows;
-      int s = 0, rc = -1;
-      if (valid) { s = a.in_snd[e0 + row]; rc = a.in_rcv[e0 + row]; }
-      if (half == 0) srcv[row] = rc;
-      for (int i = tid; i < kTM * 5; i += kThreads) smask[i] = 0u;
-      const float* pa = a.A + (size_t)(e0 + (valid ? row : 0)) * kDEP;
-      const float* ps = a.S + (size_t)s * kDEP;
-      const float* pr = a.R + (size_t)(valid ? rc : 0) * kDEP;
-      const int c_beg = half ? 80 : 0, c_end = half ? kDEP : 80;
-#pragma unroll 2
-      for (int c = c_beg; c < c_end; c += 8) {
-        uint32_t h[8], l[8];
-        if (valid) {
-          const float4 a0 = *reinterpret_cast<const float4*>(pa + c), a1 = *reinterpret_cast<const float4*>(pa + c + 4);
-          const float4 s0 = *reinterpret_cast<const float4*>(ps + c), s1 = *reinterpret_cast<const float4*>(ps + c + 4);
-          const float4 r0 = *reinterpret_cast<const float4*>(pr + c), r1 = *reinterpret_cast<const float4*>(pr + c + 4);
-          const float x[8] = {a0.x + s0.x + r0.x, a0.y + s0.y + r0.y, a0.z + s0.z + r0.z, a0.w + s0.w + r0.w,
-                              a1.x + s1.x + r1.x, a1.y + s1.y + r1.y, a1.z + s1.z + r1.z, a1.w + s1.w + r1.w};
+    if (tid < kTM) {
+      const bool valid = tid < rows;
+      srcv[tid] = valid ? a.in_rcv[e0 + tid] : -1;
+      ssnd[tid] = valid ? a.in_snd[e0 + tid] : 0;
+    }
+    __syncthreads();
+    const int n_first = srcv[0], n_last = srcv[rows - 1];
+    const int nnodes = n_last - n_first + 1;
+    for (int i = tid; i <= imin(nnodes, kTM + 7); i += kThreads)
+      snoff[i] = (short)imax(-32000, imin(32000, a.in_off[n_first + i] - e0));
+    // ---- h1 = relu(A_e + S_s + R_r): coalesced gather into the slab, then row threads split it
+    //      into tf32 hi/lo and store it to tensor memory (3 slabs of <= 64 columns)
+    for (int c0 = 0; c0 < kDEP; c0 += kStageCols) {
+      const int ncols = imin(kStageCols, kDEP - c0);
+      build_h1_slab(stage, ssnd, srcv, a.A, a.S, a.R, e0, c0, ncols);
+      __syncthreads();
+      // this thread's half of the slab row: 32 columns (or what is left)
+      const int cb = 32 * half;
 #pragma unroll
-          for (int i = 0; i < 8; ++i) split_tf32(relu_f(x[i]), h[i], l[i]);
-        } else {
+      for (int g = 0; g < 4; ++g) {
+        const int c = cb + 8 * g;
+        if (c < ncols) {                                  // warp-uniform
+          const float2* src = reinterpret_cast<const float2*>(stage + row * kStagePitch + c);
+          const float2 p0 = src[0], p1 = src[1], p2 = src[2], p3 = src[3];
+          const float x[8] = {p0.x, p0.y, p1.x, p1.y, p2.x, p2.y, p3.x, p3.y};
+          uint32_t h[8], l[8];
 #pragma unroll
-          for (int i = 0; i < 8; ++i) { h[i] = 0u; l[i] = 0u; }
+          for (int i = 0; i < 8; ++i) split_tf32(x[i], h[i], l[i]);
+          tmem_st8(lane_addr + kColAhi + c0 + c, h);
+          tmem_st8(lane_addr + kColAlo + c0 + c, l);
         }
-        tmem_st8(lane_addr + kColAhi + c, h);
-        tmem_st8(lane_addr + kColAlo + c, l);
       }
+      __syncthreads();
     }
     tmem_wait_st();
     fence_before_sync();
@@ -315,33 +360,32 @@ __global__ void __launch_bounds__(kThreads, 1) k_edge_step_tc(EdgeStepTcArgs a) 
     parity ^= 1u;
     fence_after_sync();
     // ---- epilogue: D -> +b2, relu, relu bits -> staging slab -> receiver-segmented sum
-    const int n_first = srcv[0], n_last = srcv[rows - 1];
     for (int c0 = 0; c0 < kN; c0 += kStageCols) {
       const int ncols = imin(kStageCols, kN - c0);
       for (int blk = half; blk * 16 < ncols; blk += 2) {
         uint32_t v[16];
         tmem_ld16(lane_addr + kColD + c0 + blk * 16, v);
         tmem_wait_ld();
-        uint32_t mw[5] = {0u, 0u, 0u, 0u, 0u};
+        uint32_t m16 = 0u;
+        float o[16];
 #pragma unroll
         for (int i = 0; i < 16; ++i) {
-          const int col = c0 + blk * 16 + i;
-          const float pre = __uint_as_float(v[i]) + sb2[col];
-          const bool on = (col < kDE) && (pre > 0.f);
-          stage[row * kStagePitch + blk * 16 + i] = on ? pre : 0.f;
-          if (on) mw[col % 5] |= 1u << (col / 5);
+          const float pre = __uint_as_float(v[i]);          // bias already inside (ones column x bias row)
+          const bool on = (c0 + blk * 16 + i < kDE) && (pre > 0.f);
+          o[i] = on ? pre : 0.f;
+          m16 |= on ? (1u << i) : 0u;
         }
-        if (a.maskbits && row < rows) {
+        float2* dst = reinterpret_cast<float2*>(stage + row * kStagePitch + blk * 16);
 #pragma unroll
-          for (int w = 0; w < 5; ++w)
-            if (mw[w]) atomicOr(&smask[row * 5 + w], mw[w]);
-        }
+        for (int i = 0; i < 8; ++i) dst[i] = make_float2(o[2 * i], o[2 * i + 1]);
+        smask[row * 10 + ((c0 + blk * 16) >> 4)] = (uint16_t)m16;
       }
       __syncthreads();
-      const int nnodes = n_last - n_first + 1;
       for (int item = tid; item < nnodes * ncols; item += kThreads) {
-        const int node = n_first + item / ncols, c = item - (item / ncols) * ncols;
-        const int s0 = a.in_off[node], s1 = a.in_off[node + 1];
+        const int ni = item / ncols, c = item - ni * ncols;
+        const int node = n_first + ni;
+        int s0, s1;
+        if (ni < kTM + 7) { s0 = e0 + snoff[ni]; s1 = e0 + snoff[ni + 1]; } else { s0 = a.in_off[node]; s1 = a.in_off[node + 1]; }
         const int lo = imax(s0, e0) - e0, hi = imin(s1, e0 + rows) - e0;
         if (hi <= lo) continue;
         const int col = c0 + c;
@@ -360,7 +404,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_edge_step_tc(EdgeStepTcArgs a) 
     if (a.maskbits) {
       for (int i = tid; i < rows * 5; i += kThreads) {
         const int r = i / 5, w = i - r * 5;
-        a.maskbits[(size_t)(e0 + r) * 8 + w] = smask[i];
+        a.maskbits[(size_t)(e0 + r) * 8 + w] = (uint32_t)smask[r * 10 + 2 * w] | ((uint32_t)smask[r * 10 + 2 * w + 1] << 16);
       }
     }
     fence_before_sync();

@@ -372,7 +372,7 @@ int spw_tc_selftest(const float* A, const float* W, int K, int N, float* D, floa
 #else
   if (!A || !W || !D || !scratch || !status || K > 152 || N > 160) return fail(SPW_ERR_BAD_ARG, "spw_tc_selftest: bad argument");
   cudaStream_t st = (cudaStream_t)stream;
-  SPW_KLAUNCH("k_pack_umma", tc::k_pack_umma, dim3(48), dim3(256), 0, st, W, N, 0, 0, K, N, 0, scratch, scratch + tc::kBFloats);
+  SPW_KLAUNCH("k_pack_umma", tc::k_pack_umma, dim3(48), dim3(256), 0, st, W, N, 0, 0, K, N, 0, (const float*)nullptr, scratch, scratch + tc::kBFloats);
   const size_t smem = (size_t)2 * tc::kBFloats * sizeof(float) + 64;
   set_smem(tc::k_tc_selftest, smem);
   SPW_KLAUNCH("k_tc_selftest", tc::k_tc_selftest, dim3(1), dim3(128), smem, st, A, scratch, scratch + tc::kBFloats, D, status);
@@ -440,7 +440,7 @@ int spw_forward(const SpwParams* w, const SpwGraph* g, const float* obj, float* 
 
   pack_weights(st, w, ws, L, training != 0);
 #if SPW_USE_TC
-  SPW_KLAUNCH("k_pack_umma", tc::k_pack_umma, dim3(48), dim3(256), 0, st, (const float*)w->rmp_w[1], 150, 0, 0, 150, 150, 0, ws + L.W2hi, ws + L.W2lo);
+  SPW_KLAUNCH("k_pack_umma", tc::k_pack_umma, dim3(48), dim3(256), 0, st, (const float*)w->rmp_w[1], 150, 0, 0, 150, 150, 0, (const float*)w->rmp_b[1], ws + L.W2hi, ws + L.W2lo);
 #endif
   SPW_KLAUNCH("k_deg_to_float", k_deg_to_float, dim3(grid_for(n, 256)), dim3(256), 0, st, g->in_off, n, ws + L.degf);
 
@@ -493,7 +493,7 @@ int spw_forward(const SpwParams* w, const SpwGraph* g, const float* obj, float* 
       {
         tc::EdgeStepTcArgs t;
         t.E = E; t.in_snd = g->in_snd; t.in_rcv = g->in_rcv; t.in_off = g->in_off; t.A = ws + L.A; t.S = S; t.R = R;
-        t.W2hi = ws + L.W2hi; t.W2lo = ws + L.W2lo; t.b2 = w->rmp_b[1]; t.H2S = H2S; t.part_first = ws + L.PF;
+        t.W2hi = ws + L.W2hi; t.W2lo = ws + L.W2lo; t.H2S = H2S; t.part_first = ws + L.PF;
         t.part_last = ws + L.PL; t.maskbits = a.maskbits;
         const int ttiles = (E + kTM - 1) / kTM;
         const int tgrid = ttiles < num_sms() ? ttiles : num_sms();
