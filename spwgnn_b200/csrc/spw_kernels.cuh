@@ -387,9 +387,21 @@ struct EdgeEncArgs {
   const float* b1; const float* b2; const float* b3;      // raw biases [150]
   const float* W1A; const float* bA;                      // packed rmp.w0[0:150], raw rmp.b0
   float* A;                                               // [E][152]
+  float* X1; float* X2; float* C;                         // [E][152] each, training only (null: not saved)
 };
 
 constexpr int kTME = 64;    // edge-tile rows of the forward edge kernels (two CTAs per SM)
+
+// shared tile [rows][152] -> global rows, 128-bit coalesced
+__device__ __forceinline__ void tile_to_global(const float* Xs, float* G, int e0, int rows) {
+  for (int idx = threadIdx.x; idx < rows * (kDEP / 4); idx += kThreads)
+    reinterpret_cast<float4*>(G + (size_t)e0 * kDEP)[idx] = reinterpret_cast<const float4*>(Xs)[idx];
+}
+__device__ __forceinline__ void tile_from_global(float* Xs, const float* G, int e0, int rows, int tile_rows) {
+  for (int idx = threadIdx.x; idx < tile_rows * (kDEP / 4); idx += kThreads)
+    reinterpret_cast<float4*>(Xs)[idx] = idx < rows * (kDEP / 4) ? reinterpret_cast<const float4*>(G + (size_t)e0 * kDEP)[idx]
+                                                                 : make_float4(0.f, 0.f, 0.f, 0.f);
+}
 
 // K2a: c_e = relu(rm(diff))  (4 layers) and A_e = W1a.c_e + b1, all inside one CTA tile
 __global__ void __launch_bounds__(kThreads, 2) k_edge_encode(EdgeEncArgs a) {
@@ -412,14 +424,17 @@ __global__ void __launch_bounds__(kThreads, 2) k_edge_encode(EdgeEncArgs a) {
     gemm_tile_acc<ROWS, 5>(acc, Xa, kDEP, warp * ROWS, a.RM1, kDEP, Wst);
     store_act_tile<ROWS>(acc, Xb, warp, lane, rows, [&](float v, int, int c) { return relu_f(v + a.b1[c]); });
     __syncthreads();
+    if (a.X1) tile_to_global(Xb, a.X1, e0, rows);
     zero_acc<ROWS, 5>(acc);
     gemm_tile_acc<ROWS, 5>(acc, Xb, kDEP, warp * ROWS, a.RM2, kDEP, Wst);
     store_act_tile<ROWS>(acc, Xa, warp, lane, rows, [&](float v, int, int c) { return relu_f(v + a.b2[c]); });
     __syncthreads();
+    if (a.X2) tile_to_global(Xa, a.X2, e0, rows);
     zero_acc<ROWS, 5>(acc);
     gemm_tile_acc<ROWS, 5>(acc, Xa, kDEP, warp * ROWS, a.RM3, kDEP, Wst);
     store_act_tile<ROWS>(acc, Xb, warp, lane, rows, [&](float v, int, int c) { return relu_f(v + a.b3[c]); });
     __syncthreads();
+    if (a.C) tile_to_global(Xb, a.C, e0, rows);
     zero_acc<ROWS, 5>(acc);
     gemm_tile_acc<ROWS, 5>(acc, Xb, kDEP, warp * ROWS, a.W1A, kDEP, Wst);
     // A tile -> Xa (free), then 128-bit coalesced rows to HBM
@@ -709,6 +724,7 @@ struct EdgeEncBwdArgs {
   const float* b1; const float* b2; const float* b3;
   const float* RM1T; const float* RM2T; const float* RM3T; const float* W1AT;
   const float* dA;          // [E][152] total gradient w.r.t. A_e
+  const float* X1; const float* X2; const float* C;   // [E][152] activations saved by k_edge_encode
   float* partM;             // [gridDim.x][4][160*160]: W1A, RM3, RM2, RM1
   float* part0;             // [gridDim.x][3][152]: d rm.w0 row 0, row 1, d rm.b0
 };
@@ -735,29 +751,15 @@ __global__ void __launch_bounds__(kThreads, 1) k_edge_encode_bwd(EdgeEncBwdArgs 
   for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
     const int e0 = tile * kTMB;
     const int rows = imin(kTMB, a.E - e0);
-    // ---- forward recompute: X0 (Ba) -> X1 (Bb) -> X2 (Bc) -> C (Bd)
+    // ---- layer inputs: X0 (Ba) is rebuilt (K = 2); X1 (Bb), X2 (Bc), C (Bd) come back from the forward
+    //      pass (saved with their bias "ones" column); dA tile -> Be (a dY operand: no ones column)
     build_x0<kTMB>(Ba, sdx, sdy, a.obj, a.in_snd, a.in_rcv, e0, rows, a.W0, a.b0);
-    // dA tile -> Be (a dY operand: no ones column)
-    for (int idx = tid; idx < kTMB * (kDEP / 4); idx += kThreads) {
-      const int r = idx / (kDEP / 4), c = idx - r * (kDEP / 4);
-      float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-      if (r < rows) v = reinterpret_cast<const float4*>(a.dA + (size_t)(e0 + r) * kDEP)[c];
-      reinterpret_cast<float4*>(Be + (size_t)r * kDEP)[c] = v;
-    }
+    tile_from_global(Bb, a.X1, e0, rows, kTMB);
+    tile_from_global(Bc, a.X2, e0, rows, kTMB);
+    tile_from_global(Bd, a.C, e0, rows, kTMB);
+    tile_from_global(Be, a.dA, e0, rows, kTMB);
     __syncthreads();
     float acc[8][5];
-    zero_acc<8, 5>(acc);
-    gemm_tile_acc<8, 5>(acc, Ba, kDEP, warp * 8, a.RM1, kDEP, Wst);
-    store_act_tile<8>(acc, Bb, warp, lane, rows, [&](float v, int, int c) { return relu_f(v + a.b1[c]); });
-    __syncthreads();
-    zero_acc<8, 5>(acc);
-    gemm_tile_acc<8, 5>(acc, Bb, kDEP, warp * 8, a.RM2, kDEP, Wst);
-    store_act_tile<8>(acc, Bc, warp, lane, rows, [&](float v, int, int c) { return relu_f(v + a.b2[c]); });
-    __syncthreads();
-    zero_acc<8, 5>(acc);
-    gemm_tile_acc<8, 5>(acc, Bc, kDEP, warp * 8, a.RM3, kDEP, Wst);
-    store_act_tile<8>(acc, Bd, warp, lane, rows, [&](float v, int, int c) { return relu_f(v + a.b3[c]); });
-    __syncthreads();
     // ---- backward.  Each stage: dW += X^T.dY (bias via the ones column), dX = (dY.W^T) * relu'
     auto stage = [&](const float* X, float* dY, const float* WT, float* dXout, float* part) {
       float wacc[10][10];

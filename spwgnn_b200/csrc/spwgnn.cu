@@ -118,7 +118,7 @@ struct Layout {
   size_t P, S, R, H2S, G, U;     // per-step arrays (training: 5 slots; inference: fewer)
   int slotsP, slotsSR, slotsN;   // number of step slots for P / (S,R) / (H2S,G,U)
   // backward
-  size_t dU, dG, T, dS, dR, dH2S, DP, dQ, dQ1, dA, DH1, M2, partE, partM, part0, partN;
+  size_t dU, dG, T, dS, dR, dH2S, DP, dQ, dQ1, dA, DH1, M2, EX1, EX2, EC, partE, partM, part0, partN;
   size_t total;   // floats
 };
 
@@ -160,12 +160,15 @@ Layout make_layout(int64_t n, int64_t E, int training) {
     L.dA = take((size_t)E * kDEP + 8);
     L.DH1 = take((size_t)E * kDEP + 8);
     L.M2 = take((size_t)SPW_N_STEPS * E * 8);      // relu bits of h2, 8 words per edge and step
+    L.EX1 = take((size_t)E * kDEP + 8);            // relation-encoder activations kept for the backward pass
+    L.EX2 = take((size_t)E * kDEP + 8);
+    L.EC = take((size_t)E * kDEP + 8);
     L.partE = take((size_t)kMaxCtas * 160 * 160);
     L.partM = take((size_t)kMaxCtas * 4 * 160 * 160);
     L.part0 = take((size_t)kMaxCtas * 3 * kDEP);
     L.partN = take((size_t)2 * kMaxCtas * kPartNodeElems);
   } else {
-    L.dU = L.dG = L.T = L.dS = L.dR = L.dH2S = L.DP = L.dQ = L.dQ1 = L.dA = L.DH1 = L.M2 = 0;
+    L.dU = L.dG = L.T = L.dS = L.dR = L.dH2S = L.DP = L.dQ = L.dQ1 = L.dA = L.DH1 = L.M2 = L.EX1 = L.EX2 = L.EC = 0;
     L.partE = L.partM = L.part0 = L.partN = 0;
   }
   L.total = off;
@@ -459,6 +462,7 @@ int spw_forward(const SpwParams* w, const SpwGraph* g, const float* obj, float* 
     a.E = E; a.in_snd = g->in_snd; a.in_rcv = g->in_rcv; a.obj = obj; a.W0 = w->rm_w[0]; a.b0 = w->rm_b[0];
     a.RM1 = PK(P_RM1); a.RM2 = PK(P_RM2); a.RM3 = PK(P_RM3); a.b1 = w->rm_b[1]; a.b2 = w->rm_b[2]; a.b3 = w->rm_b[3];
     a.W1A = PK(P_W1A); a.bA = w->rmp_b[0]; a.A = ws + L.A;
+    a.X1 = training ? ws + L.EX1 : nullptr; a.X2 = training ? ws + L.EX2 : nullptr; a.C = training ? ws + L.EC : nullptr;
     set_smem(k_edge_encode, edge_fwd_smem());
     SPW_KLAUNCH("k_edge_encode", k_edge_encode, dim3(egrid), dim3(kThreads), edge_fwd_smem(), st, a);
   }
@@ -666,6 +670,7 @@ int spw_backward(const SpwParams* w, const SpwGraph* g, const float* obj, const 
     a.E = E; a.in_snd = g->in_snd; a.in_rcv = g->in_rcv; a.obj = obj; a.W0 = w->rm_w[0]; a.b0 = w->rm_b[0];
     a.RM1 = PK(P_RM1); a.RM2 = PK(P_RM2); a.RM3 = PK(P_RM3); a.b1 = w->rm_b[1]; a.b2 = w->rm_b[2]; a.b3 = w->rm_b[3];
     a.RM1T = PK(P_RM1T); a.RM2T = PK(P_RM2T); a.RM3T = PK(P_RM3T); a.W1AT = PK(P_W1AT); a.dA = ws + L.dA;
+    a.X1 = ws + L.EX1; a.X2 = ws + L.EX2; a.C = ws + L.EC;
     a.partM = ws + L.partM; a.part0 = ws + L.part0;
     set_smem(k_edge_encode_bwd, edge_encb_smem());
     SPW_KLAUNCH("k_edge_encode_bwd", k_edge_encode_bwd, dim3(bgrid), dim3(kThreads), edge_encb_smem(), st, a);
