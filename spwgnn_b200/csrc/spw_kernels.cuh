@@ -152,7 +152,7 @@ struct LinArgs {
 };
 
 template <int CN, int TMR>
-__global__ void __launch_bounds__(kThreads, (TMR == 64 ? 2 : 1)) k_linear(LinArgs a) {
+__global__ void __launch_bounds__(kThreads, (TMR <= 64 ? 2 : 1)) k_linear(LinArgs a) {
   SPW_DYN_SMEM(smem_raw);
   float* smem = reinterpret_cast<float*>(smem_raw);
   constexpr int ROWS = TMR / 8;

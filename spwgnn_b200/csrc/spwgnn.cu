@@ -224,19 +224,34 @@ void launch_linear(cudaStream_t st, int M, int N, bool wide, int nseg, const Lin
   for (int s = 0; s < nseg; ++s) { a.seg[s] = segs[s]; xfloats += (size_t)kTN * segs[s].Kp; }
   a.bias = o.bias; a.rowscale = o.rowscale; a.addend = o.addend; a.ld_add = o.ld_add; a.act = o.act;
   a.mulsrc = o.mulsrc; a.ld_mul = o.ld_mul; a.mulmode = o.mulmode; a.Y = Y; a.ldy = ldy; a.accumulate = o.accumulate;
-  const int ntiles = (M + kTN - 1) / kTN;
-  const int grid = ntiles < 2 * num_sms() ? ntiles : 2 * num_sms();
-  if (wide) {
-    const size_t smem = (xfloats + 2 * kKT * kLdwE) * sizeof(float);
-    auto kern = k_linear<5, kTN>;
-    set_smem(kern, smem);
-    SPW_KLAUNCH("k_linear<5>", kern, dim3(grid), dim3(kThreads), smem, st, a);
-  } else {
-    const size_t smem = (xfloats + 2 * kKT * kLdwP) * sizeof(float);
-    auto kern = k_linear<4, kTN>;
-    set_smem(kern, smem);
-    SPW_KLAUNCH("k_linear<4>", kern, dim3(grid), dim3(kThreads), smem, st, a);
+  // rows per tile: the candidate that minimises (rounds x rows) for a grid of two CTAs per SM (wave quantisation)
+  const int cap = 2 * num_sms();
+  int best_tm = 64;
+  long best_cost = -1;
+  for (int tm = 64; tm >= 32; tm -= 8) {
+    const long nt = (M + tm - 1) / tm;
+    const long rounds = (nt + cap - 1) / cap;
+    const long cost = rounds * (tm + 6);          // +6: per-tile fixed overhead in row units
+    if (best_cost < 0 || cost < best_cost) { best_cost = cost; best_tm = tm; }
   }
+  const int ntiles = (M + best_tm - 1) / best_tm;
+  const int grid = ntiles < cap ? ntiles : cap;
+  size_t xf = 0;
+  for (int s = 0; s < nseg; ++s) xf += (size_t)best_tm * segs[s].Kp;
+  const size_t smem = (xf + 2 * kKT * (wide ? kLdwE : kLdwP)) * sizeof(float);
+#define SPW_LIN_CASE(TMV)                                                                                   \
+  case TMV:                                                                                                 \
+    if (wide) { auto kern = k_linear<5, TMV>; set_smem(kern, smem); SPW_KLAUNCH("k_linear<5>", kern, dim3(grid), dim3(kThreads), smem, st, a); } \
+    else { auto kern = k_linear<4, TMV>; set_smem(kern, smem); SPW_KLAUNCH("k_linear<4>", kern, dim3(grid), dim3(kThreads), smem, st, a); }      \
+    break;
+  switch (best_tm) {
+    SPW_LIN_CASE(64)
+    SPW_LIN_CASE(56)
+    SPW_LIN_CASE(48)
+    SPW_LIN_CASE(40)
+    SPW_LIN_CASE(32)
+  }
+#undef SPW_LIN_CASE
 }
 
 // dW[Kin][N] (+ bias row) = X^T dY over M rows, reduced in fixed order into the Keras-layout gradient
