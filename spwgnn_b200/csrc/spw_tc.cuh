@@ -244,7 +244,7 @@ constexpr size_t kEdgeStepTcSmem = (size_t)(2 * kBFloats + kTM * kStagePitch + 2
 static_assert(kEdgeStepTcSmem <= 232448, "k_edge_step_tc shared memory exceeds the 227 KB per-CTA limit");
 
 // coalesced gather of one 64-column slab of h1 = relu(A_e + S_s + R_r): half a warp per row,
-// 128-bit loads along the row, four row-pairs (12 loads per lane) in flight
+// 128-bit loads along the row, all eight row-pairs of the warp (24 loads per lane) in flight
 __device__ __forceinline__ void build_h1_slab(float* stage, const int* ssnd, const int* srcv, const float* __restrict__ A,
                                               const float* __restrict__ S, const float* __restrict__ R, int e0, int c0,
                                               int ncols) {
@@ -253,10 +253,10 @@ __device__ __forceinline__ void build_h1_slab(float* stage, const int* ssnd, con
   const bool col_ok = 4 * c4 < ncols;
   const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll 1
-  for (int it = 0; it < 8; it += 4) {
-    float4 va[4], vs[4], vr[4];
+  for (int it = 0; it < 8; it += 8) {
+    float4 va[8], vs[8], vr[8];
 #pragma unroll
-    for (int j = 0; j < 4; ++j) {
+    for (int j = 0; j < 8; ++j) {
       const int r = warp * 16 + 2 * (it + j) + sub;
       const int rc = srcv[r];
       if (rc >= 0 && col_ok) {
@@ -268,7 +268,7 @@ __device__ __forceinline__ void build_h1_slab(float* stage, const int* ssnd, con
       }
     }
 #pragma unroll
-    for (int j = 0; j < 4; ++j) {
+    for (int j = 0; j < 8; ++j) {
       const int r = warp * 16 + 2 * (it + j) + sub;
       if (!col_ok) continue;
       float2* dst = reinterpret_cast<float2*>(stage + r * kStagePitch + 4 * c4);
