@@ -111,10 +111,13 @@ size_t spw_workspace_bytes(int32_t n_nodes, int32_t n_edges, int training);
 
 /* Forward (Networks.py:58-96).  obj [n_nodes][3] = [x, y, width]/170 (main.py:91).
  * logits [n_nodes] (channel 0 of the last object-propagator output, Networks.py:94);
- * probs  [n_nodes] sigmoid(logits) or NULL.  training: keep state for spw_backward
- * (dropout is not applied: see DESIGN.md).                                                     */
+ * probs  [n_nodes] sigmoid(logits) or NULL.  training: keep state for spw_backward.
+ * dropout_rate / dropout_seed: inverted dropout on the relation and object encodings
+ * (Networks.py:77-78, rate 0.1 in the reference), applied only when training != 0 and rate > 0;
+ * the mask is a stateless hash of (seed, element index), see dropout_hash in spw_common.cuh.    */
 int spw_forward(const SpwParams* w, const SpwGraph* g, const float* obj, float* logits, float* probs,
-                void* workspace, size_t workspace_bytes, int training, void* stream);
+                void* workspace, size_t workspace_bytes, int training, float dropout_rate,
+                uint64_t dropout_seed, void* stream);
 
 /* Keras binary_crossentropy on probabilities clipped to [1e-7, 1-1e-7] (Networks.py:102), mean over
  * `count` outputs (pass the GLOBAL number of blocks when data-parallel).  Writes dlogits [n_nodes]
@@ -124,9 +127,11 @@ int spw_bce_grad(const float* logits, const float* target, int32_t n_nodes, doub
                  float* dlogits, double* stats, void* stream);
 
 /* Backward: gradients of sum_i dlogits[i]*logit[i] w.r.t. all 22 tensors, written (not
- * accumulated) to grads.  Deterministic: fixed tile->CTA assignment, fixed-order reductions.   */
+ * accumulated) to grads.  Deterministic: fixed tile->CTA assignment, fixed-order reductions.
+ * dropout_rate must equal the rate of the matching spw_forward call (the masks are implicit in the saved state). */
 int spw_backward(const SpwParams* w, const SpwGraph* g, const float* obj, const float* dlogits,
-                 void* workspace, size_t workspace_bytes, const SpwParams* grads, void* stream);
+                 void* workspace, size_t workspace_bytes, const SpwParams* grads, float dropout_rate,
+                 void* stream);
 
 #ifdef __cplusplus
 }

@@ -126,7 +126,7 @@ def case_train(keras, Networks, main, n_objects, n_traj, seed, tmpdir, with_grad
         objects=np.asarray(x['objects']), sender_relations=np.asarray(x['sender_relations']),
         receiver_relations=np.asarray(x['receiver_relations']), propagation_shape=np.asarray(x['propagation'].shape),
         target=np.asarray(y), probs=probs.detach().numpy(), loss=float(loss),
-        fit_kwargs=json.dumps(call['kwargs']),
+        fit_kwargs=json.dumps(call['kwargs']), traj_json=json.dumps(data),
     )
     for n, t, g in zip(names, tensors, grads):
         out['w:' + n] = t.detach().numpy()

@@ -225,15 +225,38 @@ def forward_dense(w, objects, sender_relations, receiver_relations, propagation=
     return (probs, logits) if return_logits else probs
 
 
-def forward_sparse(w, obj, snd, rcv, return_logits=False):
+def dropout_keep_mask(seed32, idx, rate):
+    """numpy restatement of dropout_hash / dropout_apply (spwgnn_b200/csrc/spw_common.cuh): element idx is
+    kept iff the 24-bit hash of (seed, idx) is >= float32(rate) * 2^24."""
+    M = np.uint64(0xffffffff)
+    h = (np.asarray(idx, dtype=np.uint64) * np.uint64(0x9E3779B9) + np.uint64(seed32)) & M
+    h ^= h >> np.uint64(16); h = (h * np.uint64(0x85EBCA6B)) & M
+    h ^= h >> np.uint64(13); h = (h * np.uint64(0xC2B2AE35)) & M
+    h ^= h >> np.uint64(16)
+    thresh = np.uint64(int(np.float32(rate) * np.float32(16777216.0)))
+    return (h >> np.uint64(8)) >= thresh
+
+
+def dropout_seeds(seed64):
+    lo, hi = seed64 & 0xffffffff, (seed64 >> 32) & 0xffffffff
+    return lo, (hi ^ 0x5bd1e995 ^ ((lo * 3) & 0xffffffff)) & 0xffffffff
+
+
+def forward_sparse(w, obj, snd, rcv, return_logits=False, c_scale=None, q_scale=None):
     """Same math on an explicit edge list (F8: inactive slots contribute 0).
     obj: (sum N, 3) torch; snd/rcv: (E,) int64 torch GLOBAL node ids, slot order.
+    c_scale (E,150) / q_scale (n,100): optional inverted-dropout factors (0 or 1/keep) applied to the two
+    encodings like Networks.py:77-78 does in training.
     Returns per-node probabilities (sum N,) (and logits)."""
     n = obj.shape[0]
     snd = snd.long(); rcv = rcv.long()
     diff = obj[rcv, 0:2] - obj[snd, 0:2]
     c = _relu(_mlp(w, 'rm', diff))
     q = _relu(_mlp(w, 'om', obj[:, 1:3]))
+    if c_scale is not None:
+        c = c * c_scale
+    if q_scale is not None:
+        q = q * q_scale
     p = torch.zeros(n, PROP_DIM, dtype=obj.dtype)
     z = None
     for _ in range(N_STEPS):
@@ -255,10 +278,10 @@ def bce_keras(probs, target):
     return -(target * torch.log(p) + (1.0 - target) * torch.log(1.0 - p)).mean()
 
 
-def loss_and_grads_sparse(w, obj, snd, rcv, target):
+def loss_and_grads_sparse(w, obj, snd, rcv, target, c_scale=None, q_scale=None):
     """fp64 reference gradients of the mean-BCE loss w.r.t. all 22 tensors (autograd)."""
     ws = {k: v.detach().clone().requires_grad_(True) for k, v in w.items()}
-    probs, logits = forward_sparse(ws, obj, snd, rcv, return_logits=True)
+    probs, logits = forward_sparse(ws, obj, snd, rcv, return_logits=True, c_scale=c_scale, q_scale=q_scale)
     loss = bce_keras(probs, target)
     names = tensor_names()
     grads = torch.autograd.grad(loss, [ws[k] for k in names])

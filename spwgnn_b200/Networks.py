@@ -69,7 +69,9 @@ class PropagationModel:
     def __init__(self, engine, n_objects):
         self.engine = engine
         self.n_objects = n_objects
-        self.lr = 5e-4
+        self.lr = 5e-4               # optimizers.Adam(lr=0.0005), Networks.py:101
+        self.dropout_rate = 0.1      # Dropout(0.1) on both encodings, train only, Networks.py:77-78
+        self._drop_seed = 0x5EED0001
 
     # ---- inference -----------------------------------------------------------------------------
     def _batch_from_dict(self, x, sel=None):
@@ -117,7 +119,8 @@ class PropagationModel:
     def train_on_batch(self, batch, target):
         """One optimiser step on a packed batch; returns (mean loss, binary accuracy)."""
         eng = self.engine
-        stats = eng.loss_and_grads(batch, target)
+        self._drop_seed = (self._drop_seed * 6364136223846793005 + 1442695040888963407) & 0xFFFFFFFFFFFFFFFF
+        stats = eng.loss_and_grads(batch, target, dropout_rate=self.dropout_rate, dropout_seed=self._drop_seed)
         eng.adam_step(lr=self.lr)
         s = stats.cpu().numpy() / max(batch.n_nodes, 1)
         return float(s[0]), float(s[1])
@@ -158,6 +161,45 @@ class PropagationModel:
                     l, a = self.test_on_batch(batch, tgt)
                     vl += l * len(sel); va += a * len(sel)
                 rec.update(val_loss=vl / n_val, val_binary_accuracy=va / n_val)
+            hist._add(ep, **rec)
+            if verbose:
+                print('Epoch %d/%d - ' % (ep + 1, epochs) + ' - '.join('%s: %.4f' % kv for kv in rec.items()))
+        return hist
+
+    def fit_towers(self, towers, labels, batch_size=32, epochs=1, validation_split=0.0, shuffle=True, verbose=1,
+                   seed=None, thr=REL_THRESHOLD, fully_connected=False):
+        """Fast-path training: `towers` = list of (N_t, 3) RAW [x, y, width] arrays (mixed sizes allowed),
+        `labels` = list of (N_t,) 0/1 arrays.  Relations are built on the GPU from the raw positions exactly as
+        main.py:66-81 does (threshold 170 on raw pixels); everything else follows `fit`."""
+        B = len(towers)
+        n_val = int(B * validation_split) if validation_split else 0
+        n_tr = B - n_val
+        rng = np.random.default_rng(seed)
+        dev = self.engine.device
+        hist = History()
+
+        def make(sel):
+            batch = TowerBatch.from_towers([towers[i] for i in sel], thr=thr, fully_connected=fully_connected, device=dev)
+            tgt = torch.as_tensor(np.concatenate([np.asarray(labels[i], dtype=np.float32).reshape(-1) for i in sel])).to(dev)
+            return batch, tgt
+        for ep in range(epochs):
+            order = rng.permutation(n_tr) if shuffle else np.arange(n_tr)
+            tl = ta = 0.0
+            nb = 0
+            for s0 in range(0, n_tr, batch_size):
+                sel = order[s0:s0 + batch_size]
+                batch, tgt = make(sel)
+                l, a = self.train_on_batch(batch, tgt)
+                tl += l * batch.n_nodes; ta += a * batch.n_nodes; nb += batch.n_nodes
+            rec = dict(loss=tl / max(nb, 1), binary_accuracy=ta / max(nb, 1))
+            if n_val:
+                vl = va = 0.0
+                nv = 0
+                for s0 in range(n_tr, B, batch_size):
+                    batch, tgt = make(np.arange(s0, min(s0 + batch_size, B)))
+                    l, a = self.test_on_batch(batch, tgt)
+                    vl += l * batch.n_nodes; va += a * batch.n_nodes; nv += batch.n_nodes
+                rec.update(val_loss=vl / max(nv, 1), val_binary_accuracy=va / max(nv, 1))
             hist._add(ep, **rec)
             if verbose:
                 print('Epoch %d/%d - ' % (ep + 1, epochs) + ' - '.join('%s: %.4f' % kv for kv in rec.items()))

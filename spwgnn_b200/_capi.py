@@ -69,12 +69,13 @@ class CApi:
         d.spw_workspace_bytes.restype = C.c_size_t
         d.spw_workspace_bytes.argtypes = [i32, i32, C.c_int]
         d.spw_forward.restype = C.c_int
-        d.spw_forward.argtypes = [C.POINTER(SpwParams), C.POINTER(SpwGraph), vp, vp, vp, vp, C.c_size_t, C.c_int, vp]
+        d.spw_forward.argtypes = [C.POINTER(SpwParams), C.POINTER(SpwGraph), vp, vp, vp, vp, C.c_size_t, C.c_int,
+                                  C.c_float, C.c_uint64, vp]
         d.spw_bce_grad.restype = C.c_int
         d.spw_bce_grad.argtypes = [vp, vp, i32, f64, vp, vp, vp]
         d.spw_backward.restype = C.c_int
         d.spw_backward.argtypes = [C.POINTER(SpwParams), C.POINTER(SpwGraph), vp, vp, vp, C.c_size_t,
-                                   C.POINTER(SpwParams), vp]
+                                   C.POINTER(SpwParams), C.c_float, vp]
 
     def check(self, rc):
         if rc != 0:

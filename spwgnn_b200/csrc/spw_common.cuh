@@ -178,4 +178,15 @@ __device__ __forceinline__ void wgrad_flush(const float (&acc)[TA][TB], float* p
 
 __device__ __forceinline__ float relu_f(float v) { return v > 0.f ? v : 0.f; }
 
+// Stateless inverted-dropout mask (Networks.py:77-78, rate 0.1, train only): element `idx` of a tensor is kept
+// iff a 24-bit hash of (seed, idx) is >= rate * 2^24.  The same function is restated in numpy by the tests.
+__host__ __device__ __forceinline__ uint32_t dropout_hash(uint32_t seed, uint32_t idx) {
+  uint32_t h = idx * 0x9E3779B9u + seed;
+  h ^= h >> 16; h *= 0x85EBCA6Bu; h ^= h >> 13; h *= 0xC2B2AE35u; h ^= h >> 16;
+  return h >> 8;
+}
+__device__ __forceinline__ float dropout_apply(float v, uint32_t seed, uint32_t idx, uint32_t thresh, float inv_keep) {
+  return dropout_hash(seed, idx) >= thresh ? v * inv_keep : 0.f;
+}
+
 }  // namespace spw

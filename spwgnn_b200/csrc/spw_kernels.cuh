@@ -149,6 +149,8 @@ struct LinArgs {
   int mulmode;             // 1: *= [mulsrc > 0]   2: *= (1 - mulsrc^2)
   float* Y; int ldy;       // columns N..ldy-1 are written as 0
   int accumulate;          // Y += result
+  float post_scale;        // multiplies the result before accumulation (1/keep in the backward of a dropout)
+  uint32_t drop_thresh; uint32_t drop_seed; float drop_inv_keep;   // drop_thresh > 0: inverted dropout after act
 };
 
 template <int CN, int TMR>
@@ -210,6 +212,8 @@ __global__ void __launch_bounds__(kThreads, (TMR <= 64 ? 2 : 1)) k_linear(LinArg
           else if (a.act == 2) t = tanhf(t);
           if (a.mulmode == 1) t = a.mulsrc[grow * a.ld_mul + col] > 0.f ? t : 0.f;
           else if (a.mulmode == 2) { const float m = a.mulsrc[grow * a.ld_mul + col]; t *= (1.f - m * m); }
+          if (a.drop_thresh) t = dropout_apply(t, a.drop_seed, (uint32_t)(grow * 128 + col), a.drop_thresh, a.drop_inv_keep);
+          t *= a.post_scale;
           if (a.accumulate) t += a.Y[grow * a.ldy + col];
         }
         v[i] = t;
@@ -388,6 +392,7 @@ struct EdgeEncArgs {
   const float* W1A; const float* bA;                      // packed rmp.w0[0:150], raw rmp.b0
   float* A;                                               // [E][152]
   float* X1; float* X2; float* C;                         // [E][152] each, training only (null: not saved)
+  uint32_t drop_thresh; uint32_t drop_seed; float drop_inv_keep;   // dropout on c_e (Networks.py:77)
 };
 
 constexpr int kTME = 64;    // edge-tile rows of the forward edge kernels (two CTAs per SM)
@@ -432,7 +437,11 @@ __global__ void __launch_bounds__(kThreads, 2) k_edge_encode(EdgeEncArgs a) {
     if (a.X2) tile_to_global(Xa, a.X2, e0, rows);
     zero_acc<ROWS, 5>(acc);
     gemm_tile_acc<ROWS, 5>(acc, Xa, kDEP, warp * ROWS, a.RM3, kDEP, Wst);
-    store_act_tile<ROWS>(acc, Xb, warp, lane, rows, [&](float v, int, int c) { return relu_f(v + a.b3[c]); });
+    store_act_tile<ROWS>(acc, Xb, warp, lane, rows, [&](float v, int r, int c) {
+      float t = relu_f(v + a.b3[c]);
+      if (a.drop_thresh) t = dropout_apply(t, a.drop_seed, (uint32_t)((e0 + r) * 160 + c), a.drop_thresh, a.drop_inv_keep);
+      return t;
+    });
     __syncthreads();
     if (a.C) tile_to_global(Xb, a.C, e0, rows);
     zero_acc<ROWS, 5>(acc);
@@ -725,6 +734,7 @@ struct EdgeEncBwdArgs {
   const float* RM1T; const float* RM2T; const float* RM3T; const float* W1AT;
   const float* dA;          // [E][152] total gradient w.r.t. A_e
   const float* X1; const float* X2; const float* C;   // [E][152] activations saved by k_edge_encode
+  float inv_keep;           // 1/(1-rate) of the dropout applied to c_e in the forward pass (1 if none)
   float* partM;             // [gridDim.x][4][160*160]: W1A, RM3, RM2, RM1
   float* part0;             // [gridDim.x][3][152]: d rm.w0 row 0, row 1, d rm.b0
 };
@@ -761,7 +771,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_edge_encode_bwd(EdgeEncBwdArgs 
     __syncthreads();
     float acc[8][5];
     // ---- backward.  Each stage: dW += X^T.dY (bias via the ones column), dX = (dY.W^T) * relu'
-    auto stage = [&](const float* X, float* dY, const float* WT, float* dXout, float* part) {
+    auto stage = [&](const float* X, float* dY, const float* WT, float* dXout, float* part, float scale) {
       float wacc[10][10];
 #pragma unroll
       for (int i = 0; i < 10; ++i)
@@ -780,16 +790,16 @@ __global__ void __launch_bounds__(kThreads, 1) k_edge_encode_bwd(EdgeEncBwdArgs 
           const int col = lane * 5 + i;
           if (col >= kDEP) continue;
           float v = 0.f;
-          if (row < rows && col < kDE && X[(size_t)row * kDEP + col] > 0.f) v = acc[r][i];
+          if (row < rows && col < kDE && X[(size_t)row * kDEP + col] > 0.f) v = acc[r][i] * scale;
           dXout[(size_t)row * kDEP + col] = v;
         }
       }
       __syncthreads();
     };
-    stage(Bd, Be, a.W1AT, Be, partM);                    // A = C.W1a + b   : dC  -> Be (in place)
-    stage(Bc, Be, a.RM3T, Bd, partM + 1 * 160 * 160);    // C = relu(X2.W3) : dX2 -> Bd
-    stage(Bb, Bd, a.RM2T, Be, partM + 2 * 160 * 160);    // X2              : dX1 -> Be
-    stage(Ba, Be, a.RM1T, Bd, partM + 3 * 160 * 160);    // X1              : dX0 -> Bd
+    stage(Bd, Be, a.W1AT, Be, partM, a.inv_keep);                    // A = C.W1a + b   : dC  -> Be (in place)
+    stage(Bc, Be, a.RM3T, Bd, partM + 1 * 160 * 160, 1.f);    // C = relu(X2.W3) : dX2 -> Bd
+    stage(Bb, Bd, a.RM2T, Be, partM + 2 * 160 * 160, 1.f);    // X2              : dX1 -> Be
+    stage(Ba, Be, a.RM1T, Bd, partM + 3 * 160 * 160, 1.f);    // X1              : dX0 -> Bd
     // layer 0 (K = 2): d rm.w0[0][k] = sum_r dx_r dX0[r][k], [1][k] with dy, d rm.b0[k] = sum_r dX0[r][k]
     for (int k = tid; k < kDE; k += kThreads) {
       float g0 = 0.f, g1 = 0.f, gb = 0.f;

@@ -211,6 +211,7 @@ LinSeg seg(const float* X, int ldx, int K, const float* W) {
 struct LinOpt {
   const float* bias = nullptr; const float* rowscale = nullptr; const float* addend = nullptr; int ld_add = 0;
   int act = 0; const float* mulsrc = nullptr; int ld_mul = 0; int mulmode = 0; int accumulate = 0;
+  float post_scale = 1.f; uint32_t drop_thresh = 0; uint32_t drop_seed = 0; float drop_inv_keep = 1.f;
 };
 
 // Y[M][ldy] (N valid columns) from up to 3 (X, W) segments; wide = 150-column output (CN = 5)
@@ -224,6 +225,7 @@ void launch_linear(cudaStream_t st, int M, int N, bool wide, int nseg, const Lin
   for (int s = 0; s < nseg; ++s) { a.seg[s] = segs[s]; xfloats += (size_t)kTN * segs[s].Kp; }
   a.bias = o.bias; a.rowscale = o.rowscale; a.addend = o.addend; a.ld_add = o.ld_add; a.act = o.act;
   a.mulsrc = o.mulsrc; a.ld_mul = o.ld_mul; a.mulmode = o.mulmode; a.Y = Y; a.ldy = ldy; a.accumulate = o.accumulate;
+  a.post_scale = o.post_scale; a.drop_thresh = o.drop_thresh; a.drop_seed = o.drop_seed; a.drop_inv_keep = o.drop_inv_keep;
   // rows per tile: the candidate that minimises (rounds x rows) for a grid of two CTAs per SM (wave quantisation)
   const int cap = 2 * num_sms();
   int best_tm = 64;
@@ -440,7 +442,7 @@ size_t spw_workspace_bytes(int32_t n_nodes, int32_t n_edges, int training) {
 }
 
 int spw_forward(const SpwParams* w, const SpwGraph* g, const float* obj, float* logits, float* probs, void* workspace,
-                size_t workspace_bytes, int training, void* stream) {
+                size_t workspace_bytes, int training, float dropout_rate, uint64_t dropout_seed, void* stream) {
   int rc;
   if ((rc = check_params(w, "spw_forward")) != SPW_OK) return rc;
   if ((rc = check_graph(g)) != SPW_OK) return rc;
@@ -448,6 +450,11 @@ int spw_forward(const SpwParams* w, const SpwGraph* g, const float* obj, float* 
   if (n == 0) return SPW_OK;
   if (!obj || !logits || !workspace) return fail(SPW_ERR_BAD_ARG, "spw_forward: null pointer");
   if (!aligned16(workspace)) return fail(SPW_ERR_BAD_ARG, "spw_forward: workspace not 16-byte aligned");
+  if (dropout_rate < 0.f || dropout_rate >= 1.f) return fail(SPW_ERR_BAD_ARG, "spw_forward: dropout rate %g outside [0,1)", dropout_rate);
+  const bool drop = training && dropout_rate > 0.f;
+  const uint32_t drop_thresh = drop ? (uint32_t)(dropout_rate * 16777216.0f) : 0u;
+  const float inv_keep = drop ? 1.f / (1.f - dropout_rate) : 1.f;
+  const uint32_t seed_c = (uint32_t)dropout_seed, seed_q = (uint32_t)(dropout_seed >> 32) ^ 0x5bd1e995u ^ (uint32_t)dropout_seed * 3u;
   const Layout L = make_layout(n, E, training);
   if (workspace_bytes < L.total * sizeof(float))
     return fail(SPW_ERR_WORKSPACE, "spw_forward: workspace %zu < %zu bytes", workspace_bytes, L.total * sizeof(float));
@@ -467,6 +474,7 @@ int spw_forward(const SpwParams* w, const SpwGraph* g, const float* obj, float* 
   {
     LinSeg s = seg(ws + L.Q1, kDP, kDP, PK(P_OM1));
     LinOpt o; o.bias = w->om_b[1]; o.act = 1;
+    o.drop_thresh = drop_thresh; o.drop_seed = seed_q; o.drop_inv_keep = inv_keep;      // Networks.py:78
     launch_linear(st, n, kDP, false, 1, &s, ws + L.Q, kDP, o);
   }
   // relation encoder + A_e (Networks.py:46,75 and the c_e part of :86-87)
@@ -478,6 +486,7 @@ int spw_forward(const SpwParams* w, const SpwGraph* g, const float* obj, float* 
     a.RM1 = PK(P_RM1); a.RM2 = PK(P_RM2); a.RM3 = PK(P_RM3); a.b1 = w->rm_b[1]; a.b2 = w->rm_b[2]; a.b3 = w->rm_b[3];
     a.W1A = PK(P_W1A); a.bA = w->rmp_b[0]; a.A = ws + L.A;
     a.X1 = training ? ws + L.EX1 : nullptr; a.X2 = training ? ws + L.EX2 : nullptr; a.C = training ? ws + L.EC : nullptr;
+    a.drop_thresh = drop_thresh; a.drop_seed = seed_c; a.drop_inv_keep = inv_keep;
     set_smem(k_edge_encode, edge_fwd_smem());
     SPW_KLAUNCH("k_edge_encode", k_edge_encode, dim3(egrid), dim3(kThreads), edge_fwd_smem(), st, a);
   }
@@ -560,13 +569,15 @@ int spw_bce_grad(const float* logits, const float* target, int32_t n_nodes, doub
 }
 
 int spw_backward(const SpwParams* w, const SpwGraph* g, const float* obj, const float* dlogits, void* workspace,
-                 size_t workspace_bytes, const SpwParams* grads, void* stream) {
+                 size_t workspace_bytes, const SpwParams* grads, float dropout_rate, void* stream) {
   int rc;
   if ((rc = check_params(w, "spw_backward(weights)")) != SPW_OK) return rc;
   if ((rc = check_params(grads, "spw_backward(grads)")) != SPW_OK) return rc;
   if ((rc = check_graph(g)) != SPW_OK) return rc;
   const int n = g->n_nodes, E = g->n_edges;
   if (!workspace || !aligned16(workspace)) return fail(SPW_ERR_BAD_ARG, "spw_backward: bad workspace");
+  if (dropout_rate < 0.f || dropout_rate >= 1.f) return fail(SPW_ERR_BAD_ARG, "spw_backward: dropout rate %g outside [0,1)", dropout_rate);
+  const float inv_keep = dropout_rate > 0.f ? 1.f / (1.f - dropout_rate) : 1.f;
   const Layout L = make_layout(n, E, 1);
   if (workspace_bytes < L.total * sizeof(float))
     return fail(SPW_ERR_WORKSPACE, "spw_backward: workspace %zu < %zu bytes", workspace_bytes, L.total * sizeof(float));
@@ -608,7 +619,7 @@ int spw_backward(const SpwParams* w, const SpwGraph* g, const float* obj, const 
     }
     {   // dq_pre += (dUpre.V1a^T) * relu'(q)
       LinSeg s = seg(dU, kDP, kDP, PK(P_V1AT));
-      LinOpt o; o.mulsrc = ws + L.Q; o.ld_mul = kDP; o.mulmode = 1; o.accumulate = l < SPW_N_STEPS - 1;
+      LinOpt o; o.mulsrc = ws + L.Q; o.ld_mul = kDP; o.mulmode = 1; o.accumulate = l < SPW_N_STEPS - 1; o.post_scale = inv_keep;
       launch_linear(st, n, kDP, false, 1, &s, ws + L.dQ, kDP, o);
     }
     {   // dg_pre = (dUpre.V1b^T) * (1 - g^2)
@@ -685,7 +696,7 @@ int spw_backward(const SpwParams* w, const SpwGraph* g, const float* obj, const 
     a.E = E; a.in_snd = g->in_snd; a.in_rcv = g->in_rcv; a.obj = obj; a.W0 = w->rm_w[0]; a.b0 = w->rm_b[0];
     a.RM1 = PK(P_RM1); a.RM2 = PK(P_RM2); a.RM3 = PK(P_RM3); a.b1 = w->rm_b[1]; a.b2 = w->rm_b[2]; a.b3 = w->rm_b[3];
     a.RM1T = PK(P_RM1T); a.RM2T = PK(P_RM2T); a.RM3T = PK(P_RM3T); a.W1AT = PK(P_W1AT); a.dA = ws + L.dA;
-    a.X1 = ws + L.EX1; a.X2 = ws + L.EX2; a.C = ws + L.EC;
+    a.X1 = ws + L.EX1; a.X2 = ws + L.EX2; a.C = ws + L.EC; a.inv_keep = inv_keep;
     a.partM = ws + L.partM; a.part0 = ws + L.part0;
     set_smem(k_edge_encode_bwd, edge_encb_smem());
     SPW_KLAUNCH("k_edge_encode_bwd", k_edge_encode_bwd, dim3(bgrid), dim3(kThreads), edge_encb_smem(), st, a);

@@ -42,7 +42,7 @@ class Engine:
         self._fwd = None
 
     # ---- forward ------------------------------------------------------------------------------
-    def forward(self, batch: TowerBatch, training=False, want_probs=True):
+    def forward(self, batch: TowerBatch, training=False, want_probs=True, dropout_rate=0.0, dropout_seed=0):
         """Per-block logits (and sigmoid probabilities) for a packed batch (Networks.py:58-96)."""
         api, n = self.api, batch.n_nodes
         logits = torch.empty(max(n, 1), dtype=torch.float32, device=self.device)
@@ -52,9 +52,10 @@ class Engine:
         wp = self.params.c_struct()
         api.check(api.dll.spw_forward(ctypes.byref(wp), ctypes.byref(batch.c_graph), batch.obj.data_ptr(),
                                       logits.data_ptr(), probs.data_ptr() if want_probs else None, ws.data_ptr(),
-                                      ws.numel(), int(training), _stream_ptr(self.device)))
+                                      ws.numel(), int(training), float(dropout_rate), int(dropout_seed),
+                                      _stream_ptr(self.device)))
         if training:
-            self._fwd = (batch, ws, logits)
+            self._fwd = (batch, ws, logits, float(dropout_rate))
         return logits[:n], (probs[:n] if want_probs else None)
 
     # ---- loss seed + backward -------------------------------------------------------------------
@@ -70,19 +71,20 @@ class Engine:
 
     def backward(self, dlogits):
         """Gradients of sum(dlogits*logits) w.r.t. all 22 tensors -> self.grads (overwritten)."""
-        batch, ws, _ = self._fwd
+        batch, ws, _, rate = self._fwd
         api = self.api
         wp, gp = self.params.c_struct(), self.grads.c_struct()
         dl = dlogits.contiguous()
         api.check(api.dll.spw_backward(ctypes.byref(wp), ctypes.byref(batch.c_graph), batch.obj.data_ptr(),
-                                       dl.data_ptr(), ws.data_ptr(), ws.numel(), ctypes.byref(gp),
+                                       dl.data_ptr(), ws.data_ptr(), ws.numel(), ctypes.byref(gp), rate,
                                        _stream_ptr(self.device)))
         return self.grads
 
-    def loss_and_grads(self, batch, target, count=None):
+    def loss_and_grads(self, batch, target, count=None, dropout_rate=0.0, dropout_seed=0):
         """forward(training) + BCE + backward.  `count` = number of blocks the mean runs over
         (global count under data parallelism).  Returns stats (device double[2])."""
-        logits, _ = self.forward(batch, training=True, want_probs=False)
+        logits, _ = self.forward(batch, training=True, want_probs=False, dropout_rate=dropout_rate,
+                                 dropout_seed=dropout_seed)
         dl, stats = self.bce_seed(logits, target, count if count is not None else max(batch.n_nodes, 1))
         self.backward(dl)
         return stats

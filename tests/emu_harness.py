@@ -81,7 +81,7 @@ class Emu:
             arrs.append((a, v))
         return [v for _, v in arrs], CApi.params([v.ctypes.data for _, v in arrs]), arrs
 
-    def forward(self, w, g, obj, training=False):
+    def forward(self, w, g, obj, training=False, dropout_rate=0.0, dropout_seed=0):
         api = self.api
         wl, wp, keep = self.pack_params(w)
         obj = np.ascontiguousarray(obj, dtype=np.float32)
@@ -92,7 +92,8 @@ class Emu:
         wsv = ws[off:off + nbytes // 4]
         logits = np.full(max(g.n, 1), np.nan, np.float32); probs = np.full(max(g.n, 1), np.nan, np.float32)
         api.check(api.dll.spw_forward(ctypes.byref(wp), ctypes.byref(g.c), _p(obj), _p(logits), _p(probs),
-                                      wsv.ctypes.data, nbytes, int(training), None))
+                                      wsv.ctypes.data, nbytes, int(training), float(dropout_rate), int(dropout_seed), None))
+        self._rate = float(dropout_rate)
         self._state = (wl, wp, keep, obj, ws, wsv, nbytes)
         return logits[:g.n], probs[:g.n]
 
@@ -112,5 +113,5 @@ class Emu:
             v[...] = np.nan
         dlogits = np.ascontiguousarray(dlogits, np.float32)
         api.check(api.dll.spw_backward(ctypes.byref(wp), ctypes.byref(g.c), _p(obj), _p(dlogits), wsv.ctypes.data,
-                                       nbytes, ctypes.byref(gp), None))
+                                       nbytes, ctypes.byref(gp), self._rate, None))
         return {name: v.copy() for (name, _), v in zip(PARAM_SPECS, gl)}

@@ -64,3 +64,37 @@ def test_emu_forward_backward_match_oracle(emu):
     for k in O.tensor_names():
         ref = g64[k].numpy()
         assert np.abs(grads[k] - ref).max() / max(np.abs(ref).max(), 1e-30) < 1e-5, k
+
+
+def test_emu_dropout_matches_oracle_with_same_mask(emu):
+    """Training-time inverted dropout (Networks.py:77-78): the kernels' hash mask is restated in numpy and
+    injected into the fp64 oracle; forward and all gradients must then agree."""
+    rng = np.random.default_rng(2)
+    node_off, pos, wid = _towers(rng, [9, 7, 10, 3])
+    g = emu.edges(pos, node_off, thr=330.0)
+    eo, snd, rcv, slot = O.edge_list(pos, node_off, thr=330.0)
+    obj = np.concatenate([pos, wid[:, None]], 1) / 170.0
+    w64 = O.init_weights(4, nonzero_bias=True)     # small graph: a relu-kink flip is improbable
+    wnp = {k: v.numpy() for k, v in w64.items()}
+    rate, seed = 0.1, 0x1234567855AA77
+    l0, _ = emu.forward(wnp, g, obj, training=True)
+    l0 = l0.copy()
+    logits, _ = emu.forward(wnp, g, obj, training=True, dropout_rate=rate, dropout_seed=seed)   # state kept for backward
+    assert np.abs(logits - l0).max() > 0
+    sc, sq = O.dropout_seeds(seed)
+    keep = 1.0 / (1.0 - np.float32(rate))
+    epos = g.out_pos.astype(np.uint64)                      # receiver-major position of slot-order edge e
+    c_keep = O.dropout_keep_mask(sc, epos[:, None] * np.uint64(160) + np.arange(150, dtype=np.uint64)[None, :], rate)
+    q_keep = O.dropout_keep_mask(sq, np.arange(g.n, dtype=np.uint64)[:, None] * np.uint64(128) + np.arange(100, dtype=np.uint64)[None, :], rate)
+    assert 0.05 < 1 - c_keep.mean() < 0.15 and 0.05 < 1 - q_keep.mean() < 0.15
+    cs, qs = torch.as_tensor(c_keep * float(keep)), torch.as_tensor(q_keep * float(keep))
+    o64 = torch.as_tensor(obj.astype(np.float32).astype(np.float64))
+    tgt = (rng.random(g.n) > 0.5).astype(np.float32)
+    loss64, _, l64, g64 = O.loss_and_grads_sparse(w64, o64, torch.as_tensor(snd), torch.as_tensor(rcv),
+                                                  torch.as_tensor(tgt.astype(np.float64)), c_scale=cs, q_scale=qs)
+    assert np.abs(logits - l64.numpy()).max() / np.abs(l64.numpy()).max() < 1e-5
+    dl, _ = emu.bce_grad(logits, tgt, g.n)
+    grads = emu.backward(g, dl)
+    for k in O.tensor_names():
+        ref = g64[k].numpy()
+        assert np.abs(grads[k] - ref).max() / max(np.abs(ref).max(), 1e-30) < 2e-5, k

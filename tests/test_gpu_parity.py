@@ -312,6 +312,9 @@ def test_fit_predict_facade_runs_like_main_py():
     model = PropagationNetwork(seed=5).getModel(7, 3)
     x = {'objects': objects, 'sender_relations': rs, 'receiver_relations': rr, 'propagation': np.zeros((160, 7, 100))}
     h = model.fit(x, {'target': y}, batch_size=32, epochs=4, validation_split=0.2, shuffle=True, verbose=0, seed=0)
+    h2 = model.fit_towers([raw[i] for i in range(160)], [y[i, :, 0] for i in range(160)], batch_size=32, epochs=1,
+                          validation_split=0.2, verbose=0, seed=1)
+    assert set(h2.history) == set(h.history)
     assert set(h.history) == {'loss', 'binary_accuracy', 'val_loss', 'val_binary_accuracy'}
     assert h.history['loss'][-1] < h.history['loss'][0]
     p = model.predict(x)
@@ -334,3 +337,44 @@ def test_autograd_function_bridge(eng):
     finally:
         flat.grad = None
         flat.requires_grad_(False)
+
+
+def test_dropout_matches_oracle_with_same_mask(eng):
+    """Inverted dropout of the training path (Networks.py:77-78): restate the kernels' hash mask in numpy,
+    inject it into the fp64 oracle, compare logits and all gradients; rate 0 must be bit-identical to no dropout."""
+    from spwgnn_b200.graph import TowerBatch
+    from spwgnn_b200 import synth
+    _use(eng, 'kinkfree')
+    towers = synth.make_towers('uniform', 24, 71, lo=3, hi=14)
+    raw, node_off = synth.pack_towers(towers)
+    batch = TowerBatch.from_towers(towers, want_slot_list=True)
+    eo, snd, rcv, slot = _oracle_edges(raw, node_off)
+    n, E = batch.n_nodes, batch.n_edges
+    tgt = (np.random.default_rng(8).random(n) > 0.5).astype(np.float32)
+    tg = torch.as_tensor(tgt).cuda()
+    eng.loss_and_grads(batch, tg)
+    l_plain, g_plain = eng._fwd[2][:n].clone(), eng.grads.flat.clone()
+    eng.loss_and_grads(batch, tg, dropout_rate=0.0, dropout_seed=99)
+    assert torch.equal(l_plain, eng._fwd[2][:n]) and torch.equal(g_plain, eng.grads.flat)
+    rate, seed = 0.1, 0xABCDEF0123456789
+    eng.loss_and_grads(batch, tg, dropout_rate=rate, dropout_seed=seed)
+    logits = eng._fwd[2][:n].cpu().numpy()
+    assert np.abs(logits - l_plain.cpu().numpy()).max() > 0
+    sc, sq = O.dropout_seeds(seed)
+    keep = float(1.0 / (1.0 - np.float32(rate)))
+    epos = batch.out_pos.cpu().numpy()[:E].astype(np.uint64)
+    c_keep = O.dropout_keep_mask(sc, epos[:, None] * np.uint64(160) + np.arange(150, dtype=np.uint64)[None, :], rate)
+    q_keep = O.dropout_keep_mask(sq, np.arange(n, dtype=np.uint64)[:, None] * np.uint64(128) + np.arange(100, dtype=np.uint64)[None, :], rate)
+    assert 0.08 < 1 - c_keep.mean() < 0.12
+    obj64 = torch.as_tensor((raw / 170.0).astype(np.float32).astype(np.float64))
+    args = (obj64, torch.as_tensor(snd), torch.as_tensor(rcv))
+    _, _, l64, g64 = O.loss_and_grads_sparse(eng.w64, *args, torch.as_tensor(tgt.astype(np.float64)),
+                                             c_scale=torch.as_tensor(c_keep * keep), q_scale=torch.as_tensor(q_keep * keep))
+    assert _rel(logits, l64.numpy()) < TOL
+    w32 = {k: v.float() for k, v in eng.w64.items()}
+    _, _, _, g32 = O.loss_and_grads_sparse(w32, obj64.float(), args[1], args[2], torch.as_tensor(tgt),
+                                           c_scale=torch.as_tensor((c_keep * keep).astype(np.float32)),
+                                           q_scale=torch.as_tensor((q_keep * keep).astype(np.float32)))
+    for k in O.tensor_names():
+        e = _rel(eng.grads.views[k].cpu().numpy(), g64[k].numpy())
+        assert e < max(TOL, 4 * _rel(g32[k].numpy(), g64[k].numpy())), (k, e)

@@ -139,3 +139,18 @@ def test_gradient_allreduce_world2_gloo():
         assert p.exitcode == 0
     for rank, g0, g1, stats, p5 in res:
         assert g0 == 3.0 and g1 == 3.0 and stats == [3.0, 20.0] and p5 == 5.0
+
+
+def test_trajectory_loader_matches_reference_main_py(golden_dir, tmp_path):
+    """spwgnn_b200.data against what the reference's own main.train_gnn produced (fixtures)."""
+    import json
+    from spwgnn_b200 import data as D
+    for name in ['train_n2', 'train_n4', 'train_n7', 'train_n9']:
+        g = np.load(os.path.join(golden_dir, name + '.npz'))
+        n_obj = int(g['n_objects'])
+        p = tmp_path / (name + '.txt')
+        p.write_text(str(g['traj_json']))
+        raw0, y = D.training_arrays(str(p), n_obj + 1, jenga=True)
+        assert np.array_equal(raw0 / 170.0, g['objects'])
+        assert np.array_equal(y, g['target'])
+        assert y.min() == 0.0 and y.max() == 1.0 or n_obj == 2
