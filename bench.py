@@ -36,7 +36,7 @@ FLOP_EDGE_FWD, FLOP_NODE_FWD = 1035600, 421400        # SURVEY.md section 8(d), 
 # dominant kernel: backward of the 150->150 relation-propagator layer for one step over all edges
 K_DOM = 'k_edge_step_bwd'
 K_DOM_ALGO_FLOP_PER_EDGE = 2 * 2 * 150 * 150          # dgrad + wgrad (recompute of the forward not counted)
-K_DOM_EXEC_FLOP_PER_EDGE = 3 * 2 * 152 * 160          # what the kernel executes incl. padding and recompute
+K_DOM_EXEC_FLOP_PER_EDGE = 2 * 160 * 160 + 2 * 152 * 160   # executed: wgrad (160x160 padded outputs) + dgrad GEMM
 
 
 def parse():
