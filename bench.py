@@ -12,7 +12,7 @@ backward + (N>1: one NCCL all-reduce of the flat gradient buffer) + Adam.  Synth
 `value`  : towers/s, whole job, inputs already resident in HBM, CUDA-event timed, max over ranks.
 `e2e`    : same metric through the public API from PINNED HOST buffers: every step copies the
            poses/features/targets host->device and reads the loss/accuracy scalars back.
-`roofline`: dominant kernel (k_edge_step_bwd) timed with CUDA events on its stream (spw_profile).
+`roofline`: dominant kernel (k_edge_encode_bwd) timed with CUDA events on its stream (spw_profile).
 `cpu_baseline` / `--impl reference`: the reference formulation (dense one-hot graph of
            Networks.py, fp32, torch autograd) on the host cores -- the reference itself (Keras/TF1)
            cannot be installed here; kind = "port".
@@ -33,10 +33,11 @@ TOWERS_PER_GPU = 4096
 N_BLOCKS = 10
 SEED = 1235
 FLOP_EDGE_FWD, FLOP_NODE_FWD = 1035600, 421400        # SURVEY.md section 8(d), reference formulation
-# dominant kernel: backward of the 150->150 relation-propagator layer for one step over all edges
-K_DOM = 'k_edge_step_bwd'
-K_DOM_ALGO_FLOP_PER_EDGE = 2 * 2 * 150 * 150          # dgrad + wgrad (recompute of the forward not counted)
-K_DOM_EXEC_FLOP_PER_EDGE = 2 * 160 * 160 + 2 * 152 * 160   # executed: wgrad (160x160 padded outputs) + dgrad GEMM
+# dominant kernel: backward of the relation encoder (rm 2->150->150->150->150 and the W1a part of rmp layer 0),
+# one launch per training step over all edges
+K_DOM = 'k_edge_encode_bwd'
+K_DOM_ALGO_FLOP_PER_EDGE = 2 * (135600 + 45000)       # dgrad + wgrad of those layers, reference formulation
+K_DOM_EXEC_FLOP_PER_EDGE = 4 * (2 * 160 * 160 + 2 * 152 * 160)   # executed: 4 wgrads (padded 160x160) + 4 dgrad GEMMs
 
 
 def parse():

@@ -605,7 +605,9 @@ struct EdgeStepBwdArgs {
 };
 
 // K4b: per step backward of K2b -- rebuild h1 (gather), d h2 from the saved relu bits, dW2 partials,
-// d(h1 pre-activation) = (d h2 . W2^T) * relu'(h1)
+// and (DGRAD) d(h1 pre-activation) = (d h2 . W2^T) * relu'(h1).  The GPU build runs the data gradient on the
+// tensor cores (tc::k_edge_dgrad_tc) and instantiates DGRAD = false here.
+template <bool DGRAD>
 __global__ void __launch_bounds__(kThreads, 1) k_edge_step_bwd(EdgeStepBwdArgs a) {
   SPW_DYN_SMEM(smem_raw);
   float* Xa = reinterpret_cast<float*>(smem_raw);
@@ -668,6 +670,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_edge_step_bwd(EdgeStepBwdArgs a
       if (a.first && tile == (int)blockIdx.x) wgrad_flush<10, 10, false>(wacc, part);
       else wgrad_flush<10, 10, true>(wacc, part);
     }
+    if (!DGRAD) { __syncthreads(); continue; }
     float acc[16][5];
     zero_acc<16, 5>(acc);
     gemm_tile_acc<16, 5>(acc, Xb, kDEP, warp * 16, a.W2T, kDEP, Wst);

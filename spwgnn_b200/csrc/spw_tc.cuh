@@ -237,7 +237,8 @@ struct EdgeStepTcArgs {
   const float* W2hi; const float* W2lo;               // packed B operands (k_pack_umma)
   float* H2S;                                         // [n][152]
   float* part_first; float* part_last;                // [ntiles][152] (tiles of 128 edges)
-  uint32_t* maskbits;                                 // [E][8] or null: bit (col & 31) of word (col >> 5)
+  uint32_t* maskbits;                                 // [E][8] or null: relu bits of h2, bit (col & 31) of word (col >> 5)
+  uint32_t* maskbits_h1;                              // [E][8] or null: relu bits of h1 (same layout)
 };
 
 constexpr size_t kEdgeStepTcSmem = (size_t)(2 * kBFloats + kTM * kStagePitch + 2 * kTM + (kTM + 8) / 2 + kTM * 5) * sizeof(float) + 16;
@@ -330,8 +331,9 @@ __global__ void __launch_bounds__(kThreads, 1) k_edge_step_tc(EdgeStepTcArgs a) 
       const int ncols = imin(kStageCols, kDEP - c0);
       build_h1_slab(stage, ssnd, srcv, a.A, a.S, a.R, e0, c0, ncols);
       __syncthreads();
-      // this thread's half of the slab row: 32 columns (or what is left)
+      // this thread's half of the slab row: 32 columns (or what is left) == one word of relu bits
       const int cb = 32 * half;
+      uint32_t hbits = 0u;
 #pragma unroll
       for (int g = 0; g < 4; ++g) {
         const int c = cb + 8 * g;
@@ -341,11 +343,15 @@ __global__ void __launch_bounds__(kThreads, 1) k_edge_step_tc(EdgeStepTcArgs a) 
           const float x[8] = {p0.x, p0.y, p1.x, p1.y, p2.x, p2.y, p3.x, p3.y};
           uint32_t h[8], l[8];
 #pragma unroll
-          for (int i = 0; i < 8; ++i) split_tf32(x[i], h[i], l[i]);
+          for (int i = 0; i < 8; ++i) {
+            split_tf32(x[i], h[i], l[i]);
+            hbits |= x[i] > 0.f ? (1u << (8 * g + i)) : 0u;
+          }
           tmem_st8(lane_addr + kColAhi + c0 + c, h);
           tmem_st8(lane_addr + kColAlo + c0 + c, l);
         }
       }
+      if (a.maskbits_h1 && row < rows && cb < ncols) a.maskbits_h1[(size_t)(e0 + row) * 8 + ((c0 + cb) >> 5)] = hbits;
       __syncthreads();
     }
     tmem_wait_st();
@@ -411,6 +417,159 @@ __global__ void __launch_bounds__(kThreads, 1) k_edge_step_tc(EdgeStepTcArgs a) 
     __syncthreads();
   }
   if (failed && tid == 0) a.H2S[0] = __int_as_float(0x7fc00000);   // fail loudly: poison the output (MMA barrier timed out)
+  fence_before_sync();
+  __syncthreads();
+  if (warp == 0) tmem_dealloc(tmem_base, kTmemCols);
+}
+
+// =================================================================================================
+// K4b (data gradient) on the tensor cores: d h1_pre = (d h2_pre . W2^T) * relu'(h1) per step.
+//   A = d h2_pre = relu-bits(h2) ? dH2S[receiver] : 0   (gathered per row, split, stored to TMEM)
+//   B = W2 itself, read as [N = k][K = n] (packed with transpose = 1), resident in shared memory
+//   epilogue: mask with the saved relu bits of h1, stage through the slab, 128-bit coalesced
+//   writes of DH1 and read-modify-write of dA.
+// =================================================================================================
+struct EdgeDgradTcArgs {
+  int E;
+  const int32_t* in_rcv;
+  const float* dH2S;                                  // [n][152]
+  const float* Whi; const float* Wlo;                 // packed B operands of W2^T-as-B
+  const uint32_t* maskbits;                           // relu bits of h2 [E][8]
+  const uint32_t* maskbits_h1;                        // relu bits of h1 [E][8]
+  float* dA; float* DH1;                              // [E][152]
+  int first;                                          // dA is written (first processed step) or accumulated
+  float* poison;                                      // written with NaN if an MMA barrier times out
+};
+
+constexpr size_t kEdgeDgradTcSmem = (size_t)(2 * kBFloats + kTM * kStagePitch + kTM) * sizeof(float) + 16;
+
+__global__ void __launch_bounds__(kThreads, 1) k_edge_dgrad_tc(EdgeDgradTcArgs a) {
+  SPW_DYN_SMEM(smem_raw);
+  float* Bhi_s = reinterpret_cast<float*>(smem_raw);
+  float* Blo_s = Bhi_s + kBFloats;
+  float* stage = Blo_s + kBFloats;
+  int* srcv = reinterpret_cast<int*>(stage + kTM * kStagePitch);
+  uint64_t* bar = reinterpret_cast<uint64_t*>(srcv + kTM);
+  uint32_t* tptr = reinterpret_cast<uint32_t*>(bar + 1);
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int row = 32 * (warp & 3) + lane, half = warp >> 2;
+
+  if (warp == 0) tmem_alloc(tptr, kTmemCols);
+  if (tid == 32) { mbar_init(bar, 1); fence_mbar_init(); }
+  for (int i = tid; i < kBFloats / 4; i += kThreads) {
+    reinterpret_cast<float4*>(Bhi_s)[i] = reinterpret_cast<const float4*>(a.Whi)[i];
+    reinterpret_cast<float4*>(Blo_s)[i] = reinterpret_cast<const float4*>(a.Wlo)[i];
+  }
+  fence_async_smem();
+  fence_before_sync();
+  __syncthreads();
+  fence_after_sync();
+  const uint32_t tmem_base = *tptr;
+  const uint32_t lane_addr = tmem_base + ((uint32_t)(32 * (warp & 3)) << 16);
+  uint32_t parity = 0;
+  bool failed = false;
+  const int ntiles = (a.E + kTM - 1) / kTM;
+  const int sub = lane >> 4, c4 = lane & 15;
+
+  for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+    const int e0 = tile * kTM;
+    const int rows = imin(kTM, a.E - e0);
+    if (tid < kTM) srcv[tid] = tid < rows ? a.in_rcv[e0 + tid] : -1;
+    __syncthreads();
+    // ---- A operand: gather dH2S[receiver] rows (coalesced, half a warp per row), mask, split, TMEM
+    for (int c0 = 0; c0 < kDEP; c0 += kStageCols) {
+      const int ncols = imin(kStageCols, kDEP - c0);
+      {
+        float4 v[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const int r = warp * 16 + 2 * j + sub;
+          const int rc = srcv[r];
+          v[j] = (rc >= 0 && 4 * c4 < ncols) ? *reinterpret_cast<const float4*>(a.dH2S + (size_t)rc * kDEP + c0 + 4 * c4)
+                                             : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const int r = warp * 16 + 2 * j + sub;
+          if (4 * c4 < ncols) {
+            float2* dst = reinterpret_cast<float2*>(stage + r * kStagePitch + 4 * c4);
+            dst[0] = make_float2(v[j].x, v[j].y);
+            dst[1] = make_float2(v[j].z, v[j].w);
+          }
+        }
+      }
+      __syncthreads();
+      const int cb = 32 * half;
+      if (cb < ncols) {                                    // warp-uniform
+        const uint32_t bits = row < rows ? a.maskbits[(size_t)(e0 + row) * 8 + ((c0 + cb) >> 5)] : 0u;
+#pragma unroll
+        for (int g = 0; g < 4; ++g) {
+          const int c = cb + 8 * g;
+          if (c < ncols) {
+            const float2* src = reinterpret_cast<const float2*>(stage + row * kStagePitch + c);
+            const float2 p0 = src[0], p1 = src[1], p2 = src[2], p3 = src[3];
+            const float x[8] = {p0.x, p0.y, p1.x, p1.y, p2.x, p2.y, p3.x, p3.y};
+            uint32_t h[8], l[8];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+              const bool on = (bits >> (8 * g + i)) & 1u;
+              split_tf32(on ? x[i] : 0.f, h[i], l[i]);
+            }
+            tmem_st8(lane_addr + kColAhi + c0 + c, h);
+            tmem_st8(lane_addr + kColAlo + c0 + c, l);
+          }
+        }
+      }
+      __syncthreads();
+    }
+    tmem_wait_st();
+    fence_before_sync();
+    __syncthreads();
+    if (tid == 0) {
+      fence_after_sync();
+      issue_tile_mmas(tmem_base, Bhi_s, Blo_s);
+      mma_commit(bar);
+    }
+    if (!mbar_wait(bar, parity)) failed = true;
+    parity ^= 1u;
+    fence_after_sync();
+    // ---- epilogue: D * relu'(h1) -> slab -> DH1 (write) and dA (write or accumulate), coalesced
+    for (int c0 = 0; c0 < kN; c0 += kStageCols) {
+      const int ncols = imin(kStageCols, kDEP - c0);       // columns 152..159 are never stored
+      for (int blk = half; blk * 16 < imin(kStageCols, kN - c0); blk += 2) {
+        uint32_t v[16];
+        tmem_ld16(lane_addr + kColD + c0 + blk * 16, v);
+        tmem_wait_ld();
+        const int col0 = c0 + blk * 16;
+        const uint32_t bits = (row < rows && col0 < kDE) ? (a.maskbits_h1[(size_t)(e0 + row) * 8 + (col0 >> 5)] >> (col0 & 31)) : 0u;
+        float o[16];
+#pragma unroll
+        for (int i = 0; i < 16; ++i) o[i] = ((bits >> i) & 1u) && (col0 + i < kDE) ? __uint_as_float(v[i]) : 0.f;
+        float2* dst = reinterpret_cast<float2*>(stage + row * kStagePitch + blk * 16);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) dst[i] = make_float2(o[2 * i], o[2 * i + 1]);
+      }
+      __syncthreads();
+      const int n4 = ncols >> 2;                           // float4 per row in this slab (16, 16, 6)
+      for (int idx = tid; idx < rows * n4; idx += kThreads) {
+        const int r = idx / n4, q = idx - r * n4;
+        const float2* src = reinterpret_cast<const float2*>(stage + r * kStagePitch + 4 * q);
+        const float2 p0 = src[0], p1 = src[1];
+        float4 val = make_float4(p0.x, p0.y, p1.x, p1.y);
+        const size_t g = (size_t)(e0 + r) * kDEP + c0 + 4 * q;
+        *reinterpret_cast<float4*>(a.DH1 + g) = val;
+        if (!a.first) {
+          const float4 old = *reinterpret_cast<const float4*>(a.dA + g);
+          val.x += old.x; val.y += old.y; val.z += old.z; val.w += old.w;
+        }
+        *reinterpret_cast<float4*>(a.dA + g) = val;
+      }
+      __syncthreads();
+    }
+    fence_before_sync();
+    __syncthreads();
+  }
+  if (failed && tid == 0) a.poison[0] = __int_as_float(0x7fc00000);
   fence_before_sync();
   __syncthreads();
   if (warp == 0) tmem_dealloc(tmem_base, kTmemCols);

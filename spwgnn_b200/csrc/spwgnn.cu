@@ -114,11 +114,11 @@ size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
 
 struct Layout {
   size_t pack[P_COUNT];
-  size_t Q1, Q, degf, A, PF, PL, W2hi, W2lo;
+  size_t Q1, Q, degf, A, PF, PL, W2hi, W2lo, W2Thi, W2Tlo;
   size_t P, S, R, H2S, G, U;     // per-step arrays (training: 5 slots; inference: fewer)
   int slotsP, slotsSR, slotsN;   // number of step slots for P / (S,R) / (H2S,G,U)
   // backward
-  size_t dU, dG, T, dS, dR, dH2S, DP, dQ, dQ1, dA, DH1, M2, EX1, EX2, EC, partE, partM, part0, partN;
+  size_t dU, dG, T, dS, dR, dH2S, DP, dQ, dQ1, dA, DH1, M2, M1, EX1, EX2, EC, partE, partM, part0, partN;
   size_t total;   // floats
 };
 
@@ -132,6 +132,8 @@ Layout make_layout(int64_t n, int64_t E, int training) {
   const size_t nt = (size_t)((E + kTME - 1) / kTME) + 1;
   L.W2hi = take(24320);
   L.W2lo = take(24320);
+  L.W2Thi = take(24320);
+  L.W2Tlo = take(24320);
   L.Q1 = take(n * kDP);
   L.Q = take(n * kDP);
   L.degf = take(n);
@@ -160,6 +162,7 @@ Layout make_layout(int64_t n, int64_t E, int training) {
     L.dA = take((size_t)E * kDEP + 8);
     L.DH1 = take((size_t)E * kDEP + 8);
     L.M2 = take((size_t)SPW_N_STEPS * E * 8);      // relu bits of h2, 8 words per edge and step
+    L.M1 = take((size_t)SPW_N_STEPS * E * 8);      // relu bits of h1 (tensor-core data-gradient epilogue)
     L.EX1 = take((size_t)E * kDEP + 8);            // relation-encoder activations kept for the backward pass
     L.EX2 = take((size_t)E * kDEP + 8);
     L.EC = take((size_t)E * kDEP + 8);
@@ -168,7 +171,7 @@ Layout make_layout(int64_t n, int64_t E, int training) {
     L.part0 = take((size_t)kMaxCtas * 3 * kDEP);
     L.partN = take((size_t)2 * kMaxCtas * kPartNodeElems);
   } else {
-    L.dU = L.dG = L.T = L.dS = L.dR = L.dH2S = L.DP = L.dQ = L.dQ1 = L.dA = L.DH1 = L.M2 = L.EX1 = L.EX2 = L.EC = 0;
+    L.dU = L.dG = L.T = L.dS = L.dR = L.dH2S = L.DP = L.dQ = L.dQ1 = L.dA = L.DH1 = L.M2 = L.M1 = L.EX1 = L.EX2 = L.EC = 0;
     L.partE = L.partM = L.part0 = L.partN = 0;
   }
   L.total = off;
@@ -466,6 +469,8 @@ int spw_forward(const SpwParams* w, const SpwGraph* g, const float* obj, float* 
   pack_weights(st, w, ws, L, training != 0);
 #if SPW_USE_TC
   SPW_KLAUNCH("k_pack_umma", tc::k_pack_umma, dim3(48), dim3(256), 0, st, (const float*)w->rmp_w[1], 150, 0, 0, 150, 150, 0, (const float*)w->rmp_b[1], ws + L.W2hi, ws + L.W2lo);
+  if (training)   // B operand of the data gradient: [N = k][K = n] = W2[k][n]
+    SPW_KLAUNCH("k_pack_umma", tc::k_pack_umma, dim3(48), dim3(256), 0, st, (const float*)w->rmp_w[1], 150, 0, 0, 150, 150, 1, (const float*)nullptr, ws + L.W2Thi, ws + L.W2Tlo);
 #endif
   SPW_KLAUNCH("k_deg_to_float", k_deg_to_float, dim3(grid_for(n, 256)), dim3(256), 0, st, g->in_off, n, ws + L.degf);
 
@@ -523,6 +528,7 @@ int spw_forward(const SpwParams* w, const SpwGraph* g, const float* obj, float* 
         t.E = E; t.in_snd = g->in_snd; t.in_rcv = g->in_rcv; t.in_off = g->in_off; t.A = ws + L.A; t.S = S; t.R = R;
         t.W2hi = ws + L.W2hi; t.W2lo = ws + L.W2lo; t.H2S = H2S; t.part_first = ws + L.PF;
         t.part_last = ws + L.PL; t.maskbits = a.maskbits;
+        t.maskbits_h1 = training ? reinterpret_cast<uint32_t*>(ws + L.M1) + (size_t)l * E * 8 : nullptr;
         const int ttiles = (E + kTM - 1) / kTM;
         const int tgrid = ttiles < num_sms() ? ttiles : num_sms();
         set_smem(tc::k_edge_step_tc, tc::kEdgeStepTcSmem);
@@ -643,8 +649,25 @@ int spw_backward(const SpwParams* w, const SpwGraph* g, const float* obj, const 
       a.W2T = PK(P_W2T); a.dH2S = ws + L.dH2S; a.dA = ws + L.dA; a.DH1 = ws + L.DH1;
       a.maskbits = reinterpret_cast<const uint32_t*>(ws + L.M2) + (size_t)l * E * 8;
       a.partW2 = ws + L.partE; a.first = (l == SPW_N_STEPS - 1);
-      set_smem(k_edge_step_bwd, edge_bwd_smem());
-      SPW_KLAUNCH("k_edge_step_bwd", k_edge_step_bwd, dim3(egrid), dim3(kThreads), edge_bwd_smem(), st, a);
+#if SPW_USE_TC
+      {
+        auto kw = k_edge_step_bwd<false>;
+        set_smem(kw, edge_bwd_smem());
+        SPW_KLAUNCH("k_edge_step_bwd", kw, dim3(egrid), dim3(kThreads), edge_bwd_smem(), st, a);
+        tc::EdgeDgradTcArgs t;
+        t.E = E; t.in_rcv = g->in_rcv; t.dH2S = ws + L.dH2S; t.Whi = ws + L.W2Thi; t.Wlo = ws + L.W2Tlo;
+        t.maskbits = a.maskbits; t.maskbits_h1 = reinterpret_cast<const uint32_t*>(ws + L.M1) + (size_t)l * E * 8;
+        t.dA = ws + L.dA; t.DH1 = ws + L.DH1; t.first = a.first; t.poison = ws + L.dA;
+        set_smem(tc::k_edge_dgrad_tc, tc::kEdgeDgradTcSmem);
+        SPW_KLAUNCH("k_edge_dgrad_tc", tc::k_edge_dgrad_tc, dim3(egrid), dim3(kThreads), tc::kEdgeDgradTcSmem, st, t);
+      }
+#else
+      {
+        auto kw = k_edge_step_bwd<true>;
+        set_smem(kw, edge_bwd_smem());
+        SPW_KLAUNCH("k_edge_step_bwd", kw, dim3(egrid), dim3(kThreads), edge_bwd_smem(), st, a);
+      }
+#endif
     }
     if (l > 0) {
       float* dS = ws + L.dS + (size_t)(l - 1) * nE;
