@@ -305,7 +305,8 @@ __global__ void __launch_bounds__(kThreads, MINB) k_wgrad(WgArgs a) {
 // fixed-order sum over per-CTA partials -> compact Keras-layout gradient (+ bias from row Kin)
 struct RedArgs {
   const float* part; int nparts; int part_stride; int src_ld;   // src_ld: row length (linear layout only)
-  int TA, TB;                                                   // > 0: thread-major layout of wgrad_flush<TA,TB>
+  int TA, TB;                                                   // > 0: thread-major layout of wgrad_flush<TA,TB>;
+                                                                // TA < 0: tensor-core layout [2][160][128] of tc::k_wgrad_tc (TB = first feature of tile 1)
   int Kin, N;
   float* dW; int dst_ld, dst_row0, dst_col0;   // null: skip the matrix
   float* db; int db_off;                       // null: skip the bias row
@@ -321,6 +322,8 @@ __global__ void __launch_bounds__(256) k_reduce_parts(RedArgs a) {
     if (a.TA > 0) {
       const int ja = k / a.TA, ea = k - ja * a.TA, jb = n / a.TB, eb = n - jb * a.TB;
       p = a.part + (size_t)(ea * a.TB + eb) * kThreads + (ja * 16 + jb);
+    } else if (a.TA < 0) {
+      p = k < 128 ? a.part + (size_t)n * 128 + k : a.part + (size_t)(160 + n) * 128 + (k - a.TB);
     } else {
       p = a.part + (size_t)k * a.src_ld + n;
     }

@@ -575,6 +575,209 @@ __global__ void __launch_bounds__(kThreads, 1) k_edge_dgrad_tc(EdgeDgradTcArgs a
   if (warp == 0) tmem_dealloc(tmem_base, kTmemCols);
 }
 
+// =================================================================================================
+// Weight gradient on the tensor cores:  dW[k][n] (+)= sum_rows X[row][k] * dY[row][n]   (k <= 150: row 150
+// of dW is the bias gradient, picked up by the ones column of X).
+//   The contraction runs over edge rows, so  A = X^T : TMEM lane = feature k, column = row within a 32-row
+//   chunk; two overlapping M = 128 tiles cover the features: tile 0 = features 0..127, tile 1 = 23..150.
+//   B = dY^T chunk in shared memory, K-major: [k-step of 8 rows][2][n = 160][4 rows].
+//   D0 / D1 (TMEM) accumulate ONE 128-row tile (48 MMAs each), then are added -- with round-to-nearest
+//   FADDs -- into a per-CTA partial in global memory (layout [tile][n][lane], coalesced): the tensor core
+//   truncates when it accumulates, so long accumulation chains in TMEM would bias the sum.
+//   TMEM map: D0 [0,160) | D1 [160,320) | A0_hi [320,352) A0_lo [352,384) A1_hi [384,416) A1_lo [416,448)
+// =================================================================================================
+constexpr int kWgChunk = 32;
+constexpr uint32_t kWgColD0 = 0, kWgColD1 = 160, kWgColA = 320;
+constexpr int kWgFeat1 = 23;                 // first feature of M-tile 1 (lane j <-> feature 23 + j)
+constexpr int kWgBFloats = 4 * kBStepFloats; // 5120 floats per hi / lo chunk operand
+constexpr size_t kWgPartFloats = 2 * 160 * 128;
+
+struct WgradTcArgs {
+  int M;
+  int x_mode;                  // 0: X plain [M][152] (ones column included); 1: relu(A + S[snd] + R[rcv]), ones column set
+  const float* X; const float* S; const float* R; const int32_t* in_snd; const int32_t* in_rcv;
+  int y_mode;                  // 0: dY plain [M][152]; 1: relu-bits ? dY[rcv[row]] : 0  (dY = dH2S)
+  const float* dY; const uint32_t* maskbits;
+  float* part;                 // [gridDim.x][2][160][128]
+  int first;                   // this launch initialises the partials (otherwise it accumulates into them)
+  float* poison;
+};
+
+constexpr size_t kWgradTcSmem = (size_t)(4 * kWgChunk * kDEP + 2 * kWgBFloats) * sizeof(float) + 16;
+
+__device__ __forceinline__ void wg_load_chunk(const WgradTcArgs& a, float* sx, float* sy, int r0) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  constexpr int C4 = kDEP / 4;
+  const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
+  // 4 rows per warp, 2 column passes, all loads first
+  float4 vx[4][2], vs[4][2], vr[4][2], vy[4][2];
+  uint32_t bits[4][2];
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const int row = r0 + warp * 4 + j;
+    const bool valid = row < a.M;
+    int snd = 0, rcv = 0;
+    if (valid && (a.x_mode == 1 || a.y_mode == 1)) { rcv = a.in_rcv[row]; if (a.x_mode == 1) snd = a.in_snd[row]; }
+#pragma unroll
+    for (int p = 0; p < 2; ++p) {
+      const int c = lane + 32 * p;
+      const bool ok = valid && c < C4;
+      vx[j][p] = ok ? reinterpret_cast<const float4*>(a.X + (size_t)row * kDEP)[c] : z4;
+      if (a.x_mode == 1) {
+        vs[j][p] = ok ? reinterpret_cast<const float4*>(a.S + (size_t)snd * kDEP)[c] : z4;
+        vr[j][p] = ok ? reinterpret_cast<const float4*>(a.R + (size_t)rcv * kDEP)[c] : z4;
+      }
+      if (a.y_mode == 1) {
+        vy[j][p] = ok ? reinterpret_cast<const float4*>(a.dY + (size_t)rcv * kDEP)[c] : z4;
+        bits[j][p] = ok ? (a.maskbits[(size_t)row * 8 + (c >> 3)] >> ((4 * c) & 31)) : 0u;
+      } else {
+        vy[j][p] = ok ? reinterpret_cast<const float4*>(a.dY + (size_t)row * kDEP)[c] : z4;
+        bits[j][p] = 0xfu;
+      }
+    }
+  }
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const int lr = warp * 4 + j;
+    const bool valid = r0 + lr < a.M;
+#pragma unroll
+    for (int p = 0; p < 2; ++p) {
+      const int c = lane + 32 * p;
+      if (c >= C4) continue;
+      float4 x = vx[j][p];
+      if (a.x_mode == 1) {
+        x.x = relu_f(x.x + vs[j][p].x + vr[j][p].x); x.y = relu_f(x.y + vs[j][p].y + vr[j][p].y);
+        x.z = relu_f(x.z + vs[j][p].z + vr[j][p].z); x.w = relu_f(x.w + vs[j][p].w + vr[j][p].w);
+        if (c == C4 - 1) { x.z = valid ? 1.f : 0.f; x.w = 0.f; }
+      }
+      float4 y = vy[j][p];
+      const uint32_t b = bits[j][p];
+      y.x = (b & 1u) ? y.x : 0.f; y.y = (b & 2u) ? y.y : 0.f; y.z = (b & 4u) ? y.z : 0.f; y.w = (b & 8u) ? y.w : 0.f;
+      if (c == C4 - 1) { y.z = 0.f; y.w = 0.f; }            // columns 150 / 151 of a gradient operand are zero
+      reinterpret_cast<float4*>(sx + lr * kDEP)[c] = x;
+      reinterpret_cast<float4*>(sy + lr * kDEP)[c] = y;
+    }
+  }
+}
+
+__global__ void __launch_bounds__(kThreads, 1) k_wgrad_tc(WgradTcArgs a) {
+  SPW_DYN_SMEM(smem_raw);
+  float* slab = reinterpret_cast<float*>(smem_raw);            // [2 buffers][X | dY][32][152]
+  float* Bhi_s = slab + 4 * kWgChunk * kDEP;
+  float* Blo_s = Bhi_s + kWgBFloats;
+  uint64_t* bar = reinterpret_cast<uint64_t*>(Blo_s + kWgBFloats);
+  uint32_t* tptr = reinterpret_cast<uint32_t*>(bar + 1);
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int L = 32 * (warp & 3) + lane, mt = warp >> 2;         // TMEM lane, M-tile handled by this thread
+  const int feat = mt == 0 ? L : kWgFeat1 + L;                  // feature (row of dW) of this lane in its M-tile
+
+  if (warp == 0) tmem_alloc(tptr, kTmemCols);
+  if (tid == 32) { mbar_init(bar, 1); fence_mbar_init(); }
+  fence_before_sync();
+  __syncthreads();
+  fence_after_sync();
+  const uint32_t tmem_base = *tptr;
+  const uint32_t lane_addr = tmem_base + ((uint32_t)(32 * (warp & 3)) << 16);
+  const uint32_t colA_hi = kWgColA + 64 * mt, colA_lo = colA_hi + 32;
+  const uint32_t idesc = make_idesc_tf32(128, kN);
+  uint32_t parity = 0;
+  bool failed = false, pending = false, first_flush = a.first != 0;
+  float* part = a.part + (size_t)blockIdx.x * kWgPartFloats;
+  const int ntiles = (a.M + kTM - 1) / kTM;
+  int buf = 0;
+
+  for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+    for (int ch = 0; ch < kTM / kWgChunk; ++ch) {
+      const int r0 = tile * kTM + ch * kWgChunk;
+      float* sx = slab + buf * (2 * kWgChunk * kDEP);
+      float* sy = sx + kWgChunk * kDEP;
+      wg_load_chunk(a, sx, sy, r0);                    // overlaps the MMAs of the previous chunk
+      __syncthreads();
+      if (pending) {                                   // A / B regions are free once those MMAs are done
+        if (!mbar_wait(bar, parity)) failed = true;
+        parity ^= 1u;
+        fence_after_sync();
+        pending = false;
+      }
+      // A = X^T: this lane's feature, 32 rows of the chunk as 32 TMEM columns
+#pragma unroll
+      for (int j0 = 0; j0 < kWgChunk; j0 += 8) {
+        uint32_t h[8], l[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) split_tf32(sx[(j0 + i) * kDEP + feat], h[i], l[i]);
+        tmem_st8(lane_addr + colA_hi + j0, h);
+        tmem_st8(lane_addr + colA_lo + j0, l);
+      }
+      // B = dY^T: [k-step][2][n][4 rows]
+      for (int idx = tid; idx < 8 * kN; idx += kThreads) {
+        const int n = idx % kN, kc = idx / kN;
+        float y[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) y[i] = n < kDEP ? sy[(4 * kc + i) * kDEP + n] : 0.f;
+        uint32_t h[4], l[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) split_tf32(y[i], h[i], l[i]);
+        reinterpret_cast<uint4*>(Bhi_s)[idx] = make_uint4(h[0], h[1], h[2], h[3]);
+        reinterpret_cast<uint4*>(Blo_s)[idx] = make_uint4(l[0], l[1], l[2], l[3]);
+      }
+      tmem_wait_st();
+      fence_async_smem();
+      fence_before_sync();
+      __syncthreads();
+      if (tid == 0) {
+        fence_after_sync();
+        const uint32_t bhi = smem_u32(Bhi_s), blo = smem_u32(Blo_s);
+#pragma unroll 1
+        for (int ks = 0; ks < kWgChunk / 8; ++ks) {
+          const uint64_t dhi = make_b_desc(bhi + ks * (kBStepFloats * 4), kN * 16, 128);
+          const uint64_t dlo = make_b_desc(blo + ks * (kBStepFloats * 4), kN * 16, 128);
+          const uint32_t acc = (ch > 0 || ks > 0) ? 1u : 0u;
+#pragma unroll
+          for (int t = 0; t < 2; ++t) {
+            const uint32_t d = tmem_base + (t ? kWgColD1 : kWgColD0);
+            const uint32_t ahi = tmem_base + kWgColA + 64 * t + 8 * ks, alo = ahi + 32;
+            mma_tf32_ts(d, alo, dhi, idesc, acc);
+            mma_tf32_ts(d, ahi, dlo, idesc, 1u);
+            mma_tf32_ts(d, ahi, dhi, idesc, 1u);
+          }
+        }
+        mma_commit(bar);
+      }
+      pending = true;
+      buf ^= 1;
+    }
+    // tile done: wait for its MMAs, add D into the per-CTA partial with round-to-nearest adds
+    if (!mbar_wait(bar, parity)) failed = true;
+    parity ^= 1u;
+    fence_after_sync();
+    pending = false;
+    {
+      float* pp = part + (size_t)mt * (160 * 128) + L;
+      const uint32_t dcol = mt ? kWgColD1 : kWgColD0;
+#pragma unroll 1
+      for (int c = 0; c < kN; c += 16) {
+        uint32_t v[16];
+        tmem_ld16(lane_addr + dcol + c, v);
+        float old[16];
+        if (!first_flush) {
+#pragma unroll
+          for (int i = 0; i < 16; ++i) old[i] = pp[(size_t)(c + i) * 128];
+        }
+        tmem_wait_ld();
+#pragma unroll
+        for (int i = 0; i < 16; ++i) pp[(size_t)(c + i) * 128] = first_flush ? __uint_as_float(v[i]) : old[i] + __uint_as_float(v[i]);
+      }
+    }
+    first_flush = false;
+    fence_before_sync();
+    __syncthreads();
+  }
+  if (failed && tid == 0) a.poison[0] = __int_as_float(0x7fc00000);
+  fence_before_sync();
+  __syncthreads();
+  if (warp == 0) tmem_dealloc(tmem_base, kTmemCols);
+}
+
 }  // namespace tc
 }  // namespace spw
 #endif  // SPW_EMU

@@ -166,7 +166,7 @@ Layout make_layout(int64_t n, int64_t E, int training) {
     L.EX1 = take((size_t)E * kDEP + 8);            // relation-encoder activations kept for the backward pass
     L.EX2 = take((size_t)E * kDEP + 8);
     L.EC = take((size_t)E * kDEP + 8);
-    L.partE = take((size_t)kMaxCtas * 160 * 160);
+    L.partE = take((size_t)kMaxCtas * 2 * 160 * 128);
     L.partM = take((size_t)kMaxCtas * 4 * 160 * 160);
     L.part0 = take((size_t)kMaxCtas * 3 * kDEP);
     L.partN = take((size_t)2 * kMaxCtas * kPartNodeElems);
@@ -651,9 +651,12 @@ int spw_backward(const SpwParams* w, const SpwGraph* g, const float* obj, const 
       a.partW2 = ws + L.partE; a.first = (l == SPW_N_STEPS - 1);
 #if SPW_USE_TC
       {
-        auto kw = k_edge_step_bwd<false>;
-        set_smem(kw, edge_bwd_smem());
-        SPW_KLAUNCH("k_edge_step_bwd", kw, dim3(egrid), dim3(kThreads), edge_bwd_smem(), st, a);
+        tc::WgradTcArgs wg;
+        wg.M = E; wg.x_mode = 1; wg.X = ws + L.A; wg.S = S; wg.R = R; wg.in_snd = g->in_snd; wg.in_rcv = g->in_rcv;
+        wg.y_mode = 1; wg.dY = ws + L.dH2S; wg.maskbits = a.maskbits; wg.part = ws + L.partE; wg.first = a.first;
+        wg.poison = ws + L.partE;
+        set_smem(tc::k_wgrad_tc, tc::kWgradTcSmem);
+        SPW_KLAUNCH("k_wgrad_tc", tc::k_wgrad_tc, dim3(egrid), dim3(kThreads), tc::kWgradTcSmem, st, wg);
         tc::EdgeDgradTcArgs t;
         t.E = E; t.in_rcv = g->in_rcv; t.dH2S = ws + L.dH2S; t.Whi = ws + L.W2Thi; t.Wlo = ws + L.W2Tlo;
         t.maskbits = a.maskbits; t.maskbits_h1 = reinterpret_cast<const uint32_t*>(ws + L.M1) + (size_t)l * E * 8;
@@ -712,7 +715,11 @@ int spw_backward(const SpwParams* w, const SpwGraph* g, const float* obj, const 
   // ---- edge-level weight gradients --------------------------------------------------------------
   if (E > 0) {
     // rmp layer 1 (W2, b2) from the per-step kernel's per-CTA partials
+#if SPW_USE_TC
+    launch_reduce(st, ws + L.partE, egrid, (int)tc::kWgPartFloats, 0, -1, tc::kWgFeat1, kDE, kDE, {grads->rmp_w[1], 150, 0, 0, grads->rmp_b[1], 0});
+#else
     launch_reduce(st, ws + L.partE, egrid, 160 * 160, 0, 10, 10, kDE, kDE, {grads->rmp_w[1], 150, 0, 0, grads->rmp_b[1], 0});
+#endif
     const int btiles = (E + kTMB - 1) / kTMB;
     const int bgrid = btiles < num_sms() ? btiles : num_sms();
     EdgeEncBwdArgs a;
