@@ -603,73 +603,70 @@ struct WgradTcArgs {
   float* poison;
 };
 
-constexpr size_t kWgradTcSmem = (size_t)(4 * kWgChunk * kDEP + 2 * kWgBFloats) * sizeof(float) + 16;
+// shared memory: 2 stages x { XA, XS, XR, YD : [32][152] floats, bits [32][8] words, idx [64] } + B hi/lo
+constexpr int kWgStageFloats = 4 * kWgChunk * kDEP + kWgChunk * 8 + 64;
+constexpr size_t kWgradTcSmem = (size_t)(2 * kWgStageFloats + 2 * kWgBFloats) * sizeof(float) + 16;
 
-__device__ __forceinline__ void wg_load_chunk(const WgradTcArgs& a, float* sx, float* sy, int r0) {
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+__device__ __forceinline__ void cp_async16_zfill(float* sdst, const float* gsrc, bool valid) {
+  const unsigned s = smem_u32(sdst);
+  const int sz = valid ? 16 : 0;
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;\n" ::"r"(s), "l"(gsrc), "r"(sz));
+}
+
+// issue the asynchronous copies of one 32-row chunk (raw gather rows; combined later, on the fly)
+template <int XMODE, int YMODE>
+__device__ __forceinline__ void wg_issue_chunk(const WgradTcArgs& a, float* st, int r0) {
   constexpr int C4 = kDEP / 4;
-  const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
-  // 4 rows per warp, 2 column passes, all loads first
-  float4 vx[4][2], vs[4][2], vr[4][2], vy[4][2];
-  uint32_t bits[4][2];
-#pragma unroll
-  for (int j = 0; j < 4; ++j) {
-    const int row = r0 + warp * 4 + j;
+  float* XA = st; float* XS = XA + kWgChunk * kDEP; float* XR = XS + kWgChunk * kDEP; float* YD = XR + kWgChunk * kDEP;
+  uint32_t* BT = reinterpret_cast<uint32_t*>(YD + kWgChunk * kDEP);
+  const int* idx = reinterpret_cast<const int*>(BT + kWgChunk * 8);      // [0,32): snd, [32,64): rcv of this chunk
+  for (int i = threadIdx.x; i < kWgChunk * C4; i += kThreads) {
+    const int r = i / C4, c = i - r * C4;
+    const int row = r0 + r;
     const bool valid = row < a.M;
-    int snd = 0, rcv = 0;
-    if (valid && (a.x_mode == 1 || a.y_mode == 1)) { rcv = a.in_rcv[row]; if (a.x_mode == 1) snd = a.in_snd[row]; }
-#pragma unroll
-    for (int p = 0; p < 2; ++p) {
-      const int c = lane + 32 * p;
-      const bool ok = valid && c < C4;
-      vx[j][p] = ok ? reinterpret_cast<const float4*>(a.X + (size_t)row * kDEP)[c] : z4;
-      if (a.x_mode == 1) {
-        vs[j][p] = ok ? reinterpret_cast<const float4*>(a.S + (size_t)snd * kDEP)[c] : z4;
-        vr[j][p] = ok ? reinterpret_cast<const float4*>(a.R + (size_t)rcv * kDEP)[c] : z4;
-      }
-      if (a.y_mode == 1) {
-        vy[j][p] = ok ? reinterpret_cast<const float4*>(a.dY + (size_t)rcv * kDEP)[c] : z4;
-        bits[j][p] = ok ? (a.maskbits[(size_t)row * 8 + (c >> 3)] >> ((4 * c) & 31)) : 0u;
-      } else {
-        vy[j][p] = ok ? reinterpret_cast<const float4*>(a.dY + (size_t)row * kDEP)[c] : z4;
-        bits[j][p] = 0xfu;
-      }
+    const size_t rowc = valid ? (size_t)row : 0;
+    cp_async16_zfill(XA + r * kDEP + 4 * c, a.X + rowc * kDEP + 4 * c, valid);
+    if (XMODE == 1) {
+      cp_async16_zfill(XS + r * kDEP + 4 * c, a.S + (size_t)idx[r] * kDEP + 4 * c, valid);
+      cp_async16_zfill(XR + r * kDEP + 4 * c, a.R + (size_t)idx[32 + r] * kDEP + 4 * c, valid);
     }
+    if (YMODE == 1) cp_async16_zfill(YD + r * kDEP + 4 * c, a.dY + (size_t)idx[32 + r] * kDEP + 4 * c, valid);
+    else cp_async16_zfill(YD + r * kDEP + 4 * c, a.dY + rowc * kDEP + 4 * c, valid);
   }
-#pragma unroll
-  for (int j = 0; j < 4; ++j) {
-    const int lr = warp * 4 + j;
-    const bool valid = r0 + lr < a.M;
-#pragma unroll
-    for (int p = 0; p < 2; ++p) {
-      const int c = lane + 32 * p;
-      if (c >= C4) continue;
-      float4 x = vx[j][p];
-      if (a.x_mode == 1) {
-        x.x = relu_f(x.x + vs[j][p].x + vr[j][p].x); x.y = relu_f(x.y + vs[j][p].y + vr[j][p].y);
-        x.z = relu_f(x.z + vs[j][p].z + vr[j][p].z); x.w = relu_f(x.w + vs[j][p].w + vr[j][p].w);
-        if (c == C4 - 1) { x.z = valid ? 1.f : 0.f; x.w = 0.f; }
-      }
-      float4 y = vy[j][p];
-      const uint32_t b = bits[j][p];
-      y.x = (b & 1u) ? y.x : 0.f; y.y = (b & 2u) ? y.y : 0.f; y.z = (b & 4u) ? y.z : 0.f; y.w = (b & 8u) ? y.w : 0.f;
-      if (c == C4 - 1) { y.z = 0.f; y.w = 0.f; }            // columns 150 / 151 of a gradient operand are zero
-      reinterpret_cast<float4*>(sx + lr * kDEP)[c] = x;
-      reinterpret_cast<float4*>(sy + lr * kDEP)[c] = y;
-    }
+  if (YMODE == 1 && threadIdx.x < kWgChunk * 2) {
+    const int r = threadIdx.x >> 1, h = threadIdx.x & 1;
+    const int row = r0 + r;
+    const bool valid = row < a.M;
+    cp_async16_zfill(reinterpret_cast<float*>(BT + r * 8 + 4 * h),
+                     reinterpret_cast<const float*>(a.maskbits + (valid ? (size_t)row : 0) * 8 + 4 * h), valid);
+  }
+  cp_async_commit();
+}
+
+// edge indices of a chunk -> the stage's idx array (plain loads; consumed one iteration later)
+__device__ __forceinline__ void wg_load_idx(const WgradTcArgs& a, float* st, int r0) {
+  int* idx = reinterpret_cast<int*>(st + 4 * kWgChunk * kDEP + kWgChunk * 8);
+  const int t = threadIdx.x;
+  if (t < 64) {
+    const int row = r0 + (t & 31);
+    int v = 0;
+    if (row < a.M) v = t < 32 ? a.in_snd[row] : a.in_rcv[row];
+    idx[t] = v;
   }
 }
 
+template <int XMODE, int YMODE>
 __global__ void __launch_bounds__(kThreads, 1) k_wgrad_tc(WgradTcArgs a) {
   SPW_DYN_SMEM(smem_raw);
-  float* slab = reinterpret_cast<float*>(smem_raw);            // [2 buffers][X | dY][32][152]
-  float* Bhi_s = slab + 4 * kWgChunk * kDEP;
+  float* stages = reinterpret_cast<float*>(smem_raw);
+  float* Bhi_s = stages + 2 * kWgStageFloats;
   float* Blo_s = Bhi_s + kWgBFloats;
   uint64_t* bar = reinterpret_cast<uint64_t*>(Blo_s + kWgBFloats);
   uint32_t* tptr = reinterpret_cast<uint32_t*>(bar + 1);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int L = 32 * (warp & 3) + lane, mt = warp >> 2;         // TMEM lane, M-tile handled by this thread
   const int feat = mt == 0 ? L : kWgFeat1 + L;                  // feature (row of dW) of this lane in its M-tile
+  constexpr bool kGather = (XMODE == 1) || (YMODE == 1);
 
   if (warp == 0) tmem_alloc(tptr, kTmemCols);
   if (tid == 32) { mbar_init(bar, 1); fence_mbar_init(); }
@@ -684,74 +681,104 @@ __global__ void __launch_bounds__(kThreads, 1) k_wgrad_tc(WgradTcArgs a) {
   bool failed = false, pending = false, first_flush = a.first != 0;
   float* part = a.part + (size_t)blockIdx.x * kWgPartFloats;
   const int ntiles = (a.M + kTM - 1) / kTM;
-  int buf = 0;
-
-  for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
-    for (int ch = 0; ch < kTM / kWgChunk; ++ch) {
-      const int r0 = tile * kTM + ch * kWgChunk;
-      float* sx = slab + buf * (2 * kWgChunk * kDEP);
-      float* sy = sx + kWgChunk * kDEP;
-      wg_load_chunk(a, sx, sy, r0);                    // overlaps the MMAs of the previous chunk
-      __syncthreads();
-      if (pending) {                                   // A / B regions are free once those MMAs are done
-        if (!mbar_wait(bar, parity)) failed = true;
-        parity ^= 1u;
-        fence_after_sync();
-        pending = false;
-      }
-      // A = X^T: this lane's feature, 32 rows of the chunk as 32 TMEM columns
-#pragma unroll
-      for (int j0 = 0; j0 < kWgChunk; j0 += 8) {
-        uint32_t h[8], l[8];
-#pragma unroll
-        for (int i = 0; i < 8; ++i) split_tf32(sx[(j0 + i) * kDEP + feat], h[i], l[i]);
-        tmem_st8(lane_addr + colA_hi + j0, h);
-        tmem_st8(lane_addr + colA_lo + j0, l);
-      }
-      // B = dY^T: [k-step][2][n][4 rows]
-      for (int idx = tid; idx < 8 * kN; idx += kThreads) {
-        const int n = idx % kN, kc = idx / kN;
-        float y[4];
-#pragma unroll
-        for (int i = 0; i < 4; ++i) y[i] = n < kDEP ? sy[(4 * kc + i) * kDEP + n] : 0.f;
-        uint32_t h[4], l[4];
-#pragma unroll
-        for (int i = 0; i < 4; ++i) split_tf32(y[i], h[i], l[i]);
-        reinterpret_cast<uint4*>(Bhi_s)[idx] = make_uint4(h[0], h[1], h[2], h[3]);
-        reinterpret_cast<uint4*>(Blo_s)[idx] = make_uint4(l[0], l[1], l[2], l[3]);
-      }
-      tmem_wait_st();
-      fence_async_smem();
-      fence_before_sync();
-      __syncthreads();
-      if (tid == 0) {
-        fence_after_sync();
-        const uint32_t bhi = smem_u32(Bhi_s), blo = smem_u32(Blo_s);
-#pragma unroll 1
-        for (int ks = 0; ks < kWgChunk / 8; ++ks) {
-          const uint64_t dhi = make_b_desc(bhi + ks * (kBStepFloats * 4), kN * 16, 128);
-          const uint64_t dlo = make_b_desc(blo + ks * (kBStepFloats * 4), kN * 16, 128);
-          const uint32_t acc = (ch > 0 || ks > 0) ? 1u : 0u;
-#pragma unroll
-          for (int t = 0; t < 2; ++t) {
-            const uint32_t d = tmem_base + (t ? kWgColD1 : kWgColD0);
-            const uint32_t ahi = tmem_base + kWgColA + 64 * t + 8 * ks, alo = ahi + 32;
-            mma_tf32_ts(d, alo, dhi, idesc, acc);
-            mma_tf32_ts(d, ahi, dlo, idesc, 1u);
-            mma_tf32_ts(d, ahi, dhi, idesc, 1u);
-          }
-        }
-        mma_commit(bar);
-      }
-      pending = true;
-      buf ^= 1;
+  constexpr int kCh = kTM / kWgChunk;                           // chunks per tile
+  // this CTA's chunks, in order: q-th chunk = (tile blockIdx.x + (q / kCh) * gridDim.x, chunk q % kCh)
+  const int my_tiles = blockIdx.x < ntiles ? (ntiles - 1 - blockIdx.x) / gridDim.x + 1 : 0;
+  const int nq = my_tiles * kCh;
+  auto row0_of = [&](int q) { return (blockIdx.x + (q / kCh) * gridDim.x) * kTM + (q % kCh) * kWgChunk; };
+  // prologue: indices of chunks 0 and 1, copies of chunk 0
+  if (nq > 0) {
+    if (kGather) wg_load_idx(a, stages, row0_of(0));
+    __syncthreads();
+    wg_issue_chunk<XMODE, YMODE>(a, stages, row0_of(0));
+    if (kGather && nq > 1) wg_load_idx(a, stages + kWgStageFloats, row0_of(1));
+  }
+  for (int q = 0; q < nq; ++q) {
+    const int ch = q % kCh;
+    float* st = stages + (q & 1) * kWgStageFloats;
+    float* stn = stages + ((q + 1) & 1) * kWgStageFloats;
+    __syncthreads();                                   // idx of chunk q+1 visible; stage q+1 no longer read (chunk q-1 done)
+    if (q + 1 < nq) {
+      wg_issue_chunk<XMODE, YMODE>(a, stn, row0_of(q + 1));
+      cp_async_wait<1>();                              // chunk q has landed (this thread's copies)
+    } else {
+      cp_async_wait<0>();
     }
-    // tile done: wait for its MMAs, add D into the per-CTA partial with round-to-nearest adds
-    if (!mbar_wait(bar, parity)) failed = true;
-    parity ^= 1u;
-    fence_after_sync();
-    pending = false;
-    {
+    __syncthreads();                                   // ... and everybody else's
+    if (kGather && q + 2 < nq) wg_load_idx(a, st, row0_of(q + 2));   // idx slot of stage q is free: chunk q's copies are done
+    if (pending) {                                     // A / B operand regions are free once the previous MMAs are done
+      if (!mbar_wait(bar, parity)) failed = true;
+      parity ^= 1u;
+      fence_after_sync();
+      pending = false;
+    }
+    const float* XA = st; const float* XS = XA + kWgChunk * kDEP; const float* XR = XS + kWgChunk * kDEP;
+    const float* YD = XR + kWgChunk * kDEP;
+    const uint32_t* BT = reinterpret_cast<const uint32_t*>(YD + kWgChunk * kDEP);
+    const int r0 = row0_of(q);
+    // A = X^T: this lane's feature, 32 rows of the chunk as 32 TMEM columns
+#pragma unroll
+    for (int j0 = 0; j0 < kWgChunk; j0 += 8) {
+      uint32_t h[8], l[8];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const int o = (j0 + i) * kDEP + feat;
+        float x = XA[o];
+        if (XMODE == 1) {
+          x = relu_f(x + XS[o] + XR[o]);
+          if (feat == kDE) x = (r0 + j0 + i < a.M) ? 1.f : 0.f;        // ones column -> bias gradient row
+        }
+        split_tf32(x, h[i], l[i]);
+      }
+      tmem_st8(lane_addr + colA_hi + j0, h);
+      tmem_st8(lane_addr + colA_lo + j0, l);
+    }
+    // B = dY^T: [k-step][2][n][4 rows]
+    for (int idx = tid; idx < 8 * kN; idx += kThreads) {
+      const int n = idx % kN, kc = idx / kN;
+      uint32_t h[4], l[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        float y = 0.f;
+        if (n < kDE) {
+          y = YD[(4 * kc + i) * kDEP + n];
+          if (YMODE == 1) y = ((BT[(4 * kc + i) * 8 + (n >> 5)] >> (n & 31)) & 1u) ? y : 0.f;
+        }
+        split_tf32(y, h[i], l[i]);
+      }
+      reinterpret_cast<uint4*>(Bhi_s)[idx] = make_uint4(h[0], h[1], h[2], h[3]);
+      reinterpret_cast<uint4*>(Blo_s)[idx] = make_uint4(l[0], l[1], l[2], l[3]);
+    }
+    tmem_wait_st();
+    fence_async_smem();
+    fence_before_sync();
+    __syncthreads();
+    if (tid == 0) {
+      fence_after_sync();
+      const uint32_t bhi = smem_u32(Bhi_s), blo = smem_u32(Blo_s);
+#pragma unroll 1
+      for (int ks = 0; ks < kWgChunk / 8; ++ks) {
+        const uint64_t dhi = make_b_desc(bhi + ks * (kBStepFloats * 4), kN * 16, 128);
+        const uint64_t dlo = make_b_desc(blo + ks * (kBStepFloats * 4), kN * 16, 128);
+        const uint32_t acc = (ch > 0 || ks > 0) ? 1u : 0u;
+#pragma unroll
+        for (int t = 0; t < 2; ++t) {
+          const uint32_t d = tmem_base + (t ? kWgColD1 : kWgColD0);
+          const uint32_t ahi = tmem_base + kWgColA + 64 * t + 8 * ks, alo = ahi + 32;
+          mma_tf32_ts(d, alo, dhi, idesc, acc);
+          mma_tf32_ts(d, ahi, dlo, idesc, 1u);
+          mma_tf32_ts(d, ahi, dhi, idesc, 1u);
+        }
+      }
+      mma_commit(bar);
+    }
+    pending = true;
+    if (ch == kCh - 1) {
+      // tile done: wait for its MMAs, add D into the per-CTA partial with round-to-nearest adds
+      if (!mbar_wait(bar, parity)) failed = true;
+      parity ^= 1u;
+      fence_after_sync();
+      pending = false;
       float* pp = part + (size_t)mt * (160 * 128) + L;
       const uint32_t dcol = mt ? kWgColD1 : kWgColD0;
 #pragma unroll 1
@@ -767,10 +794,9 @@ __global__ void __launch_bounds__(kThreads, 1) k_wgrad_tc(WgradTcArgs a) {
 #pragma unroll
         for (int i = 0; i < 16; ++i) pp[(size_t)(c + i) * 128] = first_flush ? __uint_as_float(v[i]) : old[i] + __uint_as_float(v[i]);
       }
+      first_flush = false;
+      fence_before_sync();
     }
-    first_flush = false;
-    fence_before_sync();
-    __syncthreads();
   }
   if (failed && tid == 0) a.poison[0] = __int_as_float(0x7fc00000);
   fence_before_sync();

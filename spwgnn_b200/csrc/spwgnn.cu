@@ -655,8 +655,9 @@ int spw_backward(const SpwParams* w, const SpwGraph* g, const float* obj, const 
         wg.M = E; wg.x_mode = 1; wg.X = ws + L.A; wg.S = S; wg.R = R; wg.in_snd = g->in_snd; wg.in_rcv = g->in_rcv;
         wg.y_mode = 1; wg.dY = ws + L.dH2S; wg.maskbits = a.maskbits; wg.part = ws + L.partE; wg.first = a.first;
         wg.poison = ws + L.partE;
-        set_smem(tc::k_wgrad_tc, tc::kWgradTcSmem);
-        SPW_KLAUNCH("k_wgrad_tc", tc::k_wgrad_tc, dim3(egrid), dim3(kThreads), tc::kWgradTcSmem, st, wg);
+        auto kwg = tc::k_wgrad_tc<1, 1>;
+        set_smem(kwg, tc::kWgradTcSmem);
+        SPW_KLAUNCH("k_wgrad_tc", kwg, dim3(egrid), dim3(kThreads), tc::kWgradTcSmem, st, wg);
         tc::EdgeDgradTcArgs t;
         t.E = E; t.in_rcv = g->in_rcv; t.dH2S = ws + L.dH2S; t.Whi = ws + L.W2Thi; t.Wlo = ws + L.W2Tlo;
         t.maskbits = a.maskbits; t.maskbits_h1 = reinterpret_cast<const uint32_t*>(ws + L.M1) + (size_t)l * E * 8;
