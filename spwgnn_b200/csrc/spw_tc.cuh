@@ -471,37 +471,51 @@ __global__ void __launch_bounds__(kThreads, 1) k_edge_dgrad_tc(EdgeDgradTcArgs a
   const int ntiles = (a.E + kTM - 1) / kTM;
   const int sub = lane >> 4, c4 = lane & 15;
 
+  auto gather_slab = [&](float4 (&v)[8], int c0) {     // dH2S[receiver] rows of one 64-column slab, 8 loads in flight
+    const int ncols = imin(kStageCols, kDEP - c0);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const int rc = srcv[warp * 16 + 2 * j + sub];
+      v[j] = (rc >= 0 && 4 * c4 < ncols) ? *reinterpret_cast<const float4*>(a.dH2S + (size_t)rc * kDEP + c0 + 4 * c4)
+                                         : make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+  };
   for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
     const int e0 = tile * kTM;
     const int rows = imin(kTM, a.E - e0);
     if (tid < kTM) srcv[tid] = tid < rows ? a.in_rcv[e0 + tid] : -1;
+    // relu bits of this thread's row (h2: operand mask, h1: epilogue mask), fetched once per tile
+    uint32_t b2w[8] = {0u, 0u, 0u, 0u, 0u, 0u, 0u, 0u}, b1w[8] = {0u, 0u, 0u, 0u, 0u, 0u, 0u, 0u};
+    if (row < rows) {
+      const uint4* p2 = reinterpret_cast<const uint4*>(a.maskbits + (size_t)(e0 + row) * 8);
+      const uint4* p1 = reinterpret_cast<const uint4*>(a.maskbits_h1 + (size_t)(e0 + row) * 8);
+      const uint4 q0 = p2[0], q1 = p2[1], r0 = p1[0], r1 = p1[1];
+      b2w[0] = q0.x; b2w[1] = q0.y; b2w[2] = q0.z; b2w[3] = q0.w; b2w[4] = q1.x;
+      b1w[0] = r0.x; b1w[1] = r0.y; b1w[2] = r0.z; b1w[3] = r0.w; b1w[4] = r1.x;
+    }
     __syncthreads();
-    // ---- A operand: gather dH2S[receiver] rows (coalesced, half a warp per row), mask, split, TMEM
-    for (int c0 = 0; c0 < kDEP; c0 += kStageCols) {
+    // ---- A operand: gather dH2S[receiver] rows (coalesced, half a warp per row), mask, split, TMEM.
+    //      The gather of slab s+1 is in flight while slab s is split and stored.
+    float4 v[8];
+    gather_slab(v, 0);
+#pragma unroll
+    for (int sl = 0; sl < 3; ++sl) {
+      const int c0 = sl * kStageCols;
       const int ncols = imin(kStageCols, kDEP - c0);
-      {
-        float4 v[8];
 #pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          const int r = warp * 16 + 2 * j + sub;
-          const int rc = srcv[r];
-          v[j] = (rc >= 0 && 4 * c4 < ncols) ? *reinterpret_cast<const float4*>(a.dH2S + (size_t)rc * kDEP + c0 + 4 * c4)
-                                             : make_float4(0.f, 0.f, 0.f, 0.f);
-        }
-#pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          const int r = warp * 16 + 2 * j + sub;
-          if (4 * c4 < ncols) {
-            float2* dst = reinterpret_cast<float2*>(stage + r * kStagePitch + 4 * c4);
-            dst[0] = make_float2(v[j].x, v[j].y);
-            dst[1] = make_float2(v[j].z, v[j].w);
-          }
+      for (int j = 0; j < 8; ++j) {
+        const int r = warp * 16 + 2 * j + sub;
+        if (4 * c4 < ncols) {
+          float2* dst = reinterpret_cast<float2*>(stage + r * kStagePitch + 4 * c4);
+          dst[0] = make_float2(v[j].x, v[j].y);
+          dst[1] = make_float2(v[j].z, v[j].w);
         }
       }
       __syncthreads();
+      if (sl < 2) gather_slab(v, c0 + kStageCols);
       const int cb = 32 * half;
       if (cb < ncols) {                                    // warp-uniform
-        const uint32_t bits = row < rows ? a.maskbits[(size_t)(e0 + row) * 8 + ((c0 + cb) >> 5)] : 0u;
+        const uint32_t bits = b2w[2 * sl + half];
 #pragma unroll
         for (int g = 0; g < 4; ++g) {
           const int c = cb + 8 * g;
@@ -534,35 +548,52 @@ __global__ void __launch_bounds__(kThreads, 1) k_edge_dgrad_tc(EdgeDgradTcArgs a
     parity ^= 1u;
     fence_after_sync();
     // ---- epilogue: D * relu'(h1) -> slab -> DH1 (write) and dA (write or accumulate), coalesced
-    for (int c0 = 0; c0 < kN; c0 += kStageCols) {
+#pragma unroll
+    for (int sl = 0; sl < 3; ++sl) {
+      const int c0 = sl * kStageCols;
       const int ncols = imin(kStageCols, kDEP - c0);       // columns 152..159 are never stored
       for (int blk = half; blk * 16 < imin(kStageCols, kN - c0); blk += 2) {
-        uint32_t v[16];
-        tmem_ld16(lane_addr + kColD + c0 + blk * 16, v);
+        uint32_t vv[16];
+        tmem_ld16(lane_addr + kColD + c0 + blk * 16, vv);
         tmem_wait_ld();
         const int col0 = c0 + blk * 16;
-        const uint32_t bits = (row < rows && col0 < kDE) ? (a.maskbits_h1[(size_t)(e0 + row) * 8 + (col0 >> 5)] >> (col0 & 31)) : 0u;
+        const uint32_t bits = b1w[col0 >> 5] >> (col0 & 31);
         float o[16];
 #pragma unroll
-        for (int i = 0; i < 16; ++i) o[i] = ((bits >> i) & 1u) && (col0 + i < kDE) ? __uint_as_float(v[i]) : 0.f;
+        for (int i = 0; i < 16; ++i) o[i] = ((bits >> i) & 1u) && (col0 + i < kDE) ? __uint_as_float(vv[i]) : 0.f;
         float2* dst = reinterpret_cast<float2*>(stage + row * kStagePitch + blk * 16);
 #pragma unroll
         for (int i = 0; i < 8; ++i) dst[i] = make_float2(o[2 * i], o[2 * i + 1]);
       }
       __syncthreads();
       const int n4 = ncols >> 2;                           // float4 per row in this slab (16, 16, 6)
-      for (int idx = tid; idx < rows * n4; idx += kThreads) {
-        const int r = idx / n4, q = idx - r * n4;
-        const float2* src = reinterpret_cast<const float2*>(stage + r * kStagePitch + 4 * q);
-        const float2 p0 = src[0], p1 = src[1];
-        float4 val = make_float4(p0.x, p0.y, p1.x, p1.y);
-        const size_t g = (size_t)(e0 + r) * kDEP + c0 + 4 * q;
-        *reinterpret_cast<float4*>(a.DH1 + g) = val;
+      const int total = rows * n4;
+      for (int base = 0; base < total; base += 4 * kThreads) {
+        float4 old[4];
         if (!a.first) {
-          const float4 old = *reinterpret_cast<const float4*>(a.dA + g);
-          val.x += old.x; val.y += old.y; val.z += old.z; val.w += old.w;
+#pragma unroll
+          for (int u = 0; u < 4; ++u) {
+            const int idx = base + u * kThreads + tid;
+            if (idx < total) {
+              const int r = idx / n4, q = idx - r * n4;
+              old[u] = *reinterpret_cast<const float4*>(a.dA + (size_t)(e0 + r) * kDEP + c0 + 4 * q);
+            }
+          }
         }
-        *reinterpret_cast<float4*>(a.dA + g) = val;
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          const int idx = base + u * kThreads + tid;
+          if (idx < total) {
+            const int r = idx / n4, q = idx - r * n4;
+            const float2* src = reinterpret_cast<const float2*>(stage + r * kStagePitch + 4 * q);
+            const float2 p0 = src[0], p1 = src[1];
+            float4 val = make_float4(p0.x, p0.y, p1.x, p1.y);
+            const size_t g = (size_t)(e0 + r) * kDEP + c0 + 4 * q;
+            *reinterpret_cast<float4*>(a.DH1 + g) = val;
+            if (!a.first) { val.x += old[u].x; val.y += old[u].y; val.z += old[u].z; val.w += old[u].w; }
+            *reinterpret_cast<float4*>(a.dA + g) = val;
+          }
+        }
       }
       __syncthreads();
     }
