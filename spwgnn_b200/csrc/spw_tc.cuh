@@ -244,41 +244,45 @@ struct EdgeStepTcArgs {
 constexpr size_t kEdgeStepTcSmem = (size_t)(2 * kBFloats + kTM * kStagePitch + 2 * kTM + (kTM + 8) / 2 + kTM * 5) * sizeof(float) + 16;
 static_assert(kEdgeStepTcSmem <= 232448, "k_edge_step_tc shared memory exceeds the 227 KB per-CTA limit");
 
-// coalesced gather of one 64-column slab of h1 = relu(A_e + S_s + R_r): half a warp per row,
-// 128-bit loads along the row, all eight row-pairs of the warp (24 loads per lane) in flight
-__device__ __forceinline__ void build_h1_slab(float* stage, const int* ssnd, const int* srcv, const float* __restrict__ A,
-                                              const float* __restrict__ S, const float* __restrict__ R, int e0, int c0,
-                                              int ncols) {
+// coalesced gather of one 64-column slab of h1 = relu(A_e + S_s + R_r): half a warp per row, 128-bit loads
+// along the row, all eight row-pairs of the warp (24 loads per lane) in flight; split into a load half
+// (registers) and a store half (slab) so that the loads of slab s+1 overlap the processing of slab s.
+struct H1Regs { float4 va[8], vs[8], vr[8]; };
+
+__device__ __forceinline__ void h1_slab_load(H1Regs& g, const int* ssnd, const int* srcv, const float* __restrict__ A,
+                                             const float* __restrict__ S, const float* __restrict__ R, int e0, int c0,
+                                             int ncols) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int sub = lane >> 4, c4 = lane & 15;
   const bool col_ok = 4 * c4 < ncols;
   const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
-#pragma unroll 1
-  for (int it = 0; it < 8; it += 8) {
-    float4 va[8], vs[8], vr[8];
 #pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      const int r = warp * 16 + 2 * (it + j) + sub;
-      const int rc = srcv[r];
-      if (rc >= 0 && col_ok) {
-        va[j] = *reinterpret_cast<const float4*>(A + (size_t)(e0 + r) * kDEP + c0 + 4 * c4);
-        vs[j] = *reinterpret_cast<const float4*>(S + (size_t)ssnd[r] * kDEP + c0 + 4 * c4);
-        vr[j] = *reinterpret_cast<const float4*>(R + (size_t)rc * kDEP + c0 + 4 * c4);
-      } else {
-        va[j] = z4; vs[j] = z4; vr[j] = z4;
-      }
+  for (int j = 0; j < 8; ++j) {
+    const int r = warp * 16 + 2 * j + sub;
+    const int rc = srcv[r];
+    if (rc >= 0 && col_ok) {
+      g.va[j] = *reinterpret_cast<const float4*>(A + (size_t)(e0 + r) * kDEP + c0 + 4 * c4);
+      g.vs[j] = *reinterpret_cast<const float4*>(S + (size_t)ssnd[r] * kDEP + c0 + 4 * c4);
+      g.vr[j] = *reinterpret_cast<const float4*>(R + (size_t)rc * kDEP + c0 + 4 * c4);
+    } else {
+      g.va[j] = z4; g.vs[j] = z4; g.vr[j] = z4;
     }
+  }
+}
+
+__device__ __forceinline__ void h1_slab_store(const H1Regs& g, float* stage, const int* srcv, int c0, int ncols) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int sub = lane >> 4, c4 = lane & 15;
+  if (4 * c4 >= ncols) return;
 #pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      const int r = warp * 16 + 2 * (it + j) + sub;
-      if (!col_ok) continue;
-      float2* dst = reinterpret_cast<float2*>(stage + r * kStagePitch + 4 * c4);
-      dst[0] = make_float2(relu_f(va[j].x + vs[j].x + vr[j].x), relu_f(va[j].y + vs[j].y + vr[j].y));
-      if (c0 + 4 * c4 == kDE - 2)     // columns 150 / 151: the ones column that picks up the bias row, and the pad
-        dst[1] = make_float2(srcv[r] >= 0 ? 1.f : 0.f, 0.f);
-      else
-        dst[1] = make_float2(relu_f(va[j].z + vs[j].z + vr[j].z), relu_f(va[j].w + vs[j].w + vr[j].w));
-    }
+  for (int j = 0; j < 8; ++j) {
+    const int r = warp * 16 + 2 * j + sub;
+    float2* dst = reinterpret_cast<float2*>(stage + r * kStagePitch + 4 * c4);
+    dst[0] = make_float2(relu_f(g.va[j].x + g.vs[j].x + g.vr[j].x), relu_f(g.va[j].y + g.vs[j].y + g.vr[j].y));
+    if (c0 + 4 * c4 == kDE - 2)     // columns 150 / 151: the ones column that picks up the bias row, and the pad
+      dst[1] = make_float2(srcv[r] >= 0 ? 1.f : 0.f, 0.f);
+    else
+      dst[1] = make_float2(relu_f(g.va[j].z + g.vs[j].z + g.vr[j].z), relu_f(g.va[j].w + g.vs[j].w + g.vr[j].w));
   }
 }
 
@@ -327,10 +331,15 @@ __global__ void __launch_bounds__(kThreads, 1) k_edge_step_tc(EdgeStepTcArgs a) 
       snoff[i] = (short)imax(-32000, imin(32000, a.in_off[n_first + i] - e0));
     // ---- h1 = relu(A_e + S_s + R_r): coalesced gather into the slab, then row threads split it
     //      into tf32 hi/lo and store it to tensor memory (3 slabs of <= 64 columns)
-    for (int c0 = 0; c0 < kDEP; c0 += kStageCols) {
+    H1Regs hreg;
+    h1_slab_load(hreg, ssnd, srcv, a.A, a.S, a.R, e0, 0, kStageCols);
+#pragma unroll
+    for (int sl = 0; sl < 3; ++sl) {
+      const int c0 = sl * kStageCols;
       const int ncols = imin(kStageCols, kDEP - c0);
-      build_h1_slab(stage, ssnd, srcv, a.A, a.S, a.R, e0, c0, ncols);
+      h1_slab_store(hreg, stage, srcv, c0, ncols);
       __syncthreads();
+      if (sl < 2) h1_slab_load(hreg, ssnd, srcv, a.A, a.S, a.R, e0, c0 + kStageCols, imin(kStageCols, kDEP - c0 - kStageCols));
       // this thread's half of the slab row: 32 columns (or what is left) == one word of relu bits
       const int cb = 32 * half;
       uint32_t hbits = 0u;
