@@ -12,7 +12,7 @@ backward + (N>1: one NCCL all-reduce of the flat gradient buffer) + Adam.  Synth
 `value`  : towers/s, whole job, inputs already resident in HBM, CUDA-event timed, max over ranks.
 `e2e`    : same metric through the public API from PINNED HOST buffers: every step copies the
            poses/features/targets host->device and reads the loss/accuracy scalars back.
-`roofline`: dominant kernel (k_edge_encode_bwd) timed with CUDA events on its stream (spw_profile).
+`roofline`: the dominant modelled kernel, timed with CUDA events on its stream (spw_profile).
 `cpu_baseline` / `--impl reference`: the reference formulation (dense one-hot graph of
            Networks.py, fp32, torch autograd) on the host cores -- the reference itself (Keras/TF1)
            cannot be installed here; kind = "port".
@@ -33,11 +33,17 @@ TOWERS_PER_GPU = 4096
 N_BLOCKS = 10
 SEED = 1235
 FLOP_EDGE_FWD, FLOP_NODE_FWD = 1035600, 421400        # SURVEY.md section 8(d), reference formulation
-# dominant kernel: backward of the relation encoder (rm 2->150->150->150->150 and the W1a part of rmp layer 0),
-# one launch per training step over all edges
-K_DOM = 'k_edge_encode_bwd'
-K_DOM_ALGO_FLOP_PER_EDGE = 2 * (135600 + 45000)       # dgrad + wgrad of those layers, reference formulation
-K_DOM_EXEC_FLOP_PER_EDGE = 4 * (2 * 160 * 160 + 2 * 152 * 160)   # executed: 4 wgrads (padded 160x160) + 4 dgrad GEMMs
+# Kernels with a fixed per-edge FLOP model.  The roofline entry is computed for whichever of
+# them takes the largest share of the step.  algo = reference-formulation FLOPs of the layer the launch implements
+# (per edge); exec = FLOPs the kernel issues (padding, 3xTF32 split: three tf32 MMAs per product);
+# pipe = where they run.
+_MMA = 2 * 128 * 160 * 8                               # FLOPs of one tcgen05.mma kind::tf32 M128 N160 K8
+KERNEL_MODELS = {
+    'k_wgrad_tc': dict(algo=2 * 150 * 150, exec=6 * _MMA / 8.0, pipe='tensor'),        # 2 M-tiles x 3 MMAs per 8 edge rows
+    'k_edge_dgrad_tc': dict(algo=2 * 150 * 150, exec=57 * _MMA / 128.0, pipe='tensor'),  # 19 k-steps x 3 MMAs per 128 rows
+    'k_edge_step_tc': dict(algo=2 * 150 * 150, exec=57 * _MMA / 128.0, pipe='tensor'),
+    'k_edge_encode': dict(algo=2 * (67800 + 22500), exec=4 * 2 * 152 * 160, pipe='fp32'),
+}
 
 
 def parse():
@@ -51,7 +57,7 @@ def parse():
     return ap.parse_args()
 
 
-def dominant_kernel_traffic():
+def dominant_kernel_traffic(K_DOM):
     """dram__bytes_read.sum + dram__bytes_write.sum per launch of the dominant kernel, from the committed ncu
     --set full summary (profiles/), or None."""
     import glob
@@ -312,13 +318,17 @@ def main():
         return
 
     peaks = load_peaks()
-    traffic = dominant_kernel_traffic()
+    modelled = [(v[1], k) for k, v in kern.items() if k in KERNEL_MODELS]
+    K_DOM = max(modelled)[1] if modelled else 'k_wgrad_tc'
+    model = KERNEL_MODELS[K_DOM]
+    traffic = dominant_kernel_traffic(K_DOM)
     towers_per_s = T * world * K / (ms * 1e-3)
     e2e_per_s = T * world * K / (ms_e2e * 1e-3)
     dom_cnt, dom_ms = kern.get(K_DOM, (0, 0.0))
     dom_avg_s = (dom_ms / dom_cnt) * 1e-3 if dom_cnt else float('nan')
-    achieved_tf = E * K_DOM_ALGO_FLOP_PER_EDGE / dom_avg_s / 1e12 if dom_cnt else None
-    exec_tf = E * K_DOM_EXEC_FLOP_PER_EDGE / dom_avg_s / 1e12 if dom_cnt else None
+    achieved_tf = E * model['algo'] / dom_avg_s / 1e12 if dom_cnt else None
+    exec_tf = E * model['exec'] / dom_avg_s / 1e12 if dom_cnt else None
+    tf32_peak = peaks['tf'] / 2.0                      # tf32 runs at half the bf16 rate (B200_PROFILING.md)
     step_algo_flop = 3.0 * (E * FLOP_EDGE_FWD + n * FLOP_NODE_FWD)
     cpu_rate, cpu_dt, cpu_threads = cpu_reference_rate(args.cpu_sample, 3, 1) if world == 1 else (None, None, None)
 
@@ -343,13 +353,17 @@ def main():
             'frac': (achieved_tf / peaks['tf']) if achieved_tf else None,
             'traffic': traffic[0] if traffic else None, 'traffic_source': traffic[1] if traffic else None,
             'peak_source': peaks['src'],
-            'note': 'the dominant kernel is still an fp32 FFMA kernel: its fraction of the tensor peak is small by '
-                    'construction; fp32_pipe gives the pipe it runs on.  The forward edge step already runs on the '
-                    'tensor cores (k_edge_step_tc, tcgen05 3xTF32).',
+            'note': 'dominant = the kernel with a fixed FLOP model that takes the largest share of the step; achieved = '
+                    'algorithmic (reference-formulation, fp32) FLOPs / launch time against the measured bf16 tensor peak; '
+                    'executed_tflops counts what the kernel issues (3xTF32: three tf32 MMAs per product) against the '
+                    'pipe it runs on.',
+            'pipe': model['pipe'],
+            'executed_frac_of_pipe': (exec_tf / (tf32_peak if model['pipe'] == 'tensor' else fp32_peak_tf)) if exec_tf else None,
+            'tf32_peak_assumed': tf32_peak,
             'launch_ms': dom_avg_s * 1e3 if dom_cnt else None, 'launches_timed': dom_cnt,
             'share_of_kernel_time': dom_ms / total_kernel_ms,
             'executed_tflops': exec_tf,
-            'fp32_pipe': {'peak_tflops_measured': fp32_peak_tf, 'frac_executed': (exec_tf / fp32_peak_tf) if exec_tf else None},
+            'fp32_pipe': {'peak_tflops_measured': fp32_peak_tf},
             'step_algorithmic_tflops': step_algo_flop / (ms / K * 1e-3) / 1e12,
             'hbm_algorithmic_gbs': (4044.0 * n) / (ms / K * 1e-3) / 1e9,
             'kernels': {k: {'launches': v[0], 'ms': v[1], 'share': v[1] / total_kernel_ms} for k, v in sorted(kern.items())},

@@ -394,7 +394,7 @@ struct EdgeEncArgs {
   const float* b1; const float* b2; const float* b3;      // raw biases [150]
   const float* W1A; const float* bA;                      // packed rmp.w0[0:150], raw rmp.b0
   float* A;                                               // [E][152]
-  float* X1; float* X2; float* C;                         // [E][152] each, training only (null: not saved)
+  float* X0; float* X1; float* X2; float* C;              // [E][152] each, training only (null: not saved)
   uint32_t drop_thresh; uint32_t drop_seed; float drop_inv_keep;   // dropout on c_e (Networks.py:77)
 };
 
@@ -427,6 +427,7 @@ __global__ void __launch_bounds__(kThreads, 2) k_edge_encode(EdgeEncArgs a) {
     const int rows = imin(kTME, a.E - e0);
     build_x0<kTME>(Xa, sdx, sdy, a.obj, a.in_snd, a.in_rcv, e0, rows, a.W0, a.b0);
     __syncthreads();
+    if (a.X0) tile_to_global(Xa, a.X0, e0, rows);
     float acc[ROWS][5];
     zero_acc<ROWS, 5>(acc);
     gemm_tile_acc<ROWS, 5>(acc, Xa, kDEP, warp * ROWS, a.RM1, kDEP, Wst);

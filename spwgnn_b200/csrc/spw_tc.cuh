@@ -440,12 +440,14 @@ __global__ void __launch_bounds__(kThreads, 1) k_edge_step_tc(EdgeStepTcArgs a) 
 // =================================================================================================
 struct EdgeDgradTcArgs {
   int E;
-  const int32_t* in_rcv;
-  const float* dH2S;                                  // [n][152]
-  const float* Whi; const float* Wlo;                 // packed B operands of W2^T-as-B
-  const uint32_t* maskbits;                           // relu bits of h2 [E][8]
-  const uint32_t* maskbits_h1;                        // relu bits of h1 [E][8]
-  float* dA; float* DH1;                              // [E][152]
+  const int32_t* in_rcv;                              // row r reads dH2S[in_rcv[r]]; null: row r reads dH2S[r]
+  const float* dH2S;                                  // [n][152] (or [E][152] when in_rcv is null)
+  const float* Whi; const float* Wlo;                 // packed B operands ([N = out][K = in])
+  const uint32_t* maskbits;                           // operand mask bits [E][8] (relu bits of h2) or null: none
+  const uint32_t* maskbits_h1;                        // output mask bits [E][8] (relu bits of h1) or null: none
+  const float* act;                                   // output mask by sign: keep where act[E][152] > 0 (or null)
+  float scale;                                        // multiplies the output (1/keep of a dropout; else 1)
+  float* dA; float* DH1;                              // DH1 [E][152] written; dA (may be null) accumulated / written
   int first;                                          // dA is written (first processed step) or accumulated
   float* poison;                                      // written with NaN if an MMA barrier times out
 };
@@ -492,14 +494,19 @@ __global__ void __launch_bounds__(kThreads, 1) k_edge_dgrad_tc(EdgeDgradTcArgs a
   for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
     const int e0 = tile * kTM;
     const int rows = imin(kTM, a.E - e0);
-    if (tid < kTM) srcv[tid] = tid < rows ? a.in_rcv[e0 + tid] : -1;
+    if (tid < kTM) srcv[tid] = tid < rows ? (a.in_rcv ? a.in_rcv[e0 + tid] : e0 + tid) : -1;
     // relu bits of this thread's row (h2: operand mask, h1: epilogue mask), fetched once per tile
-    uint32_t b2w[8] = {0u, 0u, 0u, 0u, 0u, 0u, 0u, 0u}, b1w[8] = {0u, 0u, 0u, 0u, 0u, 0u, 0u, 0u};
-    if (row < rows) {
+    uint32_t b2w[8], b1w[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) { b2w[i] = 0xffffffffu; b1w[i] = 0xffffffffu; }
+    if (row < rows && a.maskbits) {
       const uint4* p2 = reinterpret_cast<const uint4*>(a.maskbits + (size_t)(e0 + row) * 8);
-      const uint4* p1 = reinterpret_cast<const uint4*>(a.maskbits_h1 + (size_t)(e0 + row) * 8);
-      const uint4 q0 = p2[0], q1 = p2[1], r0 = p1[0], r1 = p1[1];
+      const uint4 q0 = p2[0], q1 = p2[1];
       b2w[0] = q0.x; b2w[1] = q0.y; b2w[2] = q0.z; b2w[3] = q0.w; b2w[4] = q1.x;
+    }
+    if (row < rows && a.maskbits_h1) {
+      const uint4* p1 = reinterpret_cast<const uint4*>(a.maskbits_h1 + (size_t)(e0 + row) * 8);
+      const uint4 r0 = p1[0], r1 = p1[1];
       b1w[0] = r0.x; b1w[1] = r0.y; b1w[2] = r0.z; b1w[3] = r0.w; b1w[4] = r1.x;
     }
     __syncthreads();
@@ -578,15 +585,16 @@ __global__ void __launch_bounds__(kThreads, 1) k_edge_dgrad_tc(EdgeDgradTcArgs a
       const int n4 = ncols >> 2;                           // float4 per row in this slab (16, 16, 6)
       const int total = rows * n4;
       for (int base = 0; base < total; base += 4 * kThreads) {
-        float4 old[4];
-        if (!a.first) {
+        float4 old[4], actv[4];
+        const bool rmw = a.dA && !a.first;
 #pragma unroll
-          for (int u = 0; u < 4; ++u) {
-            const int idx = base + u * kThreads + tid;
-            if (idx < total) {
-              const int r = idx / n4, q = idx - r * n4;
-              old[u] = *reinterpret_cast<const float4*>(a.dA + (size_t)(e0 + r) * kDEP + c0 + 4 * q);
-            }
+        for (int u = 0; u < 4; ++u) {
+          const int idx = base + u * kThreads + tid;
+          if (idx < total) {
+            const int r = idx / n4, q = idx - r * n4;
+            const size_t g = (size_t)(e0 + r) * kDEP + c0 + 4 * q;
+            if (rmw) old[u] = *reinterpret_cast<const float4*>(a.dA + g);
+            if (a.act) actv[u] = *reinterpret_cast<const float4*>(a.act + g);
           }
         }
 #pragma unroll
@@ -596,11 +604,18 @@ __global__ void __launch_bounds__(kThreads, 1) k_edge_dgrad_tc(EdgeDgradTcArgs a
             const int r = idx / n4, q = idx - r * n4;
             const float2* src = reinterpret_cast<const float2*>(stage + r * kStagePitch + 4 * q);
             const float2 p0 = src[0], p1 = src[1];
-            float4 val = make_float4(p0.x, p0.y, p1.x, p1.y);
+            float4 val = make_float4(p0.x * a.scale, p0.y * a.scale, p1.x * a.scale, p1.y * a.scale);
+            if (a.act) {
+              val.x = actv[u].x > 0.f ? val.x : 0.f; val.y = actv[u].y > 0.f ? val.y : 0.f;
+              val.z = actv[u].z > 0.f ? val.z : 0.f; val.w = actv[u].w > 0.f ? val.w : 0.f;
+              if (c0 + 4 * q == kDE - 2) { val.z = 0.f; val.w = 0.f; }      // columns 150 / 151 carry no gradient
+            }
             const size_t g = (size_t)(e0 + r) * kDEP + c0 + 4 * q;
             *reinterpret_cast<float4*>(a.DH1 + g) = val;
-            if (!a.first) { val.x += old[u].x; val.y += old[u].y; val.z += old[u].z; val.w += old[u].w; }
-            *reinterpret_cast<float4*>(a.dA + g) = val;
+            if (a.dA) {
+              if (rmw) { val.x += old[u].x; val.y += old[u].y; val.z += old[u].z; val.w += old[u].w; }
+              *reinterpret_cast<float4*>(a.dA + g) = val;
+            }
           }
         }
       }
@@ -842,6 +857,38 @@ __global__ void __launch_bounds__(kThreads, 1) k_wgrad_tc(WgradTcArgs a) {
   fence_before_sync();
   __syncthreads();
   if (warp == 0) tmem_dealloc(tmem_base, kTmemCols);
+}
+
+// relation-encoder layer 0 (K = 2) gradients from G0 = d(pre-activation of X0):
+//   part[cta][0][k] = sum_e dx_e G0[e][k], [1][k] with dy, [2][k] = sum_e G0[e][k]   (fixed order per CTA)
+__global__ void __launch_bounds__(kThreads, 2) k_enc0_bwd(int E, const int32_t* __restrict__ in_snd,
+                                                          const int32_t* __restrict__ in_rcv, const float* __restrict__ obj,
+                                                          const float* __restrict__ G0, float* __restrict__ part) {
+  __shared__ float sdx[kTM], sdy[kTM];
+  const int tid = threadIdx.x;
+  float g0 = 0.f, g1 = 0.f, gb = 0.f;
+  const int ntiles = (E + kTM - 1) / kTM;
+  for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+    const int e0 = tile * kTM, rows = imin(kTM, E - e0);
+    __syncthreads();
+    if (tid < rows) {
+      const int s = in_snd[e0 + tid], rc = in_rcv[e0 + tid];
+      sdx[tid] = obj[3 * (size_t)rc] - obj[3 * (size_t)s];
+      sdy[tid] = obj[3 * (size_t)rc + 1] - obj[3 * (size_t)s + 1];
+    }
+    __syncthreads();
+    if (tid < kDE) {
+#pragma unroll 4
+      for (int r = 0; r < rows; ++r) {
+        const float d = G0[(size_t)(e0 + r) * kDEP + tid];
+        g0 = fmaf(sdx[r], d, g0); g1 = fmaf(sdy[r], d, g1); gb += d;
+      }
+    }
+  }
+  if (tid < kDEP) {
+    float* p = part + (size_t)blockIdx.x * (3 * kDEP);
+    p[tid] = tid < kDE ? g0 : 0.f; p[kDEP + tid] = tid < kDE ? g1 : 0.f; p[2 * kDEP + tid] = tid < kDE ? gb : 0.f;
+  }
 }
 
 }  // namespace tc

@@ -114,11 +114,11 @@ size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
 
 struct Layout {
   size_t pack[P_COUNT];
-  size_t Q1, Q, degf, A, PF, PL, W2hi, W2lo, W2Thi, W2Tlo;
+  size_t Q1, Q, degf, A, PF, PL, W2hi, W2lo, W2Thi, W2Tlo, ENCT;   // ENCT: 4 x (hi, lo) transposed encoder operands
   size_t P, S, R, H2S, G, U;     // per-step arrays (training: 5 slots; inference: fewer)
   int slotsP, slotsSR, slotsN;   // number of step slots for P / (S,R) / (H2S,G,U)
   // backward
-  size_t dU, dG, T, dS, dR, dH2S, DP, dQ, dQ1, dA, DH1, M2, M1, EX1, EX2, EC, partE, partM, part0, partN;
+  size_t dU, dG, T, dS, dR, dH2S, DP, dQ, dQ1, dA, DH1, M2, M1, EX0, EX1, EX2, EC, GB, partE, partM, part0, partN;
   size_t total;   // floats
 };
 
@@ -134,6 +134,7 @@ Layout make_layout(int64_t n, int64_t E, int training) {
   L.W2lo = take(24320);
   L.W2Thi = take(24320);
   L.W2Tlo = take(24320);
+  L.ENCT = take((size_t)8 * 24320);
   L.Q1 = take(n * kDP);
   L.Q = take(n * kDP);
   L.degf = take(n);
@@ -163,15 +164,17 @@ Layout make_layout(int64_t n, int64_t E, int training) {
     L.DH1 = take((size_t)E * kDEP + 8);
     L.M2 = take((size_t)SPW_N_STEPS * E * 8);      // relu bits of h2, 8 words per edge and step
     L.M1 = take((size_t)SPW_N_STEPS * E * 8);      // relu bits of h1 (tensor-core data-gradient epilogue)
-    L.EX1 = take((size_t)E * kDEP + 8);            // relation-encoder activations kept for the backward pass
+    L.EX0 = take((size_t)E * kDEP + 8);            // relation-encoder activations kept for the backward pass
+    L.EX1 = take((size_t)E * kDEP + 8);
+    L.GB = take((size_t)E * kDEP + 8);             // second gradient buffer of the layer-by-layer encoder backward
     L.EX2 = take((size_t)E * kDEP + 8);
     L.EC = take((size_t)E * kDEP + 8);
     L.partE = take((size_t)kMaxCtas * 2 * 160 * 128);
     L.partM = take((size_t)kMaxCtas * 4 * 160 * 160);
-    L.part0 = take((size_t)kMaxCtas * 3 * kDEP);
+    L.part0 = take((size_t)2 * kMaxCtas * 3 * kDEP);
     L.partN = take((size_t)2 * kMaxCtas * kPartNodeElems);
   } else {
-    L.dU = L.dG = L.T = L.dS = L.dR = L.dH2S = L.DP = L.dQ = L.dQ1 = L.dA = L.DH1 = L.M2 = L.M1 = L.EX1 = L.EX2 = L.EC = 0;
+    L.dU = L.dG = L.T = L.dS = L.dR = L.dH2S = L.DP = L.dQ = L.dQ1 = L.dA = L.DH1 = L.M2 = L.M1 = L.EX0 = L.EX1 = L.EX2 = L.EC = L.GB = 0;
     L.partE = L.partM = L.part0 = L.partN = 0;
   }
   L.total = off;
@@ -469,8 +472,13 @@ int spw_forward(const SpwParams* w, const SpwGraph* g, const float* obj, float* 
   pack_weights(st, w, ws, L, training != 0);
 #if SPW_USE_TC
   SPW_KLAUNCH("k_pack_umma", tc::k_pack_umma, dim3(48), dim3(256), 0, st, (const float*)w->rmp_w[1], 150, 0, 0, 150, 150, 0, (const float*)w->rmp_b[1], ws + L.W2hi, ws + L.W2lo);
-  if (training)   // B operand of the data gradient: [N = k][K = n] = W2[k][n]
+  if (training) {   // B operands of the data gradients: [N = k_in][K = n_out] = W[k_in][n_out]
     SPW_KLAUNCH("k_pack_umma", tc::k_pack_umma, dim3(48), dim3(256), 0, st, (const float*)w->rmp_w[1], 150, 0, 0, 150, 150, 1, (const float*)nullptr, ws + L.W2Thi, ws + L.W2Tlo);
+    const float* encw[4] = {w->rmp_w[0], w->rm_w[3], w->rm_w[2], w->rm_w[1]};       // W1a, RM3, RM2, RM1
+    for (int i = 0; i < 4; ++i)
+      SPW_KLAUNCH("k_pack_umma", tc::k_pack_umma, dim3(48), dim3(256), 0, st, encw[i], 150, 0, 0, 150, 150, 1, (const float*)nullptr,
+                  ws + L.ENCT + (size_t)(2 * i) * 24320, ws + L.ENCT + (size_t)(2 * i + 1) * 24320);
+  }
 #endif
   SPW_KLAUNCH("k_deg_to_float", k_deg_to_float, dim3(grid_for(n, 256)), dim3(256), 0, st, g->in_off, n, ws + L.degf);
 
@@ -491,6 +499,7 @@ int spw_forward(const SpwParams* w, const SpwGraph* g, const float* obj, float* 
     a.RM1 = PK(P_RM1); a.RM2 = PK(P_RM2); a.RM3 = PK(P_RM3); a.b1 = w->rm_b[1]; a.b2 = w->rm_b[2]; a.b3 = w->rm_b[3];
     a.W1A = PK(P_W1A); a.bA = w->rmp_b[0]; a.A = ws + L.A;
     a.X1 = training ? ws + L.EX1 : nullptr; a.X2 = training ? ws + L.EX2 : nullptr; a.C = training ? ws + L.EC : nullptr;
+    a.X0 = (training && SPW_USE_TC) ? ws + L.EX0 : nullptr;
     a.drop_thresh = drop_thresh; a.drop_seed = seed_c; a.drop_inv_keep = inv_keep;
     set_smem(k_edge_encode, edge_fwd_smem());
     SPW_KLAUNCH("k_edge_encode", k_edge_encode, dim3(egrid), dim3(kThreads), edge_fwd_smem(), st, a);
@@ -661,7 +670,7 @@ int spw_backward(const SpwParams* w, const SpwGraph* g, const float* obj, const 
         tc::EdgeDgradTcArgs t;
         t.E = E; t.in_rcv = g->in_rcv; t.dH2S = ws + L.dH2S; t.Whi = ws + L.W2Thi; t.Wlo = ws + L.W2Tlo;
         t.maskbits = a.maskbits; t.maskbits_h1 = reinterpret_cast<const uint32_t*>(ws + L.M1) + (size_t)l * E * 8;
-        t.dA = ws + L.dA; t.DH1 = ws + L.DH1; t.first = a.first; t.poison = ws + L.dA;
+        t.act = nullptr; t.scale = 1.f; t.dA = ws + L.dA; t.DH1 = ws + L.DH1; t.first = a.first; t.poison = ws + L.dA;
         set_smem(tc::k_edge_dgrad_tc, tc::kEdgeDgradTcSmem);
         SPW_KLAUNCH("k_edge_dgrad_tc", tc::k_edge_dgrad_tc, dim3(egrid), dim3(kThreads), tc::kEdgeDgradTcSmem, st, t);
       }
@@ -721,6 +730,34 @@ int spw_backward(const SpwParams* w, const SpwGraph* g, const float* obj, const 
 #else
     launch_reduce(st, ws + L.partE, egrid, 160 * 160, 0, 10, 10, kDE, kDE, {grads->rmp_w[1], 150, 0, 0, grads->rmp_b[1], 0});
 #endif
+#if SPW_USE_TC
+    {   // relation-encoder backward, layer by layer on the tensor cores (activations X0, X1, X2, C saved by the forward pass)
+      const float* acts[4] = {ws + L.EC, ws + L.EX2, ws + L.EX1, ws + L.EX0};       // layer inputs: C, X2, X1, X0
+      float* gw[4] = {grads->rmp_w[0], grads->rm_w[3], grads->rm_w[2], grads->rm_w[1]};
+      float* gb[4] = {grads->rmp_b[0], grads->rm_b[3], grads->rm_b[2], grads->rm_b[1]};
+      const float* dY = ws + L.dA;
+      float* gout[2] = {ws + L.DH1, ws + L.GB};
+      auto kwg = tc::k_wgrad_tc<0, 0>;
+      set_smem(kwg, tc::kWgradTcSmem);
+      set_smem(tc::k_edge_dgrad_tc, tc::kEdgeDgradTcSmem);
+      for (int i = 0; i < 4; ++i) {
+        tc::WgradTcArgs wg;
+        memset(&wg, 0, sizeof(wg));
+        wg.M = E; wg.x_mode = 0; wg.X = acts[i]; wg.y_mode = 0; wg.dY = dY; wg.part = ws + L.partE; wg.first = 1; wg.poison = ws + L.partE;
+        SPW_KLAUNCH("k_wgrad_tc", kwg, dim3(egrid), dim3(kThreads), tc::kWgradTcSmem, st, wg);
+        launch_reduce(st, ws + L.partE, egrid, (int)tc::kWgPartFloats, 0, -1, tc::kWgFeat1, kDE, kDE, {gw[i], 150, 0, 0, gb[i], 0});
+        tc::EdgeDgradTcArgs t;
+        memset(&t, 0, sizeof(t));
+        t.E = E; t.in_rcv = nullptr; t.dH2S = dY; t.Whi = ws + L.ENCT + (size_t)(2 * i) * 24320; t.Wlo = ws + L.ENCT + (size_t)(2 * i + 1) * 24320;
+        t.act = acts[i]; t.scale = i == 0 ? inv_keep : 1.f; t.dA = nullptr; t.DH1 = gout[i & 1]; t.first = 1; t.poison = gout[i & 1];
+        SPW_KLAUNCH("k_edge_dgrad_tc", tc::k_edge_dgrad_tc, dim3(egrid), dim3(kThreads), tc::kEdgeDgradTcSmem, st, t);
+        dY = gout[i & 1];
+      }
+      const int g0grid = egrid < 2 * num_sms() ? egrid : 2 * num_sms();
+      SPW_KLAUNCH("k_enc0_bwd", tc::k_enc0_bwd, dim3(g0grid), dim3(kThreads), 0, st, E, g->in_snd, g->in_rcv, obj, dY, ws + L.part0);
+      launch_reduce(st, ws + L.part0, g0grid, 3 * kDEP, kDEP, 0, 0, 2, kDE, {grads->rm_w[0], 150, 0, 0, grads->rm_b[0], 0});
+    }
+#else
     const int btiles = (E + kTMB - 1) / kTMB;
     const int bgrid = btiles < num_sms() ? btiles : num_sms();
     EdgeEncBwdArgs a;
@@ -738,6 +775,7 @@ int spw_backward(const SpwParams* w, const SpwGraph* g, const float* obj, const 
     launch_reduce(st, ws + L.partM + 3 * 160 * 160, bgrid, ps, 0, 10, 10, kDE, kDE, {grads->rm_w[1], 150, 0, 0, grads->rm_b[1], 0});
     // layer 0: part0 rows [w0 row 0 | w0 row 1 | b0], each kDEP long  ->  treat as Kin = 2 (+ bias row)
     launch_reduce(st, ws + L.part0, bgrid, 3 * kDEP, kDEP, 0, 0, 2, kDE, {grads->rm_w[0], 150, 0, 0, grads->rm_b[0], 0});
+#endif
   } else {
     cudaMemsetAsync(grads->rmp_w[1], 0, 22500 * sizeof(float), st);
     cudaMemsetAsync(grads->rmp_b[1], 0, 150 * sizeof(float), st);

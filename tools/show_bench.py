@@ -12,8 +12,8 @@ for l in open(path):
     for k, v in sorted((r.get('kernels') or {}).items(), key=lambda kv: -kv[1]['ms']):
         if v['share'] > 0.004:
             print('  %-20s %4d launches %8.3f ms/step %5.1f%%' % (k, v['launches'], v['ms'] / steps, 100 * v['share']))
-    print('  dominant %s: achieved %.2f TF (frac %.4f of tensor peak), executed %.2f TF = %.3f of fp32 pipe %.1f TF; step algorithmic %.1f TF' % (
-        r.get('kernel'), r.get('achieved') or 0, r.get('frac') or 0, r.get('executed_tflops') or 0,
-        (r.get('fp32_pipe') or {}).get('frac_executed') or 0, (r.get('fp32_pipe') or {}).get('peak_tflops_measured') or 0, r.get('step_algorithmic_tflops') or 0))
+    print('  dominant %s (%s pipe): achieved %.2f TF (frac %.4f of tensor peak), executed %.2f TF = %.3f of its pipe; fp32 pipe %.1f TF; step algorithmic %.1f TF' % (
+        r.get('kernel'), r.get('pipe'), r.get('achieved') or 0, r.get('frac') or 0, r.get('executed_tflops') or 0,
+        r.get('executed_frac_of_pipe') or 0, (r.get('fp32_pipe') or {}).get('peak_tflops_measured') or 0, r.get('step_algorithmic_tflops') or 0))
     if d.get('cpu_baseline'):
         print('  cpu_baseline %.0f towers/s on %d cores' % (d['cpu_baseline']['value'], d['cpu_baseline']['cores']))
