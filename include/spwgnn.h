@@ -79,6 +79,14 @@ int spw_ffma_peak(float* out, int grid, int iters, void* stream);
 /* tcgen05 / TMEM self test (3xTF32): D[128][160] = A[128][152] . W[K][N] (K<=152, N<=160); scratch: 48640 floats;
  * status (device int): 1 = ok, -1 = the MMA completion barrier timed out. */
 int spw_tc_selftest(const float* A, const float* W, int K, int N, float* D, float* scratch, int* status, void* stream);
+/* generic tensor-core linear layer (the node-level / relation-encoder building block), exposed for unit tests:
+ *   Y[M][ldy] = post(act([X0 | X1].W + rowscale*bias + addend)), W in Keras layout [K0 + K1][N] (Blocks.py:22-27);
+ *   act 0 none / 1 relu / 2 tanh; mulmode 1: *= [mulsrc > 0], 2: *= (1 - mulsrc^2); NB (MMA N) = 112 or 160, N <= NB,
+ *   2*ceil((K0+K1)/8)*8 + NB <= 512; scratch: 2 * ceil((K0 + K1) / 8) * 8 * NB floats; X1 may be null (K1 = 0). */
+int spw_tc_linear(int M, const float* X0, int ldx0, int K0, const float* X1, int ldx1, int K1, const float* W, int N, int NB,
+                  const float* bias, const float* rowscale, const float* addend, int ld_add, int act, const float* mulsrc,
+                  int ld_mul, int mulmode, float* Y, int ldy, int accumulate, float post_scale, int ones_col, float* scratch,
+                  void* stream);
 
 /* ---- edge-index construction (replaces main.py:66-81) ------------------------------------
  * Edge m->j (m != j, same tower) is active iff sqrt(dx*dx + dy*dy) < thr evaluated in IEEE

@@ -1,0 +1,264 @@
+// spw_rows_tc.cuh -- generic fused linear layer on the tensor cores (tcgen05, 3xTF32), sm_100a only.
+//
+//   Y = post( act( [X0 | X1] . W + rowscale*bias + addend ) )          (same epilogue contract as k_linear)
+//
+// One 128-row tile per MMA group.  The row thread (TMEM lane) reads its own row from global memory, splits it
+// into tf32 hi / lo and stores it straight to tensor memory (A operand, one 32-bit column per k); the packed
+// weights (B operand, hi / lo, [k-step][2][NB][4]) stay resident in shared memory for the whole launch; the
+// accumulator D lives in the top NB columns of tensor memory and is read back by the same row threads, which
+// apply the epilogue and write 16-byte pieces of their row.
+//   TMEM map: A_hi [0, 8 ks) | A_lo [8 ks, 16 ks) | D [512 - NB, 512)            (16 ks + NB <= 512)
+//   Up to two row segments are concatenated along K (K0 % 4 == 0 then), e.g. [g | p] . [V1b ; V1c].
+#pragma once
+#ifndef SPW_EMU
+#include "spw_tc.cuh"
+
+namespace spw {
+namespace tc {
+
+// ---- batched weight packing into B operands of NB columns ------------------------------------------
+// dst rows [k_off, k_lim) <- src (Keras [in][out], ld) block at (row0, col0): K valid rows, N valid columns;
+// transpose: dst[k][n] = src[row0 + n][col0 + k].  Rows / columns beyond K / N are zero.
+struct PackTcDesc {
+  const float* src; int ld, row0, col0, K, N, transpose;
+  float* hi; float* lo; int NB, k_off, k_lim;
+};
+constexpr int kMaxPackTc = 24;
+struct PackTcArgs { PackTcDesc d[kMaxPackTc]; int n; };
+
+__global__ void __launch_bounds__(256) k_pack_tc(PackTcArgs a) {
+  const PackTcDesc d = a.d[blockIdx.y];
+  const int total = (d.k_lim - d.k_off) * d.NB;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+    const int kk = i / d.NB, n = i - kk * d.NB;          // kk: row within this descriptor
+    const int k = d.k_off + kk;
+    float v = 0.f;
+    if (kk < d.K && n < d.N)
+      v = d.transpose ? d.src[(size_t)(d.row0 + n) * d.ld + d.col0 + kk] : d.src[(size_t)(d.row0 + kk) * d.ld + d.col0 + n];
+    uint32_t h, l;
+    split_tf32(v, h, l);
+    const size_t o = (size_t)(k >> 3) * (8 * d.NB) + (size_t)((k >> 2) & 1) * (4 * d.NB) + (size_t)n * 4 + (k & 3);
+    d.hi[o] = __uint_as_float(h);
+    d.lo[o] = __uint_as_float(l);
+  }
+}
+
+// relation-encoder layer 0 (Networks.py:58-62,69,75; K = 2), one 16-byte piece of a row per thread:
+//   X0[e][k] = relu(dx*W0[0][k] + dy*W0[1][k] + b0[k]),  [dx, dy] = pos_receiver - pos_sender;  X0[e][150] = 1, X0[e][151] = 0
+__global__ void __launch_bounds__(256) k_edge_enc0(int E, const int32_t* __restrict__ in_snd, const int32_t* __restrict__ in_rcv,
+                                                   const float* __restrict__ obj, const float* __restrict__ W0,
+                                                   const float* __restrict__ b0, float* __restrict__ X0) {
+  constexpr int C4 = kDEP / 4;
+  const long long total = (long long)E * C4;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int e = (int)(i / C4), c = (int)(i - (long long)e * C4) * 4;
+    const int s = in_snd[e], rc = in_rcv[e];
+    const float dx = obj[3 * (size_t)rc] - obj[3 * (size_t)s], dy = obj[3 * (size_t)rc + 1] - obj[3 * (size_t)s + 1];
+    float v[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int k = c + j;
+      v[j] = k < kDE ? relu_f(fmaf(dy, __ldg(W0 + kDE + k), fmaf(dx, __ldg(W0 + k), __ldg(b0 + k)))) : (k == kDE ? 1.f : 0.f);
+    }
+    *reinterpret_cast<float4*>(X0 + (size_t)e * kDEP + c) = make_float4(v[0], v[1], v[2], v[3]);
+  }
+}
+
+struct RowsTcArgs {
+  int M, nseg;
+  const float* X[2]; int ldx[2]; int K[2];     // row segments: K valid columns each (K[0] % 4 == 0 when nseg == 2)
+  const float* Bhi; const float* Blo;          // packed operands, ks k-steps
+  int ks;                                      // ceil((K[0] + K[1]) / 8)
+  int N;                                       // valid output columns (<= NB)
+  const float* bias;                           // [N] or null (any alignment)
+  const float* rowscale;                       // [M] multiplier of the bias or null
+  const float* addend; int ld_add;             // pre-activation addend or null
+  int act;                                     // 0 none, 1 relu, 2 tanh
+  const float* mulsrc; int ld_mul; int mulmode;   // 1: *= [mulsrc > 0]   2: *= (1 - mulsrc^2)
+  float* Y; int ldy;                           // columns N..ldy-1 are written as 0 (ones_col: 1)
+  int accumulate; float post_scale;
+  uint32_t drop_thresh, drop_seed; float drop_inv_keep; int drop_stride;   // element index = row * drop_stride + col
+  int ones_col;                                // >= N: Y[row][ones_col] = 1 (bias pick-up column of a later X^T.dY); -1: none
+  float* poison;                               // written with NaN if an MMA barrier times out
+};
+
+template <int NB>
+constexpr size_t rows_tc_smem(int ks) { return (size_t)2 * ks * 8 * NB * sizeof(float) + 32; }
+
+// 8 consecutive columns [c, c+8) of the concatenated row of this thread -> x[8] (zeros beyond the valid columns)
+__device__ __forceinline__ void rows_load8(const RowsTcArgs& a, const float* p0, const float* p1, bool valid, int c, float4& u,
+                                           float4& v) {
+  const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
+  u = z; v = z;
+  if (!valid) return;
+#pragma unroll
+  for (int g = 0; g < 2; ++g) {
+    float4& dst = g ? v : u;
+    int cc = c + 4 * g;
+    const float* p = p0;
+    int K = a.K[0];
+    if (a.nseg == 2 && cc >= a.K[0]) { cc -= a.K[0]; p = p1; K = a.K[1]; }
+    if (cc + 3 < K) {
+      dst = *reinterpret_cast<const float4*>(p + cc);
+    } else {
+      if (cc < K) dst.x = p[cc];
+      if (cc + 1 < K) dst.y = p[cc + 1];
+      if (cc + 2 < K) dst.z = p[cc + 2];
+    }
+  }
+}
+
+template <int NB>
+__global__ void __launch_bounds__(kThreads, 1) k_rows_tc(RowsTcArgs a) {
+  SPW_DYN_SMEM(smem_raw);
+  const int bfl = a.ks * 8 * NB;                                 // floats per hi / lo operand
+  float* Bhi_s = reinterpret_cast<float*>(smem_raw);
+  float* Blo_s = Bhi_s + bfl;
+  uint64_t* bar = reinterpret_cast<uint64_t*>(Blo_s + bfl);
+  uint32_t* tptr = reinterpret_cast<uint32_t*>(bar + 1);
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int row = 32 * (warp & 3) + lane, half = warp >> 2;
+
+  for (int i = tid; i < bfl / 4; i += kThreads) {                // weights: asynchronous, overlapped with the first row loads
+    cp_async16(Bhi_s + 4 * i, a.Bhi + 4 * i);
+    cp_async16(Blo_s + 4 * i, a.Blo + 4 * i);
+  }
+  cp_async_commit();
+  if (warp == 0) tmem_alloc(tptr, kTmemCols);
+  if (tid == 32) { mbar_init(bar, 1); fence_mbar_init(); }
+  fence_before_sync();
+  __syncthreads();
+  fence_after_sync();
+  const uint32_t tmem_base = *tptr;
+  const uint32_t lane_addr = tmem_base + ((uint32_t)(32 * (warp & 3)) << 16);
+  const uint32_t colAhi = 0, colAlo = 8 * a.ks, colD = kTmemCols - NB;
+  const uint32_t idesc = make_idesc_tf32(128, NB);
+  uint32_t parity = 0;
+  bool failed = false, first = true;
+  const int ntiles = (a.M + kTM - 1) / kTM;
+  const int ks_h0 = (a.ks + 1) >> 1;                             // k-steps [0, ks_h0) belong to half 0, the rest to half 1
+  const int ks_lo = half ? ks_h0 : 0, ks_hi = half ? a.ks : ks_h0;
+
+  for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+    const int r0 = tile * kTM;
+    const bool valid = r0 + row < a.M;
+    const size_t grow = (size_t)(r0 + row);
+    const float* p0 = a.X[0] + grow * a.ldx[0];
+    const float* p1 = a.nseg == 2 ? a.X[1] + grow * a.ldx[1] : nullptr;
+    // ---- A operand: this thread's k-steps of its row, four k-steps (8 x 16-byte loads) in flight
+    for (int k0 = ks_lo; k0 < ks_hi; k0 += 4) {
+      float4 u[4], v[4];
+#pragma unroll
+      for (int j = 0; j < 4; ++j)
+        if (k0 + j < ks_hi) rows_load8(a, p0, p1, valid, 8 * (k0 + j), u[j], v[j]);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        if (k0 + j < ks_hi) {                                    // warp-uniform
+          const float x[8] = {u[j].x, u[j].y, u[j].z, u[j].w, v[j].x, v[j].y, v[j].z, v[j].w};
+          uint32_t h[8], l[8];
+#pragma unroll
+          for (int i = 0; i < 8; ++i) split_tf32(x[i], h[i], l[i]);
+          tmem_st8(lane_addr + colAhi + 8 * (k0 + j), h);
+          tmem_st8(lane_addr + colAlo + 8 * (k0 + j), l);
+        }
+      }
+    }
+    tmem_wait_st();
+    if (first) { cp_async_wait<0>(); fence_async_smem(); first = false; }
+    fence_before_sync();
+    __syncthreads();
+    if (tid == 0) {
+      fence_after_sync();
+      const uint32_t bhi = smem_u32(Bhi_s), blo = smem_u32(Blo_s);
+      const uint32_t d = tmem_base + colD;
+      // correction products first, main products last (the tensor core truncates when it accumulates)
+#pragma unroll 1
+      for (int ks = 0; ks < a.ks; ++ks) {
+        const uint64_t dhi = make_b_desc(bhi + ks * (8 * NB * 4), NB * 16, 128);
+        const uint64_t dlo = make_b_desc(blo + ks * (8 * NB * 4), NB * 16, 128);
+        mma_tf32_ts(d, tmem_base + colAlo + 8 * ks, dhi, idesc, ks > 0 ? 1u : 0u);
+        mma_tf32_ts(d, tmem_base + colAhi + 8 * ks, dlo, idesc, 1u);
+      }
+#pragma unroll 1
+      for (int ks = 0; ks < a.ks; ++ks) {
+        const uint64_t dhi = make_b_desc(bhi + ks * (8 * NB * 4), NB * 16, 128);
+        mma_tf32_ts(d, tmem_base + colAhi + 8 * ks, dhi, idesc, 1u);
+      }
+      mma_commit(bar);
+    }
+    if (!mbar_wait(bar, parity)) failed = true;
+    parity ^= 1u;
+    fence_after_sync();
+    // ---- epilogue: 16-column blocks of this thread's row, alternating between the two halves
+    const float rs = (valid && a.rowscale) ? a.rowscale[grow] : 1.f;
+    for (int blk = half; blk * 16 < NB; blk += 2) {
+      const int col0 = blk * 16;
+      if (col0 >= a.ldy) break;                                  // warp-uniform
+      uint32_t vv[16];
+      tmem_ld16(lane_addr + colD + col0, vv);
+      tmem_wait_ld();
+      if (!valid) continue;
+#pragma unroll
+      for (int g = 0; g < 4; ++g) {
+        const int c = col0 + 4 * g;
+        if (c >= a.ldy) break;
+        float t[4] = {__uint_as_float(vv[4 * g]), __uint_as_float(vv[4 * g + 1]), __uint_as_float(vv[4 * g + 2]),
+                      __uint_as_float(vv[4 * g + 3])};
+        float ad[4] = {0.f, 0.f, 0.f, 0.f}, mu[4] = {0.f, 0.f, 0.f, 0.f}, yo[4] = {0.f, 0.f, 0.f, 0.f};
+        const bool full = c + 3 < a.N;
+        if (full) {
+          if (a.addend) { const float4 q = *reinterpret_cast<const float4*>(a.addend + grow * a.ld_add + c); ad[0] = q.x; ad[1] = q.y; ad[2] = q.z; ad[3] = q.w; }
+          if (a.mulmode) { const float4 q = *reinterpret_cast<const float4*>(a.mulsrc + grow * a.ld_mul + c); mu[0] = q.x; mu[1] = q.y; mu[2] = q.z; mu[3] = q.w; }
+          if (a.accumulate) { const float4 q = *reinterpret_cast<const float4*>(a.Y + grow * a.ldy + c); yo[0] = q.x; yo[1] = q.y; yo[2] = q.z; yo[3] = q.w; }
+        } else {
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            if (c + i < a.N) {
+              if (a.addend) ad[i] = a.addend[grow * a.ld_add + c + i];
+              if (a.mulmode) mu[i] = a.mulsrc[grow * a.ld_mul + c + i];
+              if (a.accumulate) yo[i] = a.Y[grow * a.ldy + c + i];
+            }
+          }
+        }
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const int col = c + i;
+          float r = 0.f;
+          if (col < a.N) {
+            r = t[i];
+            if (a.bias) r = fmaf(rs, __ldg(a.bias + col), r);
+            if (a.addend) r += ad[i];
+            if (a.act == 1) r = relu_f(r);
+            else if (a.act == 2) r = tanhf(r);
+            if (a.mulmode == 1) r = mu[i] > 0.f ? r : 0.f;
+            else if (a.mulmode == 2) r *= (1.f - mu[i] * mu[i]);
+            if (a.drop_thresh) r = dropout_apply(r, a.drop_seed, (uint32_t)(grow * a.drop_stride + col), a.drop_thresh, a.drop_inv_keep);
+            r *= a.post_scale;
+            if (a.accumulate) r += yo[i];
+          } else if (col == a.ones_col) {
+            r = 1.f;
+          }
+          t[i] = r;
+        }
+        if (c + 3 < a.ldy) {
+          *reinterpret_cast<float4*>(a.Y + grow * a.ldy + c) = make_float4(t[0], t[1], t[2], t[3]);
+        } else {
+#pragma unroll
+          for (int i = 0; i < 4; ++i)
+            if (c + i < a.ldy) a.Y[grow * a.ldy + c + i] = t[i];
+        }
+      }
+    }
+    fence_before_sync();
+    __syncthreads();
+  }
+  if (failed && tid == 0) a.poison[0] = __int_as_float(0x7fc00000);
+  if (first) cp_async_wait<0>();
+  fence_before_sync();
+  __syncthreads();
+  if (warp == 0) tmem_dealloc(tmem_base, kTmemCols);
+}
+
+}  // namespace tc
+}  // namespace spw
+#endif  // SPW_EMU

@@ -5,6 +5,7 @@
 #include "spw_edges.cuh"
 #include "spw_kernels.cuh"
 #include "spw_tc.cuh"
+#include "spw_rows_tc.cuh"
 
 #include <stdarg.h>
 #include <stdio.h>
@@ -112,8 +113,21 @@ const PackShape kPackShape[P_COUNT] = {
 
 size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
 
+// ---- tensor-core B operands of the generic rows kernel (tc::k_rows_tc): hi at tcp[id], lo right behind it ----
+enum TcId {
+  T_OM1, T_RM1, T_RM2, T_RM3, T_W1A, T_W1B, T_W1C, T_W3, T_V1A, T_V1BC, T_V2P,
+  T_V2PT, T_V1AT, T_V1BT, T_V1CT, T_W3T, T_W1BT, T_W1CT, T_OM1T, T_COUNT
+};
+struct TcShape { int ks, NB; };   // k-steps of 8 rows, MMA N
+const TcShape kTcShape[T_COUNT] = {
+    {13, 112}, {19, 160}, {19, 160}, {19, 160}, {19, 160}, {13, 160}, {13, 160}, {19, 112}, {13, 112}, {25, 112}, {13, 112},
+    {13, 112}, {13, 112}, {13, 112}, {13, 112}, {13, 160}, {19, 112}, {19, 112}, {13, 112}};
+inline size_t tc_floats(int id) { return (size_t)kTcShape[id].ks * 8 * kTcShape[id].NB; }
+
 struct Layout {
   size_t pack[P_COUNT];
+  size_t tcp[T_COUNT];
+  size_t QV;                     // q.V1a + c1, constant over the steps
   size_t Q1, Q, degf, A, PF, PL, W2hi, W2lo, W2Thi, W2Tlo, ENCT;   // ENCT: 4 x (hi, lo) transposed encoder operands
   size_t P, S, R, H2S, G, U;     // per-step arrays (training: 5 slots; inference: fewer)
   int slotsP, slotsSR, slotsN;   // number of step slots for P / (S,R) / (H2S,G,U)
@@ -135,8 +149,10 @@ Layout make_layout(int64_t n, int64_t E, int training) {
   L.W2Thi = take(24320);
   L.W2Tlo = take(24320);
   L.ENCT = take((size_t)8 * 24320);
+  for (int i = 0; i < T_COUNT; ++i) L.tcp[i] = take(2 * tc_floats(i));
   L.Q1 = take(n * kDP);
   L.Q = take(n * kDP);
+  L.QV = take(n * kDP);
   L.degf = take(n);
   L.A = take((size_t)E * kDEP + 8);
   L.PF = take(nt * kDEP);
@@ -218,6 +234,8 @@ struct LinOpt {
   const float* bias = nullptr; const float* rowscale = nullptr; const float* addend = nullptr; int ld_add = 0;
   int act = 0; const float* mulsrc = nullptr; int ld_mul = 0; int mulmode = 0; int accumulate = 0;
   float post_scale = 1.f; uint32_t drop_thresh = 0; uint32_t drop_seed = 0; float drop_inv_keep = 1.f;
+  int drop_stride = 128;         // dropout element index = row * drop_stride + column
+  int ones_col = -1;             // tensor-core kernel only: Y[row][ones_col] = 1
 };
 
 // Y[M][ldy] (N valid columns) from up to 3 (X, W) segments; wide = 150-column output (CN = 5)
@@ -260,6 +278,54 @@ void launch_linear(cudaStream_t st, int M, int N, bool wide, int nseg, const Lin
     SPW_LIN_CASE(32)
   }
 #undef SPW_LIN_CASE
+}
+
+// ---- one fused linear layer on rows: tensor cores (tc::k_rows_tc) in the GPU build, FFMA (k_linear) in the emulator ----
+struct RowsSeg { const float* X; int ldx; int K; };
+struct LinId { int tc; int pk0, pk1; };     // B operand of the tensor-core kernel; packed FFMA matrices of the segments
+
+#if SPW_USE_TC
+void launch_rows_tc_raw(cudaStream_t st, const float* Bhi, const float* Blo, int NB, int M, int N, int nseg, const RowsSeg* sg,
+                        float* Y, int ldy, const LinOpt& o) {
+  if (M <= 0) return;
+  tc::RowsTcArgs a;
+  memset(&a, 0, sizeof(a));
+  a.M = M; a.nseg = nseg; a.N = N;
+  int ktot = 0;
+  for (int s = 0; s < nseg; ++s) { a.X[s] = sg[s].X; a.ldx[s] = sg[s].ldx; a.K[s] = sg[s].K; ktot += sg[s].K; }
+  a.ks = (ktot + 7) / 8;
+  a.Bhi = Bhi; a.Blo = Blo;
+  a.bias = o.bias; a.rowscale = o.rowscale; a.addend = o.addend; a.ld_add = o.ld_add; a.act = o.act;
+  a.mulsrc = o.mulsrc; a.ld_mul = o.ld_mul; a.mulmode = o.mulmode; a.Y = Y; a.ldy = ldy; a.accumulate = o.accumulate;
+  a.post_scale = o.post_scale; a.drop_thresh = o.drop_thresh; a.drop_seed = o.drop_seed; a.drop_inv_keep = o.drop_inv_keep;
+  a.drop_stride = o.drop_stride; a.ones_col = o.ones_col; a.poison = Y;
+  const int ntiles = (M + kTM - 1) / kTM;
+  const int grid = ntiles < num_sms() ? ntiles : num_sms();
+  if (NB == 160) {
+    const size_t smem = tc::rows_tc_smem<160>(a.ks);
+    auto kern = tc::k_rows_tc<160>; set_smem(kern, tc::rows_tc_smem<160>(19));
+    SPW_KLAUNCH("k_rows_tc<160>", kern, dim3(grid), dim3(kThreads), smem, st, a);
+  } else {
+    const size_t smem = tc::rows_tc_smem<112>(a.ks);
+    auto kern = tc::k_rows_tc<112>; set_smem(kern, tc::rows_tc_smem<112>(25));
+    SPW_KLAUNCH("k_rows_tc<112>", kern, dim3(grid), dim3(kThreads), smem, st, a);
+  }
+}
+void launch_rows_tc(cudaStream_t st, float* ws, const Layout& L, int id, int M, int N, int nseg, const RowsSeg* sg, float* Y,
+                    int ldy, const LinOpt& o) {
+  launch_rows_tc_raw(st, ws + L.tcp[id], ws + L.tcp[id] + tc_floats(id), kTcShape[id].NB, M, N, nseg, sg, Y, ldy, o);
+}
+#endif
+
+void run_linear(cudaStream_t st, float* ws, const Layout& L, LinId id, int M, int N, int nseg, const RowsSeg* sg, float* Y,
+                int ldy, const LinOpt& o) {
+#if SPW_USE_TC
+  launch_rows_tc(st, ws, L, id.tc, M, N, nseg, sg, Y, ldy, o);
+#else
+  LinSeg s[2];
+  for (int i = 0; i < nseg; ++i) s[i] = seg(sg[i].X, sg[i].ldx, sg[i].K, ws + L.pack[i == 0 ? id.pk0 : id.pk1]);
+  launch_linear(st, M, N, N > 128, nseg, s, Y, ldy, o);
+#endif
 }
 
 // dW[Kin][N] (+ bias row) = X^T dY over M rows, reduced in fixed order into the Keras-layout gradient
@@ -338,6 +404,42 @@ void pack_weights(cudaStream_t st, const SpwParams* w, float* ws, const Layout& 
   SPW_KLAUNCH("k_pack_weights", k_pack_weights, dim3(24, n), dim3(256), 0, st, pa);
 }
 
+#if SPW_USE_TC
+void pack_tc(cudaStream_t st, const SpwParams* w, float* ws, const Layout& L, bool with_transposes) {
+  tc::PackTcArgs pa;
+  memset(&pa, 0, sizeof(pa));
+  int n = 0;
+  auto add = [&](int id, const float* src, int ld, int row0, int col0, int K, int N, int transpose) {
+    tc::PackTcDesc& d = pa.d[n++];
+    d.src = src; d.ld = ld; d.row0 = row0; d.col0 = col0; d.K = K; d.N = N; d.transpose = transpose;
+    d.hi = ws + L.tcp[id]; d.lo = d.hi + tc_floats(id); d.NB = kTcShape[id].NB; d.k_off = 0; d.k_lim = 8 * kTcShape[id].ks;
+  };
+  add(T_OM1, w->om_w[1], 100, 0, 0, 100, 100, 0);
+  add(T_RM1, w->rm_w[1], 150, 0, 0, 150, 150, 0);
+  add(T_RM2, w->rm_w[2], 150, 0, 0, 150, 150, 0);
+  add(T_RM3, w->rm_w[3], 150, 0, 0, 150, 150, 0);
+  add(T_W1A, w->rmp_w[0], 150, 0, 0, 150, 150, 0);      // Networks.py:86 concat order: [rel_enc | sender | receiver]
+  add(T_W1B, w->rmp_w[0], 150, 150, 0, 100, 150, 0);
+  add(T_W1C, w->rmp_w[0], 150, 250, 0, 100, 150, 0);
+  add(T_W3, w->rmp_w[2], 100, 0, 0, 150, 100, 0);
+  add(T_V1A, w->omp_w[0], 100, 0, 0, 100, 100, 0);      // Networks.py:89 concat order: [obj_enc | effect | prop]
+  add(T_V1BC, w->omp_w[0], 100, 100, 0, 200, 100, 0);   // rows [V1b ; V1c] are consecutive: one K = 200 operand for [g | p]
+  add(T_V2P, w->omp_w[1], 101, 0, 1, 100, 100, 0);      // channels 1..100 (Networks.py:80)
+  if (with_transposes) {   // transposed: dst[k][n] = src[row0 + n][col0 + k];  K = #cols of the source block, N = #rows
+    add(T_V2PT, w->omp_w[1], 101, 0, 1, 100, 100, 1);
+    add(T_V1AT, w->omp_w[0], 100, 0, 0, 100, 100, 1);
+    add(T_V1BT, w->omp_w[0], 100, 100, 0, 100, 100, 1);
+    add(T_V1CT, w->omp_w[0], 100, 200, 0, 100, 100, 1);
+    add(T_W3T, w->rmp_w[2], 100, 0, 0, 100, 150, 1);
+    add(T_W1BT, w->rmp_w[0], 150, 150, 0, 150, 100, 1);
+    add(T_W1CT, w->rmp_w[0], 150, 250, 0, 150, 100, 1);
+    add(T_OM1T, w->om_w[1], 100, 0, 0, 100, 100, 1);
+  }
+  pa.n = n;
+  SPW_KLAUNCH("k_pack_tc", tc::k_pack_tc, dim3(16, n), dim3(256), 0, st, pa);
+}
+#endif
+
 size_t edge_fwd_smem() { return (size_t)(2 * (kTME * kDEP + 8) + 2 * kKT * kLdwE + 2 * kTME) * sizeof(float); }
 size_t edge_bwd_smem() { return (size_t)(2 * (kTM * kDEP + 8) + 2 * kKT * kLdwE + kTM + 5 * kTM) * sizeof(float); }
 size_t edge_encb_smem() { return (size_t)(5 * (kTMB * kDEP + 8) + 2 * kKT * kLdwE + 2 * kTMB) * sizeof(float); }
@@ -406,6 +508,41 @@ int spw_tc_selftest(const float* A, const float* W, int K, int N, float* D, floa
 #endif
 }
 
+// generic tensor-core linear layer (tc::k_rows_tc), exposed for unit tests:
+//   Y[M][ldy] = post(act([X0 | X1].W + rowscale*bias + addend)), W Keras layout [K0 + K1][N] (ld = N); NB = 112 or 160;
+//   scratch: 2 * ceil((K0 + K1) / 8) * 8 * NB floats
+int spw_tc_linear(int M, const float* X0, int ldx0, int K0, const float* X1, int ldx1, int K1, const float* W, int N, int NB,
+                  const float* bias, const float* rowscale, const float* addend, int ld_add, int act, const float* mulsrc,
+                  int ld_mul, int mulmode, float* Y, int ldy, int accumulate, float post_scale, int ones_col, float* scratch,
+                  void* stream) {
+#if !SPW_USE_TC
+  (void)M; (void)X0; (void)ldx0; (void)K0; (void)X1; (void)ldx1; (void)K1; (void)W; (void)N; (void)NB; (void)bias; (void)rowscale;
+  (void)addend; (void)ld_add; (void)act; (void)mulsrc; (void)ld_mul; (void)mulmode; (void)Y; (void)ldy; (void)accumulate;
+  (void)post_scale; (void)ones_col; (void)scratch; (void)stream;
+  return fail(SPW_ERR_UNSUPPORTED, "spw_tc_linear: tensor-core path is not emulated");
+#else
+  if (M < 0 || !X0 || !W || !Y || !scratch || K0 <= 0 || K1 < 0 || N <= 0) return fail(SPW_ERR_BAD_ARG, "spw_tc_linear: bad argument");
+  if (NB != 112 && NB != 160) return fail(SPW_ERR_UNSUPPORTED, "spw_tc_linear: NB must be 112 or 160");
+  const int ks = (K0 + K1 + 7) / 8;
+  if (N > NB || 16 * ks + NB > 512) return fail(SPW_ERR_UNSUPPORTED, "spw_tc_linear: K = %d, N = %d do not fit tensor memory", K0 + K1, N);
+  if ((ldx0 & 3) || (K1 && ((ldx1 & 3) || (K0 & 3))) || (ldy & 3) || (addend && (ld_add & 3)) || (mulmode && (ld_mul & 3)))
+    return fail(SPW_ERR_BAD_ARG, "spw_tc_linear: leading dimensions must be multiples of 4");
+  cudaStream_t st = (cudaStream_t)stream;
+  tc::PackTcArgs pa;
+  memset(&pa, 0, sizeof(pa));
+  tc::PackTcDesc& d = pa.d[0];
+  d.src = W; d.ld = N; d.K = K0 + K1; d.N = N; d.hi = scratch; d.lo = scratch + (size_t)ks * 8 * NB; d.NB = NB; d.k_lim = 8 * ks;
+  pa.n = 1;
+  SPW_KLAUNCH("k_pack_tc", tc::k_pack_tc, dim3(16, 1), dim3(256), 0, st, pa);
+  RowsSeg sg[2] = {{X0, ldx0, K0}, {X1, ldx1, K1}};
+  LinOpt o;
+  o.bias = bias; o.rowscale = rowscale; o.addend = addend; o.ld_add = ld_add; o.act = act; o.mulsrc = mulsrc; o.ld_mul = ld_mul;
+  o.mulmode = mulmode; o.accumulate = accumulate; o.post_scale = post_scale; o.ones_col = ones_col;
+  launch_rows_tc_raw(st, d.hi, d.lo, NB, M, N, K1 > 0 ? 2 : 1, sg, Y, ldy, o);
+  return check_launch("spw_tc_linear");
+#endif
+}
+
 int spw_edges_count(const double* pos_xy, const int32_t* node_off, int32_t n_towers, int32_t n_nodes,
                     int32_t max_nodes_per_tower, double thr, int fully_connected, int32_t* deg_out, int32_t* deg_in,
                     int32_t* edge_off, void* stream) {
@@ -469,7 +606,11 @@ int spw_forward(const SpwParams* w, const SpwGraph* g, const float* obj, float* 
   auto PK = [&](int id) { return ws + L.pack[id]; };
   const size_t nP = (size_t)n * kDP, nE = (size_t)n * kDEP;
 
+#if SPW_USE_TC
+  pack_tc(st, w, ws, L, training != 0);
+#else
   pack_weights(st, w, ws, L, training != 0);
+#endif
 #if SPW_USE_TC
   SPW_KLAUNCH("k_pack_umma", tc::k_pack_umma, dim3(48), dim3(256), 0, st, (const float*)w->rmp_w[1], 150, 0, 0, 150, 150, 0, (const float*)w->rmp_b[1], ws + L.W2hi, ws + L.W2lo);
   if (training) {   // B operands of the data gradients: [N = k_in][K = n_out] = W[k_in][n_out]
@@ -485,14 +626,40 @@ int spw_forward(const SpwParams* w, const SpwGraph* g, const float* obj, float* 
   // object encoder (Networks.py:47,76): q1 = relu(om0([y,w])), q = relu(om1(q1))
   SPW_KLAUNCH("k_obj_enc0", k_obj_enc0, dim3(grid_for((int64_t)n * kDP, 256)), dim3(256), 0, st, obj, n, w->om_w[0], w->om_b[0], ws + L.Q1);
   {
-    LinSeg s = seg(ws + L.Q1, kDP, kDP, PK(P_OM1));
+    RowsSeg s = {ws + L.Q1, kDP, kDP};
     LinOpt o; o.bias = w->om_b[1]; o.act = 1;
     o.drop_thresh = drop_thresh; o.drop_seed = seed_q; o.drop_inv_keep = inv_keep;      // Networks.py:78
-    launch_linear(st, n, kDP, false, 1, &s, ws + L.Q, kDP, o);
+    run_linear(st, ws, L, {T_OM1, P_OM1, 0}, n, kDP, 1, &s, ws + L.Q, kDP, o);
+  }
+  {   // the object-encoding part of omp layer 0 is the same in all five steps: qv = q.V1a + c1   (Networks.py:89)
+    RowsSeg s = {ws + L.Q, kDP, kDP};
+    LinOpt o; o.bias = w->omp_b[0];
+    run_linear(st, ws, L, {T_V1A, P_V1A, 0}, n, kDP, 1, &s, ws + L.QV, kDP, o);
   }
   // relation encoder + A_e (Networks.py:46,75 and the c_e part of :86-87)
   const int etiles = (E + kTME - 1) / kTME;
   const int egrid = etiles < 2 * num_sms() ? etiles : 2 * num_sms();
+#if SPW_USE_TC
+  if (E > 0) {   // layer by layer on the tensor cores; training keeps X0, X1, X2, C for the backward pass, inference runs in place
+    float* X0 = training ? ws + L.EX0 : ws + L.A;
+    float* X1 = training ? ws + L.EX1 : ws + L.A;
+    float* X2 = training ? ws + L.EX2 : ws + L.A;
+    float* C = training ? ws + L.EC : ws + L.A;
+    SPW_KLAUNCH("k_edge_enc0", tc::k_edge_enc0, dim3(grid_for((int64_t)E * (kDEP / 4), 256)), dim3(256), 0, st, E, g->in_snd, g->in_rcv,
+                obj, (const float*)w->rm_w[0], (const float*)w->rm_b[0], X0);
+    LinOpt o; o.act = 1; o.ones_col = kDE;
+    RowsSeg s0 = {X0, kDEP, kDE}, s1 = {X1, kDEP, kDE}, s2 = {X2, kDEP, kDE}, s3 = {C, kDEP, kDE};
+    o.bias = w->rm_b[1];
+    launch_rows_tc(st, ws, L, T_RM1, E, kDE, 1, &s0, X1, kDEP, o);
+    o.bias = w->rm_b[2];
+    launch_rows_tc(st, ws, L, T_RM2, E, kDE, 1, &s1, X2, kDEP, o);
+    o.bias = w->rm_b[3];
+    o.drop_thresh = drop_thresh; o.drop_seed = seed_c; o.drop_inv_keep = inv_keep; o.drop_stride = 160;   // Networks.py:77
+    launch_rows_tc(st, ws, L, T_RM3, E, kDE, 1, &s2, C, kDEP, o);
+    LinOpt oa; oa.bias = w->rmp_b[0];
+    launch_rows_tc(st, ws, L, T_W1A, E, kDE, 1, &s3, ws + L.A, kDEP, oa);
+  }
+#else
   if (E > 0) {
     EdgeEncArgs a;
     a.E = E; a.in_snd = g->in_snd; a.in_rcv = g->in_rcv; a.obj = obj; a.W0 = w->rm_w[0]; a.b0 = w->rm_b[0];
@@ -504,6 +671,7 @@ int spw_forward(const SpwParams* w, const SpwGraph* g, const float* obj, float* 
     set_smem(k_edge_encode, edge_fwd_smem());
     SPW_KLAUNCH("k_edge_encode", k_edge_encode, dim3(egrid), dim3(kThreads), edge_fwd_smem(), st, a);
   }
+#endif
   // nodes without in-edges keep an all-zero aggregate
   cudaMemsetAsync(ws + L.H2S, 0, (size_t)L.slotsN * nE * sizeof(float), st);
   cudaMemsetAsync(ws + L.P, 0, nP * sizeof(float), st);          // propagation input is zeros (main.py:68)
@@ -519,11 +687,10 @@ int spw_forward(const SpwParams* w, const SpwGraph* g, const float* obj, float* 
     float* G = ws + L.G + (size_t)(training ? l : 0) * nP;
     float* U = ws + L.U + (size_t)(training ? l : 0) * nP;
     if (l > 0) {   // S = P.W1b, R = P.W1c   (sender / receiver parts of rmp layer 0, Networks.py:84-87)
-      LinSeg s1 = seg(Pin, kDP, kDP, PK(P_W1B));
-      LinSeg s2 = seg(Pin, kDP, kDP, PK(P_W1C));
+      RowsSeg s = {Pin, kDP, kDP};
       LinOpt o;
-      launch_linear(st, n, kDE, true, 1, &s1, S, kDEP, o);
-      launch_linear(st, n, kDE, true, 1, &s2, R, kDEP, o);
+      run_linear(st, ws, L, {T_W1B, P_W1B, 0}, n, kDE, 1, &s, S, kDEP, o);
+      run_linear(st, ws, L, {T_W1C, P_W1C, 0}, n, kDE, 1, &s, R, kDEP, o);
     }
     if (E > 0) {
       if (!training && l > 0) cudaMemsetAsync(H2S, 0, nE * sizeof(float), st);
@@ -553,19 +720,19 @@ int spw_forward(const SpwParams* w, const SpwGraph* g, const float* obj, float* 
 #endif
     }
     {   // g = tanh(W3.sum h2 + deg.b3)   (Networks.py:87-88)
-      LinSeg s = seg(H2S, kDEP, kDE, PK(P_W3));
+      RowsSeg s = {H2S, kDEP, kDE};
       LinOpt o; o.bias = w->rmp_b[2]; o.rowscale = ws + L.degf; o.act = 2;
-      launch_linear(st, n, kDP, false, 1, &s, G, kDP, o);
+      run_linear(st, ws, L, {T_W3, P_W3, 0}, n, kDP, 1, &s, G, kDP, o);
     }
-    {   // u = relu(V1.[q, g, p] + c1)    (Networks.py:89-90, hidden layer of omp)
-      LinSeg s[3] = {seg(ws + L.Q, kDP, kDP, PK(P_V1A)), seg(G, kDP, kDP, PK(P_V1B)), seg(Pin, kDP, kDP, PK(P_V1C))};
-      LinOpt o; o.bias = w->omp_b[0]; o.act = 1;
-      launch_linear(st, n, kDP, false, l == 0 ? 2 : 3, s, U, kDP, o);   // p^0 = 0: skip its segment
+    {   // u = relu(V1.[q, g, p] + c1) = relu(qv + [g | p].[V1b ; V1c])    (Networks.py:89-90, hidden layer of omp)
+      RowsSeg s[2] = {{G, kDP, kDP}, {Pin, kDP, kDP}};
+      LinOpt o; o.addend = ws + L.QV; o.ld_add = kDP; o.act = 1;
+      run_linear(st, ws, L, {T_V1BC, P_V1B, P_V1C}, n, kDP, l == 0 ? 1 : 2, s, U, kDP, o);   // p^0 = 0: skip its segment
     }
     if (l < SPW_N_STEPS - 1) {   // p = tanh(z[1:] + p)   (Networks.py:80,91)
-      LinSeg s = seg(U, kDP, kDP, PK(P_V2P));
+      RowsSeg s = {U, kDP, kDP};
       LinOpt o; o.bias = w->omp_b[1] + 1; o.addend = Pin; o.ld_add = kDP; o.act = 2;
-      launch_linear(st, n, kDP, false, 1, &s, Pout, kDP, o);
+      run_linear(st, ws, L, {T_V2P, P_V2P, 0}, n, kDP, 1, &s, Pout, kDP, o);
     } else {                     // head: channel 0 of the last z (Networks.py:93-96)
       SPW_KLAUNCH("k_logit", k_logit, dim3(grid_for(n, 8)), dim3(256), 0, st, U, n, w->omp_w[1], w->omp_b[1], logits, probs);
     }
@@ -628,29 +795,29 @@ int spw_backward(const SpwParams* w, const SpwGraph* g, const float* obj, const 
     float* dG = ws + L.dG + (size_t)l * nP;
     const float* Tl = l < 4 ? ws + L.T + (size_t)l * nP : nullptr;   // d(pre-tanh of p^{l+1})
     if (l < SPW_N_STEPS - 1) {   // dUpre = (T.V2p^T) * relu'(u)
-      LinSeg s = seg(Tl, kDP, kDP, PK(P_V2PT));
+      RowsSeg s = {Tl, kDP, kDP};
       LinOpt o; o.mulsrc = U; o.ld_mul = kDP; o.mulmode = 1;
-      launch_linear(st, n, kDP, false, 1, &s, dU, kDP, o);
+      run_linear(st, ws, L, {T_V2PT, P_V2PT, 0}, n, kDP, 1, &s, dU, kDP, o);
     }
     {   // dq_pre += (dUpre.V1a^T) * relu'(q)
-      LinSeg s = seg(dU, kDP, kDP, PK(P_V1AT));
+      RowsSeg s = {dU, kDP, kDP};
       LinOpt o; o.mulsrc = ws + L.Q; o.ld_mul = kDP; o.mulmode = 1; o.accumulate = l < SPW_N_STEPS - 1; o.post_scale = inv_keep;
-      launch_linear(st, n, kDP, false, 1, &s, ws + L.dQ, kDP, o);
+      run_linear(st, ws, L, {T_V1AT, P_V1AT, 0}, n, kDP, 1, &s, ws + L.dQ, kDP, o);
     }
     {   // dg_pre = (dUpre.V1b^T) * (1 - g^2)
-      LinSeg s = seg(dU, kDP, kDP, PK(P_V1BT));
+      RowsSeg s = {dU, kDP, kDP};
       LinOpt o; o.mulsrc = G; o.ld_mul = kDP; o.mulmode = 2;
-      launch_linear(st, n, kDP, false, 1, &s, dG, kDP, o);
+      run_linear(st, ws, L, {T_V1BT, P_V1BT, 0}, n, kDP, 1, &s, dG, kDP, o);
     }
     if (l > 0) {   // DP = dUpre.V1c^T (+ residual T)
-      LinSeg s = seg(dU, kDP, kDP, PK(P_V1CT));
+      RowsSeg s = {dU, kDP, kDP};
       LinOpt o; o.addend = Tl; o.ld_add = kDP;
-      launch_linear(st, n, kDP, false, 1, &s, ws + L.DP, kDP, o);
+      run_linear(st, ws, L, {T_V1CT, P_V1CT, 0}, n, kDP, 1, &s, ws + L.DP, kDP, o);
     }
     {   // d(sum h2) = dg_pre.W3^T
-      LinSeg s = seg(dG, kDP, kDP, PK(P_W3T));
+      RowsSeg s = {dG, kDP, kDP};
       LinOpt o;
-      launch_linear(st, n, kDE, true, 1, &s, ws + L.dH2S, kDEP, o);
+      run_linear(st, ws, L, {T_W3T, P_W3T, 0}, n, kDE, 1, &s, ws + L.dH2S, kDEP, o);
     }
     if (E > 0) {
       EdgeStepBwdArgs a;
@@ -693,9 +860,12 @@ int spw_backward(const SpwParams* w, const SpwGraph* g, const float* obj, const 
         cudaMemsetAsync(dR, 0, nE * sizeof(float), st);
       }
       // T^{l} = (dS.W1b^T + dR.W1c^T + DP) * (1 - (p^l)^2)       (p^l = Pin of this step)
-      LinSeg s[2] = {seg(dS, kDEP, kDE, PK(P_W1BT)), seg(dR, kDEP, kDE, PK(P_W1CT))};
+      //   two K = 150 products: the first one is added into DP, the second one finishes T
+      RowsSeg s1 = {dS, kDEP, kDE}, s2 = {dR, kDEP, kDE};
+      LinOpt o1; o1.accumulate = 1;
+      run_linear(st, ws, L, {T_W1BT, P_W1BT, 0}, n, kDP, 1, &s1, ws + L.DP, kDP, o1);
       LinOpt o; o.addend = ws + L.DP; o.ld_add = kDP; o.mulsrc = Pin; o.ld_mul = kDP; o.mulmode = 2;
-      launch_linear(st, n, kDP, false, 2, s, ws + L.T + (size_t)(l - 1) * nP, kDP, o);
+      run_linear(st, ws, L, {T_W1CT, P_W1CT, 0}, n, kDP, 1, &s2, ws + L.T + (size_t)(l - 1) * nP, kDP, o);
     }
   }
 
@@ -716,9 +886,9 @@ int spw_backward(const SpwParams* w, const SpwGraph* g, const float* obj, const 
   // object encoder
   launch_wgrad(st, n, ws + L.Q1, kDP, kDP, 0, nullptr, 0, ws + L.dQ, kDP, kDP, partN, {grads->om_w[1], 100, 0, 0, grads->om_b[1], 0});
   {
-    LinSeg s = seg(ws + L.dQ, kDP, kDP, PK(P_OM1T));
+    RowsSeg s = {ws + L.dQ, kDP, kDP};
     LinOpt o; o.mulsrc = ws + L.Q1; o.ld_mul = kDP; o.mulmode = 1;
-    launch_linear(st, n, kDP, false, 1, &s, ws + L.dQ1, kDP, o);
+    run_linear(st, ws, L, {T_OM1T, P_OM1T, 0}, n, kDP, 1, &s, ws + L.dQ1, kDP, o);
   }
   launch_wgrad(st, n, obj + 1, 3, 2, 0, nullptr, 0, ws + L.dQ1, kDP, kDP, partN, {grads->om_w[0], 100, 0, 0, grads->om_b[0], 0});
 

@@ -48,7 +48,7 @@ def test_host_side_argument_checks(built_lib):
     assert api.dll.spw_edges_count(None, None, -1, 0, 0, 170.0, 0, None, None, None, None) == -1
     p = SpwParams()                                                       # all-null tensors
     g = SpwGraph()
-    assert api.dll.spw_forward(ctypes.byref(p), ctypes.byref(g), None, None, None, None, 0, 0, None) == -1
+    assert api.dll.spw_forward(ctypes.byref(p), ctypes.byref(g), None, None, None, None, 0, 0, 0.0, 0, None) == -1
     assert b'tensor 0' in api.dll.spw_last_error()
 
 
