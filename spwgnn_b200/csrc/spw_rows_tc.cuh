@@ -108,6 +108,23 @@ __device__ __forceinline__ void rows_load8(const RowsTcArgs& a, const float* p0,
   }
 }
 
+// 16 consecutive floats row[col0 .. col0+16) -> o (zeros at columns >= lim); 16-byte loads where the pointer allows it
+__device__ __forceinline__ void rows_load16(const float* __restrict__ rowp, int col0, int lim, bool vec_ok, float (&o)[16]) {
+#pragma unroll
+  for (int g = 0; g < 4; ++g) {
+    const int c = col0 + 4 * g;
+    if (vec_ok && c + 3 < lim) {
+      const float4 q = *reinterpret_cast<const float4*>(rowp + c);
+      o[4 * g] = q.x; o[4 * g + 1] = q.y; o[4 * g + 2] = q.z; o[4 * g + 3] = q.w;
+    } else {
+#pragma unroll
+      for (int i = 0; i < 4; ++i) o[4 * g + i] = c + i < lim ? rowp[c + i] : 0.f;
+    }
+  }
+}
+
+constexpr int kRowsKpt = 13;     // k-steps per thread at most (ks <= 25, two threads per row)
+
 template <int NB>
 __global__ void __launch_bounds__(kThreads, 1) k_rows_tc(RowsTcArgs a) {
   SPW_DYN_SMEM(smem_raw);
@@ -138,29 +155,34 @@ __global__ void __launch_bounds__(kThreads, 1) k_rows_tc(RowsTcArgs a) {
   const int ntiles = (a.M + kTM - 1) / kTM;
   const int ks_h0 = (a.ks + 1) >> 1;                             // k-steps [0, ks_h0) belong to half 0, the rest to half 1
   const int ks_lo = half ? ks_h0 : 0, ks_hi = half ? a.ks : ks_h0;
+  const bool bias_vec = (reinterpret_cast<uintptr_t>(a.bias) & 15) == 0;
+
+  // this thread's k-steps of its row of a tile -> registers (all loads in flight at once)
+  float4 pu[kRowsKpt], pv[kRowsKpt];
+  auto load_tile = [&](int tile) {
+    const size_t gr = (size_t)tile * kTM + row;
+    const bool ok = gr < (size_t)a.M;
+    const float* p0 = a.X[0] + gr * a.ldx[0];
+    const float* p1 = a.nseg == 2 ? a.X[1] + gr * a.ldx[1] : nullptr;
+#pragma unroll
+    for (int j = 0; j < kRowsKpt; ++j)
+      if (ks_lo + j < ks_hi) rows_load8(a, p0, p1, ok, 8 * (ks_lo + j), pu[j], pv[j]);
+  };
+  if ((int)blockIdx.x < ntiles) load_tile(blockIdx.x);
 
   for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
-    const int r0 = tile * kTM;
-    const bool valid = r0 + row < a.M;
-    const size_t grow = (size_t)(r0 + row);
-    const float* p0 = a.X[0] + grow * a.ldx[0];
-    const float* p1 = a.nseg == 2 ? a.X[1] + grow * a.ldx[1] : nullptr;
-    // ---- A operand: this thread's k-steps of its row, four k-steps (8 x 16-byte loads) in flight
-    for (int k0 = ks_lo; k0 < ks_hi; k0 += 4) {
-      float4 u[4], v[4];
+    const size_t grow = (size_t)tile * kTM + row;
+    const bool valid = grow < (size_t)a.M;
+    // ---- A operand: split into tf32 hi / lo, store to tensor memory
 #pragma unroll
-      for (int j = 0; j < 4; ++j)
-        if (k0 + j < ks_hi) rows_load8(a, p0, p1, valid, 8 * (k0 + j), u[j], v[j]);
+    for (int j = 0; j < kRowsKpt; ++j) {
+      if (ks_lo + j < ks_hi) {                                   // warp-uniform
+        const float x[8] = {pu[j].x, pu[j].y, pu[j].z, pu[j].w, pv[j].x, pv[j].y, pv[j].z, pv[j].w};
+        uint32_t h[8], l[8];
 #pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        if (k0 + j < ks_hi) {                                    // warp-uniform
-          const float x[8] = {u[j].x, u[j].y, u[j].z, u[j].w, v[j].x, v[j].y, v[j].z, v[j].w};
-          uint32_t h[8], l[8];
-#pragma unroll
-          for (int i = 0; i < 8; ++i) split_tf32(x[i], h[i], l[i]);
-          tmem_st8(lane_addr + colAhi + 8 * (k0 + j), h);
-          tmem_st8(lane_addr + colAlo + 8 * (k0 + j), l);
-        }
+        for (int i = 0; i < 8; ++i) split_tf32(x[i], h[i], l[i]);
+        tmem_st8(lane_addr + colAhi + 8 * (ks_lo + j), h);
+        tmem_st8(lane_addr + colAlo + 8 * (ks_lo + j), l);
       }
     }
     tmem_wait_st();
@@ -186,6 +208,8 @@ __global__ void __launch_bounds__(kThreads, 1) k_rows_tc(RowsTcArgs a) {
       }
       mma_commit(bar);
     }
+    // rows of this CTA's next tile: in flight while the MMAs run and the epilogue is written
+    if (tile + (int)gridDim.x < ntiles) load_tile(tile + gridDim.x);
     if (!mbar_wait(bar, parity)) failed = true;
     parity ^= 1u;
     fence_after_sync();
@@ -196,56 +220,67 @@ __global__ void __launch_bounds__(kThreads, 1) k_rows_tc(RowsTcArgs a) {
       if (col0 >= a.ldy) break;                                  // warp-uniform
       uint32_t vv[16];
       tmem_ld16(lane_addr + colD + col0, vv);
+      float r[16], m[16];
+      if (valid && a.bias) rows_load16(a.bias, col0, a.N, bias_vec, m);
       tmem_wait_ld();
       if (!valid) continue;
 #pragma unroll
-      for (int g = 0; g < 4; ++g) {
-        const int c = col0 + 4 * g;
-        if (c >= a.ldy) break;
-        float t[4] = {__uint_as_float(vv[4 * g]), __uint_as_float(vv[4 * g + 1]), __uint_as_float(vv[4 * g + 2]),
-                      __uint_as_float(vv[4 * g + 3])};
-        float ad[4] = {0.f, 0.f, 0.f, 0.f}, mu[4] = {0.f, 0.f, 0.f, 0.f}, yo[4] = {0.f, 0.f, 0.f, 0.f};
-        const bool full = c + 3 < a.N;
-        if (full) {
-          if (a.addend) { const float4 q = *reinterpret_cast<const float4*>(a.addend + grow * a.ld_add + c); ad[0] = q.x; ad[1] = q.y; ad[2] = q.z; ad[3] = q.w; }
-          if (a.mulmode) { const float4 q = *reinterpret_cast<const float4*>(a.mulsrc + grow * a.ld_mul + c); mu[0] = q.x; mu[1] = q.y; mu[2] = q.z; mu[3] = q.w; }
-          if (a.accumulate) { const float4 q = *reinterpret_cast<const float4*>(a.Y + grow * a.ldy + c); yo[0] = q.x; yo[1] = q.y; yo[2] = q.z; yo[3] = q.w; }
+      for (int i = 0; i < 16; ++i) r[i] = __uint_as_float(vv[i]);
+      if (a.bias) {
+#pragma unroll
+        for (int i = 0; i < 16; ++i) r[i] = fmaf(rs, m[i], r[i]);
+      }
+      if (a.addend) {
+        rows_load16(a.addend + grow * a.ld_add, col0, a.N, true, m);
+#pragma unroll
+        for (int i = 0; i < 16; ++i) r[i] += m[i];
+      }
+      if (a.act == 1) {
+#pragma unroll
+        for (int i = 0; i < 16; ++i) r[i] = relu_f(r[i]);
+      } else if (a.act == 2) {
+#pragma unroll
+        for (int i = 0; i < 16; ++i) r[i] = tanhf(r[i]);
+      }
+      if (a.mulmode) {
+        rows_load16(a.mulsrc + grow * a.ld_mul, col0, a.N, true, m);
+        if (a.mulmode == 1) {
+#pragma unroll
+          for (int i = 0; i < 16; ++i) r[i] = m[i] > 0.f ? r[i] : 0.f;
         } else {
 #pragma unroll
-          for (int i = 0; i < 4; ++i) {
-            if (c + i < a.N) {
-              if (a.addend) ad[i] = a.addend[grow * a.ld_add + c + i];
-              if (a.mulmode) mu[i] = a.mulsrc[grow * a.ld_mul + c + i];
-              if (a.accumulate) yo[i] = a.Y[grow * a.ldy + c + i];
-            }
-          }
+          for (int i = 0; i < 16; ++i) r[i] *= (1.f - m[i] * m[i]);
         }
+      }
+      if (a.drop_thresh) {
 #pragma unroll
-        for (int i = 0; i < 4; ++i) {
-          const int col = c + i;
-          float r = 0.f;
-          if (col < a.N) {
-            r = t[i];
-            if (a.bias) r = fmaf(rs, __ldg(a.bias + col), r);
-            if (a.addend) r += ad[i];
-            if (a.act == 1) r = relu_f(r);
-            else if (a.act == 2) r = tanhf(r);
-            if (a.mulmode == 1) r = mu[i] > 0.f ? r : 0.f;
-            else if (a.mulmode == 2) r *= (1.f - mu[i] * mu[i]);
-            if (a.drop_thresh) r = dropout_apply(r, a.drop_seed, (uint32_t)(grow * a.drop_stride + col), a.drop_thresh, a.drop_inv_keep);
-            r *= a.post_scale;
-            if (a.accumulate) r += yo[i];
-          } else if (col == a.ones_col) {
-            r = 1.f;
-          }
-          t[i] = r;
-        }
+        for (int i = 0; i < 16; ++i)
+          r[i] = dropout_apply(r[i], a.drop_seed, (uint32_t)(grow * a.drop_stride + col0 + i), a.drop_thresh, a.drop_inv_keep);
+      }
+      if (a.post_scale != 1.f) {
+#pragma unroll
+        for (int i = 0; i < 16; ++i) r[i] *= a.post_scale;
+      }
+      if (a.accumulate) {
+        rows_load16(a.Y + grow * a.ldy, col0, a.N, true, m);
+#pragma unroll
+        for (int i = 0; i < 16; ++i) r[i] += m[i];
+      }
+      if (col0 + 16 > a.N) {                                     // columns beyond N: zero (or the ones column)
+#pragma unroll
+        for (int i = 0; i < 16; ++i)
+          if (col0 + i >= a.N) r[i] = (col0 + i == a.ones_col) ? 1.f : 0.f;
+      }
+      float* yrow = a.Y + grow * a.ldy;
+#pragma unroll
+      for (int g = 0; g < 4; ++g) {
+        const int c = col0 + 4 * g;
         if (c + 3 < a.ldy) {
-          *reinterpret_cast<float4*>(a.Y + grow * a.ldy + c) = make_float4(t[0], t[1], t[2], t[3]);
+          *reinterpret_cast<float4*>(yrow + c) = make_float4(r[4 * g], r[4 * g + 1], r[4 * g + 2], r[4 * g + 3]);
         } else {
 #pragma unroll
           for (int i = 0; i < 4; ++i)
-            if (c + i < a.ldy) a.Y[grow * a.ldy + c + i] = t[i];
+            if (c + i < a.ldy) yrow[c + i] = r[4 * g + i];
         }
       }
     }

@@ -909,18 +909,17 @@ int spw_backward(const SpwParams* w, const SpwGraph* g, const float* obj, const 
       float* gout[2] = {ws + L.DH1, ws + L.GB};
       auto kwg = tc::k_wgrad_tc<0, 0>;
       set_smem(kwg, tc::kWgradTcSmem);
-      set_smem(tc::k_edge_dgrad_tc, tc::kEdgeDgradTcSmem);
       for (int i = 0; i < 4; ++i) {
         tc::WgradTcArgs wg;
         memset(&wg, 0, sizeof(wg));
         wg.M = E; wg.x_mode = 0; wg.X = acts[i]; wg.y_mode = 0; wg.dY = dY; wg.part = ws + L.partE; wg.first = 1; wg.poison = ws + L.partE;
         SPW_KLAUNCH("k_wgrad_tc", kwg, dim3(egrid), dim3(kThreads), tc::kWgradTcSmem, st, wg);
         launch_reduce(st, ws + L.partE, egrid, (int)tc::kWgPartFloats, 0, -1, tc::kWgFeat1, kDE, kDE, {gw[i], 150, 0, 0, gb[i], 0});
-        tc::EdgeDgradTcArgs t;
-        memset(&t, 0, sizeof(t));
-        t.E = E; t.in_rcv = nullptr; t.dH2S = dY; t.Whi = ws + L.ENCT + (size_t)(2 * i) * 24320; t.Wlo = ws + L.ENCT + (size_t)(2 * i + 1) * 24320;
-        t.act = acts[i]; t.scale = i == 0 ? inv_keep : 1.f; t.dA = nullptr; t.DH1 = gout[i & 1]; t.first = 1; t.poison = gout[i & 1];
-        SPW_KLAUNCH("k_edge_dgrad_tc", tc::k_edge_dgrad_tc, dim3(egrid), dim3(kThreads), tc::kEdgeDgradTcSmem, st, t);
+        // data gradient of the layer: (dY . W^T) * relu'(layer input), times 1/keep through the dropout on c_e
+        RowsSeg sg = {dY, kDEP, kDE};
+        LinOpt o; o.mulsrc = acts[i]; o.ld_mul = kDEP; o.mulmode = 1; o.post_scale = i == 0 ? inv_keep : 1.f;
+        launch_rows_tc_raw(st, ws + L.ENCT + (size_t)(2 * i) * 24320, ws + L.ENCT + (size_t)(2 * i + 1) * 24320, 160, E, kDE, 1, &sg,
+                           gout[i & 1], kDEP, o);
         dY = gout[i & 1];
       }
       const int g0grid = egrid < 2 * num_sms() ? egrid : 2 * num_sms();
