@@ -47,7 +47,7 @@ __global__ void __launch_bounds__(256) k_pack_tc(PackTcArgs a) {
 //   X0[e][k] = relu(dx*W0[0][k] + dy*W0[1][k] + b0[k]),  [dx, dy] = pos_receiver - pos_sender;  X0[e][150] = 1, X0[e][151] = 0
 __global__ void __launch_bounds__(256) k_edge_enc0(int E, const int32_t* __restrict__ in_snd, const int32_t* __restrict__ in_rcv,
                                                    const float* __restrict__ obj, const float* __restrict__ W0,
-                                                   const float* __restrict__ b0, float* __restrict__ X0) {
+                                                   const float* __restrict__ b0, float* __restrict__ X0, uint32_t* __restrict__ bits) {
   constexpr int C4 = kDEP / 4;
   const long long total = (long long)E * C4;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
@@ -62,6 +62,22 @@ __global__ void __launch_bounds__(256) k_edge_enc0(int E, const int32_t* __restr
     }
     *reinterpret_cast<float4*>(X0 + (size_t)e * kDEP + c) = make_float4(v[0], v[1], v[2], v[3]);
   }
+  if (bits) {   // sign bits of X0 (the mask of the layer's data gradient): one 32-column word per thread
+    const long long nw = (long long)E * 8;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < nw; i += (long long)gridDim.x * blockDim.x) {
+      const int e = (int)(i >> 3), w = (int)(i & 7);
+      uint32_t m = 0u;
+      if (w < 5) {
+        const int s = in_snd[e], rc = in_rcv[e];
+        const float dx = obj[3 * (size_t)rc] - obj[3 * (size_t)s], dy = obj[3 * (size_t)rc + 1] - obj[3 * (size_t)s + 1];
+        for (int j = 0; j < 32; ++j) {
+          const int k = 32 * w + j;
+          if (k < kDE && fmaf(dy, __ldg(W0 + kDE + k), fmaf(dx, __ldg(W0 + k), __ldg(b0 + k))) > 0.f) m |= 1u << j;
+        }
+      }
+      bits[i] = m;
+    }
+  }
 }
 
 struct RowsTcArgs {
@@ -74,7 +90,9 @@ struct RowsTcArgs {
   const float* rowscale;                       // [M] multiplier of the bias or null
   const float* addend; int ld_add;             // pre-activation addend or null
   int act;                                     // 0 none, 1 relu, 2 tanh
-  const float* mulsrc; int ld_mul; int mulmode;   // 1: *= [mulsrc > 0]   2: *= (1 - mulsrc^2)
+  const float* mulsrc; int ld_mul; int mulmode;   // 1: *= [mulsrc > 0]   2: *= (1 - mulsrc^2)   3: *= bit of bits_in
+  const uint32_t* bits_in;                     // [M][8] words: bit (col & 31) of word (col >> 5)   (mulmode 3)
+  uint32_t* bits_out;                          // [M][8] or null: sign bits of the result, same layout
   float* Y; int ldy;                           // columns N..ldy-1 are written as 0 (ones_col: 1)
   int accumulate; float post_scale;
   uint32_t drop_thresh, drop_seed; float drop_inv_keep; int drop_stride;   // element index = row * drop_stride + col
@@ -242,7 +260,11 @@ __global__ void __launch_bounds__(kThreads, 1) k_rows_tc(RowsTcArgs a) {
 #pragma unroll
         for (int i = 0; i < 16; ++i) r[i] = tanhf(r[i]);
       }
-      if (a.mulmode) {
+      if (a.mulmode == 3) {                                      // 16 mask bits of this block: half-word blk of the row
+        const uint32_t bits = reinterpret_cast<const uint16_t*>(a.bits_in)[grow * 16 + blk];
+#pragma unroll
+        for (int i = 0; i < 16; ++i) r[i] = ((bits >> i) & 1u) ? r[i] : 0.f;
+      } else if (a.mulmode) {
         rows_load16(a.mulsrc + grow * a.ld_mul, col0, a.N, true, m);
         if (a.mulmode == 1) {
 #pragma unroll
@@ -265,6 +287,12 @@ __global__ void __launch_bounds__(kThreads, 1) k_rows_tc(RowsTcArgs a) {
         rows_load16(a.Y + grow * a.ldy, col0, a.N, true, m);
 #pragma unroll
         for (int i = 0; i < 16; ++i) r[i] += m[i];
+      }
+      if (a.bits_out) {
+        uint32_t bits = 0u;
+#pragma unroll
+        for (int i = 0; i < 16; ++i) bits |= (col0 + i < a.N && r[i] > 0.f) ? (1u << i) : 0u;
+        reinterpret_cast<uint16_t*>(a.bits_out)[grow * 16 + blk] = (uint16_t)bits;
       }
       if (col0 + 16 > a.N) {                                     // columns beyond N: zero (or the ones column)
 #pragma unroll

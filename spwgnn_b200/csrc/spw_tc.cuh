@@ -859,35 +859,237 @@ __global__ void __launch_bounds__(kThreads, 1) k_wgrad_tc(WgradTcArgs a) {
   if (warp == 0) tmem_dealloc(tmem_base, kTmemCols);
 }
 
+// =================================================================================================
+// Weight gradient of a plain linear layer on the tensor cores (node-level layers and the relation encoder):
+//   dW[k][n] = sum_rows X[row % xmod][k] * dY[row][n],  k < Kx;  row Kx of dW = sum_rows one[row] * dY[row][n] (bias
+//   gradient; one = rowscale[row % rsmod] or 1).  Same operand roles as k_wgrad_tc: A = X^T chunk in tensor memory
+//   (lane = feature), B = dY^T chunk in shared memory, D accumulates one 128-row tile and is flushed with round-to-
+//   nearest adds into a per-CTA partial [2][160][128].  Kx + 1 <= 128 needs one M-tile only: then the two warp
+//   groups split the chunk rows (operand build) and the accumulator columns (flush) between them.
+// =================================================================================================
+struct WgradRowsArgs {
+  int M;
+  const float* X; int ldx; int Kx; int xmod;          // X row = row % xmod (xmod = 0: row); ldx % 4 == 0
+  const float* rowscale; int rsmod;                   // value of the virtual column Kx (null: 1)
+  const float* dY; int ldy; int Ny;                   // ldy % 4 == 0
+  int NB;                                             // MMA N: 112 or 160 (>= Ny)
+  float* part;                                        // [gridDim.x][2][160][128]
+  float* poison;
+};
+
+__device__ __forceinline__ void cp_async4_zfill(float* sdst, const float* gsrc, bool valid) {
+  const unsigned s = smem_u32(sdst);
+  const int sz = valid ? 4 : 0;
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;\n" ::"r"(s), "l"(gsrc), "r"(sz));
+}
+
+// stage layout (floats): XA [32][152] | (unused) | (unused) | YD [32][152] | (unused bits) | RS [32] ...   (same size as k_wgrad_tc's)
+__device__ __forceinline__ void wgr_issue_chunk(const WgradRowsArgs& a, float* st, int r0, int cx4, int cy4) {
+  float* XA = st; float* YD = st + 3 * kWgChunk * kDEP;
+  float* RS = YD + kWgChunk * kDEP + kWgChunk * 8;
+  for (int i = threadIdx.x; i < kWgChunk * cx4; i += kThreads) {
+    const int r = i / cx4, c = i - r * cx4;
+    const int row = r0 + r;
+    const bool valid = row < a.M;
+    const size_t xr = valid ? (size_t)(a.xmod ? row % a.xmod : row) : 0;
+    cp_async16_zfill(XA + r * kDEP + 4 * c, a.X + xr * a.ldx + 4 * c, valid);
+  }
+  for (int i = threadIdx.x; i < kWgChunk * cy4; i += kThreads) {
+    const int r = i / cy4, c = i - r * cy4;
+    const int row = r0 + r;
+    const bool valid = row < a.M;
+    cp_async16_zfill(YD + r * kDEP + 4 * c, a.dY + (valid ? (size_t)row : 0) * a.ldy + 4 * c, valid);
+  }
+  if (a.rowscale && threadIdx.x < kWgChunk) {
+    const int row = r0 + threadIdx.x;
+    const bool valid = row < a.M;
+    cp_async4_zfill(RS + threadIdx.x, a.rowscale + (valid ? (size_t)(a.rsmod ? row % a.rsmod : row) : 0), valid);
+  }
+  cp_async_commit();
+}
+
+__global__ void __launch_bounds__(kThreads, 1) k_wgrad_rows_tc(WgradRowsArgs a) {
+  SPW_DYN_SMEM(smem_raw);
+  float* stages = reinterpret_cast<float*>(smem_raw);
+  float* Bhi_s = stages + 2 * kWgStageFloats;
+  float* Blo_s = Bhi_s + kWgBFloats;
+  uint64_t* bar = reinterpret_cast<uint64_t*>(Blo_s + kWgBFloats);
+  uint32_t* tptr = reinterpret_cast<uint32_t*>(bar + 1);
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int L = 32 * (warp & 3) + lane, grp = warp >> 2;        // TMEM lane, warp group
+  const int nmt = a.Kx + 1 > 128 ? 2 : 1;                       // M-tiles
+  const int feat1 = nmt == 2 ? a.Kx + 1 - 128 : 0;              // first feature of M-tile 1
+  const int mt = nmt == 2 ? grp : 0;                            // M-tile this thread builds / flushes
+  const int feat = mt == 0 ? L : feat1 + L;
+  const int NB = a.NB;
+  const int cx4 = (a.Kx + 3) >> 2, cy4 = (a.Ny + 3) >> 2;
+  const int bstep = 2 * NB * 4;                                 // floats per k-step of the B operand
+
+  if (warp == 0) tmem_alloc(tptr, kTmemCols);
+  if (tid == 32) { mbar_init(bar, 1); fence_mbar_init(); }
+  fence_before_sync();
+  __syncthreads();
+  fence_after_sync();
+  const uint32_t tmem_base = *tptr;
+  const uint32_t lane_addr = tmem_base + ((uint32_t)(32 * (warp & 3)) << 16);
+  const uint32_t colA_hi = kWgColA + 64 * mt, colA_lo = colA_hi + 32;
+  const uint32_t idesc = make_idesc_tf32(128, NB);
+  uint32_t parity = 0;
+  bool failed = false, pending = false, first_flush = true;
+  float* part = a.part + (size_t)blockIdx.x * kWgPartFloats;
+  const int ntiles = (a.M + kTM - 1) / kTM;
+  constexpr int kCh = kTM / kWgChunk;                           // chunks per tile
+  const int my_tiles = (int)blockIdx.x < ntiles ? (ntiles - 1 - (int)blockIdx.x) / (int)gridDim.x + 1 : 0;
+  const int nq = my_tiles * kCh;
+  auto row0_of = [&](int q) { return (blockIdx.x + (q / kCh) * gridDim.x) * kTM + (q % kCh) * kWgChunk; };
+  // rows of the chunk this thread turns into A columns: all 32 (two M-tiles) or its group's 16 (one M-tile)
+  const int j_lo = nmt == 2 ? 0 : 16 * grp, j_hi = nmt == 2 ? kWgChunk : 16 * grp + 16;
+  if (nq > 0) wgr_issue_chunk(a, stages, row0_of(0), cx4, cy4);
+  for (int q = 0; q < nq; ++q) {
+    const int ch = q % kCh;
+    float* st = stages + (q & 1) * kWgStageFloats;
+    float* stn = stages + ((q + 1) & 1) * kWgStageFloats;
+    __syncthreads();                                   // stage q+1 no longer read (chunk q-1 done)
+    if (q + 1 < nq) {
+      wgr_issue_chunk(a, stn, row0_of(q + 1), cx4, cy4);
+      cp_async_wait<1>();                              // chunk q has landed (this thread's copies)
+    } else {
+      cp_async_wait<0>();
+    }
+    __syncthreads();                                   // ... and everybody else's
+    if (pending) {                                     // A / B operand regions are free once the previous MMAs are done
+      if (!mbar_wait(bar, parity)) failed = true;
+      parity ^= 1u;
+      fence_after_sync();
+      pending = false;
+    }
+    const float* XA = st; const float* YD = st + 3 * kWgChunk * kDEP;
+    const float* RS = YD + kWgChunk * kDEP + kWgChunk * 8;
+    const int r0 = row0_of(q);
+    // A = X^T: this lane's feature, rows of the chunk as TMEM columns
+    for (int j0 = j_lo; j0 < j_hi; j0 += 8) {
+      uint32_t h[8], l[8];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        float x = 0.f;
+        if (feat < a.Kx) x = XA[(j0 + i) * kDEP + feat];
+        else if (feat == a.Kx && r0 + j0 + i < a.M) x = a.rowscale ? RS[j0 + i] : 1.f;
+        split_tf32(x, h[i], l[i]);
+      }
+      tmem_st8(lane_addr + colA_hi + j0, h);
+      tmem_st8(lane_addr + colA_lo + j0, l);
+    }
+    // B = dY^T: [k-step][2][n][4 rows]
+    for (int idx = tid; idx < 8 * NB; idx += kThreads) {
+      const int n = idx % NB, kc = idx / NB;
+      uint32_t h[4], l[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const float y = n < a.Ny ? YD[(4 * kc + i) * kDEP + n] : 0.f;
+        split_tf32(y, h[i], l[i]);
+      }
+      reinterpret_cast<uint4*>(Bhi_s)[idx] = make_uint4(h[0], h[1], h[2], h[3]);
+      reinterpret_cast<uint4*>(Blo_s)[idx] = make_uint4(l[0], l[1], l[2], l[3]);
+    }
+    tmem_wait_st();
+    fence_async_smem();
+    fence_before_sync();
+    __syncthreads();
+    if (tid == 0) {
+      fence_after_sync();
+      const uint32_t bhi = smem_u32(Bhi_s), blo = smem_u32(Blo_s);
+#pragma unroll 1
+      for (int ks = 0; ks < kWgChunk / 8; ++ks) {
+        const uint64_t dhi = make_b_desc(bhi + ks * (bstep * 4), NB * 16, 128);
+        const uint64_t dlo = make_b_desc(blo + ks * (bstep * 4), NB * 16, 128);
+        const uint32_t acc = (ch > 0 || ks > 0) ? 1u : 0u;
+        for (int t = 0; t < nmt; ++t) {
+          const uint32_t d = tmem_base + (t ? kWgColD1 : kWgColD0);
+          const uint32_t ahi = tmem_base + kWgColA + 64 * t + 8 * ks, alo = ahi + 32;
+          mma_tf32_ts(d, alo, dhi, idesc, acc);
+          mma_tf32_ts(d, ahi, dlo, idesc, 1u);
+          mma_tf32_ts(d, ahi, dhi, idesc, 1u);
+        }
+      }
+      mma_commit(bar);
+    }
+    pending = true;
+    if (ch == kCh - 1) {
+      // tile done: wait for its MMAs, add D into the per-CTA partial with round-to-nearest adds
+      if (!mbar_wait(bar, parity)) failed = true;
+      parity ^= 1u;
+      fence_after_sync();
+      pending = false;
+      float* pp = part + (size_t)mt * (160 * 128) + L;
+      const uint32_t dcol = mt ? kWgColD1 : kWgColD0;
+      // columns of this thread: everything (two M-tiles) or its group's share of the 16-column blocks (one M-tile)
+      const int nblk = NB / 16;
+      const int b_lo = nmt == 2 ? 0 : (grp ? (nblk + 1) / 2 : 0), b_hi = nmt == 2 ? nblk : (grp ? nblk : (nblk + 1) / 2);
+#pragma unroll 1
+      for (int b = b_lo; b < b_hi; ++b) {
+        const int c = 16 * b;
+        uint32_t v[16];
+        tmem_ld16(lane_addr + dcol + c, v);
+        float old[16];
+        if (!first_flush) {
+#pragma unroll
+          for (int i = 0; i < 16; ++i) old[i] = pp[(size_t)(c + i) * 128];
+        }
+        tmem_wait_ld();
+#pragma unroll
+        for (int i = 0; i < 16; ++i) pp[(size_t)(c + i) * 128] = first_flush ? __uint_as_float(v[i]) : old[i] + __uint_as_float(v[i]);
+      }
+      first_flush = false;
+      fence_before_sync();
+    }
+  }
+  if (failed && tid == 0) a.poison[0] = __int_as_float(0x7fc00000);
+  fence_before_sync();
+  __syncthreads();
+  if (warp == 0) tmem_dealloc(tmem_base, kTmemCols);
+}
+
 // relation-encoder layer 0 (K = 2) gradients from G0 = d(pre-activation of X0):
 //   part[cta][0][k] = sum_e dx_e G0[e][k], [1][k] with dy, [2][k] = sum_e G0[e][k]   (fixed order per CTA)
-__global__ void __launch_bounds__(kThreads, 2) k_enc0_bwd(int E, const int32_t* __restrict__ in_snd,
-                                                          const int32_t* __restrict__ in_rcv, const float* __restrict__ obj,
-                                                          const float* __restrict__ G0, float* __restrict__ part) {
+constexpr int kEnc0Threads = 640;    // 4 row quarters x 160 columns
+__global__ void __launch_bounds__(kEnc0Threads, 2) k_enc0_bwd(int E, const int32_t* __restrict__ in_snd,
+                                                              const int32_t* __restrict__ in_rcv, const float* __restrict__ obj,
+                                                              const float* __restrict__ G0, float* __restrict__ part) {
   __shared__ float sdx[kTM], sdy[kTM];
-  const int tid = threadIdx.x;
+  __shared__ float sred[3][3][160];
+  const int tid = threadIdx.x, qr = tid / 160, c = tid - qr * 160;       // row quarter, column
   float g0 = 0.f, g1 = 0.f, gb = 0.f;
   const int ntiles = (E + kTM - 1) / kTM;
   for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
     const int e0 = tile * kTM, rows = imin(kTM, E - e0);
     __syncthreads();
-    if (tid < rows) {
-      const int s = in_snd[e0 + tid], rc = in_rcv[e0 + tid];
-      sdx[tid] = obj[3 * (size_t)rc] - obj[3 * (size_t)s];
-      sdy[tid] = obj[3 * (size_t)rc + 1] - obj[3 * (size_t)s + 1];
+    if (tid < kTM) {
+      float dx = 0.f, dy = 0.f;
+      if (tid < rows) {
+        const int s = in_snd[e0 + tid], rc = in_rcv[e0 + tid];
+        dx = obj[3 * (size_t)rc] - obj[3 * (size_t)s];
+        dy = obj[3 * (size_t)rc + 1] - obj[3 * (size_t)s + 1];
+      }
+      sdx[tid] = dx; sdy[tid] = dy;
     }
     __syncthreads();
-    if (tid < kDE) {
-#pragma unroll 4
-      for (int r = 0; r < rows; ++r) {
-        const float d = G0[(size_t)(e0 + r) * kDEP + tid];
+    if (c < kDE) {
+      const int ra = 32 * qr, rb = imin(rows, ra + 32);
+      const float* gp = G0 + (size_t)e0 * kDEP + c;
+#pragma unroll 8
+      for (int r = ra; r < rb; ++r) {
+        const float d = gp[(size_t)r * kDEP];
         g0 = fmaf(sdx[r], d, g0); g1 = fmaf(sdy[r], d, g1); gb += d;
       }
     }
   }
-  if (tid < kDEP) {
+  __syncthreads();
+  if (qr > 0) { sred[qr - 1][0][c] = g0; sred[qr - 1][1][c] = g1; sred[qr - 1][2][c] = gb; }
+  __syncthreads();
+  if (qr == 0 && c < kDEP) {                                      // fixed order: quarter 0 + 1 + 2 + 3
+    for (int k = 0; k < 3; ++k) { g0 += sred[k][0][c]; g1 += sred[k][1][c]; gb += sred[k][2][c]; }
     float* p = part + (size_t)blockIdx.x * (3 * kDEP);
-    p[tid] = tid < kDE ? g0 : 0.f; p[kDEP + tid] = tid < kDE ? g1 : 0.f; p[2 * kDEP + tid] = tid < kDE ? gb : 0.f;
+    p[c] = c < kDE ? g0 : 0.f; p[kDEP + c] = c < kDE ? g1 : 0.f; p[2 * kDEP + c] = c < kDE ? gb : 0.f;
   }
 }
 

@@ -132,6 +132,7 @@ struct Layout {
   size_t P, S, R, H2S, G, U;     // per-step arrays (training: 5 slots; inference: fewer)
   int slotsP, slotsSR, slotsN;   // number of step slots for P / (S,R) / (H2S,G,U)
   // backward
+  size_t EB;                     // sign bits of the relation-encoder activations X0, X1, X2, C: 4 x [E][8] words
   size_t dU, dG, T, dS, dR, dH2S, DP, dQ, dQ1, dA, DH1, M2, M1, EX0, EX1, EX2, EC, GB, partE, partM, part0, partN;
   size_t total;   // floats
 };
@@ -185,12 +186,13 @@ Layout make_layout(int64_t n, int64_t E, int training) {
     L.GB = take((size_t)E * kDEP + 8);             // second gradient buffer of the layer-by-layer encoder backward
     L.EX2 = take((size_t)E * kDEP + 8);
     L.EC = take((size_t)E * kDEP + 8);
+    L.EB = take((size_t)4 * E * 8);
     L.partE = take((size_t)kMaxCtas * 2 * 160 * 128);
     L.partM = take((size_t)kMaxCtas * 4 * 160 * 160);
     L.part0 = take((size_t)2 * kMaxCtas * 3 * kDEP);
     L.partN = take((size_t)2 * kMaxCtas * kPartNodeElems);
   } else {
-    L.dU = L.dG = L.T = L.dS = L.dR = L.dH2S = L.DP = L.dQ = L.dQ1 = L.dA = L.DH1 = L.M2 = L.M1 = L.EX0 = L.EX1 = L.EX2 = L.EC = L.GB = 0;
+    L.dU = L.dG = L.T = L.dS = L.dR = L.dH2S = L.DP = L.dQ = L.dQ1 = L.dA = L.DH1 = L.M2 = L.M1 = L.EX0 = L.EX1 = L.EX2 = L.EC = L.GB = 0; L.EB = 0;
     L.partE = L.partM = L.part0 = L.partN = 0;
   }
   L.total = off;
@@ -236,6 +238,9 @@ struct LinOpt {
   float post_scale = 1.f; uint32_t drop_thresh = 0; uint32_t drop_seed = 0; float drop_inv_keep = 1.f;
   int drop_stride = 128;         // dropout element index = row * drop_stride + column
   int ones_col = -1;             // tensor-core kernel only: Y[row][ones_col] = 1
+  const char* tag = nullptr;     // profile name of the launch (default: the kernel's)
+  const uint32_t* bits_in = nullptr;   // tensor-core kernel only: mulmode 3 multiplies by these mask bits ([M][8] words)
+  uint32_t* bits_out = nullptr;        // tensor-core kernel only: sign bits of the result
 };
 
 // Y[M][ldy] (N valid columns) from up to 3 (X, W) segments; wide = 150-column output (CN = 5)
@@ -298,17 +303,17 @@ void launch_rows_tc_raw(cudaStream_t st, const float* Bhi, const float* Blo, int
   a.bias = o.bias; a.rowscale = o.rowscale; a.addend = o.addend; a.ld_add = o.ld_add; a.act = o.act;
   a.mulsrc = o.mulsrc; a.ld_mul = o.ld_mul; a.mulmode = o.mulmode; a.Y = Y; a.ldy = ldy; a.accumulate = o.accumulate;
   a.post_scale = o.post_scale; a.drop_thresh = o.drop_thresh; a.drop_seed = o.drop_seed; a.drop_inv_keep = o.drop_inv_keep;
-  a.drop_stride = o.drop_stride; a.ones_col = o.ones_col; a.poison = Y;
+  a.drop_stride = o.drop_stride; a.ones_col = o.ones_col; a.poison = Y; a.bits_in = o.bits_in; a.bits_out = o.bits_out;
   const int ntiles = (M + kTM - 1) / kTM;
   const int grid = ntiles < num_sms() ? ntiles : num_sms();
   if (NB == 160) {
     const size_t smem = tc::rows_tc_smem<160>(a.ks);
     auto kern = tc::k_rows_tc<160>; set_smem(kern, tc::rows_tc_smem<160>(19));
-    SPW_KLAUNCH("k_rows_tc<160>", kern, dim3(grid), dim3(kThreads), smem, st, a);
+    SPW_KLAUNCH(o.tag ? o.tag : "k_rows_tc<160>", kern, dim3(grid), dim3(kThreads), smem, st, a);
   } else {
     const size_t smem = tc::rows_tc_smem<112>(a.ks);
     auto kern = tc::k_rows_tc<112>; set_smem(kern, tc::rows_tc_smem<112>(25));
-    SPW_KLAUNCH("k_rows_tc<112>", kern, dim3(grid), dim3(kThreads), smem, st, a);
+    SPW_KLAUNCH(o.tag ? o.tag : "k_rows_tc<112>", kern, dim3(grid), dim3(kThreads), smem, st, a);
   }
 }
 void launch_rows_tc(cudaStream_t st, float* ws, const Layout& L, int id, int M, int N, int nseg, const RowsSeg* sg, float* Y,
@@ -347,6 +352,20 @@ void launch_wgrad(cudaStream_t st, int M, const float* X, int ldx, int Kin, int 
   WgArgs a;
   a.M = M; a.X = X; a.ldx = ldx; a.Kin = Kin; a.xmod = xmod; a.rowscale = rowscale; a.rsmod = rsmod; a.dY = dY; a.ldy = ldy; a.N = N;
   a.part = part;
+#if SPW_USE_TC
+  if (Kin >= 8 && N >= 8 && (ldx & 3) == 0 && (ldy & 3) == 0 && Kin <= 150 && N <= 160) {   // tensor cores
+    tc::WgradRowsArgs t;
+    t.M = M; t.X = X; t.ldx = ldx; t.Kx = Kin; t.xmod = xmod; t.rowscale = rowscale; t.rsmod = rsmod; t.dY = dY; t.ldy = ldy; t.Ny = N;
+    t.NB = N <= 112 ? 112 : 160; t.part = part; t.poison = part;
+    const int tt = (M + kTM - 1) / kTM;
+    int tgrid = tt < num_sms() ? tt : num_sms();
+    if (tgrid > kMaxCtas) tgrid = kMaxCtas;
+    set_smem(tc::k_wgrad_rows_tc, tc::kWgradTcSmem);
+    SPW_KLAUNCH("k_wgrad_rows_tc", tc::k_wgrad_rows_tc, dim3(tgrid), dim3(kThreads), tc::kWgradTcSmem, st, t);
+    launch_reduce(st, part, tgrid, (int)tc::kWgPartFloats, 0, -1, Kin + 1 > 128 ? Kin + 1 - 128 : 0, Kin, N, out);
+    return;
+  }
+#endif
   const int ntiles = (M + kTW - 1) / kTW;
   const bool wa = Kin + 1 > 112, wb = N > 112;
   const int LX = wa ? 160 : 112, LY = wb ? 160 : 112;
@@ -645,18 +664,20 @@ int spw_forward(const SpwParams* w, const SpwGraph* g, const float* obj, float* 
     float* X1 = training ? ws + L.EX1 : ws + L.A;
     float* X2 = training ? ws + L.EX2 : ws + L.A;
     float* C = training ? ws + L.EC : ws + L.A;
+    uint32_t* EB = training ? reinterpret_cast<uint32_t*>(ws + L.EB) : nullptr;     // sign bits of X0, X1, X2, C
+    const size_t nb = (size_t)E * 8;
     SPW_KLAUNCH("k_edge_enc0", tc::k_edge_enc0, dim3(grid_for((int64_t)E * (kDEP / 4), 256)), dim3(256), 0, st, E, g->in_snd, g->in_rcv,
-                obj, (const float*)w->rm_w[0], (const float*)w->rm_b[0], X0);
-    LinOpt o; o.act = 1; o.ones_col = kDE;
+                obj, (const float*)w->rm_w[0], (const float*)w->rm_b[0], X0, EB);
+    LinOpt o; o.act = 1; o.ones_col = kDE; o.tag = "k_rows_tc<160>:enc_fwd";
     RowsSeg s0 = {X0, kDEP, kDE}, s1 = {X1, kDEP, kDE}, s2 = {X2, kDEP, kDE}, s3 = {C, kDEP, kDE};
-    o.bias = w->rm_b[1];
+    o.bias = w->rm_b[1]; o.bits_out = EB ? EB + nb : nullptr;
     launch_rows_tc(st, ws, L, T_RM1, E, kDE, 1, &s0, X1, kDEP, o);
-    o.bias = w->rm_b[2];
+    o.bias = w->rm_b[2]; o.bits_out = EB ? EB + 2 * nb : nullptr;
     launch_rows_tc(st, ws, L, T_RM2, E, kDE, 1, &s1, X2, kDEP, o);
-    o.bias = w->rm_b[3];
+    o.bias = w->rm_b[3]; o.bits_out = EB ? EB + 3 * nb : nullptr;
     o.drop_thresh = drop_thresh; o.drop_seed = seed_c; o.drop_inv_keep = inv_keep; o.drop_stride = 160;   // Networks.py:77
     launch_rows_tc(st, ws, L, T_RM3, E, kDE, 1, &s2, C, kDEP, o);
-    LinOpt oa; oa.bias = w->rmp_b[0];
+    LinOpt oa; oa.bias = w->rmp_b[0]; oa.tag = "k_rows_tc<160>:enc_fwd";
     launch_rows_tc(st, ws, L, T_W1A, E, kDE, 1, &s3, ws + L.A, kDEP, oa);
   }
 #else
@@ -917,13 +938,15 @@ int spw_backward(const SpwParams* w, const SpwGraph* g, const float* obj, const 
         launch_reduce(st, ws + L.partE, egrid, (int)tc::kWgPartFloats, 0, -1, tc::kWgFeat1, kDE, kDE, {gw[i], 150, 0, 0, gb[i], 0});
         // data gradient of the layer: (dY . W^T) * relu'(layer input), times 1/keep through the dropout on c_e
         RowsSeg sg = {dY, kDEP, kDE};
-        LinOpt o; o.mulsrc = acts[i]; o.ld_mul = kDEP; o.mulmode = 1; o.post_scale = i == 0 ? inv_keep : 1.f;
+        LinOpt o; o.mulmode = 3; o.post_scale = i == 0 ? inv_keep : 1.f;
+        o.bits_in = reinterpret_cast<const uint32_t*>(ws + L.EB) + (size_t)(3 - i) * E * 8;     // bits of C, X2, X1, X0
+        o.tag = "k_rows_tc<160>:enc_bwd";
         launch_rows_tc_raw(st, ws + L.ENCT + (size_t)(2 * i) * 24320, ws + L.ENCT + (size_t)(2 * i + 1) * 24320, 160, E, kDE, 1, &sg,
                            gout[i & 1], kDEP, o);
         dY = gout[i & 1];
       }
-      const int g0grid = egrid < 2 * num_sms() ? egrid : 2 * num_sms();
-      SPW_KLAUNCH("k_enc0_bwd", tc::k_enc0_bwd, dim3(g0grid), dim3(kThreads), 0, st, E, g->in_snd, g->in_rcv, obj, dY, ws + L.part0);
+      const int g0grid = etiles < 2 * num_sms() ? etiles : 2 * num_sms();
+      SPW_KLAUNCH("k_enc0_bwd", tc::k_enc0_bwd, dim3(g0grid), dim3(tc::kEnc0Threads), 0, st, E, g->in_snd, g->in_rcv, obj, dY, ws + L.part0);
       launch_reduce(st, ws + L.part0, g0grid, 3 * kDEP, kDEP, 0, 0, 2, kDE, {grads->rm_w[0], 150, 0, 0, grads->rm_b[0], 0});
     }
 #else
