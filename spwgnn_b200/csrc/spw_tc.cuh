@@ -15,6 +15,20 @@
 #ifndef SPW_EMU
 #include "spw_common.cuh"
 
+// Per-phase clock64() accounting of the tile loops (development builds only: -DSPW_PHASE_TIMING; tools/phase_test.py)
+#ifdef SPW_PHASE_TIMING
+#include <stdio.h>
+#define SPW_PH_DECL long long ph_t[8] = {0, 0, 0, 0, 0, 0, 0, 0}; long long ph_last = clock64();
+#define SPW_PH(i) do { const long long ph_now = clock64(); ph_t[i] += ph_now - ph_last; ph_last = ph_now; } while (0)
+#define SPW_PH_REPORT(name) do { if (blockIdx.x == 0 && (threadIdx.x == 0 || threadIdx.x == 255)) \
+  printf("%s tid %d: p0 %lld p1 %lld p2 %lld p3 %lld p4 %lld p5 %lld p6 %lld p7 %lld\n", name, \
+         (int)threadIdx.x, ph_t[0], ph_t[1], ph_t[2], ph_t[3], ph_t[4], ph_t[5], ph_t[6], ph_t[7]); } while (0)
+#else
+#define SPW_PH_DECL
+#define SPW_PH(i)
+#define SPW_PH_REPORT(name)
+#endif
+
 namespace spw {
 namespace tc {
 
@@ -316,7 +330,9 @@ __global__ void __launch_bounds__(kThreads, 1) k_edge_step_tc(EdgeStepTcArgs a) 
   bool failed = false;
   const int ntiles = (a.E + kTM - 1) / kTM;
 
+  SPW_PH_DECL
   for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+    SPW_PH(7);
     const int e0 = tile * kTM;
     const int rows = imin(kTM, a.E - e0);
     if (tid < kTM) {
@@ -331,6 +347,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_edge_step_tc(EdgeStepTcArgs a) 
       snoff[i] = (short)imax(-32000, imin(32000, a.in_off[n_first + i] - e0));
     // ---- h1 = relu(A_e + S_s + R_r): coalesced gather into the slab, then row threads split it
     //      into tf32 hi/lo and store it to tensor memory (3 slabs of <= 64 columns)
+    SPW_PH(0);                                            // p0: indices
     H1Regs hreg;
     h1_slab_load(hreg, ssnd, srcv, a.A, a.S, a.R, e0, 0, kStageCols);
 #pragma unroll
@@ -366,6 +383,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_edge_step_tc(EdgeStepTcArgs a) 
     tmem_wait_st();
     fence_before_sync();
     __syncthreads();
+    SPW_PH(1);                                            // p1: gather + split + STTM
     if (tid == 0) {
       fence_after_sync();
       issue_tile_mmas(tmem_base, Bhi_s, Blo_s);
@@ -374,6 +392,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_edge_step_tc(EdgeStepTcArgs a) 
     if (!mbar_wait(bar, parity)) failed = true;
     parity ^= 1u;
     fence_after_sync();
+    SPW_PH(2);                                            // p2: MMA
     // ---- epilogue: D -> +b2, relu, relu bits -> staging slab -> receiver-segmented sum
     for (int c0 = 0; c0 < kN; c0 += kStageCols) {
       const int ncols = imin(kStageCols, kN - c0);
@@ -416,6 +435,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_edge_step_tc(EdgeStepTcArgs a) 
       }
       __syncthreads();
     }
+    SPW_PH(3);                                            // p3: epilogue + segmented sum
     if (a.maskbits) {
       for (int i = tid; i < rows * 5; i += kThreads) {
         const int r = i / 5, w = i - r * 5;
@@ -424,7 +444,9 @@ __global__ void __launch_bounds__(kThreads, 1) k_edge_step_tc(EdgeStepTcArgs a) 
     }
     fence_before_sync();
     __syncthreads();
+    SPW_PH(4);                                            // p4: mask bits + tile-end sync
   }
+  SPW_PH_REPORT("k_edge_step_tc");
   if (failed && tid == 0) a.H2S[0] = __int_as_float(0x7fc00000);   // fail loudly: poison the output (MMA barrier timed out)
   fence_before_sync();
   __syncthreads();
@@ -491,7 +513,9 @@ __global__ void __launch_bounds__(kThreads, 1) k_edge_dgrad_tc(EdgeDgradTcArgs a
                                          : make_float4(0.f, 0.f, 0.f, 0.f);
     }
   };
+  SPW_PH_DECL
   for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+    SPW_PH(7);
     const int e0 = tile * kTM;
     const int rows = imin(kTM, a.E - e0);
     if (tid < kTM) srcv[tid] = tid < rows ? (a.in_rcv ? a.in_rcv[e0 + tid] : e0 + tid) : -1;
@@ -555,6 +579,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_edge_dgrad_tc(EdgeDgradTcArgs a
     tmem_wait_st();
     fence_before_sync();
     __syncthreads();
+    SPW_PH(1);                                            // p1: indices, bits, gather + split + STTM
     if (tid == 0) {
       fence_after_sync();
       issue_tile_mmas(tmem_base, Bhi_s, Blo_s);
@@ -563,6 +588,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_edge_dgrad_tc(EdgeDgradTcArgs a
     if (!mbar_wait(bar, parity)) failed = true;
     parity ^= 1u;
     fence_after_sync();
+    SPW_PH(2);                                            // p2: MMA
     // ---- epilogue: D * relu'(h1) -> slab -> DH1 (write) and dA (write or accumulate), coalesced
 #pragma unroll
     for (int sl = 0; sl < 3; ++sl) {
@@ -623,7 +649,9 @@ __global__ void __launch_bounds__(kThreads, 1) k_edge_dgrad_tc(EdgeDgradTcArgs a
     }
     fence_before_sync();
     __syncthreads();
+    SPW_PH(3);                                            // p3: epilogue
   }
+  SPW_PH_REPORT("k_edge_dgrad_tc");
   if (failed && tid == 0) a.poison[0] = __int_as_float(0x7fc00000);
   fence_before_sync();
   __syncthreads();
@@ -637,8 +665,9 @@ __global__ void __launch_bounds__(kThreads, 1) k_edge_dgrad_tc(EdgeDgradTcArgs a
 //   chunk; two overlapping M = 128 tiles cover the features: tile 0 = features 0..127, tile 1 = 23..150.
 //   B = dY^T chunk in shared memory, K-major: [k-step of 8 rows][2][n = 160][4 rows].
 //   D0 / D1 (TMEM) accumulate ONE 128-row tile (48 MMAs each), then are added -- with round-to-nearest
-//   FADDs -- into a per-CTA partial in global memory (layout [tile][n][lane], coalesced): the tensor core
-//   truncates when it accumulates, so long accumulation chains in TMEM would bias the sum.
+//   FADDs -- into 160 registers per thread (the tensor core truncates when it accumulates, so long accumulation
+//   chains in TMEM would bias the sum); the per-CTA partial goes to global memory once, at the end
+//   (layout [tile][n][lane], coalesced).
 //   TMEM map: D0 [0,160) | D1 [160,320) | A0_hi [320,352) A0_lo [352,384) A1_hi [384,416) A1_lo [416,448)
 // =================================================================================================
 constexpr int kWgChunk = 32;
@@ -733,8 +762,12 @@ __global__ void __launch_bounds__(kThreads, 1) k_wgrad_tc(WgradTcArgs a) {
   const uint32_t colA_hi = kWgColA + 64 * mt, colA_lo = colA_hi + 32;
   const uint32_t idesc = make_idesc_tf32(128, kN);
   uint32_t parity = 0;
-  bool failed = false, pending = false, first_flush = a.first != 0;
+  bool failed = false, pending = false;
   float* part = a.part + (size_t)blockIdx.x * kWgPartFloats;
+  // D accumulates ONE tile in tensor memory; the sum over this CTA's tiles lives in registers (round-to-nearest adds)
+  float acc[kN];
+#pragma unroll
+  for (int c = 0; c < kN; ++c) acc[c] = 0.f;
   const int ntiles = (a.M + kTM - 1) / kTM;
   constexpr int kCh = kTM / kWgChunk;                           // chunks per tile
   // this CTA's chunks, in order: q-th chunk = (tile blockIdx.x + (q / kCh) * gridDim.x, chunk q % kCh)
@@ -748,18 +781,22 @@ __global__ void __launch_bounds__(kThreads, 1) k_wgrad_tc(WgradTcArgs a) {
     wg_issue_chunk<XMODE, YMODE>(a, stages, row0_of(0));
     if (kGather && nq > 1) wg_load_idx(a, stages + kWgStageFloats, row0_of(1));
   }
+  SPW_PH_DECL
   for (int q = 0; q < nq; ++q) {
+    SPW_PH(7);
     const int ch = q % kCh;
     float* st = stages + (q & 1) * kWgStageFloats;
     float* stn = stages + ((q + 1) & 1) * kWgStageFloats;
     __syncthreads();                                   // idx of chunk q+1 visible; stage q+1 no longer read (chunk q-1 done)
     if (q + 1 < nq) {
       wg_issue_chunk<XMODE, YMODE>(a, stn, row0_of(q + 1));
+      SPW_PH(0);                                       // p0: issue of the next chunk's copies
       cp_async_wait<1>();                              // chunk q has landed (this thread's copies)
     } else {
       cp_async_wait<0>();
     }
     __syncthreads();                                   // ... and everybody else's
+    SPW_PH(1);                                         // p1: wait for chunk q's copies
     if (kGather && q + 2 < nq) wg_load_idx(a, st, row0_of(q + 2));   // idx slot of stage q is free: chunk q's copies are done
     if (pending) {                                     // A / B operand regions are free once the previous MMAs are done
       if (!mbar_wait(bar, parity)) failed = true;
@@ -767,6 +804,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_wgrad_tc(WgradTcArgs a) {
       fence_after_sync();
       pending = false;
     }
+    SPW_PH(2);                                         // p2: idx loads + wait for the previous chunk's MMAs
     const float* XA = st; const float* XS = XA + kWgChunk * kDEP; const float* XR = XS + kWgChunk * kDEP;
     const float* YD = XR + kWgChunk * kDEP;
     const uint32_t* BT = reinterpret_cast<const uint32_t*>(YD + kWgChunk * kDEP);
@@ -788,6 +826,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_wgrad_tc(WgradTcArgs a) {
       tmem_st8(lane_addr + colA_hi + j0, h);
       tmem_st8(lane_addr + colA_lo + j0, l);
     }
+    SPW_PH(3);                                         // p3: A operand build
     // B = dY^T: [k-step][2][n][4 rows]
     for (int idx = tid; idx < 8 * kN; idx += kThreads) {
       const int n = idx % kN, kc = idx / kN;
@@ -808,6 +847,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_wgrad_tc(WgradTcArgs a) {
     fence_async_smem();
     fence_before_sync();
     __syncthreads();
+    SPW_PH(4);                                         // p4: B operand build + sync
     if (tid == 0) {
       fence_after_sync();
       const uint32_t bhi = smem_u32(Bhi_s), blo = smem_u32(Blo_s);
@@ -828,31 +868,43 @@ __global__ void __launch_bounds__(kThreads, 1) k_wgrad_tc(WgradTcArgs a) {
       mma_commit(bar);
     }
     pending = true;
+    SPW_PH(5);                                         // p5: MMA issue
     if (ch == kCh - 1) {
       // tile done: wait for its MMAs, add D into the per-CTA partial with round-to-nearest adds
       if (!mbar_wait(bar, parity)) failed = true;
       parity ^= 1u;
       fence_after_sync();
       pending = false;
-      float* pp = part + (size_t)mt * (160 * 128) + L;
       const uint32_t dcol = mt ? kWgColD1 : kWgColD0;
-#pragma unroll 1
+#pragma unroll
       for (int c = 0; c < kN; c += 16) {
         uint32_t v[16];
         tmem_ld16(lane_addr + dcol + c, v);
-        float old[16];
-        if (!first_flush) {
-#pragma unroll
-          for (int i = 0; i < 16; ++i) old[i] = pp[(size_t)(c + i) * 128];
-        }
         tmem_wait_ld();
 #pragma unroll
-        for (int i = 0; i < 16; ++i) pp[(size_t)(c + i) * 128] = first_flush ? __uint_as_float(v[i]) : old[i] + __uint_as_float(v[i]);
+        for (int i = 0; i < 16; ++i) acc[c + i] += __uint_as_float(v[i]);
       }
-      first_flush = false;
       fence_before_sync();
+      SPW_PH(6);                                       // p6: tile flush
     }
   }
+  {   // this CTA's sum over its tiles -> per-CTA partial in global memory ([tile][n][lane]: coalesced)
+    float* pp = part + (size_t)mt * (160 * 128) + L;
+    if (a.first) {
+#pragma unroll
+      for (int c = 0; c < kN; ++c) pp[(size_t)c * 128] = acc[c];
+    } else {
+#pragma unroll
+      for (int c0 = 0; c0 < kN; c0 += 16) {
+        float old[16];
+#pragma unroll
+        for (int i = 0; i < 16; ++i) old[i] = pp[(size_t)(c0 + i) * 128];
+#pragma unroll
+        for (int i = 0; i < 16; ++i) pp[(size_t)(c0 + i) * 128] = old[i] + acc[c0 + i];
+      }
+    }
+  }
+  SPW_PH_REPORT(XMODE ? "k_wgrad_tc<1,1>" : "k_wgrad_tc<0,0>");
   if (failed && tid == 0) a.poison[0] = __int_as_float(0x7fc00000);
   fence_before_sync();
   __syncthreads();
@@ -935,8 +987,14 @@ __global__ void __launch_bounds__(kThreads, 1) k_wgrad_rows_tc(WgradRowsArgs a) 
   const uint32_t colA_hi = kWgColA + 64 * mt, colA_lo = colA_hi + 32;
   const uint32_t idesc = make_idesc_tf32(128, NB);
   uint32_t parity = 0;
-  bool failed = false, pending = false, first_flush = true;
+  bool failed = false, pending = false;
   float* part = a.part + (size_t)blockIdx.x * kWgPartFloats;
+  // columns of this thread: everything (two M-tiles) or its group's share of the 16-column blocks (one M-tile)
+  const int nblk = NB / 16;
+  const int b_lo = nmt == 2 ? 0 : (grp ? (nblk + 1) / 2 : 0), b_hi = nmt == 2 ? nblk : (grp ? nblk : (nblk + 1) / 2);
+  float acc[kN];                                                // sum over this CTA's tiles (round-to-nearest adds)
+#pragma unroll
+  for (int c = 0; c < kN; ++c) acc[c] = 0.f;
   const int ntiles = (a.M + kTM - 1) / kTM;
   constexpr int kCh = kTM / kWgChunk;                           // chunks per tile
   const int my_tiles = (int)blockIdx.x < ntiles ? (ntiles - 1 - (int)blockIdx.x) / (int)gridDim.x + 1 : 0;
@@ -1020,27 +1078,28 @@ __global__ void __launch_bounds__(kThreads, 1) k_wgrad_rows_tc(WgradRowsArgs a) 
       parity ^= 1u;
       fence_after_sync();
       pending = false;
-      float* pp = part + (size_t)mt * (160 * 128) + L;
       const uint32_t dcol = mt ? kWgColD1 : kWgColD0;
-      // columns of this thread: everything (two M-tiles) or its group's share of the 16-column blocks (one M-tile)
-      const int nblk = NB / 16;
-      const int b_lo = nmt == 2 ? 0 : (grp ? (nblk + 1) / 2 : 0), b_hi = nmt == 2 ? nblk : (grp ? nblk : (nblk + 1) / 2);
-#pragma unroll 1
-      for (int b = b_lo; b < b_hi; ++b) {
-        const int c = 16 * b;
-        uint32_t v[16];
-        tmem_ld16(lane_addr + dcol + c, v);
-        float old[16];
-        if (!first_flush) {
 #pragma unroll
-          for (int i = 0; i < 16; ++i) old[i] = pp[(size_t)(c + i) * 128];
+      for (int b = 0; b < kN / 16; ++b) {
+        if (b >= b_lo && b < b_hi) {                   // warp-uniform
+          uint32_t v[16];
+          tmem_ld16(lane_addr + dcol + 16 * b, v);
+          tmem_wait_ld();
+#pragma unroll
+          for (int i = 0; i < 16; ++i) acc[16 * b + i] += __uint_as_float(v[i]);
         }
-        tmem_wait_ld();
-#pragma unroll
-        for (int i = 0; i < 16; ++i) pp[(size_t)(c + i) * 128] = first_flush ? __uint_as_float(v[i]) : old[i] + __uint_as_float(v[i]);
       }
-      first_flush = false;
       fence_before_sync();
+    }
+  }
+  {   // this CTA's sum over its tiles -> per-CTA partial in global memory ([tile][n][lane]: coalesced)
+    float* pp = part + (size_t)mt * (160 * 128) + L;
+#pragma unroll
+    for (int b = 0; b < kN / 16; ++b) {
+      if (b >= b_lo && b < b_hi) {
+#pragma unroll
+        for (int i = 0; i < 16; ++i) pp[(size_t)(16 * b + i) * 128] = acc[16 * b + i];
+      }
     }
   }
   if (failed && tid == 0) a.poison[0] = __int_as_float(0x7fc00000);

@@ -1,17 +1,21 @@
-import sys, torch, ctypes
-sys.path.insert(0, '/root/repo')
+"""Per-phase cycle counts of the tile loops (development aid): expects tools/_build/libspwgnn_phase.so
+(nvcc ... -DSPW_PHASE_TIMING) and runs one training step of the C2 workload through it; the kernels print their
+clock64() phase sums for CTA 0 (threads 0 and 255)."""
+import os
+import sys
+import torch
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import spwgnn_b200._lib as _lib
 from spwgnn_b200._capi import CApi
-api = CApi('/root/repo/tools/_build/libspwgnn_phase.so')
-import importlib
-sys.path.insert(0, '/root/repo/tests')
-from test_gpu_tc import _tc_linear
-g = torch.Generator().manual_seed(0)
-for (M, K, ldx, N, ldy, NB, tag) in [(368640, 150, 152, 150, 152, 160, 'E-level'), (40960, 100, 100, 100, 100, 112, 'node')]:
-    X = torch.randn(M, ldx, generator=g).cuda()
-    W = ((torch.rand(K, N, generator=g) * 2 - 1) * 0.2).cuda()
-    b = torch.randn(N, generator=g).cuda()
-    Y = torch.empty(M, ldy, device='cuda')
-    print(tag, flush=True)
-    for it in range(2):
-        _tc_linear(api, M, X, K, None, 0, W, N, NB, bias=b, act=1, Y=Y, ldy=ldy, ones_col=150 if N == 150 else -1)
-    torch.cuda.synchronize()
+_lib._api = CApi(os.path.join(os.path.dirname(os.path.abspath(__file__)), '_build', 'libspwgnn_phase.so'))
+from spwgnn_b200.engine import Engine
+from spwgnn_b200.graph import TowerBatch
+from spwgnn_b200 import synth
+
+towers = synth.make_towers('jenga', 4096, 3, n=10)
+eng = Engine('cuda:0', seed=1)
+batch = TowerBatch.from_towers(towers, device='cuda:0', fully_connected=True)
+print('nodes', batch.n_nodes, 'edges', batch.n_edges, flush=True)
+tgt = torch.zeros(batch.n_nodes, device='cuda')
+eng.loss_and_grads(batch, tgt)
+torch.cuda.synchronize()
