@@ -100,48 +100,22 @@ struct RowsTcArgs {
   float* poison;                               // written with NaN if an MMA barrier times out
 };
 
+// ---- k_rows_tc ------------------------------------------------------------------------------------
+// All global traffic is coalesced (a 16-byte access per lane that touches 32 different 128-byte lines costs the L1 about
+// 65 cycles; eight lanes per 128 bytes of a row cost a fifth of that): a tile's rows are fetched as 16-byte chunks in
+// (row, chunk) order into registers one tile ahead, and are transposed to the row-per-thread order tensor memory needs
+// through two 16 KB shared-memory slabs of 128 rows x 32 columns (chunk index XOR-swizzled with the row: conflict-free
+// both ways).  The accumulator goes back the same way: row threads read D from tensor memory and drop it into a slab,
+// then every thread applies the epilogue to four (row, chunk) pieces and writes them coalesced.
+constexpr int kSlabCols = 32;
+constexpr int kSlabFloats = kTM * kSlabCols;        // 4096 floats = 16 KB
+constexpr int kRowsMaxSlabs = 7;                    // ks <= 25 -> ceil(25 / 4)
+constexpr int kRowsEarlySlabs = 3;                  // correction MMAs of the first slabs are issued while the rest is staged
+
 template <int NB>
-constexpr size_t rows_tc_smem(int ks) { return (size_t)2 * ks * 8 * NB * sizeof(float) + 32; }
+constexpr size_t rows_tc_smem(int ks) { return (size_t)(2 * ks * 8 * NB + 2 * kSlabFloats + NB) * sizeof(float) + 32; }
 
-// 8 consecutive columns [c, c+8) of the concatenated row of this thread -> x[8] (zeros beyond the valid columns)
-__device__ __forceinline__ void rows_load8(const RowsTcArgs& a, const float* p0, const float* p1, bool valid, int c, float4& u,
-                                           float4& v) {
-  const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
-  u = z; v = z;
-  if (!valid) return;
-#pragma unroll
-  for (int g = 0; g < 2; ++g) {
-    float4& dst = g ? v : u;
-    int cc = c + 4 * g;
-    const float* p = p0;
-    int K = a.K[0];
-    if (a.nseg == 2 && cc >= a.K[0]) { cc -= a.K[0]; p = p1; K = a.K[1]; }
-    if (cc + 3 < K) {
-      dst = *reinterpret_cast<const float4*>(p + cc);
-    } else {
-      if (cc < K) dst.x = p[cc];
-      if (cc + 1 < K) dst.y = p[cc + 1];
-      if (cc + 2 < K) dst.z = p[cc + 2];
-    }
-  }
-}
-
-// 16 consecutive floats row[col0 .. col0+16) -> o (zeros at columns >= lim); 16-byte loads where the pointer allows it
-__device__ __forceinline__ void rows_load16(const float* __restrict__ rowp, int col0, int lim, bool vec_ok, float (&o)[16]) {
-#pragma unroll
-  for (int g = 0; g < 4; ++g) {
-    const int c = col0 + 4 * g;
-    if (vec_ok && c + 3 < lim) {
-      const float4 q = *reinterpret_cast<const float4*>(rowp + c);
-      o[4 * g] = q.x; o[4 * g + 1] = q.y; o[4 * g + 2] = q.z; o[4 * g + 3] = q.w;
-    } else {
-#pragma unroll
-      for (int i = 0; i < 4; ++i) o[4 * g + i] = c + i < lim ? rowp[c + i] : 0.f;
-    }
-  }
-}
-
-constexpr int kRowsKpt = 13;     // k-steps per thread at most (ks <= 25, two threads per row)
+__device__ __forceinline__ int slab_off(int row, int ch) { return row * kSlabCols + ((ch ^ (row & 7)) << 2); }
 
 template <int NB>
 __global__ void __launch_bounds__(kThreads, 1) k_rows_tc(RowsTcArgs a) {
@@ -149,16 +123,20 @@ __global__ void __launch_bounds__(kThreads, 1) k_rows_tc(RowsTcArgs a) {
   const int bfl = a.ks * 8 * NB;                                 // floats per hi / lo operand
   float* Bhi_s = reinterpret_cast<float*>(smem_raw);
   float* Blo_s = Bhi_s + bfl;
-  uint64_t* bar = reinterpret_cast<uint64_t*>(Blo_s + bfl);
+  float* slab = Blo_s + bfl;                                     // [2][128][32]
+  float* sbias = slab + 2 * kSlabFloats;                         // [NB]
+  uint64_t* bar = reinterpret_cast<uint64_t*>(sbias + NB);
   uint32_t* tptr = reinterpret_cast<uint32_t*>(bar + 1);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int row = 32 * (warp & 3) + lane, half = warp >> 2;
+  const int row = 32 * (warp & 3) + lane, half = warp >> 2;      // tensor-memory view: thread = (row, column half)
+  const int crow = tid >> 3, cch = tid & 7;                      // coalesced view: rows crow + 32 i (i < 4), chunk cch
 
   for (int i = tid; i < bfl / 4; i += kThreads) {                // weights: asynchronous, overlapped with the first row loads
     cp_async16(Bhi_s + 4 * i, a.Bhi + 4 * i);
     cp_async16(Blo_s + 4 * i, a.Blo + 4 * i);
   }
   cp_async_commit();
+  for (int i = tid; i < NB; i += kThreads) sbias[i] = (a.bias && i < a.N) ? a.bias[i] : 0.f;
   if (warp == 0) tmem_alloc(tptr, kTmemCols);
   if (tid == 32) { mbar_init(bar, 1); fence_mbar_init(); }
   fence_before_sync();
@@ -171,150 +149,253 @@ __global__ void __launch_bounds__(kThreads, 1) k_rows_tc(RowsTcArgs a) {
   uint32_t parity = 0;
   bool failed = false, first = true;
   const int ntiles = (a.M + kTM - 1) / kTM;
-  const int ks_h0 = (a.ks + 1) >> 1;                             // k-steps [0, ks_h0) belong to half 0, the rest to half 1
-  const int ks_lo = half ? ks_h0 : 0, ks_hi = half ? a.ks : ks_h0;
-  const bool bias_vec = (reinterpret_cast<uintptr_t>(a.bias) & 15) == 0;
+  const int ns = (a.ks + 3) >> 2;                                // operand slabs per tile (4 k-steps each)
+  const int ks_early = ns > kRowsEarlySlabs ? 4 * kRowsEarlySlabs : 0;
 
-  // this thread's k-steps of its row of a tile -> registers (all loads in flight at once)
-  float4 pu[kRowsKpt], pv[kRowsKpt];
+  // ---- rows of a tile -> registers, coalesced; unconditional loads (addresses clamped), masked when stored to the slab
+  float4 P[kRowsMaxSlabs][4];
   auto load_tile = [&](int tile) {
-    const size_t gr = (size_t)tile * kTM + row;
-    const bool ok = gr < (size_t)a.M;
-    const float* p0 = a.X[0] + gr * a.ldx[0];
-    const float* p1 = a.nseg == 2 ? a.X[1] + gr * a.ldx[1] : nullptr;
+    const float* pr0[4]; const float* pr1[4];
 #pragma unroll
-    for (int j = 0; j < kRowsKpt; ++j)
-      if (ks_lo + j < ks_hi) rows_load8(a, p0, p1, ok, 8 * (ks_lo + j), pu[j], pv[j]);
+    for (int i = 0; i < 4; ++i) {
+      size_t gr = (size_t)tile * kTM + crow + 32 * i;
+      if (gr >= (size_t)a.M) gr = (size_t)a.M - 1;
+      pr0[i] = a.X[0] + gr * a.ldx[0];
+      pr1[i] = a.nseg == 2 ? a.X[1] + gr * a.ldx[1] : pr0[i];
+    }
+#pragma unroll
+    for (int sl = 0; sl < kRowsMaxSlabs; ++sl) {
+      if (sl < ns) {                                             // block-uniform
+        int cc = kSlabCols * sl + 4 * cch;
+        bool seg1 = false;
+        if (a.nseg == 2 && cc >= a.K[0]) { cc -= a.K[0]; seg1 = true; }
+        if (cc >= (seg1 ? a.K[1] : a.K[0])) cc = 0;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) P[sl][i] = *reinterpret_cast<const float4*>((seg1 ? pr1[i] : pr0[i]) + cc);
+      }
+    }
   };
   if ((int)blockIdx.x < ntiles) load_tile(blockIdx.x);
+  SPW_PH_DECL
 
   for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
-    const size_t grow = (size_t)tile * kTM + row;
-    const bool valid = grow < (size_t)a.M;
-    // ---- A operand: split into tf32 hi / lo, store to tensor memory
+    SPW_PH(7);
+    const int r0 = tile * kTM;
+    const uint64_t dhi0 = make_b_desc(smem_u32(Bhi_s), NB * 16, 128), dlo0 = make_b_desc(smem_u32(Blo_s), NB * 16, 128);
+    constexpr uint64_t kStep = (8 * NB * 4) >> 4;                // descriptor start-address units (16 bytes) per k-step
+    const uint32_t dcol = tmem_base + colD;
+    // ---- A operand, slab by slab: registers -> slab (masked) -> row threads -> tf32 hi / lo -> tensor memory
 #pragma unroll
-    for (int j = 0; j < kRowsKpt; ++j) {
-      if (ks_lo + j < ks_hi) {                                   // warp-uniform
-        const float x[8] = {pu[j].x, pu[j].y, pu[j].z, pu[j].w, pv[j].x, pv[j].y, pv[j].z, pv[j].w};
-        uint32_t h[8], l[8];
+    for (int sl = 0; sl < kRowsMaxSlabs; ++sl) {
+      if (sl < ns) {
+        float* sb = slab + (sl & 1) * kSlabFloats;
+        {
+          int cc = kSlabCols * sl + 4 * cch;
+          int K = a.K[0];
+          if (a.nseg == 2 && cc >= a.K[0]) { cc -= a.K[0]; K = a.K[1]; }
+          const int ncol = K - cc;                               // valid columns of this chunk: >= 4 all, <= 0 none
 #pragma unroll
-        for (int i = 0; i < 8; ++i) split_tf32(x[i], h[i], l[i]);
-        tmem_st8(lane_addr + colAhi + 8 * (ks_lo + j), h);
-        tmem_st8(lane_addr + colAlo + 8 * (ks_lo + j), l);
+          for (int i = 0; i < 4; ++i) {
+            float4 q = P[sl][i];
+            const int nval = (r0 + crow + 32 * i < a.M) ? ncol : 0;
+            if (nval < 4) { if (nval < 1) q.x = 0.f; if (nval < 2) q.y = 0.f; if (nval < 3) q.z = 0.f; q.w = 0.f; }
+            *reinterpret_cast<float4*>(sb + slab_off(crow + 32 * i, cch)) = q;
+          }
+        }
+        const bool early = ks_early > 0 && sl == kRowsEarlySlabs;  // the first slabs are complete in tensor memory: start their MMAs
+        if (early) { tmem_wait_st(); fence_before_sync(); }
+        if (first && sl == 0) { cp_async_wait<0>(); fence_async_smem(); }
+        __syncthreads();
+        if (early && tid == 0) {                                 // correction products of k-steps [0, ks_early)
+          fence_after_sync();
+#pragma unroll 4
+          for (int ks = 0; ks < ks_early; ++ks) {
+            mma_tf32_ts(dcol, tmem_base + colAlo + 8 * ks, dhi0 + ks * kStep, idesc, ks > 0 ? 1u : 0u);
+            mma_tf32_ts(dcol, tmem_base + colAhi + 8 * ks, dlo0 + ks * kStep, idesc, 1u);
+          }
+        }
+#pragma unroll
+        for (int j = 0; j < 2; ++j) {                            // this thread's two k-steps of the slab
+          const int ks = 4 * sl + 2 * half + j;
+          if (ks < a.ks) {                                       // warp-uniform
+            const float4 u = *reinterpret_cast<const float4*>(sb + slab_off(row, 4 * half + 2 * j));
+            const float4 v = *reinterpret_cast<const float4*>(sb + slab_off(row, 4 * half + 2 * j + 1));
+            const float x[8] = {u.x, u.y, u.z, u.w, v.x, v.y, v.z, v.w};
+            uint32_t h[8], l[8];
+#pragma unroll
+            for (int e = 0; e < 8; ++e) split_tf32(x[e], h[e], l[e]);
+            tmem_st8(lane_addr + colAhi + 8 * ks, h);
+            tmem_st8(lane_addr + colAlo + 8 * ks, l);
+          }
+        }
       }
     }
+    first = false;
     tmem_wait_st();
-    if (first) { cp_async_wait<0>(); fence_async_smem(); first = false; }
     fence_before_sync();
+    SPW_PH(0);                                                   // p0: operand staging
     __syncthreads();
+    SPW_PH(1);
     if (tid == 0) {
       fence_after_sync();
-      const uint32_t bhi = smem_u32(Bhi_s), blo = smem_u32(Blo_s);
-      const uint32_t d = tmem_base + colD;
-      // correction products first, main products last (the tensor core truncates when it accumulates)
-#pragma unroll 1
-      for (int ks = 0; ks < a.ks; ++ks) {
-        const uint64_t dhi = make_b_desc(bhi + ks * (8 * NB * 4), NB * 16, 128);
-        const uint64_t dlo = make_b_desc(blo + ks * (8 * NB * 4), NB * 16, 128);
-        mma_tf32_ts(d, tmem_base + colAlo + 8 * ks, dhi, idesc, ks > 0 ? 1u : 0u);
-        mma_tf32_ts(d, tmem_base + colAhi + 8 * ks, dlo, idesc, 1u);
+#pragma unroll 4
+      for (int ks = ks_early; ks < a.ks; ++ks) {                 // remaining correction products
+        mma_tf32_ts(dcol, tmem_base + colAlo + 8 * ks, dhi0 + ks * kStep, idesc, ks > 0 ? 1u : 0u);
+        mma_tf32_ts(dcol, tmem_base + colAhi + 8 * ks, dlo0 + ks * kStep, idesc, 1u);
       }
-#pragma unroll 1
-      for (int ks = 0; ks < a.ks; ++ks) {
-        const uint64_t dhi = make_b_desc(bhi + ks * (8 * NB * 4), NB * 16, 128);
-        mma_tf32_ts(d, tmem_base + colAhi + 8 * ks, dhi, idesc, 1u);
-      }
+#pragma unroll 4
+      for (int ks = 0; ks < a.ks; ++ks) mma_tf32_ts(dcol, tmem_base + colAhi + 8 * ks, dhi0 + ks * kStep, idesc, 1u);   // main products last
       mma_commit(bar);
     }
+    SPW_PH(2);                                                   // p2: MMA issue
     // rows of this CTA's next tile: in flight while the MMAs run and the epilogue is written
     if (tile + (int)gridDim.x < ntiles) load_tile(tile + gridDim.x);
+    SPW_PH(3);                                                   // p3: issue of the next tile's loads
     if (!mbar_wait(bar, parity)) failed = true;
     parity ^= 1u;
     fence_after_sync();
-    // ---- epilogue: 16-column blocks of this thread's row, alternating between the two halves
-    const float rs = (valid && a.rowscale) ? a.rowscale[grow] : 1.f;
-    for (int blk = half; blk * 16 < NB; blk += 2) {
-      const int col0 = blk * 16;
-      if (col0 >= a.ldy) break;                                  // warp-uniform
-      uint32_t vv[16];
-      tmem_ld16(lane_addr + colD + col0, vv);
-      float r[16], m[16];
-      if (valid && a.bias) rows_load16(a.bias, col0, a.N, bias_vec, m);
-      tmem_wait_ld();
-      if (!valid) continue;
+    SPW_PH(4);                                                   // p4: wait for the MMAs
+    // ---- epilogue, 32 accumulator columns at a time: tensor memory -> slab (row threads) -> epilogue + store (coalesced)
+    constexpr int kEs = (NB + kSlabCols - 1) / kSlabCols;
+#pragma unroll 1
+    for (int es = 0; es < kEs; ++es) {
+      if (kSlabCols * es >= a.ldy) break;                        // block-uniform
+      float* sb = slab + (es & 1) * kSlabFloats;
+      if (kSlabCols * es + 16 * half < NB) {                     // warp-uniform
+        uint32_t vv[16];
+        tmem_ld16(lane_addr + colD + kSlabCols * es + 16 * half, vv);
+        tmem_wait_ld();
 #pragma unroll
-      for (int i = 0; i < 16; ++i) r[i] = __uint_as_float(vv[i]);
+        for (int g = 0; g < 4; ++g)
+          *reinterpret_cast<uint4*>(sb + slab_off(row, 4 * half + g)) = make_uint4(vv[4 * g], vv[4 * g + 1], vv[4 * g + 2], vv[4 * g + 3]);
+      }
+      __syncthreads();
+      const int col = kSlabCols * es + 4 * cch;
+      const bool col_ok = col < a.ldy;
+      const bool full = col + 3 < a.N;
+      float r[4][4], m[4][4];
+      bool rv[4];
+      size_t go[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const size_t grow = (size_t)r0 + crow + 32 * i;
+        rv[i] = col_ok && grow < (size_t)a.M;
+        go[i] = rv[i] ? grow : 0;
+        const float4 q = *reinterpret_cast<const float4*>(sb + slab_off(crow + 32 * i, cch));
+        r[i][0] = q.x; r[i][1] = q.y; r[i][2] = q.z; r[i][3] = q.w;
+      }
+      auto load_m = [&](const float* base, int ld) {             // the four (row, chunk) pieces of another array, zeros beyond N
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          if (full) {
+            const float4 t = *reinterpret_cast<const float4*>(base + go[i] * ld + col);
+            m[i][0] = t.x; m[i][1] = t.y; m[i][2] = t.z; m[i][3] = t.w;
+          } else {
+#pragma unroll
+            for (int e = 0; e < 4; ++e) m[i][e] = (col_ok && col + e < a.N) ? base[go[i] * ld + col + e] : 0.f;
+          }
+        }
+      };
       if (a.bias) {
+        const float4 bq = *reinterpret_cast<const float4*>(sbias + (col < NB ? col : 0));
 #pragma unroll
-        for (int i = 0; i < 16; ++i) r[i] = fmaf(rs, m[i], r[i]);
+        for (int i = 0; i < 4; ++i) {
+          const float rs = a.rowscale ? a.rowscale[go[i]] : 1.f;
+          r[i][0] = fmaf(rs, bq.x, r[i][0]); r[i][1] = fmaf(rs, bq.y, r[i][1]);
+          r[i][2] = fmaf(rs, bq.z, r[i][2]); r[i][3] = fmaf(rs, bq.w, r[i][3]);
+        }
       }
       if (a.addend) {
-        rows_load16(a.addend + grow * a.ld_add, col0, a.N, true, m);
+        load_m(a.addend, a.ld_add);
 #pragma unroll
-        for (int i = 0; i < 16; ++i) r[i] += m[i];
+        for (int i = 0; i < 4; ++i)
+#pragma unroll
+          for (int e = 0; e < 4; ++e) r[i][e] += m[i][e];
       }
       if (a.act == 1) {
 #pragma unroll
-        for (int i = 0; i < 16; ++i) r[i] = relu_f(r[i]);
+        for (int i = 0; i < 4; ++i)
+#pragma unroll
+          for (int e = 0; e < 4; ++e) r[i][e] = relu_f(r[i][e]);
       } else if (a.act == 2) {
 #pragma unroll
-        for (int i = 0; i < 16; ++i) r[i] = tanhf(r[i]);
+        for (int i = 0; i < 4; ++i)
+#pragma unroll
+          for (int e = 0; e < 4; ++e) r[i][e] = tanhf(r[i][e]);
       }
-      if (a.mulmode == 3) {                                      // 16 mask bits of this block: half-word blk of the row
-        const uint32_t bits = reinterpret_cast<const uint16_t*>(a.bits_in)[grow * 16 + blk];
+      if (a.mulmode == 3) {                                      // mask bits: word es of the row, nibble cch
 #pragma unroll
-        for (int i = 0; i < 16; ++i) r[i] = ((bits >> i) & 1u) ? r[i] : 0.f;
-      } else if (a.mulmode) {
-        rows_load16(a.mulsrc + grow * a.ld_mul, col0, a.N, true, m);
-        if (a.mulmode == 1) {
+        for (int i = 0; i < 4; ++i) {
+          const uint32_t bits = a.bits_in[go[i] * 8 + es] >> (4 * cch);
 #pragma unroll
-          for (int i = 0; i < 16; ++i) r[i] = m[i] > 0.f ? r[i] : 0.f;
-        } else {
-#pragma unroll
-          for (int i = 0; i < 16; ++i) r[i] *= (1.f - m[i] * m[i]);
+          for (int e = 0; e < 4; ++e) r[i][e] = ((bits >> e) & 1u) ? r[i][e] : 0.f;
         }
+      } else if (a.mulmode) {
+        load_m(a.mulsrc, a.ld_mul);
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+#pragma unroll
+          for (int e = 0; e < 4; ++e) r[i][e] = a.mulmode == 1 ? (m[i][e] > 0.f ? r[i][e] : 0.f) : r[i][e] * (1.f - m[i][e] * m[i][e]);
       }
       if (a.drop_thresh) {
 #pragma unroll
-        for (int i = 0; i < 16; ++i)
-          r[i] = dropout_apply(r[i], a.drop_seed, (uint32_t)(grow * a.drop_stride + col0 + i), a.drop_thresh, a.drop_inv_keep);
+        for (int i = 0; i < 4; ++i)
+#pragma unroll
+          for (int e = 0; e < 4; ++e)
+            r[i][e] = dropout_apply(r[i][e], a.drop_seed, (uint32_t)(go[i] * a.drop_stride + col + e), a.drop_thresh, a.drop_inv_keep);
       }
       if (a.post_scale != 1.f) {
 #pragma unroll
-        for (int i = 0; i < 16; ++i) r[i] *= a.post_scale;
+        for (int i = 0; i < 4; ++i)
+#pragma unroll
+          for (int e = 0; e < 4; ++e) r[i][e] *= a.post_scale;
       }
       if (a.accumulate) {
-        rows_load16(a.Y + grow * a.ldy, col0, a.N, true, m);
+        load_m(a.Y, a.ldy);
 #pragma unroll
-        for (int i = 0; i < 16; ++i) r[i] += m[i];
+        for (int i = 0; i < 4; ++i)
+#pragma unroll
+          for (int e = 0; e < 4; ++e) r[i][e] += m[i][e];
       }
-      if (a.bits_out) {
-        uint32_t bits = 0u;
+      if (a.bits_out) {                                          // sign bits: the 8 chunk-threads of a row make up word es
 #pragma unroll
-        for (int i = 0; i < 16; ++i) bits |= (col0 + i < a.N && r[i] > 0.f) ? (1u << i) : 0u;
-        reinterpret_cast<uint16_t*>(a.bits_out)[grow * 16 + blk] = (uint16_t)bits;
+        for (int i = 0; i < 4; ++i) {
+          uint32_t nib = 0u;
+#pragma unroll
+          for (int e = 0; e < 4; ++e) nib |= (rv[i] && col + e < a.N && r[i][e] > 0.f) ? (1u << e) : 0u;
+          uint32_t w = nib << (4 * cch);
+          w |= __shfl_xor_sync(0xffffffffu, w, 1);
+          w |= __shfl_xor_sync(0xffffffffu, w, 2);
+          w |= __shfl_xor_sync(0xffffffffu, w, 4);
+          if (cch == 0 && (size_t)r0 + crow + 32 * i < (size_t)a.M) a.bits_out[((size_t)r0 + crow + 32 * i) * 8 + es] = w;
+        }
       }
-      if (col0 + 16 > a.N) {                                     // columns beyond N: zero (or the ones column)
+      if (!full) {                                               // columns beyond N: zero (or the ones column)
 #pragma unroll
-        for (int i = 0; i < 16; ++i)
-          if (col0 + i >= a.N) r[i] = (col0 + i == a.ones_col) ? 1.f : 0.f;
+        for (int i = 0; i < 4; ++i)
+#pragma unroll
+          for (int e = 0; e < 4; ++e)
+            if (col + e >= a.N) r[i][e] = (col + e == a.ones_col) ? 1.f : 0.f;
       }
-      float* yrow = a.Y + grow * a.ldy;
 #pragma unroll
-      for (int g = 0; g < 4; ++g) {
-        const int c = col0 + 4 * g;
-        if (c + 3 < a.ldy) {
-          *reinterpret_cast<float4*>(yrow + c) = make_float4(r[4 * g], r[4 * g + 1], r[4 * g + 2], r[4 * g + 3]);
+      for (int i = 0; i < 4; ++i) {
+        if (!rv[i]) continue;
+        float* yp = a.Y + go[i] * a.ldy + col;
+        if (col + 3 < a.ldy) {
+          *reinterpret_cast<float4*>(yp) = make_float4(r[i][0], r[i][1], r[i][2], r[i][3]);
         } else {
 #pragma unroll
-          for (int i = 0; i < 4; ++i)
-            if (c + i < a.ldy) yrow[c + i] = r[4 * g + i];
+          for (int e = 0; e < 4; ++e)
+            if (col + e < a.ldy) yp[e] = r[i][e];
         }
       }
     }
     fence_before_sync();
+    SPW_PH(5);                                                   // p5: epilogue
     __syncthreads();
+    SPW_PH(6);
   }
+  if (a.M > 100000) SPW_PH_REPORT(a.mulmode ? "k_rows_tc:enc_bwd" : "k_rows_tc:enc_fwd");
   if (failed && tid == 0) a.poison[0] = __int_as_float(0x7fc00000);
   if (first) cp_async_wait<0>();
   fence_before_sync();
