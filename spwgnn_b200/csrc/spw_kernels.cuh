@@ -311,25 +311,38 @@ struct RedArgs {
   float* dW; int dst_ld, dst_row0, dst_col0;   // null: skip the matrix
   float* db; int db_off;                       // null: skip the bias row
 };
+// Eight lanes per output element: lane g sums parts g, g+8, g+16, ... in order, then the eight sub-sums are combined
+// in a fixed order -- deterministic, and 8 independent load chains per element instead of one long dependent one.
 __global__ void __launch_bounds__(256) k_reduce_parts(RedArgs a) {
   const int total = (a.Kin + 1) * a.N;
-  for (int idx = blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += gridDim.x * blockDim.x) {
-    const int k = idx / a.N, n = idx - k * a.N;
-    if (k == a.Kin && !a.db) continue;
-    if (k < a.Kin && !a.dW) continue;
+  const int g = threadIdx.x & 7;
+  const int per_block = blockDim.x >> 3;
+  for (int base = blockIdx.x * per_block; base < total; base += gridDim.x * per_block) {
+    const int idx = base + (threadIdx.x >> 3);
+    const bool in_range = idx < total;
+    const int k = in_range ? idx / a.N : 0, n = in_range ? idx - k * a.N : 0;
+    const bool want = in_range && !((k == a.Kin && !a.db) || (k < a.Kin && !a.dW));
     float s = 0.f;
-    const float* p;
-    if (a.TA > 0) {
-      const int ja = k / a.TA, ea = k - ja * a.TA, jb = n / a.TB, eb = n - jb * a.TB;
-      p = a.part + (size_t)(ea * a.TB + eb) * kThreads + (ja * 16 + jb);
-    } else if (a.TA < 0) {
-      p = k < 128 ? a.part + (size_t)n * 128 + k : a.part + (size_t)(160 + n) * 128 + (k - a.TB);
-    } else {
-      p = a.part + (size_t)k * a.src_ld + n;
+    if (want) {
+      const float* p;
+      if (a.TA > 0) {
+        const int ja = k / a.TA, ea = k - ja * a.TA, jb = n / a.TB, eb = n - jb * a.TB;
+        p = a.part + (size_t)(ea * a.TB + eb) * kThreads + (ja * 16 + jb);
+      } else if (a.TA < 0) {
+        p = k < 128 ? a.part + (size_t)n * 128 + k : a.part + (size_t)(160 + n) * 128 + (k - a.TB);
+      } else {
+        p = a.part + (size_t)k * a.src_ld + n;
+      }
+      for (int c = g; c < a.nparts; c += 8) s += p[(size_t)c * a.part_stride];
     }
-    for (int c = 0; c < a.nparts; ++c) s += p[(size_t)c * a.part_stride];
-    if (k < a.Kin) a.dW[(size_t)(a.dst_row0 + k) * a.dst_ld + a.dst_col0 + n] = s;
-    else a.db[a.db_off + n] = s;
+    // fixed combination order: ((s0 + s4) + (s2 + s6)) + ((s1 + s5) + (s3 + s7))
+    s += __shfl_xor_sync(0xffffffffu, s, 4);
+    s += __shfl_xor_sync(0xffffffffu, s, 2);
+    s += __shfl_xor_sync(0xffffffffu, s, 1);
+    if (want && g == 0) {
+      if (k < a.Kin) a.dW[(size_t)(a.dst_row0 + k) * a.dst_ld + a.dst_col0 + n] = s;
+      else a.db[a.db_off + n] = s;
+    }
   }
 }
 

@@ -48,34 +48,35 @@ __global__ void __launch_bounds__(256) k_pack_tc(PackTcArgs a) {
 __global__ void __launch_bounds__(256) k_edge_enc0(int E, const int32_t* __restrict__ in_snd, const int32_t* __restrict__ in_rcv,
                                                    const float* __restrict__ obj, const float* __restrict__ W0,
                                                    const float* __restrict__ b0, float* __restrict__ X0, uint32_t* __restrict__ bits) {
-  constexpr int C4 = kDEP / 4;
+  // 40 chunk-threads per row (38 write a piece of X0): the 8 threads of one 32-column word are 8 consecutive, 8-aligned lanes,
+  // so the sign bits of X0 (the mask of the layer's data gradient) come from three shuffles
+  constexpr int C4 = 40;
   const long long total = (long long)E * C4;
-  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
-    const int e = (int)(i / C4), c = (int)(i - (long long)e * C4) * 4;
-    const int s = in_snd[e], rc = in_rcv[e];
-    const float dx = obj[3 * (size_t)rc] - obj[3 * (size_t)s], dy = obj[3 * (size_t)rc + 1] - obj[3 * (size_t)s + 1];
-    float v[4];
+  const long long span = (long long)gridDim.x * blockDim.x;
+  const long long iters = (total + span - 1) / span;
+  for (long long it = 0; it < iters; ++it) {
+    const long long i = it * span + (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const bool in_range = i < total;
+    const int e = in_range ? (int)(i / C4) : 0, c4 = in_range ? (int)(i - (long long)e * C4) : 0, c = 4 * c4;
+    uint32_t nib = 0u;
+    if (in_range && c < kDEP) {
+      const int s = in_snd[e], rc = in_rcv[e];
+      const float dx = obj[3 * (size_t)rc] - obj[3 * (size_t)s], dy = obj[3 * (size_t)rc + 1] - obj[3 * (size_t)s + 1];
+      float v[4];
 #pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      const int k = c + j;
-      v[j] = k < kDE ? relu_f(fmaf(dy, __ldg(W0 + kDE + k), fmaf(dx, __ldg(W0 + k), __ldg(b0 + k)))) : (k == kDE ? 1.f : 0.f);
-    }
-    *reinterpret_cast<float4*>(X0 + (size_t)e * kDEP + c) = make_float4(v[0], v[1], v[2], v[3]);
-  }
-  if (bits) {   // sign bits of X0 (the mask of the layer's data gradient): one 32-column word per thread
-    const long long nw = (long long)E * 8;
-    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < nw; i += (long long)gridDim.x * blockDim.x) {
-      const int e = (int)(i >> 3), w = (int)(i & 7);
-      uint32_t m = 0u;
-      if (w < 5) {
-        const int s = in_snd[e], rc = in_rcv[e];
-        const float dx = obj[3 * (size_t)rc] - obj[3 * (size_t)s], dy = obj[3 * (size_t)rc + 1] - obj[3 * (size_t)s + 1];
-        for (int j = 0; j < 32; ++j) {
-          const int k = 32 * w + j;
-          if (k < kDE && fmaf(dy, __ldg(W0 + kDE + k), fmaf(dx, __ldg(W0 + k), __ldg(b0 + k))) > 0.f) m |= 1u << j;
-        }
+      for (int j = 0; j < 4; ++j) {
+        const int k = c + j;
+        v[j] = k < kDE ? relu_f(fmaf(dy, __ldg(W0 + kDE + k), fmaf(dx, __ldg(W0 + k), __ldg(b0 + k)))) : (k == kDE ? 1.f : 0.f);
+        if (k < kDE && v[j] > 0.f) nib |= 1u << j;
       }
-      bits[i] = m;
+      *reinterpret_cast<float4*>(X0 + (size_t)e * kDEP + c) = make_float4(v[0], v[1], v[2], v[3]);
+    }
+    if (bits) {                                                  // block-uniform
+      uint32_t w = nib << (4 * (c4 & 7));
+      w |= __shfl_xor_sync(0xffffffffu, w, 1);
+      w |= __shfl_xor_sync(0xffffffffu, w, 2);
+      w |= __shfl_xor_sync(0xffffffffu, w, 4);
+      if (in_range && (c4 & 7) == 0) bits[(size_t)e * 8 + (c4 >> 3)] = w;
     }
   }
 }

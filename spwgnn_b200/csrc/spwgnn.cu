@@ -342,7 +342,7 @@ void launch_reduce(cudaStream_t st, const float* part, int nparts, int part_stri
   r.part = part; r.nparts = nparts; r.part_stride = part_stride; r.src_ld = src_ld; r.TA = TA; r.TB = TB; r.Kin = Kin; r.N = N;
   r.dW = out.dW; r.dst_ld = out.dst_ld; r.dst_row0 = out.dst_row0; r.dst_col0 = out.dst_col0;
   r.db = out.db; r.db_off = out.db_off;
-  SPW_KLAUNCH("k_reduce_parts", k_reduce_parts, dim3(grid_for((int64_t)(Kin + 1) * N, 256)), dim3(256), 0, st, r);
+  SPW_KLAUNCH("k_reduce_parts", k_reduce_parts, dim3(grid_for((int64_t)(Kin + 1) * N, 32)), dim3(256), 0, st, r);
 }
 
 constexpr int kTW = 64;   // rows per tile of the node-level weight-gradient kernel
@@ -666,7 +666,7 @@ int spw_forward(const SpwParams* w, const SpwGraph* g, const float* obj, float* 
     float* C = training ? ws + L.EC : ws + L.A;
     uint32_t* EB = training ? reinterpret_cast<uint32_t*>(ws + L.EB) : nullptr;     // sign bits of X0, X1, X2, C
     const size_t nb = (size_t)E * 8;
-    SPW_KLAUNCH("k_edge_enc0", tc::k_edge_enc0, dim3(grid_for((int64_t)E * (kDEP / 4), 256)), dim3(256), 0, st, E, g->in_snd, g->in_rcv,
+    SPW_KLAUNCH("k_edge_enc0", tc::k_edge_enc0, dim3(grid_for((int64_t)E * 40, 256)), dim3(256), 0, st, E, g->in_snd, g->in_rcv,
                 obj, (const float*)w->rm_w[0], (const float*)w->rm_b[0], X0, EB);
     LinOpt o; o.act = 1; o.ones_col = kDE; o.tag = "k_rows_tc<160>:enc_fwd";
     RowsSeg s0 = {X0, kDEP, kDE}, s1 = {X1, kDEP, kDE}, s2 = {X2, kDEP, kDE}, s3 = {C, kDEP, kDE};
