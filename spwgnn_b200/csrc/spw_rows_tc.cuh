@@ -118,8 +118,149 @@ constexpr size_t rows_tc_smem(int ks) { return (size_t)(2 * ks * 8 * NB + 2 * kS
 
 __device__ __forceinline__ int slab_off(int row, int ch) { return row * kSlabCols + ((ch ^ (row & 7)) << 2); }
 
-template <int NB>
-__global__ void __launch_bounds__(kThreads, 1) k_rows_tc(RowsTcArgs a) {
+// Epilogue of PP (row, chunk) pieces of one 32-column accumulator slab: rows crow0 + rstride * i (i < PP) of the tile,
+// chunk cch (columns 32 es + 4 cch ...).  Reads the raw accumulators from the slab, applies the LinArgs contract and
+// writes 16 bytes per piece (eight lanes per 128 bytes of a row: coalesced).  Must be called by whole warps (shuffles).
+template <int NB, int PP>
+__device__ __forceinline__ void rows_epilogue(const RowsTcArgs& a, const float* sb, const float* sbias, int r0, int crow0,
+                                               int rstride, int cch, int es) {
+  const int col = kSlabCols * es + 4 * cch;
+  const bool col_ok = col < a.ldy;
+  const bool full = col + 3 < a.N;
+  float r[PP][4], m[PP][4];
+  bool rv[PP];
+  size_t go[PP];
+#pragma unroll
+  for (int i = 0; i < PP; ++i) {
+    const size_t grow = (size_t)r0 + crow0 + rstride * i;
+    rv[i] = col_ok && grow < (size_t)a.M;
+    go[i] = rv[i] ? grow : 0;
+    const float4 q = *reinterpret_cast<const float4*>(sb + slab_off(crow0 + rstride * i, cch));
+    r[i][0] = q.x; r[i][1] = q.y; r[i][2] = q.z; r[i][3] = q.w;
+  }
+  auto load_m = [&](const float* base, int ld) {             // the four (row, chunk) pieces of another array, zeros beyond N
+#pragma unroll
+    for (int i = 0; i < PP; ++i) {
+      if (full) {
+        const float4 t = *reinterpret_cast<const float4*>(base + go[i] * ld + col);
+        m[i][0] = t.x; m[i][1] = t.y; m[i][2] = t.z; m[i][3] = t.w;
+      } else {
+#pragma unroll
+        for (int e = 0; e < 4; ++e) m[i][e] = (col_ok && col + e < a.N) ? base[go[i] * ld + col + e] : 0.f;
+      }
+    }
+  };
+  if (a.bias) {
+    const float4 bq = *reinterpret_cast<const float4*>(sbias + (col < NB ? col : 0));
+#pragma unroll
+    for (int i = 0; i < PP; ++i) {
+      const float rs = a.rowscale ? a.rowscale[go[i]] : 1.f;
+      r[i][0] = fmaf(rs, bq.x, r[i][0]); r[i][1] = fmaf(rs, bq.y, r[i][1]);
+      r[i][2] = fmaf(rs, bq.z, r[i][2]); r[i][3] = fmaf(rs, bq.w, r[i][3]);
+    }
+  }
+  if (a.addend) {
+    load_m(a.addend, a.ld_add);
+#pragma unroll
+    for (int i = 0; i < PP; ++i)
+#pragma unroll
+      for (int e = 0; e < 4; ++e) r[i][e] += m[i][e];
+  }
+  if (a.act == 1) {
+#pragma unroll
+    for (int i = 0; i < PP; ++i)
+#pragma unroll
+      for (int e = 0; e < 4; ++e) r[i][e] = relu_f(r[i][e]);
+  } else if (a.act == 2) {
+#pragma unroll
+    for (int i = 0; i < PP; ++i)
+#pragma unroll
+      for (int e = 0; e < 4; ++e) r[i][e] = tanhf(r[i][e]);
+  }
+  if (a.mulmode == 3) {                                      // mask bits: word es of the row, nibble cch
+#pragma unroll
+    for (int i = 0; i < PP; ++i) {
+      const uint32_t bits = a.bits_in[go[i] * 8 + es] >> (4 * cch);
+#pragma unroll
+      for (int e = 0; e < 4; ++e) r[i][e] = ((bits >> e) & 1u) ? r[i][e] : 0.f;
+    }
+  } else if (a.mulmode) {
+    load_m(a.mulsrc, a.ld_mul);
+#pragma unroll
+    for (int i = 0; i < PP; ++i)
+#pragma unroll
+      for (int e = 0; e < 4; ++e) r[i][e] = a.mulmode == 1 ? (m[i][e] > 0.f ? r[i][e] : 0.f) : r[i][e] * (1.f - m[i][e] * m[i][e]);
+  }
+  if (a.drop_thresh) {
+#pragma unroll
+    for (int i = 0; i < PP; ++i)
+#pragma unroll
+      for (int e = 0; e < 4; ++e)
+        r[i][e] = dropout_apply(r[i][e], a.drop_seed, (uint32_t)(go[i] * a.drop_stride + col + e), a.drop_thresh, a.drop_inv_keep);
+  }
+  if (a.post_scale != 1.f) {
+#pragma unroll
+    for (int i = 0; i < PP; ++i)
+#pragma unroll
+      for (int e = 0; e < 4; ++e) r[i][e] *= a.post_scale;
+  }
+  if (a.accumulate) {
+    load_m(a.Y, a.ldy);
+#pragma unroll
+    for (int i = 0; i < PP; ++i)
+#pragma unroll
+      for (int e = 0; e < 4; ++e) r[i][e] += m[i][e];
+  }
+  if (a.bits_out) {                                          // sign bits: the 8 chunk-threads of a row make up word es
+#pragma unroll
+    for (int i = 0; i < PP; ++i) {
+      uint32_t nib = 0u;
+#pragma unroll
+      for (int e = 0; e < 4; ++e) nib |= (rv[i] && col + e < a.N && r[i][e] > 0.f) ? (1u << e) : 0u;
+      uint32_t w = nib << (4 * cch);
+      w |= __shfl_xor_sync(0xffffffffu, w, 1);
+      w |= __shfl_xor_sync(0xffffffffu, w, 2);
+      w |= __shfl_xor_sync(0xffffffffu, w, 4);
+      if (cch == 0 && (size_t)r0 + crow0 + rstride * i < (size_t)a.M) a.bits_out[((size_t)r0 + crow0 + rstride * i) * 8 + es] = w;
+    }
+  }
+  if (!full) {                                               // columns beyond N: zero (or the ones column)
+#pragma unroll
+    for (int i = 0; i < PP; ++i)
+#pragma unroll
+      for (int e = 0; e < 4; ++e)
+        if (col + e >= a.N) r[i][e] = (col + e == a.ones_col) ? 1.f : 0.f;
+  }
+#pragma unroll
+  for (int i = 0; i < PP; ++i) {
+    if (!rv[i]) continue;
+    float* yp = a.Y + go[i] * a.ldy + col;
+    if (col + 3 < a.ldy) {
+      *reinterpret_cast<float4*>(yp) = make_float4(r[i][0], r[i][1], r[i][2], r[i][3]);
+    } else {
+#pragma unroll
+      for (int e = 0; e < 4; ++e)
+        if (col + e < a.ldy) yp[e] = r[i][e];
+    }
+  }
+}
+
+__device__ __forceinline__ void tmem_ld8(uint32_t taddr, uint32_t (&v)[8]) {
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+               : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7])
+               : "r"(taddr)
+               : "memory");
+}
+
+// NT threads (256 or 512): NT / 128 threads share a row in the tensor-memory view, 1024 / NT (row, chunk) pieces per thread
+// and slab in the coalesced view.  More warps = less serial work per warp between the slab barriers.
+template <int NB, int NT>
+__global__ void __launch_bounds__(NT, 1) k_rows_tc(RowsTcArgs a) {
+  constexpr int PP = 1024 / NT;            // (row, chunk) pieces per thread and slab
+  constexpr int NPART = NT / 128;          // threads per row (tensor-memory view)
+  constexpr int KPT = 4 / NPART;           // k-steps per thread and operand slab
+  constexpr int CPT = 8 / NPART;           // 16-byte chunks per thread and accumulator slab
+  constexpr int RS = NT / 8;               // row stride between the pieces of a thread
   SPW_DYN_SMEM(smem_raw);
   const int bfl = a.ks * 8 * NB;                                 // floats per hi / lo operand
   float* Bhi_s = reinterpret_cast<float*>(smem_raw);
@@ -129,15 +270,15 @@ __global__ void __launch_bounds__(kThreads, 1) k_rows_tc(RowsTcArgs a) {
   uint64_t* bar = reinterpret_cast<uint64_t*>(sbias + NB);
   uint32_t* tptr = reinterpret_cast<uint32_t*>(bar + 1);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int row = 32 * (warp & 3) + lane, half = warp >> 2;      // tensor-memory view: thread = (row, column half)
-  const int crow = tid >> 3, cch = tid & 7;                      // coalesced view: rows crow + 32 i (i < 4), chunk cch
+  const int row = 32 * (warp & 3) + lane, part = warp >> 2;      // tensor-memory view: thread = (row, part of the slab)
+  const int crow = tid >> 3, cch = tid & 7;                      // coalesced view: rows crow + RS i (i < PP), chunk cch
 
-  for (int i = tid; i < bfl / 4; i += kThreads) {                // weights: asynchronous, overlapped with the first row loads
+  for (int i = tid; i < bfl / 4; i += NT) {                      // weights: asynchronous, overlapped with the first row loads
     cp_async16(Bhi_s + 4 * i, a.Bhi + 4 * i);
     cp_async16(Blo_s + 4 * i, a.Blo + 4 * i);
   }
   cp_async_commit();
-  for (int i = tid; i < NB; i += kThreads) sbias[i] = (a.bias && i < a.N) ? a.bias[i] : 0.f;
+  for (int i = tid; i < NB; i += NT) sbias[i] = (a.bias && i < a.N) ? a.bias[i] : 0.f;
   if (warp == 0) tmem_alloc(tptr, kTmemCols);
   if (tid == 32) { mbar_init(bar, 1); fence_mbar_init(); }
   fence_before_sync();
@@ -154,12 +295,12 @@ __global__ void __launch_bounds__(kThreads, 1) k_rows_tc(RowsTcArgs a) {
   const int ks_early = ns > kRowsEarlySlabs ? 4 * kRowsEarlySlabs : 0;
 
   // ---- rows of a tile -> registers, coalesced; unconditional loads (addresses clamped), masked when stored to the slab
-  float4 P[kRowsMaxSlabs][4];
+  float4 P[kRowsMaxSlabs][PP];
   auto load_tile = [&](int tile) {
-    const float* pr0[4]; const float* pr1[4];
+    const float* pr0[PP]; const float* pr1[PP];
 #pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      size_t gr = (size_t)tile * kTM + crow + 32 * i;
+    for (int i = 0; i < PP; ++i) {
+      size_t gr = (size_t)tile * kTM + crow + RS * i;
       if (gr >= (size_t)a.M) gr = (size_t)a.M - 1;
       pr0[i] = a.X[0] + gr * a.ldx[0];
       pr1[i] = a.nseg == 2 ? a.X[1] + gr * a.ldx[1] : pr0[i];
@@ -172,7 +313,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_rows_tc(RowsTcArgs a) {
         if (a.nseg == 2 && cc >= a.K[0]) { cc -= a.K[0]; seg1 = true; }
         if (cc >= (seg1 ? a.K[1] : a.K[0])) cc = 0;
 #pragma unroll
-        for (int i = 0; i < 4; ++i) P[sl][i] = *reinterpret_cast<const float4*>((seg1 ? pr1[i] : pr0[i]) + cc);
+        for (int i = 0; i < PP; ++i) P[sl][i] = *reinterpret_cast<const float4*>((seg1 ? pr1[i] : pr0[i]) + cc);
       }
     }
   };
@@ -196,11 +337,11 @@ __global__ void __launch_bounds__(kThreads, 1) k_rows_tc(RowsTcArgs a) {
           if (a.nseg == 2 && cc >= a.K[0]) { cc -= a.K[0]; K = a.K[1]; }
           const int ncol = K - cc;                               // valid columns of this chunk: >= 4 all, <= 0 none
 #pragma unroll
-          for (int i = 0; i < 4; ++i) {
+          for (int i = 0; i < PP; ++i) {
             float4 q = P[sl][i];
-            const int nval = (r0 + crow + 32 * i < a.M) ? ncol : 0;
+            const int nval = (r0 + crow + RS * i < a.M) ? ncol : 0;
             if (nval < 4) { if (nval < 1) q.x = 0.f; if (nval < 2) q.y = 0.f; if (nval < 3) q.z = 0.f; q.w = 0.f; }
-            *reinterpret_cast<float4*>(sb + slab_off(crow + 32 * i, cch)) = q;
+            *reinterpret_cast<float4*>(sb + slab_off(crow + RS * i, cch)) = q;
           }
         }
         const bool early = ks_early > 0 && sl == kRowsEarlySlabs;  // the first slabs are complete in tensor memory: start their MMAs
@@ -216,11 +357,11 @@ __global__ void __launch_bounds__(kThreads, 1) k_rows_tc(RowsTcArgs a) {
           }
         }
 #pragma unroll
-        for (int j = 0; j < 2; ++j) {                            // this thread's two k-steps of the slab
-          const int ks = 4 * sl + 2 * half + j;
+        for (int j = 0; j < KPT; ++j) {                          // this thread's k-steps of the slab
+          const int ks = 4 * sl + KPT * part + j;
           if (ks < a.ks) {                                       // warp-uniform
-            const float4 u = *reinterpret_cast<const float4*>(sb + slab_off(row, 4 * half + 2 * j));
-            const float4 v = *reinterpret_cast<const float4*>(sb + slab_off(row, 4 * half + 2 * j + 1));
+            const float4 u = *reinterpret_cast<const float4*>(sb + slab_off(row, 2 * (KPT * part + j)));
+            const float4 v = *reinterpret_cast<const float4*>(sb + slab_off(row, 2 * (KPT * part + j) + 1));
             const float x[8] = {u.x, u.y, u.z, u.w, v.x, v.y, v.z, v.w};
             uint32_t h[8], l[8];
 #pragma unroll
@@ -262,134 +403,17 @@ __global__ void __launch_bounds__(kThreads, 1) k_rows_tc(RowsTcArgs a) {
     for (int es = 0; es < kEs; ++es) {
       if (kSlabCols * es >= a.ldy) break;                        // block-uniform
       float* sb = slab + (es & 1) * kSlabFloats;
-      if (kSlabCols * es + 16 * half < NB) {                     // warp-uniform
-        uint32_t vv[16];
-        tmem_ld16(lane_addr + colD + kSlabCols * es + 16 * half, vv);
+      if (kSlabCols * es + 4 * CPT * part < NB) {                // warp-uniform
+        uint32_t vv[4 * CPT];
+        if (CPT == 4) tmem_ld16(lane_addr + colD + kSlabCols * es + 16 * part, reinterpret_cast<uint32_t(&)[16]>(vv[0]));
+        else tmem_ld8(lane_addr + colD + kSlabCols * es + 8 * part, reinterpret_cast<uint32_t(&)[8]>(vv[0]));
         tmem_wait_ld();
 #pragma unroll
-        for (int g = 0; g < 4; ++g)
-          *reinterpret_cast<uint4*>(sb + slab_off(row, 4 * half + g)) = make_uint4(vv[4 * g], vv[4 * g + 1], vv[4 * g + 2], vv[4 * g + 3]);
+        for (int g = 0; g < CPT; ++g)
+          *reinterpret_cast<uint4*>(sb + slab_off(row, CPT * part + g)) = make_uint4(vv[4 * g], vv[4 * g + 1], vv[4 * g + 2], vv[4 * g + 3]);
       }
       __syncthreads();
-      const int col = kSlabCols * es + 4 * cch;
-      const bool col_ok = col < a.ldy;
-      const bool full = col + 3 < a.N;
-      float r[4][4], m[4][4];
-      bool rv[4];
-      size_t go[4];
-#pragma unroll
-      for (int i = 0; i < 4; ++i) {
-        const size_t grow = (size_t)r0 + crow + 32 * i;
-        rv[i] = col_ok && grow < (size_t)a.M;
-        go[i] = rv[i] ? grow : 0;
-        const float4 q = *reinterpret_cast<const float4*>(sb + slab_off(crow + 32 * i, cch));
-        r[i][0] = q.x; r[i][1] = q.y; r[i][2] = q.z; r[i][3] = q.w;
-      }
-      auto load_m = [&](const float* base, int ld) {             // the four (row, chunk) pieces of another array, zeros beyond N
-#pragma unroll
-        for (int i = 0; i < 4; ++i) {
-          if (full) {
-            const float4 t = *reinterpret_cast<const float4*>(base + go[i] * ld + col);
-            m[i][0] = t.x; m[i][1] = t.y; m[i][2] = t.z; m[i][3] = t.w;
-          } else {
-#pragma unroll
-            for (int e = 0; e < 4; ++e) m[i][e] = (col_ok && col + e < a.N) ? base[go[i] * ld + col + e] : 0.f;
-          }
-        }
-      };
-      if (a.bias) {
-        const float4 bq = *reinterpret_cast<const float4*>(sbias + (col < NB ? col : 0));
-#pragma unroll
-        for (int i = 0; i < 4; ++i) {
-          const float rs = a.rowscale ? a.rowscale[go[i]] : 1.f;
-          r[i][0] = fmaf(rs, bq.x, r[i][0]); r[i][1] = fmaf(rs, bq.y, r[i][1]);
-          r[i][2] = fmaf(rs, bq.z, r[i][2]); r[i][3] = fmaf(rs, bq.w, r[i][3]);
-        }
-      }
-      if (a.addend) {
-        load_m(a.addend, a.ld_add);
-#pragma unroll
-        for (int i = 0; i < 4; ++i)
-#pragma unroll
-          for (int e = 0; e < 4; ++e) r[i][e] += m[i][e];
-      }
-      if (a.act == 1) {
-#pragma unroll
-        for (int i = 0; i < 4; ++i)
-#pragma unroll
-          for (int e = 0; e < 4; ++e) r[i][e] = relu_f(r[i][e]);
-      } else if (a.act == 2) {
-#pragma unroll
-        for (int i = 0; i < 4; ++i)
-#pragma unroll
-          for (int e = 0; e < 4; ++e) r[i][e] = tanhf(r[i][e]);
-      }
-      if (a.mulmode == 3) {                                      // mask bits: word es of the row, nibble cch
-#pragma unroll
-        for (int i = 0; i < 4; ++i) {
-          const uint32_t bits = a.bits_in[go[i] * 8 + es] >> (4 * cch);
-#pragma unroll
-          for (int e = 0; e < 4; ++e) r[i][e] = ((bits >> e) & 1u) ? r[i][e] : 0.f;
-        }
-      } else if (a.mulmode) {
-        load_m(a.mulsrc, a.ld_mul);
-#pragma unroll
-        for (int i = 0; i < 4; ++i)
-#pragma unroll
-          for (int e = 0; e < 4; ++e) r[i][e] = a.mulmode == 1 ? (m[i][e] > 0.f ? r[i][e] : 0.f) : r[i][e] * (1.f - m[i][e] * m[i][e]);
-      }
-      if (a.drop_thresh) {
-#pragma unroll
-        for (int i = 0; i < 4; ++i)
-#pragma unroll
-          for (int e = 0; e < 4; ++e)
-            r[i][e] = dropout_apply(r[i][e], a.drop_seed, (uint32_t)(go[i] * a.drop_stride + col + e), a.drop_thresh, a.drop_inv_keep);
-      }
-      if (a.post_scale != 1.f) {
-#pragma unroll
-        for (int i = 0; i < 4; ++i)
-#pragma unroll
-          for (int e = 0; e < 4; ++e) r[i][e] *= a.post_scale;
-      }
-      if (a.accumulate) {
-        load_m(a.Y, a.ldy);
-#pragma unroll
-        for (int i = 0; i < 4; ++i)
-#pragma unroll
-          for (int e = 0; e < 4; ++e) r[i][e] += m[i][e];
-      }
-      if (a.bits_out) {                                          // sign bits: the 8 chunk-threads of a row make up word es
-#pragma unroll
-        for (int i = 0; i < 4; ++i) {
-          uint32_t nib = 0u;
-#pragma unroll
-          for (int e = 0; e < 4; ++e) nib |= (rv[i] && col + e < a.N && r[i][e] > 0.f) ? (1u << e) : 0u;
-          uint32_t w = nib << (4 * cch);
-          w |= __shfl_xor_sync(0xffffffffu, w, 1);
-          w |= __shfl_xor_sync(0xffffffffu, w, 2);
-          w |= __shfl_xor_sync(0xffffffffu, w, 4);
-          if (cch == 0 && (size_t)r0 + crow + 32 * i < (size_t)a.M) a.bits_out[((size_t)r0 + crow + 32 * i) * 8 + es] = w;
-        }
-      }
-      if (!full) {                                               // columns beyond N: zero (or the ones column)
-#pragma unroll
-        for (int i = 0; i < 4; ++i)
-#pragma unroll
-          for (int e = 0; e < 4; ++e)
-            if (col + e >= a.N) r[i][e] = (col + e == a.ones_col) ? 1.f : 0.f;
-      }
-#pragma unroll
-      for (int i = 0; i < 4; ++i) {
-        if (!rv[i]) continue;
-        float* yp = a.Y + go[i] * a.ldy + col;
-        if (col + 3 < a.ldy) {
-          *reinterpret_cast<float4*>(yp) = make_float4(r[i][0], r[i][1], r[i][2], r[i][3]);
-        } else {
-#pragma unroll
-          for (int e = 0; e < 4; ++e)
-            if (col + e < a.ldy) yp[e] = r[i][e];
-        }
-      }
+      rows_epilogue<NB, PP>(a, sb, sbias, r0, crow, RS, cch, es);
     }
     fence_before_sync();
     SPW_PH(5);                                                   // p5: epilogue

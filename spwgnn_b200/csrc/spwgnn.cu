@@ -306,16 +306,29 @@ void launch_rows_tc_raw(cudaStream_t st, const float* Bhi, const float* Blo, int
   a.drop_stride = o.drop_stride; a.ones_col = o.ones_col; a.poison = Y; a.bits_in = o.bits_in; a.bits_out = o.bits_out;
   const int ntiles = (M + kTM - 1) / kTM;
   const int grid = ntiles < num_sms() ? ntiles : num_sms();
+  // many tiles per CTA (the relation encoder): 512 threads, less serial work per warp between the slab barriers
+  const bool wide_cta = ntiles >= 4 * num_sms();
   if (NB == 160) {
     const size_t smem = tc::rows_tc_smem<160>(a.ks);
-    auto kern = tc::k_rows_tc<160>; set_smem(kern, tc::rows_tc_smem<160>(19));
-    SPW_KLAUNCH(o.tag ? o.tag : "k_rows_tc<160>", kern, dim3(grid), dim3(kThreads), smem, st, a);
+    if (wide_cta) {
+      auto kern = tc::k_rows_tc<160, 512>; set_smem(kern, tc::rows_tc_smem<160>(19));
+      SPW_KLAUNCH(o.tag ? o.tag : "k_rows_tc<160>", kern, dim3(grid), dim3(512), smem, st, a);
+    } else {
+      auto kern = tc::k_rows_tc<160, 256>; set_smem(kern, tc::rows_tc_smem<160>(19));
+      SPW_KLAUNCH(o.tag ? o.tag : "k_rows_tc<160>", kern, dim3(grid), dim3(256), smem, st, a);
+    }
   } else {
     const size_t smem = tc::rows_tc_smem<112>(a.ks);
-    auto kern = tc::k_rows_tc<112>; set_smem(kern, tc::rows_tc_smem<112>(25));
-    SPW_KLAUNCH(o.tag ? o.tag : "k_rows_tc<112>", kern, dim3(grid), dim3(kThreads), smem, st, a);
+    if (wide_cta) {
+      auto kern = tc::k_rows_tc<112, 512>; set_smem(kern, tc::rows_tc_smem<112>(25));
+      SPW_KLAUNCH(o.tag ? o.tag : "k_rows_tc<112>", kern, dim3(grid), dim3(512), smem, st, a);
+    } else {
+      auto kern = tc::k_rows_tc<112, 256>; set_smem(kern, tc::rows_tc_smem<112>(25));
+      SPW_KLAUNCH(o.tag ? o.tag : "k_rows_tc<112>", kern, dim3(grid), dim3(256), smem, st, a);
+    }
   }
 }
+
 void launch_rows_tc(cudaStream_t st, float* ws, const Layout& L, int id, int M, int N, int nseg, const RowsSeg* sg, float* Y,
                     int ldy, const LinOpt& o) {
   launch_rows_tc_raw(st, ws + L.tcp[id], ws + L.tcp[id] + tc_floats(id), kTcShape[id].NB, M, N, nseg, sg, Y, ldy, o);

@@ -46,7 +46,7 @@ def _tc_linear(api, M, X0, K0, X1, K1, W, N, NB, bias=None, rowscale=None, adden
     torch.cuda.synchronize()
 
 
-@pytest.mark.parametrize('M', [1, 127, 128, 129, 1000, 40960])
+@pytest.mark.parametrize('M', [1, 127, 128, 129, 1000, 40960, 80001])
 def test_tc_linear_plain_shapes(M):
     """k_rows_tc: the four (K, N, NB) shapes the propagation network uses, no epilogue options."""
     from spwgnn_b200._lib import lib
