@@ -306,26 +306,14 @@ void launch_rows_tc_raw(cudaStream_t st, const float* Bhi, const float* Blo, int
   a.drop_stride = o.drop_stride; a.ones_col = o.ones_col; a.poison = Y; a.bits_in = o.bits_in; a.bits_out = o.bits_out;
   const int ntiles = (M + kTM - 1) / kTM;
   const int grid = ntiles < num_sms() ? ntiles : num_sms();
-  // many tiles per CTA (the relation encoder): 512 threads, less serial work per warp between the slab barriers
-  const bool wide_cta = ntiles >= 4 * num_sms();
+  // 512 threads: with one CTA per SM (shared and tensor memory are full) more warps mean less serial work per warp
+  // between the slab barriers (measured: 256 -> 512 threads = -15 % per launch, relation encoder and node layers alike)
   if (NB == 160) {
-    const size_t smem = tc::rows_tc_smem<160>(a.ks);
-    if (wide_cta) {
-      auto kern = tc::k_rows_tc<160, 512>; set_smem(kern, tc::rows_tc_smem<160>(19));
-      SPW_KLAUNCH(o.tag ? o.tag : "k_rows_tc<160>", kern, dim3(grid), dim3(512), smem, st, a);
-    } else {
-      auto kern = tc::k_rows_tc<160, 256>; set_smem(kern, tc::rows_tc_smem<160>(19));
-      SPW_KLAUNCH(o.tag ? o.tag : "k_rows_tc<160>", kern, dim3(grid), dim3(256), smem, st, a);
-    }
+    auto kern = tc::k_rows_tc<160, 512>; set_smem(kern, tc::rows_tc_smem<160>(19));
+    SPW_KLAUNCH(o.tag ? o.tag : "k_rows_tc<160>", kern, dim3(grid), dim3(512), tc::rows_tc_smem<160>(a.ks), st, a);
   } else {
-    const size_t smem = tc::rows_tc_smem<112>(a.ks);
-    if (wide_cta) {
-      auto kern = tc::k_rows_tc<112, 512>; set_smem(kern, tc::rows_tc_smem<112>(25));
-      SPW_KLAUNCH(o.tag ? o.tag : "k_rows_tc<112>", kern, dim3(grid), dim3(512), smem, st, a);
-    } else {
-      auto kern = tc::k_rows_tc<112, 256>; set_smem(kern, tc::rows_tc_smem<112>(25));
-      SPW_KLAUNCH(o.tag ? o.tag : "k_rows_tc<112>", kern, dim3(grid), dim3(256), smem, st, a);
-    }
+    auto kern = tc::k_rows_tc<112, 512>; set_smem(kern, tc::rows_tc_smem<112>(25));
+    SPW_KLAUNCH(o.tag ? o.tag : "k_rows_tc<112>", kern, dim3(grid), dim3(512), tc::rows_tc_smem<112>(a.ks), st, a);
   }
 }
 
