@@ -261,7 +261,8 @@ static_assert(kEdgeStepTcSmem <= 232448, "k_edge_step_tc shared memory exceeds t
 // coalesced gather of one 64-column slab of h1 = relu(A_e + S_s + R_r): half a warp per row, 128-bit loads
 // along the row, all eight row-pairs of the warp (24 loads per lane) in flight; split into a load half
 // (registers) and a store half (slab) so that the loads of slab s+1 overlap the processing of slab s.
-struct H1Regs { float4 va[8], vs[8], vr[8]; };
+constexpr int kStThreads = 512;      // four threads per row (one 16-column quarter of every slab each): more warps, less serial work per warp
+struct H1Regs { float4 va[4], vs[4], vr[4]; };
 
 __device__ __forceinline__ void h1_slab_load(H1Regs& g, const int* ssnd, const int* srcv, const float* __restrict__ A,
                                              const float* __restrict__ S, const float* __restrict__ R, int e0, int c0,
@@ -271,8 +272,8 @@ __device__ __forceinline__ void h1_slab_load(H1Regs& g, const int* ssnd, const i
   const bool col_ok = 4 * c4 < ncols;
   const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
-  for (int j = 0; j < 8; ++j) {
-    const int r = warp * 16 + 2 * j + sub;
+  for (int j = 0; j < 4; ++j) {
+    const int r = warp * 8 + 2 * j + sub;
     const int rc = srcv[r];
     if (rc >= 0 && col_ok) {
       g.va[j] = *reinterpret_cast<const float4*>(A + (size_t)(e0 + r) * kDEP + c0 + 4 * c4);
@@ -289,8 +290,8 @@ __device__ __forceinline__ void h1_slab_store(const H1Regs& g, float* stage, con
   const int sub = lane >> 4, c4 = lane & 15;
   if (4 * c4 >= ncols) return;
 #pragma unroll
-  for (int j = 0; j < 8; ++j) {
-    const int r = warp * 16 + 2 * j + sub;
+  for (int j = 0; j < 4; ++j) {
+    const int r = warp * 8 + 2 * j + sub;
     float2* dst = reinterpret_cast<float2*>(stage + r * kStagePitch + 4 * c4);
     dst[0] = make_float2(relu_f(g.va[j].x + g.vs[j].x + g.vr[j].x), relu_f(g.va[j].y + g.vs[j].y + g.vr[j].y));
     if (c0 + 4 * c4 == kDE - 2)     // columns 150 / 151: the ones column that picks up the bias row, and the pad
@@ -300,7 +301,7 @@ __device__ __forceinline__ void h1_slab_store(const H1Regs& g, float* stage, con
   }
 }
 
-__global__ void __launch_bounds__(kThreads, 1) k_edge_step_tc(EdgeStepTcArgs a) {
+__global__ void __launch_bounds__(kStThreads, 1) k_edge_step_tc(EdgeStepTcArgs a) {
   SPW_DYN_SMEM(smem_raw);
   float* Bhi_s = reinterpret_cast<float*>(smem_raw);
   float* Blo_s = Bhi_s + kBFloats;
@@ -312,11 +313,11 @@ __global__ void __launch_bounds__(kThreads, 1) k_edge_step_tc(EdgeStepTcArgs a) 
   uint64_t* bar = reinterpret_cast<uint64_t*>(smask + kTM * 10);
   uint32_t* tptr = reinterpret_cast<uint32_t*>(bar + 1);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int row = 32 * (warp & 3) + lane, half = warp >> 2;
+  const int row = 32 * (warp & 3) + lane, q = warp >> 2;  // TMEM lane, column quarter of a slab
 
   if (warp == 0) tmem_alloc(tptr, kTmemCols);
   if (tid == 32) { mbar_init(bar, 1); fence_mbar_init(); }
-  for (int i = tid; i < kBFloats / 4; i += kThreads) {
+  for (int i = tid; i < kBFloats / 4; i += kStThreads) {
     reinterpret_cast<float4*>(Bhi_s)[i] = reinterpret_cast<const float4*>(a.W2hi)[i];
     reinterpret_cast<float4*>(Blo_s)[i] = reinterpret_cast<const float4*>(a.W2lo)[i];
   }
@@ -343,11 +344,11 @@ __global__ void __launch_bounds__(kThreads, 1) k_edge_step_tc(EdgeStepTcArgs a) 
     __syncthreads();
     const int n_first = srcv[0], n_last = srcv[rows - 1];
     const int nnodes = n_last - n_first + 1;
-    for (int i = tid; i <= imin(nnodes, kTM + 7); i += kThreads)
+    for (int i = tid; i <= imin(nnodes, kTM + 7); i += kStThreads)
       snoff[i] = (short)imax(-32000, imin(32000, a.in_off[n_first + i] - e0));
+    SPW_PH(0);                                            // p0: indices
     // ---- h1 = relu(A_e + S_s + R_r): coalesced gather into the slab, then row threads split it
     //      into tf32 hi/lo and store it to tensor memory (3 slabs of <= 64 columns)
-    SPW_PH(0);                                            // p0: indices
     H1Regs hreg;
     h1_slab_load(hreg, ssnd, srcv, a.A, a.S, a.R, e0, 0, kStageCols);
 #pragma unroll
@@ -357,11 +358,11 @@ __global__ void __launch_bounds__(kThreads, 1) k_edge_step_tc(EdgeStepTcArgs a) 
       h1_slab_store(hreg, stage, srcv, c0, ncols);
       __syncthreads();
       if (sl < 2) h1_slab_load(hreg, ssnd, srcv, a.A, a.S, a.R, e0, c0 + kStageCols, imin(kStageCols, kDEP - c0 - kStageCols));
-      // this thread's half of the slab row: 32 columns (or what is left) == one word of relu bits
-      const int cb = 32 * half;
+      // this thread's quarter of the slab row: 16 columns (or what is left) == half a word of relu bits
+      const int cb = 16 * q;
       uint32_t hbits = 0u;
 #pragma unroll
-      for (int g = 0; g < 4; ++g) {
+      for (int g = 0; g < 2; ++g) {
         const int c = cb + 8 * g;
         if (c < ncols) {                                  // warp-uniform
           const float2* src = reinterpret_cast<const float2*>(stage + row * kStagePitch + c);
@@ -377,7 +378,8 @@ __global__ void __launch_bounds__(kThreads, 1) k_edge_step_tc(EdgeStepTcArgs a) 
           tmem_st8(lane_addr + kColAlo + c0 + c, l);
         }
       }
-      if (a.maskbits_h1 && row < rows && cb < ncols) a.maskbits_h1[(size_t)(e0 + row) * 8 + ((c0 + cb) >> 5)] = hbits;
+      if (a.maskbits_h1 && row < rows && cb < ncols)
+        reinterpret_cast<uint16_t*>(a.maskbits_h1)[(size_t)(e0 + row) * 16 + ((c0 + cb) >> 4)] = (uint16_t)hbits;
       __syncthreads();
     }
     tmem_wait_st();
@@ -396,26 +398,26 @@ __global__ void __launch_bounds__(kThreads, 1) k_edge_step_tc(EdgeStepTcArgs a) 
     // ---- epilogue: D -> +b2, relu, relu bits -> staging slab -> receiver-segmented sum
     for (int c0 = 0; c0 < kN; c0 += kStageCols) {
       const int ncols = imin(kStageCols, kN - c0);
-      for (int blk = half; blk * 16 < ncols; blk += 2) {
+      if (16 * q < ncols) {                               // warp-uniform: this thread's 16-column block of the slab
         uint32_t v[16];
-        tmem_ld16(lane_addr + kColD + c0 + blk * 16, v);
+        tmem_ld16(lane_addr + kColD + c0 + 16 * q, v);
         tmem_wait_ld();
         uint32_t m16 = 0u;
         float o[16];
 #pragma unroll
         for (int i = 0; i < 16; ++i) {
           const float pre = __uint_as_float(v[i]);          // bias already inside (ones column x bias row)
-          const bool on = (c0 + blk * 16 + i < kDE) && (pre > 0.f);
+          const bool on = (c0 + 16 * q + i < kDE) && (pre > 0.f);
           o[i] = on ? pre : 0.f;
           m16 |= on ? (1u << i) : 0u;
         }
-        float2* dst = reinterpret_cast<float2*>(stage + row * kStagePitch + blk * 16);
+        float2* dst = reinterpret_cast<float2*>(stage + row * kStagePitch + 16 * q);
 #pragma unroll
         for (int i = 0; i < 8; ++i) dst[i] = make_float2(o[2 * i], o[2 * i + 1]);
-        smask[row * 10 + ((c0 + blk * 16) >> 4)] = (uint16_t)m16;
+        smask[row * 10 + ((c0 + 16 * q) >> 4)] = (uint16_t)m16;
       }
       __syncthreads();
-      for (int item = tid; item < nnodes * ncols; item += kThreads) {
+      for (int item = tid; item < nnodes * ncols; item += kStThreads) {
         const int ni = item / ncols, c = item - ni * ncols;
         const int node = n_first + ni;
         int s0, s1;
@@ -437,7 +439,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_edge_step_tc(EdgeStepTcArgs a) 
     }
     SPW_PH(3);                                            // p3: epilogue + segmented sum
     if (a.maskbits) {
-      for (int i = tid; i < rows * 5; i += kThreads) {
+      for (int i = tid; i < rows * 5; i += kStThreads) {
         const int r = i / 5, w = i - r * 5;
         a.maskbits[(size_t)(e0 + r) * 8 + w] = (uint32_t)smask[r * 10 + 2 * w] | ((uint32_t)smask[r * 10 + 2 * w + 1] << 16);
       }
@@ -476,7 +478,11 @@ struct EdgeDgradTcArgs {
 
 constexpr size_t kEdgeDgradTcSmem = (size_t)(2 * kBFloats + kTM * kStagePitch + kTM) * sizeof(float) + 16;
 
-__global__ void __launch_bounds__(kThreads, 1) k_edge_dgrad_tc(EdgeDgradTcArgs a) {
+// 512 threads: four threads per row (one 16-column quarter of every 64-column slab each).  With one CTA per SM more warps
+// mean less serial work per warp between the barriers.
+constexpr int kDgThreads = 512;
+
+__global__ void __launch_bounds__(kDgThreads, 1) k_edge_dgrad_tc(EdgeDgradTcArgs a) {
   SPW_DYN_SMEM(smem_raw);
   float* Bhi_s = reinterpret_cast<float*>(smem_raw);
   float* Blo_s = Bhi_s + kBFloats;
@@ -485,11 +491,11 @@ __global__ void __launch_bounds__(kThreads, 1) k_edge_dgrad_tc(EdgeDgradTcArgs a
   uint64_t* bar = reinterpret_cast<uint64_t*>(srcv + kTM);
   uint32_t* tptr = reinterpret_cast<uint32_t*>(bar + 1);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int row = 32 * (warp & 3) + lane, half = warp >> 2;
+  const int row = 32 * (warp & 3) + lane, q = warp >> 2;        // TMEM lane, column quarter of a slab
 
   if (warp == 0) tmem_alloc(tptr, kTmemCols);
   if (tid == 32) { mbar_init(bar, 1); fence_mbar_init(); }
-  for (int i = tid; i < kBFloats / 4; i += kThreads) {
+  for (int i = tid; i < kBFloats / 4; i += kDgThreads) {
     reinterpret_cast<float4*>(Bhi_s)[i] = reinterpret_cast<const float4*>(a.Whi)[i];
     reinterpret_cast<float4*>(Blo_s)[i] = reinterpret_cast<const float4*>(a.Wlo)[i];
   }
@@ -504,11 +510,11 @@ __global__ void __launch_bounds__(kThreads, 1) k_edge_dgrad_tc(EdgeDgradTcArgs a
   const int ntiles = (a.E + kTM - 1) / kTM;
   const int sub = lane >> 4, c4 = lane & 15;
 
-  auto gather_slab = [&](float4 (&v)[8], int c0) {     // dH2S[receiver] rows of one 64-column slab, 8 loads in flight
+  auto gather_slab = [&](float4 (&v)[4], int c0) {     // dH2S[receiver] rows of one 64-column slab: half a warp per row
     const int ncols = imin(kStageCols, kDEP - c0);
 #pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      const int rc = srcv[warp * 16 + 2 * j + sub];
+    for (int j = 0; j < 4; ++j) {
+      const int rc = srcv[warp * 8 + 2 * j + sub];
       v[j] = (rc >= 0 && 4 * c4 < ncols) ? *reinterpret_cast<const float4*>(a.dH2S + (size_t)rc * kDEP + c0 + 4 * c4)
                                          : make_float4(0.f, 0.f, 0.f, 0.f);
     }
@@ -519,32 +525,30 @@ __global__ void __launch_bounds__(kThreads, 1) k_edge_dgrad_tc(EdgeDgradTcArgs a
     const int e0 = tile * kTM;
     const int rows = imin(kTM, a.E - e0);
     if (tid < kTM) srcv[tid] = tid < rows ? (a.in_rcv ? a.in_rcv[e0 + tid] : e0 + tid) : -1;
-    // relu bits of this thread's row (h2: operand mask, h1: epilogue mask), fetched once per tile
-    uint32_t b2w[8], b1w[8];
+    // relu bits of this thread's row and quarter (h2: operand mask, h1: epilogue mask): word 2 sl + (q >> 1) of slab sl
+    uint32_t b2w[3], b1w[3];
 #pragma unroll
-    for (int i = 0; i < 8; ++i) { b2w[i] = 0xffffffffu; b1w[i] = 0xffffffffu; }
+    for (int i = 0; i < 3; ++i) { b2w[i] = 0xffffffffu; b1w[i] = 0xffffffffu; }
     if (row < rows && a.maskbits) {
-      const uint4* p2 = reinterpret_cast<const uint4*>(a.maskbits + (size_t)(e0 + row) * 8);
-      const uint4 q0 = p2[0], q1 = p2[1];
-      b2w[0] = q0.x; b2w[1] = q0.y; b2w[2] = q0.z; b2w[3] = q0.w; b2w[4] = q1.x;
+#pragma unroll
+      for (int i = 0; i < 3; ++i) b2w[i] = a.maskbits[(size_t)(e0 + row) * 8 + 2 * i + (q >> 1)];
     }
     if (row < rows && a.maskbits_h1) {
-      const uint4* p1 = reinterpret_cast<const uint4*>(a.maskbits_h1 + (size_t)(e0 + row) * 8);
-      const uint4 r0 = p1[0], r1 = p1[1];
-      b1w[0] = r0.x; b1w[1] = r0.y; b1w[2] = r0.z; b1w[3] = r0.w; b1w[4] = r1.x;
+#pragma unroll
+      for (int i = 0; i < 3; ++i) b1w[i] = a.maskbits_h1[(size_t)(e0 + row) * 8 + 2 * i + (q >> 1)];
     }
     __syncthreads();
     // ---- A operand: gather dH2S[receiver] rows (coalesced, half a warp per row), mask, split, TMEM.
     //      The gather of slab s+1 is in flight while slab s is split and stored.
-    float4 v[8];
+    float4 v[4];
     gather_slab(v, 0);
 #pragma unroll
     for (int sl = 0; sl < 3; ++sl) {
       const int c0 = sl * kStageCols;
       const int ncols = imin(kStageCols, kDEP - c0);
 #pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        const int r = warp * 16 + 2 * j + sub;
+      for (int j = 0; j < 4; ++j) {
+        const int r = warp * 8 + 2 * j + sub;
         if (4 * c4 < ncols) {
           float2* dst = reinterpret_cast<float2*>(stage + r * kStagePitch + 4 * c4);
           dst[0] = make_float2(v[j].x, v[j].y);
@@ -553,11 +557,11 @@ __global__ void __launch_bounds__(kThreads, 1) k_edge_dgrad_tc(EdgeDgradTcArgs a
       }
       __syncthreads();
       if (sl < 2) gather_slab(v, c0 + kStageCols);
-      const int cb = 32 * half;
+      const int cb = 16 * q;
       if (cb < ncols) {                                    // warp-uniform
-        const uint32_t bits = b2w[2 * sl + half];
+        const uint32_t bits = b2w[sl] >> (16 * (q & 1));
 #pragma unroll
-        for (int g = 0; g < 4; ++g) {
+        for (int g = 0; g < 2; ++g) {
           const int c = cb + 8 * g;
           if (c < ncols) {
             const float2* src = reinterpret_cast<const float2*>(stage + row * kStagePitch + c);
@@ -594,49 +598,49 @@ __global__ void __launch_bounds__(kThreads, 1) k_edge_dgrad_tc(EdgeDgradTcArgs a
     for (int sl = 0; sl < 3; ++sl) {
       const int c0 = sl * kStageCols;
       const int ncols = imin(kStageCols, kDEP - c0);       // columns 152..159 are never stored
-      for (int blk = half; blk * 16 < imin(kStageCols, kN - c0); blk += 2) {
+      if (16 * q < imin(kStageCols, kN - c0)) {            // warp-uniform: this thread's 16-column block of the slab
         uint32_t vv[16];
-        tmem_ld16(lane_addr + kColD + c0 + blk * 16, vv);
+        tmem_ld16(lane_addr + kColD + c0 + 16 * q, vv);
         tmem_wait_ld();
-        const int col0 = c0 + blk * 16;
-        const uint32_t bits = b1w[col0 >> 5] >> (col0 & 31);
+        const int col0 = c0 + 16 * q;
+        const uint32_t bits = b1w[sl] >> (16 * (q & 1));
         float o[16];
 #pragma unroll
         for (int i = 0; i < 16; ++i) o[i] = ((bits >> i) & 1u) && (col0 + i < kDE) ? __uint_as_float(vv[i]) : 0.f;
-        float2* dst = reinterpret_cast<float2*>(stage + row * kStagePitch + blk * 16);
+        float2* dst = reinterpret_cast<float2*>(stage + row * kStagePitch + 16 * q);
 #pragma unroll
         for (int i = 0; i < 8; ++i) dst[i] = make_float2(o[2 * i], o[2 * i + 1]);
       }
       __syncthreads();
       const int n4 = ncols >> 2;                           // float4 per row in this slab (16, 16, 6)
       const int total = rows * n4;
-      for (int base = 0; base < total; base += 4 * kThreads) {
+      for (int base = 0; base < total; base += 4 * kDgThreads) {
         float4 old[4], actv[4];
         const bool rmw = a.dA && !a.first;
 #pragma unroll
         for (int u = 0; u < 4; ++u) {
-          const int idx = base + u * kThreads + tid;
+          const int idx = base + u * kDgThreads + tid;
           if (idx < total) {
-            const int r = idx / n4, q = idx - r * n4;
-            const size_t g = (size_t)(e0 + r) * kDEP + c0 + 4 * q;
+            const int r = idx / n4, qq = idx - r * n4;
+            const size_t g = (size_t)(e0 + r) * kDEP + c0 + 4 * qq;
             if (rmw) old[u] = *reinterpret_cast<const float4*>(a.dA + g);
             if (a.act) actv[u] = *reinterpret_cast<const float4*>(a.act + g);
           }
         }
 #pragma unroll
         for (int u = 0; u < 4; ++u) {
-          const int idx = base + u * kThreads + tid;
+          const int idx = base + u * kDgThreads + tid;
           if (idx < total) {
-            const int r = idx / n4, q = idx - r * n4;
-            const float2* src = reinterpret_cast<const float2*>(stage + r * kStagePitch + 4 * q);
+            const int r = idx / n4, qq = idx - r * n4;
+            const float2* src = reinterpret_cast<const float2*>(stage + r * kStagePitch + 4 * qq);
             const float2 p0 = src[0], p1 = src[1];
             float4 val = make_float4(p0.x * a.scale, p0.y * a.scale, p1.x * a.scale, p1.y * a.scale);
             if (a.act) {
               val.x = actv[u].x > 0.f ? val.x : 0.f; val.y = actv[u].y > 0.f ? val.y : 0.f;
               val.z = actv[u].z > 0.f ? val.z : 0.f; val.w = actv[u].w > 0.f ? val.w : 0.f;
-              if (c0 + 4 * q == kDE - 2) { val.z = 0.f; val.w = 0.f; }      // columns 150 / 151 carry no gradient
+              if (c0 + 4 * qq == kDE - 2) { val.z = 0.f; val.w = 0.f; }      // columns 150 / 151 carry no gradient
             }
-            const size_t g = (size_t)(e0 + r) * kDEP + c0 + 4 * q;
+            const size_t g = (size_t)(e0 + r) * kDEP + c0 + 4 * qq;
             *reinterpret_cast<float4*>(a.DH1 + g) = val;
             if (a.dA) {
               if (rmw) { val.x += old[u].x; val.y += old[u].y; val.z += old[u].z; val.w += old[u].w; }

@@ -730,7 +730,7 @@ int spw_forward(const SpwParams* w, const SpwGraph* g, const float* obj, float* 
         const int ttiles = (E + kTM - 1) / kTM;
         const int tgrid = ttiles < num_sms() ? ttiles : num_sms();
         set_smem(tc::k_edge_step_tc, tc::kEdgeStepTcSmem);
-        SPW_KLAUNCH("k_edge_step_tc", tc::k_edge_step_tc, dim3(tgrid), dim3(kThreads), tc::kEdgeStepTcSmem, st, t);
+        SPW_KLAUNCH("k_edge_step_tc", tc::k_edge_step_tc, dim3(tgrid), dim3(tc::kStThreads), tc::kEdgeStepTcSmem, st, t);
         if (ttiles > 1)
           SPW_KLAUNCH("k_fix_boundaries", k_fix_boundaries, dim3(grid_for(ttiles - 1, 8)), dim3(256), 0, st, E, (int)kTM, g->in_rcv, ws + L.PF, ws + L.PL, H2S);
       }
@@ -861,7 +861,7 @@ int spw_backward(const SpwParams* w, const SpwGraph* g, const float* obj, const 
         t.maskbits = a.maskbits; t.maskbits_h1 = reinterpret_cast<const uint32_t*>(ws + L.M1) + (size_t)l * E * 8;
         t.act = nullptr; t.scale = 1.f; t.dA = ws + L.dA; t.DH1 = ws + L.DH1; t.first = a.first; t.poison = ws + L.dA;
         set_smem(tc::k_edge_dgrad_tc, tc::kEdgeDgradTcSmem);
-        SPW_KLAUNCH("k_edge_dgrad_tc", tc::k_edge_dgrad_tc, dim3(egrid), dim3(kThreads), tc::kEdgeDgradTcSmem, st, t);
+        SPW_KLAUNCH("k_edge_dgrad_tc", tc::k_edge_dgrad_tc, dim3(egrid), dim3(tc::kDgThreads), tc::kEdgeDgradTcSmem, st, t);
       }
 #else
       {
