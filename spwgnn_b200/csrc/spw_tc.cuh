@@ -675,6 +675,7 @@ __global__ void __launch_bounds__(kDgThreads, 1) k_edge_dgrad_tc(EdgeDgradTcArgs
 //   TMEM map: D0 [0,160) | D1 [160,320) | A0_hi [320,352) A0_lo [352,384) A1_hi [384,416) A1_lo [416,448)
 // =================================================================================================
 constexpr int kWgChunk = 32;
+constexpr int kWgThreads = 512;              // (lane quarter, M-tile, half of the chunk rows / accumulator columns) per warp
 constexpr uint32_t kWgColD0 = 0, kWgColD1 = 160, kWgColA = 320;
 constexpr int kWgFeat1 = 23;                 // first feature of M-tile 1 (lane j <-> feature 23 + j)
 constexpr int kWgBFloats = 4 * kBStepFloats; // 5120 floats per hi / lo chunk operand
@@ -708,7 +709,7 @@ __device__ __forceinline__ void wg_issue_chunk(const WgradTcArgs& a, float* st, 
   float* XA = st; float* XS = XA + kWgChunk * kDEP; float* XR = XS + kWgChunk * kDEP; float* YD = XR + kWgChunk * kDEP;
   uint32_t* BT = reinterpret_cast<uint32_t*>(YD + kWgChunk * kDEP);
   const int* idx = reinterpret_cast<const int*>(BT + kWgChunk * 8);      // [0,32): snd, [32,64): rcv of this chunk
-  for (int i = threadIdx.x; i < kWgChunk * C4; i += kThreads) {
+  for (int i = threadIdx.x; i < kWgChunk * C4; i += kWgThreads) {
     const int r = i / C4, c = i - r * C4;
     const int row = r0 + r;
     const bool valid = row < a.M;
@@ -744,7 +745,7 @@ __device__ __forceinline__ void wg_load_idx(const WgradTcArgs& a, float* st, int
 }
 
 template <int XMODE, int YMODE>
-__global__ void __launch_bounds__(kThreads, 1) k_wgrad_tc(WgradTcArgs a) {
+__global__ void __launch_bounds__(kWgThreads, 1) k_wgrad_tc(WgradTcArgs a) {
   SPW_DYN_SMEM(smem_raw);
   float* stages = reinterpret_cast<float*>(smem_raw);
   float* Bhi_s = stages + 2 * kWgStageFloats;
@@ -752,7 +753,8 @@ __global__ void __launch_bounds__(kThreads, 1) k_wgrad_tc(WgradTcArgs a) {
   uint64_t* bar = reinterpret_cast<uint64_t*>(Blo_s + kWgBFloats);
   uint32_t* tptr = reinterpret_cast<uint32_t*>(bar + 1);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int L = 32 * (warp & 3) + lane, mt = warp >> 2;         // TMEM lane, M-tile handled by this thread
+  const int L = 32 * (warp & 3) + lane, mt = (warp >> 2) & 1;   // TMEM lane, M-tile handled by this thread
+  const int hh = warp >> 3;                                     // half of the chunk rows (operand build) / accumulator columns (flush)
   const int feat = mt == 0 ? L : kWgFeat1 + L;                  // feature (row of dW) of this lane in its M-tile
   constexpr bool kGather = (XMODE == 1) || (YMODE == 1);
 
@@ -768,10 +770,11 @@ __global__ void __launch_bounds__(kThreads, 1) k_wgrad_tc(WgradTcArgs a) {
   uint32_t parity = 0;
   bool failed = false, pending = false;
   float* part = a.part + (size_t)blockIdx.x * kWgPartFloats;
-  // D accumulates ONE tile in tensor memory; the sum over this CTA's tiles lives in registers (round-to-nearest adds)
-  float acc[kN];
+  // D accumulates ONE tile in tensor memory; the sum over this CTA's tiles lives in registers (round-to-nearest adds):
+  // this thread owns columns [80 hh, 80 hh + 80) of row L of M-tile mt
+  float acc[kN / 2];
 #pragma unroll
-  for (int c = 0; c < kN; ++c) acc[c] = 0.f;
+  for (int c = 0; c < kN / 2; ++c) acc[c] = 0.f;
   const int ntiles = (a.M + kTM - 1) / kTM;
   constexpr int kCh = kTM / kWgChunk;                           // chunks per tile
   // this CTA's chunks, in order: q-th chunk = (tile blockIdx.x + (q / kCh) * gridDim.x, chunk q % kCh)
@@ -813,9 +816,10 @@ __global__ void __launch_bounds__(kThreads, 1) k_wgrad_tc(WgradTcArgs a) {
     const float* YD = XR + kWgChunk * kDEP;
     const uint32_t* BT = reinterpret_cast<const uint32_t*>(YD + kWgChunk * kDEP);
     const int r0 = row0_of(q);
-    // A = X^T: this lane's feature, 32 rows of the chunk as 32 TMEM columns
+    // A = X^T: this lane's feature, this thread's 16 rows of the chunk as 16 TMEM columns
 #pragma unroll
-    for (int j0 = 0; j0 < kWgChunk; j0 += 8) {
+    for (int jj = 0; jj < kWgChunk / 2; jj += 8) {
+      const int j0 = 16 * hh + jj;
       uint32_t h[8], l[8];
 #pragma unroll
       for (int i = 0; i < 8; ++i) {
@@ -832,7 +836,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_wgrad_tc(WgradTcArgs a) {
     }
     SPW_PH(3);                                         // p3: A operand build
     // B = dY^T: [k-step][2][n][4 rows]
-    for (int idx = tid; idx < 8 * kN; idx += kThreads) {
+    for (int idx = tid; idx < 8 * kN; idx += kWgThreads) {
       const int n = idx % kN, kc = idx / kN;
       uint32_t h[4], l[4];
 #pragma unroll
@@ -879,9 +883,9 @@ __global__ void __launch_bounds__(kThreads, 1) k_wgrad_tc(WgradTcArgs a) {
       parity ^= 1u;
       fence_after_sync();
       pending = false;
-      const uint32_t dcol = mt ? kWgColD1 : kWgColD0;
+      const uint32_t dcol = (mt ? kWgColD1 : kWgColD0) + (kN / 2) * hh;
 #pragma unroll
-      for (int c = 0; c < kN; c += 16) {
+      for (int c = 0; c < kN / 2; c += 16) {
         uint32_t v[16];
         tmem_ld16(lane_addr + dcol + c, v);
         tmem_wait_ld();
@@ -893,13 +897,13 @@ __global__ void __launch_bounds__(kThreads, 1) k_wgrad_tc(WgradTcArgs a) {
     }
   }
   {   // this CTA's sum over its tiles -> per-CTA partial in global memory ([tile][n][lane]: coalesced)
-    float* pp = part + (size_t)mt * (160 * 128) + L;
+    float* pp = part + (size_t)mt * (160 * 128) + (size_t)(kN / 2) * hh * 128 + L;
     if (a.first) {
 #pragma unroll
-      for (int c = 0; c < kN; ++c) pp[(size_t)c * 128] = acc[c];
+      for (int c = 0; c < kN / 2; ++c) pp[(size_t)c * 128] = acc[c];
     } else {
 #pragma unroll
-      for (int c0 = 0; c0 < kN; c0 += 16) {
+      for (int c0 = 0; c0 < kN / 2; c0 += 16) {
         float old[16];
 #pragma unroll
         for (int i = 0; i < 16; ++i) old[i] = pp[(size_t)(c0 + i) * 128];
@@ -943,14 +947,14 @@ __device__ __forceinline__ void cp_async4_zfill(float* sdst, const float* gsrc, 
 __device__ __forceinline__ void wgr_issue_chunk(const WgradRowsArgs& a, float* st, int r0, int cx4, int cy4) {
   float* XA = st; float* YD = st + 3 * kWgChunk * kDEP;
   float* RS = YD + kWgChunk * kDEP + kWgChunk * 8;
-  for (int i = threadIdx.x; i < kWgChunk * cx4; i += kThreads) {
+  for (int i = threadIdx.x; i < kWgChunk * cx4; i += kWgThreads) {
     const int r = i / cx4, c = i - r * cx4;
     const int row = r0 + r;
     const bool valid = row < a.M;
     const size_t xr = valid ? (size_t)(a.xmod ? row % a.xmod : row) : 0;
     cp_async16_zfill(XA + r * kDEP + 4 * c, a.X + xr * a.ldx + 4 * c, valid);
   }
-  for (int i = threadIdx.x; i < kWgChunk * cy4; i += kThreads) {
+  for (int i = threadIdx.x; i < kWgChunk * cy4; i += kWgThreads) {
     const int r = i / cy4, c = i - r * cy4;
     const int row = r0 + r;
     const bool valid = row < a.M;
@@ -964,7 +968,7 @@ __device__ __forceinline__ void wgr_issue_chunk(const WgradRowsArgs& a, float* s
   cp_async_commit();
 }
 
-__global__ void __launch_bounds__(kThreads, 1) k_wgrad_rows_tc(WgradRowsArgs a) {
+__global__ void __launch_bounds__(kWgThreads, 1) k_wgrad_rows_tc(WgradRowsArgs a) {
   SPW_DYN_SMEM(smem_raw);
   float* stages = reinterpret_cast<float*>(smem_raw);
   float* Bhi_s = stages + 2 * kWgStageFloats;
@@ -972,10 +976,11 @@ __global__ void __launch_bounds__(kThreads, 1) k_wgrad_rows_tc(WgradRowsArgs a) 
   uint64_t* bar = reinterpret_cast<uint64_t*>(Blo_s + kWgBFloats);
   uint32_t* tptr = reinterpret_cast<uint32_t*>(bar + 1);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int L = 32 * (warp & 3) + lane, grp = warp >> 2;        // TMEM lane, warp group
+  const int L = 32 * (warp & 3) + lane, grp = warp >> 2;        // TMEM lane, warp group (0..3)
   const int nmt = a.Kx + 1 > 128 ? 2 : 1;                       // M-tiles
   const int feat1 = nmt == 2 ? a.Kx + 1 - 128 : 0;              // first feature of M-tile 1
-  const int mt = nmt == 2 ? grp : 0;                            // M-tile this thread builds / flushes
+  const int mt = nmt == 2 ? (grp & 1) : 0;                      // M-tile this thread builds / flushes
+  const int sh = nmt == 2 ? (grp >> 1) : grp, nsh = nmt == 2 ? 2 : 4;   // this thread's share of the chunk rows / accumulator blocks
   const int feat = mt == 0 ? L : feat1 + L;
   const int NB = a.NB;
   const int cx4 = (a.Kx + 3) >> 2, cy4 = (a.Ny + 3) >> 2;
@@ -993,19 +998,21 @@ __global__ void __launch_bounds__(kThreads, 1) k_wgrad_rows_tc(WgradRowsArgs a) 
   uint32_t parity = 0;
   bool failed = false, pending = false;
   float* part = a.part + (size_t)blockIdx.x * kWgPartFloats;
-  // columns of this thread: everything (two M-tiles) or its group's share of the 16-column blocks (one M-tile)
+  // 16-column accumulator blocks of this thread: its share (1 / nsh) of the NB / 16 blocks, at most 5
   const int nblk = NB / 16;
-  const int b_lo = nmt == 2 ? 0 : (grp ? (nblk + 1) / 2 : 0), b_hi = nmt == 2 ? nblk : (grp ? nblk : (nblk + 1) / 2);
-  float acc[kN];                                                // sum over this CTA's tiles (round-to-nearest adds)
+  const int b_lo = (sh * nblk) / nsh, b_hi = ((sh + 1) * nblk) / nsh;
+  float acc[5][16];                                             // sum over this CTA's tiles (round-to-nearest adds)
 #pragma unroll
-  for (int c = 0; c < kN; ++c) acc[c] = 0.f;
+  for (int b = 0; b < 5; ++b)
+#pragma unroll
+    for (int c = 0; c < 16; ++c) acc[b][c] = 0.f;
   const int ntiles = (a.M + kTM - 1) / kTM;
   constexpr int kCh = kTM / kWgChunk;                           // chunks per tile
   const int my_tiles = (int)blockIdx.x < ntiles ? (ntiles - 1 - (int)blockIdx.x) / (int)gridDim.x + 1 : 0;
   const int nq = my_tiles * kCh;
   auto row0_of = [&](int q) { return (blockIdx.x + (q / kCh) * gridDim.x) * kTM + (q % kCh) * kWgChunk; };
-  // rows of the chunk this thread turns into A columns: all 32 (two M-tiles) or its group's 16 (one M-tile)
-  const int j_lo = nmt == 2 ? 0 : 16 * grp, j_hi = nmt == 2 ? kWgChunk : 16 * grp + 16;
+  // rows of the chunk this thread turns into A columns: its share of the 32
+  const int j_lo = (kWgChunk / nsh) * sh, j_hi = j_lo + kWgChunk / nsh;
   if (nq > 0) wgr_issue_chunk(a, stages, row0_of(0), cx4, cy4);
   for (int q = 0; q < nq; ++q) {
     const int ch = q % kCh;
@@ -1042,7 +1049,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_wgrad_rows_tc(WgradRowsArgs a) 
       tmem_st8(lane_addr + colA_lo + j0, l);
     }
     // B = dY^T: [k-step][2][n][4 rows]
-    for (int idx = tid; idx < 8 * NB; idx += kThreads) {
+    for (int idx = tid; idx < 8 * NB; idx += kWgThreads) {
       const int n = idx % NB, kc = idx / NB;
       uint32_t h[4], l[4];
 #pragma unroll
@@ -1084,13 +1091,13 @@ __global__ void __launch_bounds__(kThreads, 1) k_wgrad_rows_tc(WgradRowsArgs a) 
       pending = false;
       const uint32_t dcol = mt ? kWgColD1 : kWgColD0;
 #pragma unroll
-      for (int b = 0; b < kN / 16; ++b) {
-        if (b >= b_lo && b < b_hi) {                   // warp-uniform
+      for (int bi = 0; bi < 5; ++bi) {
+        if (b_lo + bi < b_hi) {                        // warp-uniform
           uint32_t v[16];
-          tmem_ld16(lane_addr + dcol + 16 * b, v);
+          tmem_ld16(lane_addr + dcol + 16 * (b_lo + bi), v);
           tmem_wait_ld();
 #pragma unroll
-          for (int i = 0; i < 16; ++i) acc[16 * b + i] += __uint_as_float(v[i]);
+          for (int i = 0; i < 16; ++i) acc[bi][i] += __uint_as_float(v[i]);
         }
       }
       fence_before_sync();
@@ -1099,10 +1106,10 @@ __global__ void __launch_bounds__(kThreads, 1) k_wgrad_rows_tc(WgradRowsArgs a) 
   {   // this CTA's sum over its tiles -> per-CTA partial in global memory ([tile][n][lane]: coalesced)
     float* pp = part + (size_t)mt * (160 * 128) + L;
 #pragma unroll
-    for (int b = 0; b < kN / 16; ++b) {
-      if (b >= b_lo && b < b_hi) {
+    for (int bi = 0; bi < 5; ++bi) {
+      if (b_lo + bi < b_hi) {
 #pragma unroll
-        for (int i = 0; i < 16; ++i) pp[(size_t)(16 * b + i) * 128] = acc[16 * b + i];
+        for (int i = 0; i < 16; ++i) pp[(size_t)(16 * (b_lo + bi) + i) * 128] = acc[bi][i];
       }
     }
   }

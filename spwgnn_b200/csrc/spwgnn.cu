@@ -362,7 +362,7 @@ void launch_wgrad(cudaStream_t st, int M, const float* X, int ldx, int Kin, int 
     int tgrid = tt < num_sms() ? tt : num_sms();
     if (tgrid > kMaxCtas) tgrid = kMaxCtas;
     set_smem(tc::k_wgrad_rows_tc, tc::kWgradTcSmem);
-    SPW_KLAUNCH("k_wgrad_rows_tc", tc::k_wgrad_rows_tc, dim3(tgrid), dim3(kThreads), tc::kWgradTcSmem, st, t);
+    SPW_KLAUNCH("k_wgrad_rows_tc", tc::k_wgrad_rows_tc, dim3(tgrid), dim3(tc::kWgThreads), tc::kWgradTcSmem, st, t);
     launch_reduce(st, part, tgrid, (int)tc::kWgPartFloats, 0, -1, Kin + 1 > 128 ? Kin + 1 - 128 : 0, Kin, N, out);
     return;
   }
@@ -855,7 +855,7 @@ int spw_backward(const SpwParams* w, const SpwGraph* g, const float* obj, const 
         wg.poison = ws + L.partE;
         auto kwg = tc::k_wgrad_tc<1, 1>;
         set_smem(kwg, tc::kWgradTcSmem);
-        SPW_KLAUNCH("k_wgrad_tc", kwg, dim3(egrid), dim3(kThreads), tc::kWgradTcSmem, st, wg);
+        SPW_KLAUNCH("k_wgrad_tc", kwg, dim3(egrid), dim3(tc::kWgThreads), tc::kWgradTcSmem, st, wg);
         tc::EdgeDgradTcArgs t;
         t.E = E; t.in_rcv = g->in_rcv; t.dH2S = ws + L.dH2S; t.Whi = ws + L.W2Thi; t.Wlo = ws + L.W2Tlo;
         t.maskbits = a.maskbits; t.maskbits_h1 = reinterpret_cast<const uint32_t*>(ws + L.M1) + (size_t)l * E * 8;
@@ -935,7 +935,7 @@ int spw_backward(const SpwParams* w, const SpwGraph* g, const float* obj, const 
         tc::WgradTcArgs wg;
         memset(&wg, 0, sizeof(wg));
         wg.M = E; wg.x_mode = 0; wg.X = acts[i]; wg.y_mode = 0; wg.dY = dY; wg.part = ws + L.partE; wg.first = 1; wg.poison = ws + L.partE;
-        SPW_KLAUNCH("k_wgrad_tc", kwg, dim3(egrid), dim3(kThreads), tc::kWgradTcSmem, st, wg);
+        SPW_KLAUNCH("k_wgrad_tc", kwg, dim3(egrid), dim3(tc::kWgThreads), tc::kWgradTcSmem, st, wg);
         launch_reduce(st, ws + L.partE, egrid, (int)tc::kWgPartFloats, 0, -1, tc::kWgFeat1, kDE, kDE, {gw[i], 150, 0, 0, gb[i], 0});
         // data gradient of the layer: (dY . W^T) * relu'(layer input), times 1/keep through the dropout on c_e
         RowsSeg sg = {dY, kDEP, kDE};
