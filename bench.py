@@ -42,6 +42,8 @@ KERNEL_MODELS = {
     'k_wgrad_tc': dict(algo=2 * 150 * 150, exec=6 * _MMA / 8.0, pipe='tensor'),        # 2 M-tiles x 3 MMAs per 8 edge rows
     'k_edge_dgrad_tc': dict(algo=2 * 150 * 150, exec=57 * _MMA / 128.0, pipe='tensor'),  # 19 k-steps x 3 MMAs per 128 rows
     'k_edge_step_tc': dict(algo=2 * 150 * 150, exec=57 * _MMA / 128.0, pipe='tensor'),
+    'k_rows_tc<160>:enc_fwd': dict(algo=2 * 150 * 150, exec=57 * _MMA / 128.0, pipe='tensor'),   # one relation-encoder layer per launch
+    'k_rows_tc<160>:enc_bwd': dict(algo=2 * 150 * 150, exec=57 * _MMA / 128.0, pipe='tensor'),
     'k_edge_encode': dict(algo=2 * (67800 + 22500), exec=4 * 2 * 152 * 160, pipe='fp32'),
 }
 
