@@ -79,6 +79,10 @@ int spw_ffma_peak(float* out, int grid, int iters, void* stream);
 /* tcgen05 / TMEM self test (3xTF32): D[128][160] = A[128][152] . W[K][N] (K<=152, N<=160); scratch: 48640 floats;
  * status (device int): 1 = ok, -1 = the MMA completion barrier timed out. */
 int spw_tc_selftest(const float* A, const float* W, int K, int N, float* D, float* scratch, int* status, void* stream);
+/* CTA-pair (tcgen05 cta_group::2) self test: one cluster of two CTAs, each with half of the weight operand in its shared
+ * memory and its own 128 rows in tensor memory: D[256][160] = A[256][152] . W[K][N] (K <= 152, N <= 160, 3xTF32);
+ * scratch: 4 * 19 * 8 * 80 floats; status[2] (device ints): 1 = ok, -1 = the MMA completion barrier timed out. */
+int spw_tc2_selftest(const float* A, const float* W, int K, int N, float* D, float* scratch, int* status, void* stream);
 /* generic tensor-core linear layer (the node-level / relation-encoder building block), exposed for unit tests:
  *   Y[M][ldy] = post(act([X0 | X1].W + rowscale*bias + addend)), W in Keras layout [K0 + K1][N] (Blocks.py:22-27);
  *   act 0 none / 1 relu / 2 tanh; mulmode 1: *= [mulsrc > 0], 2: *= (1 - mulsrc^2); NB (MMA N) = 112 or 160, N <= NB,

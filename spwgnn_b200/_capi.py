@@ -32,7 +32,7 @@ class SpwGraph(C.Structure):
     ]
 
 
-EXPORTS = ['spw_version', 'spw_last_error', 'spw_launch_count', 'spw_profile', 'spw_profile_report', 'spw_ffma_peak', 'spw_tc_selftest', 'spw_tc_linear', 'spw_edges_count', 'spw_edges_fill', 'spw_workspace_bytes',
+EXPORTS = ['spw_version', 'spw_last_error', 'spw_launch_count', 'spw_profile', 'spw_profile_report', 'spw_ffma_peak', 'spw_tc_selftest', 'spw_tc2_selftest', 'spw_tc_linear', 'spw_edges_count', 'spw_edges_fill', 'spw_workspace_bytes',
            'spw_forward', 'spw_bce_grad', 'spw_backward']
 
 
@@ -62,6 +62,8 @@ class CApi:
         d.spw_ffma_peak.argtypes = [vp, C.c_int, C.c_int, vp]
         d.spw_tc_selftest.restype = C.c_int
         d.spw_tc_selftest.argtypes = [vp, vp, C.c_int, C.c_int, vp, vp, vp, vp]
+        d.spw_tc2_selftest.restype = C.c_int
+        d.spw_tc2_selftest.argtypes = [vp, vp, C.c_int, C.c_int, vp, vp, vp, vp]
         d.spw_tc_linear.restype = C.c_int
         d.spw_tc_linear.argtypes = [C.c_int, vp, C.c_int, C.c_int, vp, C.c_int, C.c_int, vp, C.c_int, C.c_int, vp, vp, vp, C.c_int,
                                     C.c_int, vp, C.c_int, C.c_int, vp, C.c_int, C.c_int, C.c_float, C.c_int, vp, vp]

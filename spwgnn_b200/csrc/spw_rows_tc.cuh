@@ -428,6 +428,114 @@ __global__ void __launch_bounds__(NT, 1) k_rows_tc(RowsTcArgs a) {
   if (warp == 0) tmem_dealloc(tmem_base, kTmemCols);
 }
 
+// =================================================================================================
+// CTA-pair (cta_group::2) building block, self test only this round: one cluster of two CTAs computes
+//   D[256][160] = A[256][152] . B   (3xTF32)
+// Each CTA keeps ITS 128 rows of A in its own tensor memory and HALF of the weight operand (80 of the 160 columns, hi and lo:
+// 95 KB instead of 190 KB) in its own shared memory; the leader CTA issues tcgen05.mma.cta_group::2 (M = 256, N = 160), both
+// CTAs receive the completion through a multicast commit and read their 128 rows of D from their own tensor memory.
+// =================================================================================================
+__device__ __forceinline__ uint32_t cluster_ctarank() { uint32_t r; asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r)); return r; }
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_alloc2(uint32_t* smem_dst, uint32_t ncols) {
+  asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(smem_dst)), "r"(ncols));
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::);
+}
+__device__ __forceinline__ void tmem_dealloc2(uint32_t taddr, uint32_t ncols) {
+  asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols));
+}
+__device__ __forceinline__ void mma2_tf32_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::tf32 [%0], [%1], %2, %3, {%5, %5, %5, %5, %5, %5, %5, %5}, p;\n\t"
+      "}\n" ::"r"(d_tmem),
+      "r"(a_tmem), "l"(b_desc), "r"(idesc), "r"(accumulate), "r"(0u)
+      : "memory");
+}
+__device__ __forceinline__ void mma2_commit_multicast(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(smem_u32(bar)),
+               "h"((uint16_t)3)
+               : "memory");
+}
+
+constexpr int kHalfN = kN / 2;                                   // 80 columns of the weight operand per CTA
+constexpr int kB2Floats = kKS * 8 * kHalfN;                      // floats per hi / lo half operand
+
+// Bhi / Blo: [2 halves][kKS][2][80][4] (k_pack_tc with NB = 80, one descriptor per half)
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(128, 1)
+k_tc2_selftest(const float* __restrict__ A, const float* __restrict__ Bhi, const float* __restrict__ Blo, float* __restrict__ D,
+               int* __restrict__ status) {
+  SPW_DYN_SMEM(smem_raw);
+  float* Bhi_s = reinterpret_cast<float*>(smem_raw);
+  float* Blo_s = Bhi_s + kB2Floats;
+  uint64_t* bar = reinterpret_cast<uint64_t*>(Blo_s + kB2Floats);
+  uint32_t* tptr = reinterpret_cast<uint32_t*>(bar + 1);
+  const int tid = threadIdx.x, warp = tid >> 5;
+  const uint32_t rank = cluster_ctarank();
+  if (warp == 0) tmem_alloc2(tptr, kTmemCols);
+  if (tid == 32) { mbar_init(bar, 1); fence_mbar_init(); }
+  for (int i = tid; i < kB2Floats / 4; i += 128) {               // this CTA's half of the weight columns
+    reinterpret_cast<float4*>(Bhi_s)[i] = reinterpret_cast<const float4*>(Bhi + (size_t)rank * kB2Floats)[i];
+    reinterpret_cast<float4*>(Blo_s)[i] = reinterpret_cast<const float4*>(Blo + (size_t)rank * kB2Floats)[i];
+  }
+  fence_async_smem();
+  fence_before_sync();
+  __syncthreads();
+  fence_after_sync();
+  const uint32_t tmem_base = *tptr;
+  const uint32_t lane_addr = tmem_base + ((uint32_t)(32 * (warp & 3)) << 16);
+  const float* arow = A + ((size_t)rank * 128 + tid) * kDEP;     // this CTA's 128 rows
+#pragma unroll 1
+  for (int c = 0; c < kDEP; c += 8) {
+    const float4 x0 = *reinterpret_cast<const float4*>(arow + c), x1 = *reinterpret_cast<const float4*>(arow + c + 4);
+    const float x[8] = {x0.x, x0.y, x0.z, x0.w, x1.x, x1.y, x1.z, x1.w};
+    uint32_t h[8], l[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) split_tf32(x[i], h[i], l[i]);
+    tmem_st8(lane_addr + kColAhi + c, h);
+    tmem_st8(lane_addr + kColAlo + c, l);
+  }
+  tmem_wait_st();
+  fence_before_sync();
+  cluster_sync_all();                                            // both CTAs: A in tensor memory, weights in shared memory
+  if (rank == 0 && tid == 0) {
+    fence_after_sync();
+    const uint32_t idesc = make_idesc_tf32(256, kN);
+    const uint64_t dhi0 = make_b_desc(smem_u32(Bhi_s), kHalfN * 16, 128), dlo0 = make_b_desc(smem_u32(Blo_s), kHalfN * 16, 128);
+    constexpr uint64_t kStep = (8 * kHalfN * 4) >> 4;
+    const uint32_t d = tmem_base + kColD;
+    for (int ks = 0; ks < kKS; ++ks) {
+      mma2_tf32_ts(d, tmem_base + kColAlo + 8 * ks, dhi0 + ks * kStep, idesc, ks > 0 ? 1u : 0u);
+      mma2_tf32_ts(d, tmem_base + kColAhi + 8 * ks, dlo0 + ks * kStep, idesc, 1u);
+    }
+    for (int ks = 0; ks < kKS; ++ks) mma2_tf32_ts(d, tmem_base + kColAhi + 8 * ks, dhi0 + ks * kStep, idesc, 1u);
+    mma2_commit_multicast(bar);
+  }
+  const bool ok = mbar_wait(bar, 0);
+  fence_after_sync();
+  if (!ok) {
+    if (tid == 0) status[rank] = -1;
+  } else {
+#pragma unroll 1
+    for (int c = 0; c < kN; c += 16) {
+      uint32_t v[16];
+      tmem_ld16(lane_addr + kColD + c, v);
+      tmem_wait_ld();
+#pragma unroll
+      for (int i = 0; i < 16; ++i) D[((size_t)rank * 128 + tid) * kN + c + i] = __uint_as_float(v[i]);
+    }
+    if (tid == 0) status[rank] = 1;
+  }
+  fence_before_sync();
+  cluster_sync_all();
+  if (warp == 0) tmem_dealloc2(tmem_base, kTmemCols);
+}
+
 }  // namespace tc
 }  // namespace spw
 #endif  // SPW_EMU

@@ -528,6 +528,32 @@ int spw_tc_selftest(const float* A, const float* W, int K, int N, float* D, floa
 #endif
 }
 
+// CTA-pair self test (tcgen05 cta_group::2): D[256][160] = A[256][152] . W, W a Keras [K][N] matrix (ld = N);
+// scratch: 4 * 19 * 8 * 80 floats; status[2] (device ints, one per CTA): 1 ok, -1 the completion barrier timed out
+int spw_tc2_selftest(const float* A, const float* W, int K, int N, float* D, float* scratch, int* status, void* stream) {
+#if !SPW_USE_TC
+  (void)A; (void)W; (void)K; (void)N; (void)D; (void)scratch; (void)status; (void)stream;
+  return fail(SPW_ERR_UNSUPPORTED, "spw_tc2_selftest: tensor-core path is not emulated");
+#else
+  if (!A || !W || !D || !scratch || !status || K > 152 || N > 160 || K <= 0 || N <= 0) return fail(SPW_ERR_BAD_ARG, "spw_tc2_selftest: bad argument");
+  cudaStream_t st = (cudaStream_t)stream;
+  tc::PackTcArgs pa;
+  memset(&pa, 0, sizeof(pa));
+  float* hi = scratch; float* lo = scratch + 2 * tc::kB2Floats;
+  for (int h = 0; h < 2; ++h) {
+    tc::PackTcDesc& d = pa.d[h];
+    d.src = W; d.ld = N; d.row0 = 0; d.col0 = 80 * h; d.K = K; d.N = N - 80 * h < 0 ? 0 : (N - 80 * h > 80 ? 80 : N - 80 * h);
+    d.hi = hi + (size_t)h * tc::kB2Floats; d.lo = lo + (size_t)h * tc::kB2Floats; d.NB = 80; d.k_off = 0; d.k_lim = 8 * tc::kKS;
+  }
+  pa.n = 2;
+  SPW_KLAUNCH("k_pack_tc", tc::k_pack_tc, dim3(16, 2), dim3(256), 0, st, pa);
+  const size_t smem = (size_t)2 * tc::kB2Floats * sizeof(float) + 64;
+  set_smem(tc::k_tc2_selftest, smem);
+  SPW_KLAUNCH("k_tc2_selftest", tc::k_tc2_selftest, dim3(2), dim3(128), smem, st, A, (const float*)hi, (const float*)lo, D, status);
+  return check_launch("spw_tc2_selftest");
+#endif
+}
+
 // generic tensor-core linear layer (tc::k_rows_tc), exposed for unit tests:
 //   Y[M][ldy] = post(act([X0 | X1].W + rowscale*bias + addend)), W Keras layout [K0 + K1][N] (ld = N); NB = 112 or 160;
 //   scratch: 2 * ceil((K0 + K1) / 8) * 8 * NB floats

@@ -101,3 +101,27 @@ def test_tc_linear_epilogues():
     ref = torch.relu(X[:, :150].double() @ W2.double() + b2.double())
     assert float((Y[:, :150].double() - ref).abs().max()) < 5e-6
     assert bool((Y[:, 150] == 1).all()) and bool((Y[:, 151] == 0).all())
+
+
+def test_tc2_cta_pair_selftest_matches_fp64():
+    """tcgen05 cta_group::2: two CTAs, half of the weight operand in each CTA's shared memory, M = 256."""
+    from spwgnn_b200._lib import lib
+    api = lib()
+    g = torch.Generator().manual_seed(3)
+    A = torch.randn(256, 152, generator=g, dtype=torch.float32)
+    W = (torch.rand(150, 150, generator=g, dtype=torch.float32) * 2 - 1) * 0.14
+    ref = (A[:, :150].double() @ W.double()).numpy()
+    Ad, Wd = A.cuda(), W.cuda()
+    D = torch.full((256, 160), float('nan'), device='cuda')
+    scratch = torch.empty(4 * 19 * 8 * 80, device='cuda')
+    status = torch.zeros(2, dtype=torch.int32, device='cuda')
+    st = torch.cuda.current_stream().cuda_stream
+    api.check(api.dll.spw_tc2_selftest(Ad.data_ptr(), Wd.data_ptr(), 150, 150, D.data_ptr(), scratch.data_ptr(),
+                                       status.data_ptr(), st))
+    torch.cuda.synchronize()
+    assert status.tolist() == [1, 1], 'MMA completion barrier timed out: %s' % status.tolist()
+    got = D.cpu().numpy()
+    err = np.abs(got[:, :150] - ref).max() / np.abs(ref).max()
+    print('cta_group::2 3xTF32 GEMM rel err vs fp64: %.2e' % err)
+    assert err < 2e-6
+    assert np.all(got[:, 150:] == 0.0)
