@@ -300,6 +300,105 @@ def test_full_size_properties_config2(eng):
         assert float((va[k] - v1[k]).abs().max() / v1[k].abs().max()) < 2e-5, k
 
 
+def _subsample_vs_oracle(eng, towers, logits, node_off, idx, fc):
+    """logits of the towers `idx` inside a big batch against the fp64 oracle run on just those towers"""
+    from spwgnn_b200 import synth
+    raw, off = synth.pack_towers([towers[i] for i in idx])
+    eo, snd, rcv, slot = _oracle_edges(raw, off, fc)
+    _, _, l64, _ = _oracle_all(eng.w64, raw, snd, rcv, np.zeros(len(raw)))
+    got = np.concatenate([logits[node_off[i]:node_off[i + 1]] for i in idx])
+    return _rel(got, l64.numpy())
+
+
+def test_full_size_properties_config3_jenga18(eng):
+    """BASELINE config 3 at full size: 1024 Jenga-style 18-layer (54-block) towers, contact (distance-threshold) edges.
+    Edge list bit-exact against the numpy restatement of main.py:66-81 for the whole batch; logits of a subsample
+    against the fp64 oracle; training step finite, deterministic and additive over half batches."""
+    from spwgnn_b200.graph import TowerBatch
+    from spwgnn_b200 import synth
+    _use(eng, 'kinkfree')
+    towers = synth.make_towers('jenga18', 1024, 77)
+    raw, node_off = synth.pack_towers(towers)
+    batch = TowerBatch.from_towers(towers, want_slot_list=True)
+    assert batch.n_nodes == 1024 * 54
+    eo, snd, rcv, slot = _oracle_edges(raw, node_off, False)
+    _check_edges(batch, eo, snd, rcv, slot)
+    tgt = torch.as_tensor((np.random.default_rng(5).random(batch.n_nodes) > 0.5).astype(np.float32)).cuda()
+    logits, _ = eng.forward(batch, training=True, want_probs=False)
+    logits = logits.clone()
+    dl, stats = eng.bce_seed(logits, tgt, batch.n_nodes)
+    g1 = eng.backward(dl).flat.clone()
+    assert torch.isfinite(logits).all() and torch.isfinite(g1).all()
+    assert _subsample_vs_oracle(eng, towers, logits.cpu().numpy(), node_off, [0, 511, 1023], False) < TOL
+    eng.forward(batch, training=True, want_probs=False)
+    assert torch.equal(eng.backward(dl).flat, g1)                                  # bit-identical rerun
+    h = 512 * 54
+    ga = None
+    for sl, part in ((slice(0, h), towers[:512]), (slice(h, 2 * h), towers[512:])):
+        b = TowerBatch.from_towers(part)
+        eng.forward(b, training=True, want_probs=False)
+        g = eng.backward(dl[sl].contiguous()).flat.clone()
+        ga = g if ga is None else ga + g
+    from spwgnn_b200.params import ParamBuffer
+    va, v1 = ParamBuffer('cuda:0', ga).views, ParamBuffer('cuda:0', g1).views
+    for k in O.tensor_names():
+        assert float((va[k] - v1[k]).abs().max() / v1[k].abs().max()) < 2e-5, k
+
+
+def test_full_size_properties_config4_mixed_sizes(eng):
+    """BASELINE config 4 shape (6-to-32-block towers in one ragged batch) at 8192 towers per GPU: edges bit-exact,
+    subsample against the oracle, gradient of the batch == sum over the two rank shards that dp.shard_towers makes
+    (what the NCCL all-reduce adds up)."""
+    from spwgnn_b200.graph import TowerBatch
+    from spwgnn_b200 import synth
+    from spwgnn_b200.dp import shard_towers
+    _use(eng, 'kinkfree')
+    towers = synth.make_towers('uniform', 8192, 91, lo=6, hi=32)
+    raw, node_off = synth.pack_towers(towers)
+    batch = TowerBatch.from_towers(towers, want_slot_list=True)
+    eo, snd, rcv, slot = _oracle_edges(raw, node_off, False)
+    _check_edges(batch, eo, snd, rcv, slot)
+    n = batch.n_nodes
+    tgt = (np.random.default_rng(6).random(n) > 0.5).astype(np.float32)
+    logits, _ = eng.forward(batch, training=True, want_probs=False)
+    logits = logits.clone()
+    dl, stats = eng.bce_seed(logits, torch.as_tensor(tgt).cuda(), n)
+    g1 = eng.backward(dl).flat.clone()
+    assert torch.isfinite(logits).all() and torch.isfinite(g1).all()
+    assert _subsample_vs_oracle(eng, towers, logits.cpu().numpy(), node_off, [3, 4097, 8191], False) < TOL
+    shards = shard_towers([len(t) for t in towers], 2)
+    gs = None
+    for ids in shards:
+        sub = [towers[i] for i in ids]
+        b = TowerBatch.from_towers(sub)
+        seed = torch.cat([dl[node_off[i]:node_off[i + 1]] for i in ids]).contiguous()
+        eng.forward(b, training=True, want_probs=False)
+        g = eng.backward(seed).flat.clone()
+        gs = g if gs is None else gs + g
+    from spwgnn_b200.params import ParamBuffer
+    va, v1 = ParamBuffer('cuda:0', gs).views, ParamBuffer('cuda:0', g1).views
+    for k in O.tensor_names():
+        assert float((va[k] - v1[k]).abs().max() / v1[k].abs().max()) < 2e-5, k
+
+
+def test_inference_sweep_config5_shape(eng):
+    """BASELINE config 5 shape (inference over 8-64-block towers), 20 000 towers in chunks like the sharded sweep:
+    chunked == one batch (to rounding), probabilities in [0, 1], subsample against the oracle."""
+    from spwgnn_b200.graph import TowerBatch
+    from spwgnn_b200 import synth
+    _use(eng, 'glorot')
+    towers = synth.make_towers('uniform', 20000, 101, lo=8, hi=64)
+    raw, node_off = synth.pack_towers(towers)
+    whole = TowerBatch.from_towers(towers)
+    lw, pw = eng.forward(whole, training=False)
+    lw, pw = lw.cpu().numpy(), pw.cpu().numpy()
+    assert np.isfinite(lw).all() and (pw >= 0).all() and (pw <= 1).all()
+    for a, b in ((0, 5000), (5000, 12345), (12345, 20000)):
+        lc, _ = eng.forward(TowerBatch.from_towers(towers[a:b]), training=False)
+        assert _rel(lc.cpu().numpy(), lw[node_off[a]:node_off[b]]) < 2e-6
+    assert _subsample_vs_oracle(eng, towers, lw, node_off, [1, 9999, 19999], False) < TOL
+
+
 def test_fit_predict_facade_runs_like_main_py():
     """main.py:92-98 style call: dict in, History out, loss goes down on a learnable toy target."""
     from spwgnn_b200.Networks import PropagationNetwork
