@@ -148,7 +148,9 @@ def run_reference(args, rank):
 
 # ---------------------------------------------------------------------------------------------------
 class ClockSampler:
-    Q = ('index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,'
+    """nvidia-smi clocks / throttle reasons every 20 ms, started BEFORE the warm-up so that it is up when the timed
+    region begins; stop() keeps the samples whose timestamp falls inside the timed windows."""
+    Q = ('timestamp,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,'
          'clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap')
 
     def __init__(self, gpu_index):
@@ -156,11 +158,12 @@ class ClockSampler:
         try:
             self.f = open(self.path, 'w')
             self.proc = subprocess.Popen(['nvidia-smi', '-i', str(gpu_index), '--query-gpu=' + self.Q, '--format=csv,noheader,nounits',
-                                          '-lms', '100'], stdout=self.f, stderr=subprocess.DEVNULL)
+                                          '-lms', '20'], stdout=self.f, stderr=subprocess.DEVNULL)
         except OSError:
             self.proc = None
 
-    def stop(self):
+    def stop(self, windows):
+        import datetime
         out = {'sm_mhz': None, 'sm_max_mhz': None, 'reasons': []}
         if self.proc is None:
             return out
@@ -170,26 +173,30 @@ class ClockSampler:
         except subprocess.TimeoutExpired:
             self.proc.kill()
         self.f.close()
-        sm, mx, reasons = [], [], set()
+        rows = []
         names = ['hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap']
         for line in open(self.path):
             p = [x.strip() for x in line.split(',')]
             if len(p) < 9:
                 continue
             try:
-                sm.append(float(p[1])); mx.append(float(p[2]))
+                ts = datetime.datetime.strptime(p[0], '%Y/%m/%d %H:%M:%S.%f').timestamp()
+                rows.append((ts, float(p[1]), float(p[2]), [nm for nm, v in zip(names, p[5:9]) if v.lower().startswith('active')]))
             except ValueError:
                 continue
-            for nm, v in zip(names, p[5:9]):
-                if v.lower().startswith('active'):
-                    reasons.add(nm)
         try:
             os.remove(self.path)
         except OSError:
             pass
-        if sm:
-            out = {'sm_mhz': float(np.median(sm)), 'sm_max_mhz': float(max(mx)), 'reasons': sorted(reasons),
-                   'samples': len(sm)}
+        inside = [r for r in rows if any(a - 0.02 <= r[0] <= b + 0.02 for a, b in windows)]
+        where = 'timed regions'
+        if not inside and rows:        # very short timed regions: the samples closest to them (GPU still under the same load)
+            mid = sum(a + b for a, b in windows) / (2 * len(windows))
+            inside = sorted(rows, key=lambda r: abs(r[0] - mid))[:5]
+            where = 'nearest to the timed regions'
+        if inside:
+            out = {'sm_mhz': float(np.median([r[1] for r in inside])), 'sm_max_mhz': float(max(r[2] for r in inside)),
+                   'reasons': sorted({nm for r in inside for nm in r[3]}), 'samples': len(inside), 'sampled': where}
         return out
 
 
@@ -272,17 +279,21 @@ def main():
             ms = float(t[0])
         return ms, out
 
+    sampler = ClockSampler(local_rank) if rank == 0 else None
     for _ in range(W):
         step_resident()
-    sampler = ClockSampler(local_rank) if rank == 0 else None
     l0 = api.dll.spw_launch_count()
+    tw0 = time.time()
     ms, _ = timed(step_resident, K)
+    tw1 = time.time()
     launches = api.dll.spw_launch_count() - l0
-    clocks = sampler.stop() if sampler else None
 
     for _ in range(2):
         step_e2e()
+    tw2 = time.time()
     ms_e2e, last_stats = timed(step_e2e, K)
+    tw3 = time.time()
+    clocks = sampler.stop([(tw0, tw1), (tw2, tw3)]) if sampler else None
     h2d = obj_h.numel() * 4 + pos_h.numel() * 8 + tgt_h.numel() * 4 + off_h.numel() * 4
     d2h = 16
 
