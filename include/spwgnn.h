@@ -116,6 +116,19 @@ int spw_edges_fill(const double* pos_xy, const int32_t* node_off, int32_t n_towe
                    int32_t* out_off, int32_t* out_pos, void* stream);
 
 /* ---- network ---------------------------------------------------------------------------- */
+/* ---- device-side synthetic layouts ------------------------------------------------
+ * Physics-free Jenga layout sampler of JengaBuilder.create_world (JengaBuilder.py:137-192: widths randint(50,300), gaps
+ * randint(0,50), first layer spans x in [400,1100]) with a counter-based generator (tower t, draw c -> splitmix64), so
+ * that large sweeps are generated where they are consumed.  spwgnn_b200/synth.py:g_jenga_ctr is the bit-identical numpy
+ * restatement.
+ *   spw_sample_sizes: node_off[t+1] - node_off[t] = n_lo + draw_0(t) % (n_hi - n_lo + 1), prefix-summed in place.
+ *   spw_sample_jenga: raw[n][3] = [x, y, width] in pixels (f64), obj[n][3] = raw / 170 (f32, main.py:91),
+ *                     pos[n][2] = positions for the relation test (raw, or raw / 170 with inference_glue);
+ *                     any of the three outputs may be null. */
+int spw_sample_sizes(uint64_t seed, int32_t n_towers, int32_t n_lo, int32_t n_hi, int32_t* node_off, void* stream);
+int spw_sample_jenga(uint64_t seed, int32_t n_towers, const int32_t* node_off, double* raw, float* obj, double* pos,
+                     int inference_glue, void* stream);
+
 /* Bytes of workspace spw_forward/spw_backward need.  training != 0 also reserves the node-level
  * state the backward pass reads (5 propagation steps x per-node activations) and per-edge
  * gradient staging.  The same workspace must be passed, untouched, to spw_backward.            */

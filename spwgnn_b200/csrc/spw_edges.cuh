@@ -151,4 +151,85 @@ __global__ void __launch_bounds__(kMaxNodes) k_edges_fill(
   }
 }
 
+// =================================================================================================
+// N4: physics-free Jenga layout sampler on the device -- JengaBuilder.create_world
+// (/root/reference/src/JengaBuilder.py:137-192) restated with a counter-based generator so that a 1 M-tower sweep needs
+// neither host generation nor an H2D copy.  spwgnn_b200/synth.py: g_jenga_ctr is the same algorithm in numpy; the two
+// agree bit for bit (integer / exact half-integer float64 arithmetic only).
+// =================================================================================================
+__host__ __device__ __forceinline__ uint32_t ctr_u32(uint64_t seed, uint64_t tower, uint64_t ctr) {
+  uint64_t z = seed + 0x9E3779B97F4A7C15ull * (tower + 1) + 0xD1B54A32D192ED03ull * ctr;    // splitmix64 finaliser
+  z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+  z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+  z ^= z >> 31;
+  return (uint32_t)(z >> 32);
+}
+// random.randint(a, b) of the reference: uniform integer in [a, b]
+__host__ __device__ __forceinline__ int ctr_randint(uint64_t seed, uint64_t tower, uint32_t& ctr, int a, int b) {
+  return a + (int)(ctr_u32(seed, tower, ctr++) % (uint32_t)(b - a + 1));
+}
+
+// blocks per tower: counter 0 of each tower's stream; node_off[t + 1] = N_t (scanned afterwards), node_off[0] = 0
+__global__ void __launch_bounds__(256) k_sample_sizes(uint64_t seed, int n_towers, int n_lo, int n_hi, int32_t* __restrict__ node_off) {
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t == 0) node_off[0] = 0;
+  if (t < n_towers) {
+    uint32_t ctr = 0;
+    node_off[t + 1] = ctr_randint(seed, (uint64_t)t, ctr, n_lo, n_hi);
+  }
+}
+
+// one thread per tower: [x, y, width] of its blocks in pixels (float64), plus the model input obj = raw / 170 (fp32,
+// main.py:91) and the positions the relation test runs on (raw, or raw / 170 for the inference glue, JengaBuilder.py:309-323)
+__global__ void __launch_bounds__(128) k_sample_jenga(uint64_t seed, int n_towers, const int32_t* __restrict__ node_off,
+                                                      double* __restrict__ raw, float* __restrict__ obj, double* __restrict__ pos,
+                                                      int inference_glue) {
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= n_towers) return;
+  const int base = node_off[t], n = node_off[t + 1] - base;
+  uint32_t ctr = 1;                                              // counter 0 drew the size
+  const int wmin = 50, wrange = 250, wavg = 150, gap = 50, rect_h = 80, bottom = 70;
+  const double left_most = 400.0, right_most = 1500.0 - 400.0;
+  int left = n, layer = -1, k = 0;
+  double prev_min = 0.0, prev_max = 0.0;
+  auto emit = [&](double x, double y, double w) {
+    const size_t o = (size_t)(base + k);
+    if (raw) { raw[3 * o] = x; raw[3 * o + 1] = y; raw[3 * o + 2] = w; }
+    if (obj) { obj[3 * o] = (float)(x / 170.0); obj[3 * o + 1] = (float)(y / 170.0); obj[3 * o + 2] = (float)(w / 170.0); }
+    if (pos) { pos[2 * o] = inference_glue ? x / 170.0 : x; pos[2 * o + 1] = inference_glue ? y / 170.0 : y; }
+    ++k;
+  };
+  while (left > 0) {
+    ++layer;
+    double r_edge, l_edge;
+    if (layer == 0) { r_edge = right_most; l_edge = left_most; } else { r_edge = prev_max; l_edge = prev_min; }
+    const double y = (double)(bottom + rect_h / 2 + rect_h * layer);
+    double cur_min = 0.0, cur_max = 0.0;
+    int cur = 0;
+    auto put = [&](double x, double w) {
+      emit(x, y, w);
+      cur_min = cur == 0 ? x : (x < cur_min ? x : cur_min);
+      cur_max = cur == 0 ? x : (x > cur_max ? x : cur_max);
+      ++cur; --left;
+    };
+    if (r_edge == l_edge) {                                      // single block below: centre a new one on it
+      const int x = ctr_randint(seed, (uint64_t)t, ctr, (int)(l_edge - wmin / 2), (int)(l_edge + wmin / 2));
+      const int w = ctr_randint(seed, (uint64_t)t, ctr, wmin, wmin + wrange);
+      put((double)x, (double)w);
+    } else {
+      if (layer > 0) l_edge -= (double)(wavg / 2);
+      int w = ctr_randint(seed, (uint64_t)t, ctr, wmin, wmin + wrange);
+      l_edge += (double)w;
+      while (l_edge - w / 2.0 < r_edge && left > 0) {
+        put(l_edge - w / 2.0, (double)w);
+        l_edge += (double)ctr_randint(seed, (uint64_t)t, ctr, 0, gap);
+        w = ctr_randint(seed, (uint64_t)t, ctr, wmin, wmin + wrange);
+        l_edge += (double)w;
+      }
+      if (cur == 0) put(l_edge, (double)w);                      // degenerate draw: force one block so the loop terminates
+    }
+    prev_min = cur_min; prev_max = cur_max;
+  }
+}
+
 }  // namespace spw

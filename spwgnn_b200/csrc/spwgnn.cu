@@ -625,6 +625,26 @@ int spw_edges_fill(const double* pos_xy, const int32_t* node_off, int32_t n_towe
   return check_launch("spw_edges_fill");
 }
 
+int spw_sample_sizes(uint64_t seed, int32_t n_towers, int32_t n_lo, int32_t n_hi, int32_t* node_off, void* stream) {
+  if (n_towers < 0 || n_lo < 1 || n_hi < n_lo) return fail(SPW_ERR_BAD_ARG, "spw_sample_sizes: bad size range");
+  if (n_hi > SPW_MAX_NODES) return fail(SPW_ERR_UNSUPPORTED, "spw_sample_sizes: %d blocks in a tower, limit is %d", n_hi, SPW_MAX_NODES);
+  if (!node_off) return fail(SPW_ERR_BAD_ARG, "spw_sample_sizes: null pointer");
+  cudaStream_t st = (cudaStream_t)stream;
+  SPW_KLAUNCH("k_sample_sizes", k_sample_sizes, dim3(grid_for(n_towers + 1, 256)), dim3(256), 0, st, seed, (int)n_towers, (int)n_lo, (int)n_hi, node_off);
+  if (n_towers > 0) SPW_KLAUNCH("k_scan_inplace", k_scan_inplace, dim3(1), dim3(1024), 0, st, node_off, (int)n_towers);
+  return check_launch("spw_sample_sizes");
+}
+
+int spw_sample_jenga(uint64_t seed, int32_t n_towers, const int32_t* node_off, double* raw, float* obj, double* pos,
+                     int inference_glue, void* stream) {
+  if (n_towers < 0) return fail(SPW_ERR_BAD_ARG, "spw_sample_jenga: negative size");
+  if (n_towers == 0) return SPW_OK;
+  if (!node_off || (!raw && !obj && !pos)) return fail(SPW_ERR_BAD_ARG, "spw_sample_jenga: null pointer");
+  SPW_KLAUNCH("k_sample_jenga", k_sample_jenga, dim3((n_towers + 127) / 128), dim3(128), 0, (cudaStream_t)stream, seed, (int)n_towers, node_off, raw,
+              obj, pos, inference_glue);
+  return check_launch("spw_sample_jenga");
+}
+
 size_t spw_workspace_bytes(int32_t n_nodes, int32_t n_edges, int training) {
   if (n_nodes < 0 || n_edges < 0) return 0;
   return make_layout(n_nodes, n_edges, training).total * sizeof(float);

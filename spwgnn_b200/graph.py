@@ -99,6 +99,31 @@ class TowerBatch:
         b._finish()
         return b
 
+    # -- device-side synthetic layouts ------------------------------
+    @staticmethod
+    def sample_jenga(n_towers, n_lo, n_hi, seed, device=None, fully_connected=False, inference_glue=False,
+                     thr=REL_THRESHOLD, want_raw=False, want_slot_list=False):
+        """Jenga-style layouts (JengaBuilder.create_world, JengaBuilder.py:137-192) generated ON the GPU and packed:
+        tower t gets n_lo..n_hi blocks; poses never exist on the host.  Bit-identical to synth.g_jenga_ctr.
+        Returns the TowerBatch (its .raw holds the (n, 3) float64 pixel poses when want_raw)."""
+        require_cuda()
+        api = lib()
+        device = torch.device(device if device is not None else 'cuda')
+        st = _stream_ptr(device)
+        node_off = torch.empty(n_towers + 1, dtype=torch.int32, device=device)
+        api.check(api.dll.spw_sample_sizes(int(seed), n_towers, n_lo, n_hi, node_off.data_ptr(), st))
+        node_off_h = node_off.cpu().numpy().astype(np.int64)       # (T + 1) ints back: sizes drive the allocation
+        n = int(node_off_h[-1]) if n_towers > 0 else 0
+        raw = torch.empty(max(n, 1), 3, dtype=torch.float64, device=device) if want_raw else None
+        obj = torch.empty(max(n, 1), 3, dtype=torch.float32, device=device)
+        pos = torch.empty(max(n, 1), 2, dtype=torch.float64, device=device)
+        api.check(api.dll.spw_sample_jenga(int(seed), n_towers, node_off.data_ptr(), 0 if raw is None else raw.data_ptr(),
+                                           obj.data_ptr(), pos.data_ptr(), int(bool(inference_glue)), st))
+        b = TowerBatch.from_poses(obj[:n], node_off_h, pos[:n], thr=thr, fully_connected=fully_connected, device=device,
+                                  want_slot_list=want_slot_list, max_nodes=n_hi)
+        b.raw = None if raw is None else raw[:n]
+        return b
+
     # -- compat path: the reference's dense one-hot dict ------------------------------------------
     @staticmethod
     def from_dense_relations(objects, sender_relations, receiver_relations, device=None):

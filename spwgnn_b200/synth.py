@@ -122,6 +122,39 @@ def g_jenga18(rng: random.Random, layers=18, per_layer=3):
     return np.array(out, dtype=np.float64)
 
 
+# ---- counter-based twin of g_jenga: the host restatement of the device sampler (csrc/spw_edges.cuh: k_sample_jenga) ----
+_M64 = (1 << 64) - 1
+
+
+def ctr_u32(seed, tower, ctr):
+    """draw `ctr` of tower `tower`'s stream: splitmix64 finaliser, high 32 bits (ctr_u32 in spw_edges.cuh)"""
+    z = (seed + 0x9E3779B97F4A7C15 * (tower + 1) + 0xD1B54A32D192ED03 * ctr) & _M64
+    z = ((z ^ (z >> 30)) * 0xBF58476D1CE4E5B9) & _M64
+    z = ((z ^ (z >> 27)) * 0x94D049BB133111EB) & _M64
+    z ^= z >> 31
+    return z >> 32
+
+
+class CtrRng:
+    def __init__(self, seed, tower, ctr=0):
+        self.seed, self.tower, self.ctr = seed, tower, ctr
+
+    def randint(self, a, b):
+        v = a + ctr_u32(self.seed, self.tower, self.ctr) % (b - a + 1)
+        self.ctr += 1
+        return v
+
+
+def sizes_ctr(seed, n_towers, lo, hi):
+    """blocks per tower of the device sampler (draw 0 of every tower's stream)"""
+    return np.array([CtrRng(seed, t).randint(lo, hi) for t in range(n_towers)], dtype=np.int64)
+
+
+def g_jenga_ctr(n, seed, tower):
+    """g_jenga with the counter-based generator (draws 1, 2, ... of the tower's stream): what spw_sample_jenga computes"""
+    return g_jenga(n, CtrRng(seed, tower, 1))
+
+
 def g_uniform(lo, hi, rng: random.Random):
     return g_jenga(rng.randint(lo, hi), rng)
 

@@ -98,3 +98,24 @@ def test_emu_dropout_matches_oracle_with_same_mask(emu):
     for k in O.tensor_names():
         ref = g64[k].numpy()
         assert np.abs(grads[k] - ref).max() / max(np.abs(ref).max(), 1e-30) < 2e-5, k
+
+
+def test_emu_device_sampler_matches_host_restatement(emu):
+    """the device-side Jenga layout sampler equals synth.g_jenga_ctr bit for bit, and draws
+    the same kind of layouts as the reference sampler restatement (synth.g_jenga)."""
+    from spwgnn_b200 import synth
+    seed, T, lo, hi = 0x5EED1234ABCD, 300, 2, 40
+    node_off, raw, obj, pos = emu.sample_jenga(seed, T, lo, hi)
+    sizes = synth.sizes_ctr(seed, T, lo, hi)
+    assert np.array_equal(np.diff(node_off), sizes) and node_off[0] == 0
+    ref = np.concatenate([synth.g_jenga_ctr(int(n), seed, t) for t, n in enumerate(sizes)])
+    assert np.array_equal(raw, ref)                                  # float64, bit for bit
+    assert np.array_equal(obj, (ref / 170.0).astype(np.float32))     # main.py:91
+    assert np.array_equal(pos, ref[:, :2])
+    _, _, _, pos_glue = emu.sample_jenga(seed, T, lo, hi, inference_glue=True)
+    assert np.array_equal(pos_glue, ref[:, :2] / 170.0)              # JengaBuilder.py:309-323
+    # same layout family as the reference sampler: layer heights, width range, first layer inside [400, 1100]
+    assert set(np.unique((ref[:, 1] - 110.0) % 80.0)) == {0.0}
+    assert ref[:, 2].min() >= 50 and ref[:, 2].max() <= 300
+    first = ref[node_off[:-1]]
+    assert (first[:, 0] >= 400).all() and (first[:, 0] <= 1100).all() and (first[:, 1] == 110.0).all()

@@ -22,7 +22,7 @@ def built_lib():
 def test_library_exports_every_declared_symbol(built_lib):
     from spwgnn_b200._capi import CApi, EXPORTS
     header = open(os.path.join(ROOT, 'include', 'spwgnn.h')).read()
-    declared = set(re.findall(r'\b(spw_[a-z_]+)\s*\(', header))
+    declared = set(re.findall(r'\b(spw_[a-z0-9_]+)\s*\(', header))
     assert declared == set(EXPORTS), declared ^ set(EXPORTS)
     api = CApi(built_lib)
     for name in declared:
