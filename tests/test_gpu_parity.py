@@ -186,6 +186,41 @@ def test_gradients_strict_on_small_graphs_glorot(eng):
     print('small-graph worst grad rel err %.2e' % worst)
 
 
+def test_degenerate_batches(eng):
+    """Ragged extremes: towers of one block (no relations at all), an empty tower inside a batch, an empty batch."""
+    from spwgnn_b200.graph import TowerBatch
+    _use(eng, 'glorot')
+    # (1) single-block towers only: E = 0, the relation network and the relation MLP get exactly zero gradients
+    towers = [np.array([[700.0 + 10 * i, 110.0, 100.0 + i]]) for i in range(300)]
+    from spwgnn_b200 import synth
+    raw, node_off = synth.pack_towers(towers)
+    batch = TowerBatch.from_towers(towers, want_slot_list=True)
+    assert batch.n_edges == 0 and batch.n_nodes == 300
+    tgt = (np.random.default_rng(8).random(300) > 0.5).astype(np.float32)
+    eng.loss_and_grads(batch, torch.as_tensor(tgt).cuda())
+    snd = rcv = np.zeros(0, np.int64)
+    loss, probs, logits, g64 = _oracle_all(eng.w64, raw, snd, rcv, tgt)
+    assert _rel(eng._fwd[2][:300].cpu().numpy(), logits.numpy()) < TOL
+    for k in O.tensor_names():
+        ref, got = g64[k].numpy(), eng.grads.views[k].cpu().numpy()
+        if np.abs(ref).max() == 0.0:
+            assert np.abs(got).max() == 0.0, k
+        else:
+            assert _rel(got, ref) < TOL, k
+    # (2) an empty tower and a one-block tower between ordinary ones == the ordinary ones alone
+    ordinary = synth.make_towers('jenga', 5, 55, n=7)
+    mixed = [ordinary[0], np.zeros((0, 3)), ordinary[1], np.array([[50.0, 110.0, 80.0]]), ordinary[2], ordinary[3], ordinary[4]]
+    lm, _ = eng.forward(TowerBatch.from_towers(mixed), training=False)
+    lo, _ = eng.forward(TowerBatch.from_towers(ordinary), training=False)
+    lm, lo = lm.cpu().numpy(), lo.cpu().numpy()
+    keep = np.concatenate([np.arange(0, 7), np.arange(7, 14), np.arange(15, 36)])     # drop the lone block at index 14
+    assert np.array_equal(lm[keep], lo)
+    # (3) an empty batch is a no-op, not an error
+    empty = TowerBatch.from_towers([])
+    le, pe = eng.forward(empty, training=False)
+    assert empty.n_nodes == 0 and empty.n_edges == 0
+
+
 def test_golden_fixtures_through_facade(golden_dir):
     """Fixtures produced by running the reference's own Networks.py/main.py (oracle/make_golden.py)."""
     from spwgnn_b200.Networks import PropagationNetwork
