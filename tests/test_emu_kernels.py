@@ -119,3 +119,38 @@ def test_emu_device_sampler_matches_host_restatement(emu):
     assert ref[:, 2].min() >= 50 and ref[:, 2].max() <= 300
     first = ref[node_off[:-1]]
     assert (first[:, 0] >= 400).all() and (first[:, 0] <= 1100).all() and (first[:, 1] == 110.0).all()
+
+
+def test_emu_edges_property_sweep(emu):
+    """Hypothesis-driven sweep of the edge builder (the reference has no tests; the property is
+    equality with the numpy restatement of main.py:66-81): ragged tower sizes including 0 and 1, positions on a coarse
+    lattice so that distances land exactly on / one ulp around the 170 threshold, arbitrary thresholds."""
+    from hypothesis import given, settings, strategies as st, HealthCheck
+
+    lattice = st.integers(0, 12).map(lambda k: 85.0 * k)                    # multiples of 85: many pairs at exactly 170
+    nudge = st.sampled_from([0.0, 0.0, 0.0, 2.0 ** -44, -2.0 ** -44, 0.5])   # one-ulp neighbours of the lattice
+
+    @st.composite
+    def batch(draw):
+        sizes = draw(st.lists(st.integers(0, 9), min_size=1, max_size=6))
+        n = sum(sizes)
+        xs = [draw(lattice) + draw(nudge) for _ in range(n)]
+        ys = [draw(lattice) + draw(nudge) for _ in range(n)]
+        thr = draw(st.sampled_from([170.0, 170.0, 85.0, 1.0, 240.41630560342617]))   # last: 170 * sqrt(2)
+        return sizes, np.array([xs, ys], dtype=np.float64).T.reshape(n, 2), thr
+
+    @settings(max_examples=40, deadline=None, suppress_health_check=list(HealthCheck))
+    @given(batch())
+    def check(b):
+        sizes, pos, thr = b
+        node_off = np.concatenate([[0], np.cumsum(sizes)]).astype(np.int32)
+        g = emu.edges(pos, node_off, thr=thr)
+        eo, snd, rcv, slot = O.edge_list(pos, node_off, thr=thr)
+        assert np.array_equal(eo, g.edge_off)
+        assert np.array_equal(snd, g.snd) and np.array_equal(rcv, g.rcv) and np.array_equal(slot, g.slot)
+        if g.E:
+            order = np.lexsort((np.arange(g.E), rcv))
+            assert np.array_equal(g.in_snd, snd[order]) and np.array_equal(g.in_rcv, rcv[order])
+            assert np.array_equal(g.out_pos[order], np.arange(g.E))
+
+    check()
