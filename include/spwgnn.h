@@ -128,6 +128,11 @@ int spw_edges_fill(const double* pos_xy, const int32_t* node_off, int32_t n_towe
 int spw_sample_sizes(uint64_t seed, int32_t n_towers, int32_t n_lo, int32_t n_hi, int32_t* node_off, void* stream);
 int spw_sample_jenga(uint64_t seed, int32_t n_towers, const int32_t* node_off, double* raw, float* obj, double* pos,
                      int inference_glue, void* stream);
+/*   spw_sample_tower: same outputs for TowerCreator layouts (TowerCreator.py:106-187, 265-271): 150 x 80 blocks stacked in
+ *                     layers plus one dropped block on top, which is object 0 of its tower (TowerCreator.py:451);
+ *                     every tower needs >= 2 blocks (spw_sample_sizes with n_lo >= 2); restated by synth.g_tower_ctr. */
+int spw_sample_tower(uint64_t seed, int32_t n_towers, const int32_t* node_off, double* raw, float* obj, double* pos,
+                     int inference_glue, void* stream);
 
 /* Bytes of workspace spw_forward/spw_backward need.  training != 0 also reserves the node-level
  * state the backward pass reads (5 propagation steps x per-node activations) and per-edge

@@ -232,4 +232,72 @@ __global__ void __launch_bounds__(128) k_sample_jenga(uint64_t seed, int n_tower
   }
 }
 
+// TowerCreator layouts (/root/reference/src/TowerCreator.py:106-187 create_world / create_pos_for_boxes, :265-271 drop_object):
+// 150 x 80 blocks stacked in layers of shrinking size plus ONE dropped block on top, which is object 0 (TowerCreator.py:451).
+// Tower t has N_t = node_off[t+1] - node_off[t] >= 2 blocks: N_t - 1 stacked + the dropped one.  synth.g_tower_ctr is the
+// bit-identical numpy restatement.
+__global__ void __launch_bounds__(128) k_sample_tower(uint64_t seed, int n_towers, const int32_t* __restrict__ node_off,
+                                                      double* __restrict__ raw, float* __restrict__ obj, double* __restrict__ pos,
+                                                      int inference_glue) {
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= n_towers) return;
+  const int base = node_off[t], n = node_off[t + 1] - base - 1;   // stacked blocks
+  if (n < 1) return;
+  uint32_t ctr = 1;                                              // counter 0 drew the size
+  const int rect_w = 150, rect_h = 80, bottom = 70;
+  auto emit = [&](int k, double x, double y) {
+    const size_t o = (size_t)(base + k);
+    if (raw) { raw[3 * o] = x; raw[3 * o + 1] = y; raw[3 * o + 2] = (double)rect_w; }
+    if (obj) { obj[3 * o] = (float)(x / 170.0); obj[3 * o + 1] = (float)(y / 170.0); obj[3 * o + 2] = (float)(rect_w / 170.0); }
+    if (pos) { pos[2 * o] = inference_glue ? x / 170.0 : x; pos[2 * o + 1] = inference_glue ? y / 170.0 : y; }
+  };
+  const int orientation = ctr_u32(seed, (uint64_t)t, ctr++) > 0x80000000u ? 1 : 0;     // rng.random() > 0.5
+  // layer sizes
+  unsigned char layers[kMaxNodes];
+  int nl = 0;
+  layers[nl++] = (unsigned char)ctr_randint(seed, (uint64_t)t, ctr, 1, n / 2 > 1 ? n / 2 : 1);
+  int left = n - layers[0];
+  while (left > 0) {
+    const int prev = layers[nl - 1];
+    int r;
+    if (prev == 1) {
+      r = 1;
+    } else {
+      const int hi = prev < left ? prev : left;
+      r = ctr_randint(seed, (uint64_t)t, ctr, 1, hi);
+      for (int i = 0; r == 1 && left != 1 && i < 3; ++i) r = ctr_randint(seed, (uint64_t)t, ctr, 1, hi);
+    }
+    layers[nl++] = (unsigned char)r;
+    left -= r;
+  }
+  // positions, layer by layer; only the previous layer's extreme x are needed
+  int prev_max = 0, prev_min = 0, k = 1;                         // block 0 is the dropped one
+  auto make_x = [&](int ln, int size, int idx, double mid, bool to_drop) {
+    const int var = to_drop ? 75 : 45;                           // int(150 * 0.5), int(150 * 0.3)
+    const int mean_range = rect_w + 2 * var;
+    const double mean = mid + ((idx & 1) ? -1.0 : 1.0) * (double)(((idx + 1) / 2) * mean_range);
+    if (ln > 0 && size == 1) {
+      const int r = prev_max + rect_w / 2, l = prev_min - rect_w / 2;
+      const int lo = l + 30, hi = r - 30;                        // int(150 * 0.2)
+      return ctr_randint(seed, (uint64_t)t, ctr, lo < hi ? lo : hi, lo < hi ? hi : lo);
+    }
+    const int lo = (int)(mean - (double)((1 - orientation) * var)), hi = (int)(mean + (double)(orientation * var));
+    return ctr_randint(seed, (uint64_t)t, ctr, lo, hi) + (size % 2 == 0 ? mean_range / 2 : 0);
+  };
+  auto middle = [&](int ln) { return ln == 0 ? 750.0 : (double)(int)((double)((prev_min - rect_w / 2) + (prev_max + rect_w / 2)) / 2.0); };
+  for (int ln = 0; ln < nl; ++ln) {
+    const double mid = middle(ln);
+    int cur_max = 0, cur_min = 0;
+    for (int i = 0; i < layers[ln]; ++i) {
+      const int x = make_x(ln, layers[ln], i, mid, false);
+      cur_max = i == 0 ? x : (x > cur_max ? x : cur_max);
+      cur_min = i == 0 ? x : (x < cur_min ? x : cur_min);
+      emit(k++, (double)x, (double)bottom + rect_h / 2.0 + (double)(rect_h * ln));
+    }
+    prev_max = cur_max; prev_min = cur_min;
+  }
+  const int xd = make_x(nl, 1, 0, middle(nl), true);
+  emit(0, (double)xd, (double)bottom + rect_h / 2.0 + (double)(rect_h * nl));
+}
+
 }  // namespace spw

@@ -645,6 +645,16 @@ int spw_sample_jenga(uint64_t seed, int32_t n_towers, const int32_t* node_off, d
   return check_launch("spw_sample_jenga");
 }
 
+int spw_sample_tower(uint64_t seed, int32_t n_towers, const int32_t* node_off, double* raw, float* obj, double* pos,
+                     int inference_glue, void* stream) {
+  if (n_towers < 0) return fail(SPW_ERR_BAD_ARG, "spw_sample_tower: negative size");
+  if (n_towers == 0) return SPW_OK;
+  if (!node_off || (!raw && !obj && !pos)) return fail(SPW_ERR_BAD_ARG, "spw_sample_tower: null pointer");
+  SPW_KLAUNCH("k_sample_tower", k_sample_tower, dim3((n_towers + 127) / 128), dim3(128), 0, (cudaStream_t)stream, seed, (int)n_towers, node_off, raw,
+              obj, pos, inference_glue);
+  return check_launch("spw_sample_tower");
+}
+
 size_t spw_workspace_bytes(int32_t n_nodes, int32_t n_edges, int training) {
   if (n_nodes < 0 || n_edges < 0) return 0;
   return make_layout(n_nodes, n_edges, training).total * sizeof(float);

@@ -101,8 +101,14 @@ class TowerBatch:
 
     # -- device-side synthetic layouts ------------------------------
     @staticmethod
+    def sample_tower(n_towers, n_lo, n_hi, seed, **kw):
+        """TowerCreator layouts (TowerCreator.py:106-187, 265-271) generated on the GPU: n_lo..n_hi blocks per tower
+        (>= 2: stacked blocks + the dropped one, which is object 0).  Bit-identical to synth.g_tower_ctr."""
+        return TowerBatch.sample_jenga(n_towers, n_lo, n_hi, seed, _kind='tower', **kw)
+
+    @staticmethod
     def sample_jenga(n_towers, n_lo, n_hi, seed, device=None, fully_connected=False, inference_glue=False,
-                     thr=REL_THRESHOLD, want_raw=False, want_slot_list=False):
+                     thr=REL_THRESHOLD, want_raw=False, want_slot_list=False, _kind='jenga'):
         """Jenga-style layouts (JengaBuilder.create_world, JengaBuilder.py:137-192) generated ON the GPU and packed:
         tower t gets n_lo..n_hi blocks; poses never exist on the host.  Bit-identical to synth.g_jenga_ctr.
         Returns the TowerBatch (its .raw holds the (n, 3) float64 pixel poses when want_raw)."""
@@ -117,8 +123,11 @@ class TowerBatch:
         raw = torch.empty(max(n, 1), 3, dtype=torch.float64, device=device) if want_raw else None
         obj = torch.empty(max(n, 1), 3, dtype=torch.float32, device=device)
         pos = torch.empty(max(n, 1), 2, dtype=torch.float64, device=device)
-        api.check(api.dll.spw_sample_jenga(int(seed), n_towers, node_off.data_ptr(), 0 if raw is None else raw.data_ptr(),
-                                           obj.data_ptr(), pos.data_ptr(), int(bool(inference_glue)), st))
+        if _kind == 'tower' and n_lo < 2:
+            raise SpwError('TowerCreator layouts need at least 2 blocks per tower')
+        sampler = api.dll.spw_sample_tower if _kind == 'tower' else api.dll.spw_sample_jenga
+        api.check(sampler(int(seed), n_towers, node_off.data_ptr(), 0 if raw is None else raw.data_ptr(),
+                          obj.data_ptr(), pos.data_ptr(), int(bool(inference_glue)), st))
         b = TowerBatch.from_poses(obj[:n], node_off_h, pos[:n], thr=thr, fully_connected=fully_connected, device=device,
                                   want_slot_list=want_slot_list, max_nodes=n_hi)
         b.raw = None if raw is None else raw[:n]

@@ -144,6 +144,11 @@ class CtrRng:
         self.ctr += 1
         return v
 
+    def random(self):
+        v = ctr_u32(self.seed, self.tower, self.ctr) / 4294967296.0
+        self.ctr += 1
+        return v
+
 
 def sizes_ctr(seed, n_towers, lo, hi):
     """blocks per tower of the device sampler (draw 0 of every tower's stream)"""
@@ -153,6 +158,11 @@ def sizes_ctr(seed, n_towers, lo, hi):
 def g_jenga_ctr(n, seed, tower):
     """g_jenga with the counter-based generator (draws 1, 2, ... of the tower's stream): what spw_sample_jenga computes"""
     return g_jenga(n, CtrRng(seed, tower, 1))
+
+
+def g_tower_ctr(n_total, seed, tower):
+    """g_tower with the counter-based generator: n_total - 1 stacked blocks + the dropped one (spw_sample_tower)"""
+    return g_tower(n_total - 1, CtrRng(seed, tower, 1))
 
 
 def g_uniform(lo, hi, rng: random.Random):

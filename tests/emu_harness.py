@@ -68,7 +68,7 @@ class Emu:
         g.c = api.graph(T, n, E, _p(node_off), _p(g.in_off), _p(g.in_snd), _p(g.in_rcv), _p(g.out_off), _p(g.out_pos))
         return g
 
-    def sample_jenga(self, seed, n_towers, n_lo, n_hi, inference_glue=False):
+    def sample_jenga(self, seed, n_towers, n_lo, n_hi, inference_glue=False, kind='jenga'):
         """device-side layout sampler (k_sample_sizes / k_sample_jenga) under the emulator"""
         api = self.api
         node_off = np.full(n_towers + 1, -5, np.int32)
@@ -77,7 +77,8 @@ class Emu:
         raw = np.full((max(n, 1), 3), np.nan, np.float64)
         obj = np.full((max(n, 1), 3), np.nan, np.float32)
         pos = np.full((max(n, 1), 2), np.nan, np.float64)
-        api.check(api.dll.spw_sample_jenga(int(seed), n_towers, _p(node_off), _p(raw), _p(obj), _p(pos), int(inference_glue), None))
+        fn = api.dll.spw_sample_tower if kind == 'tower' else api.dll.spw_sample_jenga
+        api.check(fn(int(seed), n_towers, _p(node_off), _p(raw), _p(obj), _p(pos), int(inference_glue), None))
         return node_off, raw[:n], obj[:n], pos[:n]
 
     @staticmethod

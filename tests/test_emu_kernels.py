@@ -121,6 +121,22 @@ def test_emu_device_sampler_matches_host_restatement(emu):
     assert (first[:, 0] >= 400).all() and (first[:, 0] <= 1100).all() and (first[:, 1] == 110.0).all()
 
 
+def test_emu_device_tower_sampler_matches_host_restatement(emu):
+    """TowerCreator layouts on the device (k_sample_tower) == synth.g_tower_ctr bit for bit; the dropped block is object 0
+    and sits on top (TowerCreator.py:265-271, 451)."""
+    from spwgnn_b200 import synth
+    seed, T, lo, hi = 987654321, 400, 2, 33
+    node_off, raw, obj, pos = emu.sample_jenga(seed, T, lo, hi, kind='tower')
+    sizes = synth.sizes_ctr(seed, T, lo, hi)
+    assert np.array_equal(np.diff(node_off), sizes)
+    ref = np.concatenate([synth.g_tower_ctr(int(n), seed, t) for t, n in enumerate(sizes)])
+    assert np.array_equal(raw, ref)
+    assert np.array_equal(obj, (ref / 170.0).astype(np.float32))
+    for t in range(T):
+        tw = raw[node_off[t]:node_off[t + 1]]
+        assert tw[0, 1] == tw[:, 1].max() and (tw[:, 2] == 150.0).all()
+
+
 def test_emu_edges_property_sweep(emu):
     """Hypothesis-driven sweep of the edge builder (the reference has no tests; the property is
     equality with the numpy restatement of main.py:66-81): ragged tower sizes including 0 and 1, positions on a coarse

@@ -455,6 +455,12 @@ def test_device_sampler_bit_exact_and_sweep(eng):
     ld, _ = eng.forward(b, training=False)
     lh, _ = eng.forward(TowerBatch.from_towers(towers), training=False)
     assert torch.equal(ld, lh)
+    # TowerCreator layouts (dropped block = object 0), 6-block towers like BASELINE config 1
+    bt = TowerBatch.sample_tower(2000, 6, 6, seed + 2, want_raw=True)
+    reft = np.concatenate([synth.g_tower_ctr(6, seed + 2, t) for t in range(2000)])
+    assert np.array_equal(bt.raw.cpu().numpy(), reft)
+    lt, _ = eng.forward(bt, training=False)
+    assert torch.isfinite(lt).all()
     # a larger sweep: 200 000 towers generated and scored without touching the host
     big = TowerBatch.sample_jenga(200000, lo, hi, seed + 1)
     lb, pb = eng.forward(big, training=False)
