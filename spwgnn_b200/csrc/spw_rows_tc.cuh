@@ -114,16 +114,33 @@ constexpr int kRowsMaxSlabs = 7;                    // ks <= 25 -> ceil(25 / 4)
 constexpr int kRowsEarlySlabs = 3;                  // correction MMAs of the first slabs are issued while the rest is staged
 
 template <int NB>
-constexpr size_t rows_tc_smem(int ks) { return (size_t)(2 * ks * 8 * NB + 2 * kSlabFloats + NB) * sizeof(float) + 32; }
+constexpr size_t rows_tc_smem(int ks) { return (size_t)(2 * ks * 8 * NB + 2 * kSlabFloats + NB + kTM * 8) * sizeof(float) + 32; }
 
 __device__ __forceinline__ int slab_off(int row, int ch) { return row * kSlabCols + ((ch ^ (row & 7)) << 2); }
+
+// Sign words of a tile ([128 rows][8 words], contiguous in global memory) staged in shared memory: one coalesced 4 KB
+// transfer per tile instead of a scattered 4-byte access per row and slab.
+__device__ __forceinline__ void rows_bits_load(const RowsTcArgs& a, uint32_t* sbits, int r0) {
+  if (a.mulmode == 3 && threadIdx.x < 256) {
+    const int r = threadIdx.x >> 1;
+    uint4 q = make_uint4(0u, 0u, 0u, 0u);
+    if (r0 + r < a.M) q = reinterpret_cast<const uint4*>(a.bits_in + (size_t)r0 * 8)[threadIdx.x];
+    reinterpret_cast<uint4*>(sbits)[threadIdx.x] = q;
+  }
+}
+__device__ __forceinline__ void rows_bits_store(const RowsTcArgs& a, const uint32_t* sbits, int r0) {
+  if (a.bits_out && threadIdx.x < 256) {
+    const int r = threadIdx.x >> 1;
+    if (r0 + r < a.M) reinterpret_cast<uint4*>(a.bits_out + (size_t)r0 * 8)[threadIdx.x] = reinterpret_cast<const uint4*>(sbits)[threadIdx.x];
+  }
+}
 
 // Epilogue of PP (row, chunk) pieces of one 32-column accumulator slab: rows crow0 + rstride * i (i < PP) of the tile,
 // chunk cch (columns 32 es + 4 cch ...).  Reads the raw accumulators from the slab, applies the LinArgs contract and
 // writes 16 bytes per piece (eight lanes per 128 bytes of a row: coalesced).  Must be called by whole warps (shuffles).
 template <int NB, int PP>
-__device__ __forceinline__ void rows_epilogue(const RowsTcArgs& a, const float* sb, const float* sbias, int r0, int crow0,
-                                               int rstride, int cch, int es) {
+__device__ __forceinline__ void rows_epilogue(const RowsTcArgs& a, const float* sb, const float* sbias, uint32_t* sbits, int r0,
+                                               int crow0, int rstride, int cch, int es) {
   const int col = kSlabCols * es + 4 * cch;
   const bool col_ok = col < a.ldy;
   const bool full = col + 3 < a.N;
@@ -180,7 +197,7 @@ __device__ __forceinline__ void rows_epilogue(const RowsTcArgs& a, const float* 
   if (a.mulmode == 3) {                                      // mask bits: word es of the row, nibble cch
 #pragma unroll
     for (int i = 0; i < PP; ++i) {
-      const uint32_t bits = a.bits_in[go[i] * 8 + es] >> (4 * cch);
+      const uint32_t bits = sbits[(crow0 + rstride * i) * 8 + es] >> (4 * cch);      // staged per tile (rows_bits_load)
 #pragma unroll
       for (int e = 0; e < 4; ++e) r[i][e] = ((bits >> e) & 1u) ? r[i][e] : 0.f;
     }
@@ -221,7 +238,7 @@ __device__ __forceinline__ void rows_epilogue(const RowsTcArgs& a, const float* 
       w |= __shfl_xor_sync(0xffffffffu, w, 1);
       w |= __shfl_xor_sync(0xffffffffu, w, 2);
       w |= __shfl_xor_sync(0xffffffffu, w, 4);
-      if (cch == 0 && (size_t)r0 + crow0 + rstride * i < (size_t)a.M) a.bits_out[((size_t)r0 + crow0 + rstride * i) * 8 + es] = w;
+      if (cch == 0) sbits[(crow0 + rstride * i) * 8 + es] = w;                         // written out per tile (rows_bits_store)
     }
   }
   if (!full) {                                               // columns beyond N: zero (or the ones column)
@@ -267,7 +284,8 @@ __global__ void __launch_bounds__(NT, 1) k_rows_tc(RowsTcArgs a) {
   float* Blo_s = Bhi_s + bfl;
   float* slab = Blo_s + bfl;                                     // [2][128][32]
   float* sbias = slab + 2 * kSlabFloats;                         // [NB]
-  uint64_t* bar = reinterpret_cast<uint64_t*>(sbias + NB);
+  uint32_t* sbits = reinterpret_cast<uint32_t*>(sbias + NB);     // [128][8] sign words of the tile (mask in or sign bits out)
+  uint64_t* bar = reinterpret_cast<uint64_t*>(sbits + kTM * 8);
   uint32_t* tptr = reinterpret_cast<uint32_t*>(bar + 1);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int row = 32 * (warp & 3) + lane, part = warp >> 2;      // tensor-memory view: thread = (row, part of the slab)
@@ -279,6 +297,7 @@ __global__ void __launch_bounds__(NT, 1) k_rows_tc(RowsTcArgs a) {
   }
   cp_async_commit();
   for (int i = tid; i < NB; i += NT) sbias[i] = (a.bias && i < a.N) ? a.bias[i] : 0.f;
+  for (int i = tid; i < kTM * 8; i += NT) sbits[i] = 0u;
   if (warp == 0) tmem_alloc(tptr, kTmemCols);
   if (tid == 32) { mbar_init(bar, 1); fence_mbar_init(); }
   fence_before_sync();
@@ -323,6 +342,7 @@ __global__ void __launch_bounds__(NT, 1) k_rows_tc(RowsTcArgs a) {
   for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
     SPW_PH(7);
     const int r0 = tile * kTM;
+    rows_bits_load(a, sbits, r0);                                // used after several barriers (epilogue)
     const uint64_t dhi0 = make_b_desc(smem_u32(Bhi_s), NB * 16, 128), dlo0 = make_b_desc(smem_u32(Blo_s), NB * 16, 128);
     constexpr uint64_t kStep = (8 * NB * 4) >> 4;                // descriptor start-address units (16 bytes) per k-step
     const uint32_t dcol = tmem_base + colD;
@@ -413,11 +433,12 @@ __global__ void __launch_bounds__(NT, 1) k_rows_tc(RowsTcArgs a) {
           *reinterpret_cast<uint4*>(sb + slab_off(row, CPT * part + g)) = make_uint4(vv[4 * g], vv[4 * g + 1], vv[4 * g + 2], vv[4 * g + 3]);
       }
       __syncthreads();
-      rows_epilogue<NB, PP>(a, sb, sbias, r0, crow, RS, cch, es);
+      rows_epilogue<NB, PP>(a, sb, sbias, sbits, r0, crow, RS, cch, es);
     }
     fence_before_sync();
     SPW_PH(5);                                                   // p5: epilogue
     __syncthreads();
+    rows_bits_store(a, sbits, r0);                               // sbits is next written after the next tile's staging barriers
     SPW_PH(6);
   }
   if (a.M > 100000) SPW_PH_REPORT(a.mulmode ? "k_rows_tc:enc_bwd" : "k_rows_tc:enc_fwd");
@@ -531,6 +552,167 @@ k_tc2_selftest(const float* __restrict__ A, const float* __restrict__ Bhi, const
     }
     if (tid == 0) status[rank] = 1;
   }
+  fence_before_sync();
+  cluster_sync_all();
+  if (warp == 0) tmem_dealloc2(tmem_base, kTmemCols);
+}
+
+// =================================================================================================
+// k_rows_pair: the 150 -> 150 layers of the relation encoder (K = 152, N = 160, rows of 152 floats) on CTA PAIRS.
+//   Each CTA of a cluster of two keeps 80 of the 160 weight columns (hi and lo, 95 KB) -- the tcgen05.mma.cta_group::2
+//   stream of the leader reads both halves -- which frees the shared memory for a whole raw input tile: the next
+//   tile's 128 rows (contiguous in HBM, 76 KB) arrive with ONE TMA bulk copy while the current tile is converted,
+//   multiplied and written, so no warp ever blocks on issuing loads.  The epilogue is k_rows_tc's (slab + coalesced stores).
+//   Per tile and CTA: wait for the bulk copy -> row threads read their row from shared memory, split, store to tensor
+//   memory -> cluster barrier -> leader issues 57 MMAs (M = 256) + multicast commit -> both CTAs run their epilogue.
+// =================================================================================================
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+// TMA bulk copy global -> shared (16-byte aligned, size a multiple of 16), completion counted in bytes on an mbarrier
+__device__ __forceinline__ void bulk_g2s(void* sdst, const void* gsrc, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(sdst)),
+               "l"(gsrc), "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
+}
+
+__device__ __forceinline__ void mbar_arrive_cta1(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+
+constexpr int kPairThreads = 512;
+constexpr int kXbufFloats = kTM * kDEP;                          // one raw input tile
+constexpr size_t kRowsPairSmem = (size_t)(2 * kB2Floats + kXbufFloats + 2 * kSlabFloats + kN + kTM * 8) * sizeof(float) + 64;
+
+// a.Bhi / a.Blo: [2 halves][kKS][2][80][4] (k_pack_tc with NB = 80, one descriptor per half); a.ldx[0] == a.ldy == 152, nseg == 1
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kPairThreads, 1) k_rows_pair(RowsTcArgs a) {
+  constexpr int NB = kN, NT = kPairThreads, PP = 1024 / NT, RS = NT / 8;
+  SPW_DYN_SMEM(smem_raw);
+  float* Bhi_s = reinterpret_cast<float*>(smem_raw);
+  float* Blo_s = Bhi_s + kB2Floats;
+  float* Xbuf = Blo_s + kB2Floats;                               // [128][152] raw rows of the current tile
+  float* slab = Xbuf + kXbufFloats;                              // [2][128][32] epilogue staging
+  float* sbias = slab + 2 * kSlabFloats;                         // [160]
+  uint32_t* sbits = reinterpret_cast<uint32_t*>(sbias + NB);     // [128][8] sign words of the tile
+  uint64_t* mma_done = reinterpret_cast<uint64_t*>(sbits + kTM * 8);
+  uint64_t* xfull = mma_done + 1;
+  uint32_t* tptr = reinterpret_cast<uint32_t*>(xfull + 1);
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int row = 32 * (warp & 3) + lane, part = warp >> 2;      // tensor-memory view: thread = (row, quarter of the k-steps)
+  const int crow = tid >> 3, cch = tid & 7;                      // coalesced view (epilogue)
+  const uint32_t rank = cluster_ctarank();
+  const int cluster = blockIdx.x >> 1, nclusters = gridDim.x >> 1;
+  const int ntiles = (a.M + kTM - 1) / kTM;
+  const int npairs = (ntiles + 1) >> 1;                          // tile pair p = tiles 2p (rank 0) and 2p + 1 (rank 1)
+  const int my_pairs = cluster < npairs ? (npairs - 1 - cluster) / nclusters + 1 : 0;
+  auto tile_of = [&](int i) { return 2 * (cluster + i * nclusters) + (int)rank; };
+
+  if (warp == 0) tmem_alloc2(tptr, kTmemCols);
+  if (tid == 32) { mbar_init(mma_done, 1); mbar_init(xfull, 1); fence_mbar_init(); }
+  for (int i = tid; i < kB2Floats / 4; i += NT) {                // this CTA's half of the weight columns
+    cp_async16(Bhi_s + 4 * i, a.Bhi + (size_t)rank * kB2Floats + 4 * i);
+    cp_async16(Blo_s + 4 * i, a.Blo + (size_t)rank * kB2Floats + 4 * i);
+  }
+  cp_async_commit();
+  for (int i = tid; i < NB; i += NT) sbias[i] = (a.bias && i < a.N) ? a.bias[i] : 0.f;
+  for (int i = tid; i < kTM * 8; i += NT) sbits[i] = 0u;
+  cp_async_wait<0>();
+  fence_async_smem();
+  fence_before_sync();
+  __syncthreads();
+  fence_after_sync();
+  const uint32_t tmem_base = *tptr;
+  const uint32_t lane_addr = tmem_base + ((uint32_t)(32 * (warp & 3)) << 16);
+  auto issue_load = [&](int i) {                                 // one thread: bulk copy of the rows of local tile i
+    const int tile = tile_of(i);
+    const int rows = tile < ntiles ? imin(kTM, a.M - tile * kTM) : 0;
+    if (rows > 0) {
+      mbar_arrive_expect_tx(xfull, (uint32_t)rows * kDEP * 4);
+      bulk_g2s(Xbuf, a.X[0] + (size_t)tile * kTM * kDEP, (uint32_t)rows * kDEP * 4, xfull);
+    } else {
+      mbar_arrive_cta1(xfull);
+    }
+  };
+  if (tid == 0 && my_pairs > 0) issue_load(0);
+  cluster_sync_all();                                            // barriers of both CTAs are initialised before any multicast commit
+  bool failed = false;
+  SPW_PH_DECL
+
+  for (int i = 0; i < my_pairs; ++i) {
+    SPW_PH(7);
+    const int tile = tile_of(i);
+    const int r0 = tile * kTM;
+    const bool valid = r0 + row < a.M;
+    rows_bits_load(a, sbits, r0);                                // used after several barriers (epilogue)
+    // ---- A operand: this thread's row from the raw tile in shared memory -> tf32 hi / lo -> tensor memory
+    if (!mbar_wait(xfull, (uint32_t)i & 1u)) failed = true;
+    SPW_PH(0);                                                   // p0: wait for the bulk copy
+#pragma unroll
+    for (int j = 0; j < 5; ++j) {
+      const int ks = part + 4 * j;                               // k-steps part, part + 4, ...
+      if (ks < kKS) {                                            // warp-uniform
+        const float4 u = *reinterpret_cast<const float4*>(Xbuf + row * kDEP + 8 * ks);
+        const float4 v = *reinterpret_cast<const float4*>(Xbuf + row * kDEP + 8 * ks + 4);
+        float x[8] = {u.x, u.y, u.z, u.w, v.x, v.y, v.z, v.w};
+#pragma unroll
+        for (int e = 0; e < 8; ++e)
+          if (!valid || 8 * ks + e >= a.K[0]) x[e] = 0.f;
+        uint32_t h[8], l[8];
+#pragma unroll
+        for (int e = 0; e < 8; ++e) split_tf32(x[e], h[e], l[e]);
+        tmem_st8(lane_addr + kColAhi + 8 * ks, h);
+        tmem_st8(lane_addr + kColAlo + 8 * ks, l);
+      }
+    }
+    tmem_wait_st();
+    fence_before_sync();
+    SPW_PH(1);                                                   // p1: operand staging from shared memory
+    __syncthreads();                                             // the raw tile has been consumed
+    if (tid == 0 && i + 1 < my_pairs) { fence_async_smem(); issue_load(i + 1); }   // next tile: lands during the MMAs and the epilogue
+    cluster_sync_all();                                          // both CTAs: A staged, D of the previous tile read
+    SPW_PH(2);                                                   // p2: CTA + cluster barrier
+    if (rank == 0 && tid == 0) {
+      fence_after_sync();
+      const uint32_t idesc = make_idesc_tf32(256, kN);
+      const uint64_t dhi0 = make_b_desc(smem_u32(Bhi_s), kHalfN * 16, 128), dlo0 = make_b_desc(smem_u32(Blo_s), kHalfN * 16, 128);
+      constexpr uint64_t kStep = (8 * kHalfN * 4) >> 4;
+      const uint32_t d = tmem_base + kColD;
+      // correction products first, main products last (the tensor core truncates when it accumulates)
+#pragma unroll 4
+      for (int ks = 0; ks < kKS; ++ks) {
+        mma2_tf32_ts(d, tmem_base + kColAlo + 8 * ks, dhi0 + ks * kStep, idesc, ks > 0 ? 1u : 0u);
+        mma2_tf32_ts(d, tmem_base + kColAhi + 8 * ks, dlo0 + ks * kStep, idesc, 1u);
+      }
+#pragma unroll 4
+      for (int ks = 0; ks < kKS; ++ks) mma2_tf32_ts(d, tmem_base + kColAhi + 8 * ks, dhi0 + ks * kStep, idesc, 1u);
+      mma2_commit_multicast(mma_done);
+    }
+    if (!mbar_wait(mma_done, (uint32_t)i & 1u)) failed = true;
+    fence_after_sync();
+    SPW_PH(3);                                                   // p3: MMA issue + wait
+    // ---- epilogue, 32 accumulator columns at a time: tensor memory -> slab (row threads) -> epilogue + store (coalesced)
+    constexpr int kEs = NB / kSlabCols;
+#pragma unroll 1
+    for (int es = 0; es < kEs; ++es) {
+      float* sb = slab + (es & 1) * kSlabFloats;
+      {
+        uint32_t vv[8];
+        tmem_ld8(lane_addr + kColD + kSlabCols * es + 8 * part, vv);
+        tmem_wait_ld();
+        *reinterpret_cast<uint4*>(sb + slab_off(row, 2 * part)) = make_uint4(vv[0], vv[1], vv[2], vv[3]);
+        *reinterpret_cast<uint4*>(sb + slab_off(row, 2 * part + 1)) = make_uint4(vv[4], vv[5], vv[6], vv[7]);
+      }
+      __syncthreads();
+      if (tile < ntiles) rows_epilogue<NB, PP>(a, sb, sbias, sbits, r0, crow, RS, cch, es);
+    }
+    fence_before_sync();
+    SPW_PH(4);                                                   // p4: epilogue
+    __syncthreads();
+    if (tile < ntiles) rows_bits_store(a, sbits, r0);
+    SPW_PH(5);
+  }
+  SPW_PH_REPORT(a.mulmode ? "k_rows_pair:enc_bwd" : "k_rows_pair:enc_fwd");
+  if (failed && tid == 0) a.poison[0] = __int_as_float(0x7fc00000);
   fence_before_sync();
   cluster_sync_all();
   if (warp == 0) tmem_dealloc2(tmem_base, kTmemCols);

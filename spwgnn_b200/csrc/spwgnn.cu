@@ -127,6 +127,7 @@ inline size_t tc_floats(int id) { return (size_t)kTcShape[id].ks * 8 * kTcShape[
 struct Layout {
   size_t pack[P_COUNT];
   size_t tcp[T_COUNT];
+  size_t tcp2;                   // CTA-pair operands of the eight 150x150 relation-encoder matrices: 8 x (hi halves | lo halves)
   size_t QV;                     // q.V1a + c1, constant over the steps
   size_t Q1, Q, degf, A, PF, PL, W2hi, W2lo, W2Thi, W2Tlo, ENCT;   // ENCT: 4 x (hi, lo) transposed encoder operands
   size_t P, S, R, H2S, G, U;     // per-step arrays (training: 5 slots; inference: fewer)
@@ -151,6 +152,7 @@ Layout make_layout(int64_t n, int64_t E, int training) {
   L.W2Tlo = take(24320);
   L.ENCT = take((size_t)8 * 24320);
   for (int i = 0; i < T_COUNT; ++i) L.tcp[i] = take(2 * tc_floats(i));
+  L.tcp2 = take((size_t)8 * 4 * 19 * 8 * 80);
   L.Q1 = take(n * kDP);
   L.Q = take(n * kDP);
   L.QV = take(n * kDP);
@@ -290,9 +292,8 @@ struct RowsSeg { const float* X; int ldx; int K; };
 struct LinId { int tc; int pk0, pk1; };     // B operand of the tensor-core kernel; packed FFMA matrices of the segments
 
 #if SPW_USE_TC
-void launch_rows_tc_raw(cudaStream_t st, const float* Bhi, const float* Blo, int NB, int M, int N, int nseg, const RowsSeg* sg,
-                        float* Y, int ldy, const LinOpt& o) {
-  if (M <= 0) return;
+tc::RowsTcArgs make_rows_args(const float* Bhi, const float* Blo, int M, int N, int nseg, const RowsSeg* sg, float* Y, int ldy,
+                              const LinOpt& o) {
   tc::RowsTcArgs a;
   memset(&a, 0, sizeof(a));
   a.M = M; a.nseg = nseg; a.N = N;
@@ -304,6 +305,13 @@ void launch_rows_tc_raw(cudaStream_t st, const float* Bhi, const float* Blo, int
   a.mulsrc = o.mulsrc; a.ld_mul = o.ld_mul; a.mulmode = o.mulmode; a.Y = Y; a.ldy = ldy; a.accumulate = o.accumulate;
   a.post_scale = o.post_scale; a.drop_thresh = o.drop_thresh; a.drop_seed = o.drop_seed; a.drop_inv_keep = o.drop_inv_keep;
   a.drop_stride = o.drop_stride; a.ones_col = o.ones_col; a.poison = Y; a.bits_in = o.bits_in; a.bits_out = o.bits_out;
+  return a;
+}
+
+void launch_rows_tc_raw(cudaStream_t st, const float* Bhi, const float* Blo, int NB, int M, int N, int nseg, const RowsSeg* sg,
+                        float* Y, int ldy, const LinOpt& o) {
+  if (M <= 0) return;
+  const tc::RowsTcArgs a = make_rows_args(Bhi, Blo, M, N, nseg, sg, Y, ldy, o);
   const int ntiles = (M + kTM - 1) / kTM;
   const int grid = ntiles < num_sms() ? ntiles : num_sms();
   // 512 threads: with one CTA per SM (shared and tensor memory are full) more warps mean less serial work per warp
@@ -457,6 +465,41 @@ void pack_tc(cudaStream_t st, const SpwParams* w, float* ws, const Layout& L, bo
   }
   pa.n = n;
   SPW_KLAUNCH("k_pack_tc", tc::k_pack_tc, dim3(16, n), dim3(256), 0, st, pa);
+}
+#endif
+
+#if SPW_USE_TC
+constexpr size_t kPairFloats = (size_t)4 * 19 * 8 * 80;      // per matrix: hi half 0, hi half 1, lo half 0, lo half 1
+// pair operand ids: 0..3 forward RM1, RM2, RM3, W1A;  4..7 transposed W1A, RM3, RM2, RM1 (the order the backward pass walks)
+void pack_tc_pair(cudaStream_t st, const SpwParams* w, float* ws, const Layout& L, bool with_transposes) {
+  tc::PackTcArgs pa;
+  memset(&pa, 0, sizeof(pa));
+  int n = 0;
+  auto add = [&](int id, const float* src, int transpose) {
+    for (int h = 0; h < 2; ++h) {
+      tc::PackTcDesc& d = pa.d[n++];
+      d.src = src; d.ld = 150; d.K = 150; d.N = h == 0 ? 80 : 70; d.transpose = transpose;
+      d.row0 = transpose ? 80 * h : 0; d.col0 = transpose ? 0 : 80 * h;
+      d.hi = ws + L.tcp2 + (size_t)id * kPairFloats + (size_t)h * tc::kB2Floats;
+      d.lo = d.hi + 2 * tc::kB2Floats; d.NB = 80; d.k_off = 0; d.k_lim = 8 * tc::kKS;
+    }
+  };
+  add(0, w->rm_w[1], 0); add(1, w->rm_w[2], 0); add(2, w->rm_w[3], 0); add(3, w->rmp_w[0], 0);
+  if (with_transposes) { add(4, w->rmp_w[0], 1); add(5, w->rm_w[3], 1); add(6, w->rm_w[2], 1); add(7, w->rm_w[1], 1); }
+  pa.n = n;
+  SPW_KLAUNCH("k_pack_tc", tc::k_pack_tc, dim3(16, n), dim3(256), 0, st, pa);
+}
+
+// one 150 -> 150 layer on [E][152] rows with the CTA-pair kernel
+void launch_rows_pair(cudaStream_t st, float* ws, const Layout& L, int pair_id, int M, const float* X, float* Y, const LinOpt& o) {
+  if (M <= 0) return;
+  RowsSeg sg = {X, kDEP, kDE};
+  const float* base = ws + L.tcp2 + (size_t)pair_id * kPairFloats;
+  tc::RowsTcArgs a = make_rows_args(base, base + 2 * tc::kB2Floats, M, kDE, 1, &sg, Y, kDEP, o);
+  const int ntiles = (M + kTM - 1) / kTM, npairs = (ntiles + 1) / 2;
+  const int nclusters = npairs < num_sms() / 2 ? npairs : num_sms() / 2;
+  set_smem(tc::k_rows_pair, tc::kRowsPairSmem);
+  SPW_KLAUNCH(o.tag ? o.tag : "k_rows_pair", tc::k_rows_pair, dim3(2 * nclusters), dim3(tc::kPairThreads), tc::kRowsPairSmem, st, a);
 }
 #endif
 
@@ -684,6 +727,8 @@ int spw_forward(const SpwParams* w, const SpwGraph* g, const float* obj, float* 
 
 #if SPW_USE_TC
   pack_tc(st, w, ws, L, training != 0);
+  const bool use_pair = E >= 64 * kTM * 2;       // CTA-pair relation-encoder layers: worth it from a few tile pairs per cluster on
+  if (use_pair) pack_tc_pair(st, w, ws, L, training != 0);
 #else
   pack_weights(st, w, ws, L, training != 0);
 #endif
@@ -728,13 +773,17 @@ int spw_forward(const SpwParams* w, const SpwGraph* g, const float* obj, float* 
     LinOpt o; o.act = 1; o.ones_col = kDE; o.tag = "k_rows_tc<160>:enc_fwd";
     RowsSeg s0 = {X0, kDEP, kDE}, s1 = {X1, kDEP, kDE}, s2 = {X2, kDEP, kDE}, s3 = {C, kDEP, kDE};
     o.bias = w->rm_b[1]; o.bits_out = EB ? EB + nb : nullptr;
+    if (use_pair) launch_rows_pair(st, ws, L, 0, E, X0, X1, o); else
     launch_rows_tc(st, ws, L, T_RM1, E, kDE, 1, &s0, X1, kDEP, o);
     o.bias = w->rm_b[2]; o.bits_out = EB ? EB + 2 * nb : nullptr;
+    if (use_pair) launch_rows_pair(st, ws, L, 1, E, X1, X2, o); else
     launch_rows_tc(st, ws, L, T_RM2, E, kDE, 1, &s1, X2, kDEP, o);
     o.bias = w->rm_b[3]; o.bits_out = EB ? EB + 3 * nb : nullptr;
     o.drop_thresh = drop_thresh; o.drop_seed = seed_c; o.drop_inv_keep = inv_keep; o.drop_stride = 160;   // Networks.py:77
+    if (use_pair) launch_rows_pair(st, ws, L, 2, E, X2, C, o); else
     launch_rows_tc(st, ws, L, T_RM3, E, kDE, 1, &s2, C, kDEP, o);
     LinOpt oa; oa.bias = w->rmp_b[0]; oa.tag = "k_rows_tc<160>:enc_fwd";
+    if (use_pair) launch_rows_pair(st, ws, L, 3, E, C, ws + L.A, oa); else
     launch_rows_tc(st, ws, L, T_W1A, E, kDE, 1, &s3, ws + L.A, kDEP, oa);
   }
 #else
@@ -998,6 +1047,7 @@ int spw_backward(const SpwParams* w, const SpwGraph* g, const float* obj, const 
         LinOpt o; o.mulmode = 3; o.post_scale = i == 0 ? inv_keep : 1.f;
         o.bits_in = reinterpret_cast<const uint32_t*>(ws + L.EB) + (size_t)(3 - i) * E * 8;     // bits of C, X2, X1, X0
         o.tag = "k_rows_tc<160>:enc_bwd";
+        if (E >= 64 * kTM * 2) launch_rows_pair(st, ws, L, 4 + i, E, dY, gout[i & 1], o); else
         launch_rows_tc_raw(st, ws + L.ENCT + (size_t)(2 * i) * 24320, ws + L.ENCT + (size_t)(2 * i + 1) * 24320, 160, E, kDE, 1, &sg,
                            gout[i & 1], kDEP, o);
         dY = gout[i & 1];
