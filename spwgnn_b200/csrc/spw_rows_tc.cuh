@@ -580,6 +580,31 @@ __device__ __forceinline__ void mbar_arrive_cta1(uint64_t* bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
 
+// arrive on the mbarrier at the same shared-memory offset in CTA `cta` of the cluster (release at cluster scope)
+__device__ __forceinline__ void mbar_arrive_remote(uint64_t* bar, uint32_t cta) {
+  uint32_t raddr;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(raddr) : "r"(smem_u32(bar)), "r"(cta));
+  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(raddr) : "memory");
+}
+// bounded wait with acquire at cluster scope (the arrivals come from both CTAs of the pair)
+__device__ __forceinline__ bool mbar_wait_cluster(uint64_t* bar, uint32_t parity) {
+  const uint32_t addr = smem_u32(bar);
+  for (int it = 0; it < (1 << 22); ++it) {
+    uint32_t ok;
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.b32 %0, 1, 0, p;\n\t"
+        "}\n"
+        : "=r"(ok)
+        : "r"(addr), "r"(parity)
+        : "memory");
+    if (ok) return true;
+  }
+  return false;
+}
+
 constexpr int kPairThreads = 512;
 constexpr int kXbufFloats = kTM * kDEP;                          // one raw input tile
 constexpr size_t kRowsPairSmem = (size_t)(2 * kB2Floats + kXbufFloats + 2 * kSlabFloats + kN + kTM * 8) * sizeof(float) + 64;
@@ -596,7 +621,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kPairThreads, 1) k_r
   uint32_t* sbits = reinterpret_cast<uint32_t*>(sbias + NB);     // [128][8] sign words of the tile
   uint64_t* mma_done = reinterpret_cast<uint64_t*>(sbits + kTM * 8);
   uint64_t* xfull = mma_done + 1;
-  uint32_t* tptr = reinterpret_cast<uint32_t*>(xfull + 1);
+  uint64_t* a_ready = xfull + 1;                                 // leader's copy is used: one arrival per CTA and tile
+  uint32_t* tptr = reinterpret_cast<uint32_t*>(a_ready + 1);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int row = 32 * (warp & 3) + lane, part = warp >> 2;      // tensor-memory view: thread = (row, quarter of the k-steps)
   const int crow = tid >> 3, cch = tid & 7;                      // coalesced view (epilogue)
@@ -608,7 +634,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kPairThreads, 1) k_r
   auto tile_of = [&](int i) { return 2 * (cluster + i * nclusters) + (int)rank; };
 
   if (warp == 0) tmem_alloc2(tptr, kTmemCols);
-  if (tid == 32) { mbar_init(mma_done, 1); mbar_init(xfull, 1); fence_mbar_init(); }
+  if (tid == 32) { mbar_init(mma_done, 1); mbar_init(xfull, 1); mbar_init(a_ready, 2); fence_mbar_init(); }
   for (int i = tid; i < kB2Floats / 4; i += NT) {                // this CTA's half of the weight columns
     cp_async16(Bhi_s + 4 * i, a.Bhi + (size_t)rank * kB2Floats + 4 * i);
     cp_async16(Blo_s + 4 * i, a.Blo + (size_t)rank * kB2Floats + 4 * i);
@@ -668,10 +694,13 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kPairThreads, 1) k_r
     fence_before_sync();
     SPW_PH(1);                                                   // p1: operand staging from shared memory
     __syncthreads();                                             // the raw tile has been consumed
-    if (tid == 0 && i + 1 < my_pairs) { fence_async_smem(); issue_load(i + 1); }   // next tile: lands during the MMAs and the epilogue
-    cluster_sync_all();                                          // both CTAs: A staged, D of the previous tile read
-    SPW_PH(2);                                                   // p2: CTA + cluster barrier
+    if (tid == 0) {
+      if (i + 1 < my_pairs) { fence_async_smem(); issue_load(i + 1); }   // next tile: lands during the MMAs and the epilogue
+      mbar_arrive_remote(a_ready, 0);                            // this CTA: A staged, D of the previous tile read
+    }
+    SPW_PH(2);                                                   // p2: CTA barrier
     if (rank == 0 && tid == 0) {
+      if (!mbar_wait_cluster(a_ready, (uint32_t)i & 1u)) failed = true;   // ... and the other CTA of the pair too
       fence_after_sync();
       const uint32_t idesc = make_idesc_tf32(256, kN);
       const uint64_t dhi0 = make_b_desc(smem_u32(Bhi_s), kHalfN * 16, 128), dlo0 = make_b_desc(smem_u32(Blo_s), kHalfN * 16, 128);
