@@ -333,12 +333,25 @@ __global__ void __launch_bounds__(256) k_reduce_parts(RedArgs a) {
       } else {
         p = a.part + (size_t)k * a.src_ld + n;
       }
+#ifndef SPW_EMU
       for (int c = g; c < a.nparts; c += 8) s += p[(size_t)c * a.part_stride];
+#else
+      if (g == 0) {   // host emulator: the same eight sub-sums and combination order, computed by one thread (shuffles are slow there)
+        float sub[8];
+        for (int gg = 0; gg < 8; ++gg) {
+          sub[gg] = 0.f;
+          for (int c = gg; c < a.nparts; c += 8) sub[gg] += p[(size_t)c * a.part_stride];
+        }
+        s = ((sub[0] + sub[4]) + (sub[2] + sub[6])) + ((sub[1] + sub[5]) + (sub[3] + sub[7]));
+      }
+#endif
     }
+#ifndef SPW_EMU
     // fixed combination order: ((s0 + s4) + (s2 + s6)) + ((s1 + s5) + (s3 + s7))
     s += __shfl_xor_sync(0xffffffffu, s, 4);
     s += __shfl_xor_sync(0xffffffffu, s, 2);
     s += __shfl_xor_sync(0xffffffffu, s, 1);
+#endif
     if (want && g == 0) {
       if (k < a.Kin) a.dW[(size_t)(a.dst_row0 + k) * a.dst_ld + a.dst_col0 + n] = s;
       else a.db[a.db_off + n] = s;
