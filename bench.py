@@ -67,9 +67,10 @@ def dominant_kernel_traffic(K_DOM):
     best = None
     for path in sorted(glob.glob(os.path.join(ROOT, 'profiles', '*_ncu_full_summary.txt'))):
         txt = open(path).read()
-        if 'kernel: ' + K_DOM not in txt:
+        m = re.search(r'^kernel: (?:void )?(?:[\w:]*::)?' + re.escape(K_DOM) + r'\b.*$', txt, re.M)
+        if not m:
             continue
-        blk = txt.split('kernel: ' + K_DOM)[1]
+        blk = txt[m.end():]
         r = re.search(r'dram__bytes_read\.sum\s+([0-9.]+) Mbyte', blk)
         w = re.search(r'dram__bytes_write\.sum\s+([0-9.]+) Mbyte', blk)
         if r and w:
