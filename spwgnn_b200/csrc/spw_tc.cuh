@@ -927,6 +927,8 @@ __global__ void __launch_bounds__(kWgThreads, 1) k_wgrad_tc(WgradTcArgs a) {
 //   nearest adds into a per-CTA partial [2][160][128].  Kx + 1 <= 128 needs one M-tile only: then the two warp
 //   groups split the chunk rows (operand build) and the accumulator columns (flush) between them.
 // =================================================================================================
+constexpr size_t wgrad_rows_smem(int ch, int nb) { return (size_t)(2 * kWgStageFloats + 2 * (ch / 8) * (2 * nb * 4)) * sizeof(float) + 32; }
+
 struct WgradRowsArgs {
   int M;
   const float* X; int ldx; int Kx; int xmod;          // X row = row % xmod (xmod = 0: row); ldx % 4 == 0
@@ -943,24 +945,27 @@ __device__ __forceinline__ void cp_async4_zfill(float* sdst, const float* gsrc, 
   asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;\n" ::"r"(s), "l"(gsrc), "r"(sz));
 }
 
-// stage layout (floats): XA [32][152] | (unused) | (unused) | YD [32][152] | (unused bits) | RS [32] ...   (same size as k_wgrad_tc's)
+// stage layout (floats; CH = rows per chunk, 32 or 64): XA [CH][152] | YD [CH][152] | ... | RS [CH] at 4 * 32 * 152
+// (the stage has the size of k_wgrad_tc's: 64-row chunks fit because the plain mode needs two arrays, not four)
+constexpr int kWgrRsOff = 4 * kWgChunk * kDEP;
+template <int CH>
 __device__ __forceinline__ void wgr_issue_chunk(const WgradRowsArgs& a, float* st, int r0, int cx4, int cy4) {
-  float* XA = st; float* YD = st + 3 * kWgChunk * kDEP;
-  float* RS = YD + kWgChunk * kDEP + kWgChunk * 8;
-  for (int i = threadIdx.x; i < kWgChunk * cx4; i += kWgThreads) {
+  float* XA = st; float* YD = st + CH * kDEP;
+  float* RS = st + kWgrRsOff;
+  for (int i = threadIdx.x; i < CH * cx4; i += kWgThreads) {
     const int r = i / cx4, c = i - r * cx4;
     const int row = r0 + r;
     const bool valid = row < a.M;
     const size_t xr = valid ? (size_t)(a.xmod ? row % a.xmod : row) : 0;
     cp_async16_zfill(XA + r * kDEP + 4 * c, a.X + xr * a.ldx + 4 * c, valid);
   }
-  for (int i = threadIdx.x; i < kWgChunk * cy4; i += kWgThreads) {
+  for (int i = threadIdx.x; i < CH * cy4; i += kWgThreads) {
     const int r = i / cy4, c = i - r * cy4;
     const int row = r0 + r;
     const bool valid = row < a.M;
     cp_async16_zfill(YD + r * kDEP + 4 * c, a.dY + (valid ? (size_t)row : 0) * a.ldy + 4 * c, valid);
   }
-  if (a.rowscale && threadIdx.x < kWgChunk) {
+  if (a.rowscale && threadIdx.x < CH) {
     const int row = r0 + threadIdx.x;
     const bool valid = row < a.M;
     cp_async4_zfill(RS + threadIdx.x, a.rowscale + (valid ? (size_t)(a.rsmod ? row % a.rsmod : row) : 0), valid);
@@ -968,12 +973,14 @@ __device__ __forceinline__ void wgr_issue_chunk(const WgradRowsArgs& a, float* s
   cp_async_commit();
 }
 
+// CH = 64 (half as many chunk iterations) needs Kx + 1 <= 128 (one M-tile: tensor-memory columns) and NB = 112 (shared memory)
+template <int CH>
 __global__ void __launch_bounds__(kWgThreads, 1) k_wgrad_rows_tc(WgradRowsArgs a) {
   SPW_DYN_SMEM(smem_raw);
   float* stages = reinterpret_cast<float*>(smem_raw);
   float* Bhi_s = stages + 2 * kWgStageFloats;
-  float* Blo_s = Bhi_s + kWgBFloats;
-  uint64_t* bar = reinterpret_cast<uint64_t*>(Blo_s + kWgBFloats);
+  float* Blo_s = Bhi_s + (CH / 8) * (2 * a.NB * 4);
+  uint64_t* bar = reinterpret_cast<uint64_t*>(Blo_s + (CH / 8) * (2 * a.NB * 4));
   uint32_t* tptr = reinterpret_cast<uint32_t*>(bar + 1);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int L = 32 * (warp & 3) + lane, grp = warp >> 2;        // TMEM lane, warp group (0..3)
@@ -993,7 +1000,7 @@ __global__ void __launch_bounds__(kWgThreads, 1) k_wgrad_rows_tc(WgradRowsArgs a
   fence_after_sync();
   const uint32_t tmem_base = *tptr;
   const uint32_t lane_addr = tmem_base + ((uint32_t)(32 * (warp & 3)) << 16);
-  const uint32_t colA_hi = kWgColA + 64 * mt, colA_lo = colA_hi + 32;
+  const uint32_t colA_hi = kWgColA + 2 * CH * mt, colA_lo = colA_hi + CH;
   const uint32_t idesc = make_idesc_tf32(128, NB);
   uint32_t parity = 0;
   bool failed = false, pending = false;
@@ -1007,20 +1014,20 @@ __global__ void __launch_bounds__(kWgThreads, 1) k_wgrad_rows_tc(WgradRowsArgs a
 #pragma unroll
     for (int c = 0; c < 16; ++c) acc[b][c] = 0.f;
   const int ntiles = (a.M + kTM - 1) / kTM;
-  constexpr int kCh = kTM / kWgChunk;                           // chunks per tile
+  constexpr int kCh = kTM / CH;                                 // chunks per tile
   const int my_tiles = (int)blockIdx.x < ntiles ? (ntiles - 1 - (int)blockIdx.x) / (int)gridDim.x + 1 : 0;
   const int nq = my_tiles * kCh;
-  auto row0_of = [&](int q) { return (blockIdx.x + (q / kCh) * gridDim.x) * kTM + (q % kCh) * kWgChunk; };
-  // rows of the chunk this thread turns into A columns: its share of the 32
-  const int j_lo = (kWgChunk / nsh) * sh, j_hi = j_lo + kWgChunk / nsh;
-  if (nq > 0) wgr_issue_chunk(a, stages, row0_of(0), cx4, cy4);
+  auto row0_of = [&](int q) { return (blockIdx.x + (q / kCh) * gridDim.x) * kTM + (q % kCh) * CH; };
+  // rows of the chunk this thread turns into A columns: its share of the CH
+  const int j_lo = (CH / nsh) * sh, j_hi = j_lo + CH / nsh;
+  if (nq > 0) wgr_issue_chunk<CH>(a, stages, row0_of(0), cx4, cy4);
   for (int q = 0; q < nq; ++q) {
     const int ch = q % kCh;
     float* st = stages + (q & 1) * kWgStageFloats;
     float* stn = stages + ((q + 1) & 1) * kWgStageFloats;
     __syncthreads();                                   // stage q+1 no longer read (chunk q-1 done)
     if (q + 1 < nq) {
-      wgr_issue_chunk(a, stn, row0_of(q + 1), cx4, cy4);
+      wgr_issue_chunk<CH>(a, stn, row0_of(q + 1), cx4, cy4);
       cp_async_wait<1>();                              // chunk q has landed (this thread's copies)
     } else {
       cp_async_wait<0>();
@@ -1032,8 +1039,8 @@ __global__ void __launch_bounds__(kWgThreads, 1) k_wgrad_rows_tc(WgradRowsArgs a
       fence_after_sync();
       pending = false;
     }
-    const float* XA = st; const float* YD = st + 3 * kWgChunk * kDEP;
-    const float* RS = YD + kWgChunk * kDEP + kWgChunk * 8;
+    const float* XA = st; const float* YD = st + CH * kDEP;
+    const float* RS = st + kWgrRsOff;
     const int r0 = row0_of(q);
     // A = X^T: this lane's feature, rows of the chunk as TMEM columns
     for (int j0 = j_lo; j0 < j_hi; j0 += 8) {
@@ -1049,7 +1056,7 @@ __global__ void __launch_bounds__(kWgThreads, 1) k_wgrad_rows_tc(WgradRowsArgs a
       tmem_st8(lane_addr + colA_lo + j0, l);
     }
     // B = dY^T: [k-step][2][n][4 rows]
-    for (int idx = tid; idx < 8 * NB; idx += kWgThreads) {
+    for (int idx = tid; idx < (CH / 4) * NB; idx += kWgThreads) {
       const int n = idx % NB, kc = idx / NB;
       uint32_t h[4], l[4];
 #pragma unroll
@@ -1068,13 +1075,13 @@ __global__ void __launch_bounds__(kWgThreads, 1) k_wgrad_rows_tc(WgradRowsArgs a
       fence_after_sync();
       const uint32_t bhi = smem_u32(Bhi_s), blo = smem_u32(Blo_s);
 #pragma unroll 1
-      for (int ks = 0; ks < kWgChunk / 8; ++ks) {
+      for (int ks = 0; ks < CH / 8; ++ks) {
         const uint64_t dhi = make_b_desc(bhi + ks * (bstep * 4), NB * 16, 128);
         const uint64_t dlo = make_b_desc(blo + ks * (bstep * 4), NB * 16, 128);
         const uint32_t acc = (ch > 0 || ks > 0) ? 1u : 0u;
         for (int t = 0; t < nmt; ++t) {
           const uint32_t d = tmem_base + (t ? kWgColD1 : kWgColD0);
-          const uint32_t ahi = tmem_base + kWgColA + 64 * t + 8 * ks, alo = ahi + 32;
+          const uint32_t ahi = tmem_base + kWgColA + 2 * CH * t + 8 * ks, alo = ahi + CH;
           mma_tf32_ts(d, alo, dhi, idesc, acc);
           mma_tf32_ts(d, ahi, dlo, idesc, 1u);
           mma_tf32_ts(d, ahi, dhi, idesc, 1u);

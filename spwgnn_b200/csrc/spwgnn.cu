@@ -369,8 +369,13 @@ void launch_wgrad(cudaStream_t st, int M, const float* X, int ldx, int Kin, int 
     const int tt = (M + kTM - 1) / kTM;
     int tgrid = tt < num_sms() ? tt : num_sms();
     if (tgrid > kMaxCtas) tgrid = kMaxCtas;
-    set_smem(tc::k_wgrad_rows_tc, tc::kWgradTcSmem);
-    SPW_KLAUNCH("k_wgrad_rows_tc", tc::k_wgrad_rows_tc, dim3(tgrid), dim3(tc::kWgThreads), tc::kWgradTcSmem, st, t);
+    if (Kin + 1 <= 128 && t.NB == 112) {           // one M-tile and a narrow B operand: 64-row chunks fit
+      auto kern = tc::k_wgrad_rows_tc<64>; set_smem(kern, tc::wgrad_rows_smem(64, 112));
+      SPW_KLAUNCH("k_wgrad_rows_tc", kern, dim3(tgrid), dim3(tc::kWgThreads), tc::wgrad_rows_smem(64, 112), st, t);
+    } else {
+      auto kern = tc::k_wgrad_rows_tc<32>; set_smem(kern, tc::wgrad_rows_smem(32, 160));
+      SPW_KLAUNCH("k_wgrad_rows_tc", kern, dim3(tgrid), dim3(tc::kWgThreads), tc::wgrad_rows_smem(32, t.NB), st, t);
+    }
     launch_reduce(st, part, tgrid, (int)tc::kWgPartFloats, 0, -1, Kin + 1 > 128 ? Kin + 1 - 128 : 0, Kin, N, out);
     return;
   }
