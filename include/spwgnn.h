@@ -92,6 +92,16 @@ int spw_tc_linear(int M, const float* X0, int ldx0, int K0, const float* X1, int
                   int ld_mul, int mulmode, float* Y, int ldy, int accumulate, float post_scale, int ones_col, float* scratch,
                   void* stream);
 
+/* pipelined column-slab linear layer (the round-2 building block of every GEMM-shaped layer), exposed for unit tests.
+ * Activations are stored column-slab major: element (row, c) of a view at p + ((col0 + c) >> 3) * slab + row * 8 + ((col0 + c) & 7)
+ * (slab = allocated rows * 8 floats, col0 % 4 == 0).  Y = post(act(X.W + rowscale*bias + addend)); mulmode 3 multiplies by the
+ * word-major sign bits bits_in ([8][M][4 bytes]); bits_out receives the sign bits of the result.  scratch: 2*ceil(K/8)*8*NB floats. */
+int spw_csl_linear(int M, const float* X, long long x_slab, int x_col0, int K, const float* W, int N, int NB, const float* bias,
+                   const float* rowscale, const float* addend, long long add_slab, int add_col0, int act, const float* mulsrc,
+                   long long mul_slab, int mul_col0, int mulmode, const uint8_t* bits_in, uint8_t* bits_out, float* Y,
+                   long long y_slab, int y_col0, int accumulate, float post_scale, int ones_col, int write_pad, float* scratch,
+                   void* stream);
+
 /* ---- edge-index construction (replaces main.py:66-81) ------------------------------------
  * Edge m->j (m != j, same tower) is active iff sqrt(dx*dx + dy*dy) < thr evaluated in IEEE
  * double with separately rounded multiplies/add/sqrt -- numpy's np.linalg.norm(...,axis=1) --

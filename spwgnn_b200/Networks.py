@@ -137,8 +137,8 @@ class PropagationModel:
         shuffles the rest and steps once per mini-batch; epoch metrics are sample-weighted means."""
         tgt_all = np.asarray(y['target'] if isinstance(y, dict) else y, dtype=np.float32)
         B = tgt_all.shape[0]
-        n_val = int(B * validation_split) if validation_split else 0
-        n_tr = B - n_val
+        n_tr = int(B * (1. - validation_split)) if validation_split else B     # Keras: split_at = int(len(x) * (1 - split))
+        n_val = B - n_tr
         rng = np.random.default_rng(seed)
         dev = self.engine.device
         hist = History()
@@ -172,8 +172,8 @@ class PropagationModel:
         `labels` = list of (N_t,) 0/1 arrays.  Relations are built on the GPU from the raw positions exactly as
         main.py:66-81 does (threshold 170 on raw pixels); everything else follows `fit`."""
         B = len(towers)
-        n_val = int(B * validation_split) if validation_split else 0
-        n_tr = B - n_val
+        n_tr = int(B * (1. - validation_split)) if validation_split else B
+        n_val = B - n_tr
         rng = np.random.default_rng(seed)
         dev = self.engine.device
         hist = History()

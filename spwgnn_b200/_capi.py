@@ -32,7 +32,7 @@ class SpwGraph(C.Structure):
     ]
 
 
-EXPORTS = ['spw_version', 'spw_last_error', 'spw_launch_count', 'spw_profile', 'spw_profile_report', 'spw_ffma_peak', 'spw_tc_selftest', 'spw_tc2_selftest', 'spw_tc_linear', 'spw_edges_count', 'spw_edges_fill', 'spw_sample_sizes', 'spw_sample_jenga', 'spw_sample_tower', 'spw_workspace_bytes',
+EXPORTS = ['spw_version', 'spw_last_error', 'spw_launch_count', 'spw_profile', 'spw_profile_report', 'spw_ffma_peak', 'spw_tc_selftest', 'spw_tc2_selftest', 'spw_tc_linear', 'spw_csl_linear', 'spw_edges_count', 'spw_edges_fill', 'spw_sample_sizes', 'spw_sample_jenga', 'spw_sample_tower', 'spw_workspace_bytes',
            'spw_forward', 'spw_bce_grad', 'spw_backward']
 
 
@@ -67,6 +67,10 @@ class CApi:
         d.spw_tc_linear.restype = C.c_int
         d.spw_tc_linear.argtypes = [C.c_int, vp, C.c_int, C.c_int, vp, C.c_int, C.c_int, vp, C.c_int, C.c_int, vp, vp, vp, C.c_int,
                                     C.c_int, vp, C.c_int, C.c_int, vp, C.c_int, C.c_int, C.c_float, C.c_int, vp, vp]
+        d.spw_csl_linear.restype = C.c_int
+        ll = C.c_longlong
+        d.spw_csl_linear.argtypes = [C.c_int, vp, ll, C.c_int, C.c_int, vp, C.c_int, C.c_int, vp, vp, vp, ll, C.c_int, C.c_int, vp, ll,
+                                     C.c_int, C.c_int, vp, vp, vp, ll, C.c_int, C.c_int, C.c_float, C.c_int, C.c_int, vp, vp]
         d.spw_edges_count.restype = C.c_int
         d.spw_edges_count.argtypes = [vp, vp, i32, i32, i32, f64, C.c_int, vp, vp, vp, vp]
         d.spw_edges_fill.restype = C.c_int

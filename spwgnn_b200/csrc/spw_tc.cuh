@@ -15,7 +15,7 @@
 #ifndef SPW_EMU
 #include "spw_common.cuh"
 
-// Per-phase clock64() accounting of the tile loops (development builds only: -DSPW_PHASE_TIMING; tools/phase_test.py)
+// Per-phase clock64() accounting of the tile loops (development builds only: -DSPW_PHASE_TIMING; tools/phase_probe.py)
 #ifdef SPW_PHASE_TIMING
 #include <stdio.h>
 #define SPW_PH_DECL long long ph_t[8] = {0, 0, 0, 0, 0, 0, 0, 0}; long long ph_last = clock64();
@@ -117,6 +117,7 @@ __device__ __forceinline__ void fence_mbar_init() { asm volatile("fence.mbarrier
 // bounded wait: returns false on timeout instead of hanging the GPU
 __device__ __forceinline__ bool mbar_wait(uint64_t* bar, uint32_t parity) {
   const uint32_t a = smem_u32(bar);
+#pragma unroll 1
   for (int it = 0; it < (1 << 22); ++it) {
     uint32_t ok;
     asm volatile(

@@ -6,9 +6,12 @@
 #include "spw_kernels.cuh"
 #include "spw_tc.cuh"
 #include "spw_rows_tc.cuh"
+#include "spw_pipe_tc.cuh"
+#include "spw_csl.cuh"
 
 #include <stdarg.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <atomic>
@@ -83,15 +86,24 @@ int check_launch(const char* what) {
   return SPW_OK;
 }
 
-int num_sms() {
-  static int sms = 0;
-  if (sms == 0) {
-    int dev = 0;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    if (sms <= 0) sms = 148;
+int num_sms() {       // SM count of the CURRENT device (cached per device id)
+  static int sms[64] = {0};
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (dev < 0 || dev >= 64) dev = 0;
+  if (sms[dev] == 0) {
+    int v = 0;
+    cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev);
+    sms[dev] = v > 0 ? v : 148;
   }
-  return sms;
+  return sms[dev];
+}
+
+// development switch: SPW_PIPE=0 in the environment selects the round-1 (unpipelined) edge-step kernels
+bool use_pipe() {
+  static int v = -1;
+  if (v < 0) { const char* e = getenv("SPW_PIPE"); v = (e && e[0] == '0') ? 0 : 1; }
+  return v != 0;
 }
 
 constexpr int kMaxCtas = 160;
@@ -508,6 +520,40 @@ void launch_rows_pair(cudaStream_t st, float* ws, const Layout& L, int pair_id, 
 }
 #endif
 
+
+#if SPW_USE_TC
+// ---- CSL data path (spw_csl.cuh) ------------------------------------------------------------------
+// one pipelined linear layer: nks k-steps of the packed operand (Bhi, Blo), MMA N = NB, compile-time epilogue mask `epi`.
+// Every (NB, k-steps per thread, epilogue) combination the network (and the unit tests) use is instantiated here; anything
+// else is refused loudly.
+#define SPW_LIN_TABLE(X)                                                                                                   \
+  X(100, 100, 0u) X(100, 150, 0u) X(100, 200, 0u) X(150, 100, 0u) X(150, 150, 0u)                                         \
+  X(100, 100, csl::EPI_BIAS | csl::EPI_RELU) X(100, 100, csl::EPI_BIAS | csl::EPI_RELU | csl::EPI_DROP) X(100, 100, csl::EPI_BIAS) \
+  X(150, 150, csl::EPI_BIAS | csl::EPI_RELU | csl::EPI_ONES) X(150, 150, csl::EPI_BIAS | csl::EPI_RELU | csl::EPI_ONES | csl::EPI_BITS_OUT) \
+  X(150, 150, csl::EPI_BIAS | csl::EPI_RELU | csl::EPI_ONES | csl::EPI_BITS_OUT | csl::EPI_DROP) X(150, 150, csl::EPI_BIAS) \
+  X(100, 150, csl::EPI_BIAS | csl::EPI_ROWSCALE | csl::EPI_TANH) X(100, 200, csl::EPI_ADD | csl::EPI_RELU)                 \
+  X(100, 100, csl::EPI_BIAS | csl::EPI_ADD | csl::EPI_TANH) X(100, 100, csl::EPI_MUL_POS)                                 \
+  X(100, 100, csl::EPI_MUL_POS | csl::EPI_SCALE) X(100, 100, csl::EPI_MUL_POS | csl::EPI_SCALE | csl::EPI_ACC)            \
+  X(100, 100, csl::EPI_MUL_TANH) X(100, 100, csl::EPI_ADD) X(100, 150, csl::EPI_ACC) X(100, 150, csl::EPI_ADD | csl::EPI_MUL_TANH) \
+  X(150, 150, csl::EPI_MUL_BITS | csl::EPI_SCALE)
+
+int launch_lin(cudaStream_t st, uint32_t epi, const csl::LinCArgs& a, const char* tag) {
+  if (a.M <= 0) return SPW_OK;
+  const int ntiles = (a.M + kTM - 1) / kTM;
+  const int grid = ntiles < num_sms() ? ntiles : num_sms();
+#define SPW_LIN_X(NV, KV, EPIV)                                                                                            \
+  if (a.N == NV && a.K == KV && epi == (uint32_t)(EPIV)) {                                                                \
+    auto kern = csl::k_lin<NV, KV, (uint32_t)(EPIV)>;                                                                     \
+    const size_t sm = csl::lin_smem(NV <= 112 ? 112 : 160, (KV + 7) / 8); set_smem(kern, sm);                             \
+    SPW_KLAUNCH(tag, kern, dim3(grid), dim3(csl::kThreadsC), sm, st, a);                                                   \
+    return SPW_OK;                                                                                                        \
+  }
+  SPW_LIN_TABLE(SPW_LIN_X)
+#undef SPW_LIN_X
+  return fail(SPW_ERR_UNSUPPORTED, "launch_lin(%s): no kernel instance for K = %d, N = %d, epilogue mask 0x%x", tag, a.K, a.N, epi);
+}
+#endif
+
 size_t edge_fwd_smem() { return (size_t)(2 * (kTME * kDEP + 8) + 2 * kKT * kLdwE + 2 * kTME) * sizeof(float); }
 size_t edge_bwd_smem() { return (size_t)(2 * (kTM * kDEP + 8) + 2 * kKT * kLdwE + kTM + 5 * kTM) * sizeof(float); }
 size_t edge_encb_smem() { return (size_t)(5 * (kTMB * kDEP + 8) + 2 * kKT * kLdwE + 2 * kTMB) * sizeof(float); }
@@ -634,6 +680,64 @@ int spw_tc_linear(int M, const float* X0, int ldx0, int K0, const float* X1, int
   o.mulmode = mulmode; o.accumulate = accumulate; o.post_scale = post_scale; o.ones_col = ones_col;
   launch_rows_tc_raw(st, d.hi, d.lo, NB, M, N, K1 > 0 ? 2 : 1, sg, Y, ldy, o);
   return check_launch("spw_tc_linear");
+#endif
+}
+
+
+// pipelined CSL linear layer (csl::k_lin), exposed for unit tests.  Arrays are column-slab major: element (row, c) of a view
+// at p + ((col0 + c) >> 3) * slab + row * 8 + ((col0 + c) & 7).  W: Keras [K][N] (ld = N).  bits_in / bits_out: word-major sign
+// bits [8][M][4 bytes].  scratch: 2 * ceil(K / 8) * 8 * NB floats.
+int spw_csl_linear(int M, const float* X, long long x_slab, int x_col0, int K, const float* W, int N, int NB, const float* bias,
+                   const float* rowscale, const float* addend, long long add_slab, int add_col0, int act, const float* mulsrc,
+                   long long mul_slab, int mul_col0, int mulmode, const uint8_t* bits_in, uint8_t* bits_out, float* Y,
+                   long long y_slab, int y_col0, int accumulate, float post_scale, int ones_col, int write_pad, float* scratch,
+                   void* stream) {
+#if !SPW_USE_TC
+  (void)M; (void)X; (void)x_slab; (void)x_col0; (void)K; (void)W; (void)N; (void)NB; (void)bias; (void)rowscale; (void)addend;
+  (void)add_slab; (void)add_col0; (void)act; (void)mulsrc; (void)mul_slab; (void)mul_col0; (void)mulmode; (void)bits_in;
+  (void)bits_out; (void)Y; (void)y_slab; (void)y_col0; (void)accumulate; (void)post_scale; (void)ones_col; (void)write_pad;
+  (void)scratch; (void)stream;
+  return fail(SPW_ERR_UNSUPPORTED, "spw_csl_linear: tensor-core path is not emulated");
+#else
+  if (M < 0 || !X || !W || !Y || !scratch || K <= 0 || N <= 0) return fail(SPW_ERR_BAD_ARG, "spw_csl_linear: bad argument");
+  if (NB != 112 && NB != 160) return fail(SPW_ERR_UNSUPPORTED, "spw_csl_linear: NB must be 112 or 160");
+  const int nks = (K + 7) / 8;
+  if (N > NB || 16 * nks + NB > 512) return fail(SPW_ERR_UNSUPPORTED, "spw_csl_linear: K = %d, N = %d do not fit tensor memory", K, N);
+  if ((x_col0 & 3) || (y_col0 & 3) || (add_col0 & 3) || (mul_col0 & 3)) return fail(SPW_ERR_BAD_ARG, "spw_csl_linear: column offsets must be multiples of 4");
+  cudaStream_t st = (cudaStream_t)stream;
+  tc::PackTcArgs pa;
+  memset(&pa, 0, sizeof(pa));
+  tc::PackTcDesc& d = pa.d[0];
+  d.src = W; d.ld = N; d.K = K; d.N = N; d.hi = scratch; d.lo = scratch + (size_t)nks * 8 * NB; d.NB = NB; d.k_lim = 8 * nks;
+  pa.n = 1;
+  SPW_KLAUNCH("k_pack_tc", tc::k_pack_tc, dim3(16, 1), dim3(256), 0, st, pa);
+  csl::LinCArgs a;
+  memset(&a, 0, sizeof(a));
+  a.M = M; a.K = K; a.nks = nks; a.N = N;
+  a.X = {const_cast<float*>(X), x_slab, x_col0};
+  a.Bhi = d.hi; a.Blo = d.lo; a.bias = bias; a.rowscale = rowscale;
+  a.addend = {const_cast<float*>(addend), add_slab, add_col0};
+  a.mulsrc = {const_cast<float*>(mulsrc), mul_slab, mul_col0};
+  a.bits_in = bits_in; a.bits_in_rows = M; a.bits_out = bits_out; a.bits_out_rows = M;
+  a.Y = {Y, y_slab, y_col0}; a.post_scale = post_scale; a.ones_col = ones_col; a.write_pad = write_pad;
+  a.drop_stride = 128; a.poison = Y;
+  uint32_t epi = 0;
+  if (bias) epi |= csl::EPI_BIAS;
+  if (rowscale) epi |= csl::EPI_ROWSCALE;
+  if (addend) epi |= csl::EPI_ADD;
+  if (act == 1) epi |= csl::EPI_RELU;
+  if (act == 2) epi |= csl::EPI_TANH;
+  if (mulmode == 1) epi |= csl::EPI_MUL_POS;
+  if (mulmode == 2) epi |= csl::EPI_MUL_TANH;
+  if (mulmode == 3) epi |= csl::EPI_MUL_BITS;
+  if (post_scale != 1.f) epi |= csl::EPI_SCALE;
+  if (accumulate) epi |= csl::EPI_ACC;
+  if (bits_out) epi |= csl::EPI_BITS_OUT;
+  if (ones_col >= 0) epi |= csl::EPI_ONES;
+  if (NB != (N <= 112 ? 112 : 160)) return fail(SPW_ERR_UNSUPPORTED, "spw_csl_linear: NB must be 112 for N <= 112, else 160");
+  int rc = launch_lin(st, epi, a, "k_lin");
+  if (rc != SPW_OK) return rc;
+  return check_launch("spw_csl_linear");
 #endif
 }
 
@@ -839,8 +943,13 @@ int spw_forward(const SpwParams* w, const SpwGraph* g, const float* obj, float* 
         t.maskbits_h1 = training ? reinterpret_cast<uint32_t*>(ws + L.M1) + (size_t)l * E * 8 : nullptr;
         const int ttiles = (E + kTM - 1) / kTM;
         const int tgrid = ttiles < num_sms() ? ttiles : num_sms();
-        set_smem(tc::k_edge_step_tc, tc::kEdgeStepTcSmem);
-        SPW_KLAUNCH("k_edge_step_tc", tc::k_edge_step_tc, dim3(tgrid), dim3(tc::kStThreads), tc::kEdgeStepTcSmem, st, t);
+        if (use_pipe()) {
+          set_smem(tc::k_edge_step_p, tc::kEdgeStepPSmem);
+          SPW_KLAUNCH("k_edge_step_p", tc::k_edge_step_p, dim3(tgrid), dim3(tc::kPipeThreads), tc::kEdgeStepPSmem, st, t);
+        } else {
+          set_smem(tc::k_edge_step_tc, tc::kEdgeStepTcSmem);
+          SPW_KLAUNCH("k_edge_step_tc", tc::k_edge_step_tc, dim3(tgrid), dim3(tc::kStThreads), tc::kEdgeStepTcSmem, st, t);
+        }
         if (ttiles > 1)
           SPW_KLAUNCH("k_fix_boundaries", k_fix_boundaries, dim3(grid_for(ttiles - 1, 8)), dim3(256), 0, st, E, (int)kTM, g->in_rcv, ws + L.PF, ws + L.PL, H2S);
       }
@@ -909,7 +1018,8 @@ int spw_backward(const SpwParams* w, const SpwGraph* g, const float* obj, const 
   }
   if (!obj || !dlogits) return fail(SPW_ERR_BAD_ARG, "spw_backward: null pointer");
   const int etiles = (E + kTM - 1) / kTM;
-  const int egrid = etiles < num_sms() ? etiles : num_sms();
+  int egrid = etiles < num_sms() ? etiles : num_sms();
+  if (egrid > kMaxCtas) egrid = kMaxCtas;         // the per-CTA partial buffers (partE) hold kMaxCtas entries
   float* partN = ws + L.partN;
 
   // head: dUpre^5 = dlogit (x) V2[:,0] * relu'
@@ -970,8 +1080,13 @@ int spw_backward(const SpwParams* w, const SpwGraph* g, const float* obj, const 
         t.E = E; t.in_rcv = g->in_rcv; t.dH2S = ws + L.dH2S; t.Whi = ws + L.W2Thi; t.Wlo = ws + L.W2Tlo;
         t.maskbits = a.maskbits; t.maskbits_h1 = reinterpret_cast<const uint32_t*>(ws + L.M1) + (size_t)l * E * 8;
         t.act = nullptr; t.scale = 1.f; t.dA = ws + L.dA; t.DH1 = ws + L.DH1; t.first = a.first; t.poison = ws + L.dA;
-        set_smem(tc::k_edge_dgrad_tc, tc::kEdgeDgradTcSmem);
-        SPW_KLAUNCH("k_edge_dgrad_tc", tc::k_edge_dgrad_tc, dim3(egrid), dim3(tc::kDgThreads), tc::kEdgeDgradTcSmem, st, t);
+        if (use_pipe()) {
+          set_smem(tc::k_edge_dgrad_p, tc::kEdgeDgradPSmem);
+          SPW_KLAUNCH("k_edge_dgrad_p", tc::k_edge_dgrad_p, dim3(egrid), dim3(tc::kPipeThreads), tc::kEdgeDgradPSmem, st, t);
+        } else {
+          set_smem(tc::k_edge_dgrad_tc, tc::kEdgeDgradTcSmem);
+          SPW_KLAUNCH("k_edge_dgrad_tc", tc::k_edge_dgrad_tc, dim3(egrid), dim3(tc::kDgThreads), tc::kEdgeDgradTcSmem, st, t);
+        }
       }
 #else
       {

@@ -7,7 +7,7 @@ import ctypes
 
 import torch
 
-from ._lib import lib, require_cuda
+from ._lib import lib, require_cuda, SpwError
 from .graph import TowerBatch, _stream_ptr
 from .params import ParamBuffer, FLAT_SIZE
 
@@ -45,15 +45,16 @@ class Engine:
     def forward(self, batch: TowerBatch, training=False, want_probs=True, dropout_rate=0.0, dropout_seed=0):
         """Per-block logits (and sigmoid probabilities) for a packed batch (Networks.py:58-96)."""
         api, n = self.api, batch.n_nodes
-        logits = torch.empty(max(n, 1), dtype=torch.float32, device=self.device)
-        probs = torch.empty(max(n, 1), dtype=torch.float32, device=self.device) if want_probs else None
-        nbytes = api.dll.spw_workspace_bytes(n, batch.n_edges, int(training))
-        ws = (self.ws if training else self.ws_inf).get(nbytes)
-        wp = self.params.c_struct()
-        api.check(api.dll.spw_forward(ctypes.byref(wp), ctypes.byref(batch.c_graph), batch.obj.data_ptr(),
-                                      logits.data_ptr(), probs.data_ptr() if want_probs else None, ws.data_ptr(),
-                                      ws.numel(), int(training), float(dropout_rate), int(dropout_seed),
-                                      _stream_ptr(self.device)))
+        with torch.cuda.device(self.device):        # kernels launch on the current device: make it this engine's
+            logits = torch.empty(max(n, 1), dtype=torch.float32, device=self.device)
+            probs = torch.empty(max(n, 1), dtype=torch.float32, device=self.device) if want_probs else None
+            nbytes = api.dll.spw_workspace_bytes(n, batch.n_edges, int(training))
+            ws = (self.ws if training else self.ws_inf).get(nbytes)
+            wp = self.params.c_struct()
+            api.check(api.dll.spw_forward(ctypes.byref(wp), ctypes.byref(batch.c_graph), batch.obj.data_ptr(),
+                                          logits.data_ptr(), probs.data_ptr() if want_probs else None, ws.data_ptr(),
+                                          ws.numel(), int(training), float(dropout_rate), int(dropout_seed),
+                                          _stream_ptr(self.device)))
         if training:
             self._fwd = (batch, ws, logits, float(dropout_rate))
         return logits[:n], (probs[:n] if want_probs else None)
@@ -63,21 +64,25 @@ class Engine:
         """Keras binary_crossentropy (Networks.py:102).  Returns (dlogits, stats) with stats a device
         double[2] = [sum of per-block losses, number of correct predictions]."""
         api, n = self.api, logits.numel()
-        dlogits = torch.empty(max(n, 1), dtype=torch.float32, device=self.device)
-        stats = torch.zeros(2, dtype=torch.float64, device=self.device)
-        api.check(api.dll.spw_bce_grad(logits.data_ptr(), target.data_ptr(), n, float(count), dlogits.data_ptr(),
-                                       stats.data_ptr(), _stream_ptr(self.device)))
+        with torch.cuda.device(self.device):
+            dlogits = torch.empty(max(n, 1), dtype=torch.float32, device=self.device)
+            stats = torch.zeros(2, dtype=torch.float64, device=self.device)
+            api.check(api.dll.spw_bce_grad(logits.data_ptr(), target.data_ptr(), n, float(count), dlogits.data_ptr(),
+                                           stats.data_ptr(), _stream_ptr(self.device)))
         return dlogits[:n], stats
 
     def backward(self, dlogits):
         """Gradients of sum(dlogits*logits) w.r.t. all 22 tensors -> self.grads (overwritten)."""
+        if self._fwd is None:
+            raise SpwError('backward without a training forward')
         batch, ws, _, rate = self._fwd
         api = self.api
         wp, gp = self.params.c_struct(), self.grads.c_struct()
         dl = dlogits.contiguous()
-        api.check(api.dll.spw_backward(ctypes.byref(wp), ctypes.byref(batch.c_graph), batch.obj.data_ptr(),
-                                       dl.data_ptr(), ws.data_ptr(), ws.numel(), ctypes.byref(gp), rate,
-                                       _stream_ptr(self.device)))
+        with torch.cuda.device(self.device):
+            api.check(api.dll.spw_backward(ctypes.byref(wp), ctypes.byref(batch.c_graph), batch.obj.data_ptr(),
+                                           dl.data_ptr(), ws.data_ptr(), ws.numel(), ctypes.byref(gp), rate,
+                                           _stream_ptr(self.device)))
         return self.grads
 
     def loss_and_grads(self, batch, target, count=None, dropout_rate=0.0, dropout_seed=0):
@@ -111,9 +116,13 @@ class PropNetFunction(torch.autograd.Function):
         assert flat_params.data_ptr() == engine.params.flat.data_ptr(), 'pass engine.params.flat'
         logits, _ = engine.forward(batch, training=True, want_probs=False)
         ctx.engine = engine
+        ctx.saved = engine._fwd              # the engine keeps ONE training step's state (workspace) in flight
         return logits.clone()
 
     @staticmethod
     def backward(ctx, dlogits):
+        if ctx.engine._fwd is not ctx.saved:
+            raise SpwError('PropNetFunction.backward: a later training forward on the same Engine overwrote the state '
+                           'saved for this one (one Engine keeps one training step in flight)')
         g = ctx.engine.backward(dlogits)
         return g.flat.clone(), None, None
