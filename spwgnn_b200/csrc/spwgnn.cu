@@ -8,6 +8,8 @@
 #include "spw_rows_tc.cuh"
 #include "spw_pipe_tc.cuh"
 #include "spw_csl.cuh"
+#include "spw_csl_kernels.cuh"
+#include "spw_csl_wgrad.cuh"
 
 #include <stdarg.h>
 #include <stdio.h>
@@ -97,6 +99,17 @@ int num_sms() {       // SM count of the CURRENT device (cached per device id)
     sms[dev] = v > 0 ? v : 148;
   }
   return sms[dev];
+}
+
+// development switch: SPW_CSL=0 in the environment selects the round-1 data path (row-major activations)
+bool use_csl() {
+  static int v = -1;
+  if (v < 0) { const char* e = getenv("SPW_CSL"); v = (e && e[0] == '0') ? 0 : 1; }
+#if SPW_USE_TC
+  return v != 0;
+#else
+  return false;
+#endif
 }
 
 // development switch: SPW_PIPE=0 in the environment selects the round-1 (unpipelined) edge-step kernels
@@ -558,6 +571,10 @@ size_t edge_fwd_smem() { return (size_t)(2 * (kTME * kDEP + 8) + 2 * kKT * kLdwE
 size_t edge_bwd_smem() { return (size_t)(2 * (kTM * kDEP + 8) + 2 * kKT * kLdwE + kTM + 5 * kTM) * sizeof(float); }
 size_t edge_encb_smem() { return (size_t)(5 * (kTMB * kDEP + 8) + 2 * kKT * kLdwE + 2 * kTMB) * sizeof(float); }
 
+#if SPW_USE_TC
+#include "spw_csl_path.inl"
+#endif
+
 }  // namespace
 
 // =================================================================================================
@@ -809,6 +826,9 @@ int spw_sample_tower(uint64_t seed, int32_t n_towers, const int32_t* node_off, d
 
 size_t spw_workspace_bytes(int32_t n_nodes, int32_t n_edges, int training) {
   if (n_nodes < 0 || n_edges < 0) return 0;
+#if SPW_USE_TC
+  if (use_csl()) return make_layout_c(n_nodes, n_edges, training).total * sizeof(float);
+#endif
   return make_layout(n_nodes, n_edges, training).total * sizeof(float);
 }
 
@@ -822,6 +842,11 @@ int spw_forward(const SpwParams* w, const SpwGraph* g, const float* obj, float* 
   if (!obj || !logits || !workspace) return fail(SPW_ERR_BAD_ARG, "spw_forward: null pointer");
   if (!aligned16(workspace)) return fail(SPW_ERR_BAD_ARG, "spw_forward: workspace not 16-byte aligned");
   if (dropout_rate < 0.f || dropout_rate >= 1.f) return fail(SPW_ERR_BAD_ARG, "spw_forward: dropout rate %g outside [0,1)", dropout_rate);
+#if SPW_USE_TC
+  if (use_csl())
+    return forward_csl(w, g, obj, logits, probs, reinterpret_cast<float*>(workspace), workspace_bytes, training, dropout_rate, dropout_seed,
+                       (cudaStream_t)stream);
+#endif
   const bool drop = training && dropout_rate > 0.f;
   const uint32_t drop_thresh = drop ? (uint32_t)(dropout_rate * 16777216.0f) : 0u;
   const float inv_keep = drop ? 1.f / (1.f - dropout_rate) : 1.f;
@@ -1000,6 +1025,12 @@ int spw_backward(const SpwParams* w, const SpwGraph* g, const float* obj, const 
   const int n = g->n_nodes, E = g->n_edges;
   if (!workspace || !aligned16(workspace)) return fail(SPW_ERR_BAD_ARG, "spw_backward: bad workspace");
   if (dropout_rate < 0.f || dropout_rate >= 1.f) return fail(SPW_ERR_BAD_ARG, "spw_backward: dropout rate %g outside [0,1)", dropout_rate);
+#if SPW_USE_TC
+  if (use_csl() && n > 0) {
+    if (!obj || !dlogits) return fail(SPW_ERR_BAD_ARG, "spw_backward: null pointer");
+    return backward_csl(w, g, obj, dlogits, reinterpret_cast<float*>(workspace), workspace_bytes, grads, dropout_rate, (cudaStream_t)stream);
+  }
+#endif
   const float inv_keep = dropout_rate > 0.f ? 1.f / (1.f - dropout_rate) : 1.f;
   const Layout L = make_layout(n, E, 1);
   if (workspace_bytes < L.total * sizeof(float))
