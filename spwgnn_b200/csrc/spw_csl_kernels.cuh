@@ -114,6 +114,7 @@ struct EdgeStepCArgs {
   float* H2S; long long h_slab;                         // [n][150] CSL (k_seg_fix_c completes it)
   float* part_first; float* part_last;                  // [ceil(E / 32)][160] row-major
   uint8_t* bits_h2; uint8_t* bits_h1; long long bits_rows;   // byte-slab [19][bits_rows] or null
+  float* H1;                                            // [E][150] CSL or null: h1 (column 150 = 1) kept for the weight gradient
   float* poison;
 };
 constexpr size_t kEdgeStepCSmem = (size_t)(2 * kBFloats) * sizeof(float) + 64;
@@ -154,6 +155,7 @@ __global__ void __launch_bounds__(kThreadsC, 1) k_edge_step_c(EdgeStepCArgs a) {
     const long long es = (long long)a.E * 4;
     bool failed = false;
     XR<KJ> x;
+    SPW_PH_DECL
     int s_nx = 0, r_nx = -1;                             // sender / receiver of this thread's row in the tile being built
     int r_cur = -1;                                      // receiver of the row in the tile whose epilogue runs
     auto load_idx = [&](int i, int& s, int& r) {
@@ -188,6 +190,11 @@ __global__ void __launch_bounds__(kThreadsC, 1) k_edge_step_c(EdgeStepCArgs a) {
             x.v[j][4 * h + 2] = relu_f(va[h].z + vs[h].z + vr[h].z); x.v[j][4 * h + 3] = relu_f(va[h].w + vs[h].w + vr[h].w);
           }
           if (ks == NKS - 1) { x.v[j][6] = rv ? 1.f : 0.f; x.v[j][7] = 0.f; }      // columns 150 (ones) and 151 (pad)
+          if (a.H1 && rv) {                             // h1 for the backward pass (the weight gradient streams it)
+            float* hp = a.H1 + (long long)(2 * q) * es + e * 4;
+            *reinterpret_cast<float4*>(hp + (long long)(8 * j) * es) = make_float4(x.v[j][0], x.v[j][1], x.v[j][2], x.v[j][3]);
+            *reinterpret_cast<float4*>(hp + (long long)(8 * j + 1) * es) = make_float4(x.v[j][4], x.v[j][5], x.v[j][6], x.v[j][7]);
+          }
           if (a.bits_h1 && rv) {
             uint32_t b = 0u;
 #pragma unroll
@@ -217,16 +224,21 @@ __global__ void __launch_bounds__(kThreadsC, 1) k_edge_step_c(EdgeStepCArgs a) {
       const bool has_next = i + 1 < cnt;
       const uint32_t parity = (uint32_t)i & 1u;
       int r_built = -1;
+      SPW_PH(7);
       if (has_next) {                                    // under the MMAs of tile i
         build_x(i + 1, s_nx, r_nx);
         r_built = r_nx;
         load_idx(i + 2, s_nx, r_nx);                     // indices one tile ahead of the gathers that need them
       }
+      SPW_PH(0);                                         // p0: operand build
       if (!mbar_wait(barC, parity)) failed = true;
       fence_after_sync();
+      SPW_PH(1);
       if (has_next) store_lo<KJ>(x, lane_addr, colLo, q, NKS);
+      SPW_PH(2);
       if (!mbar_wait(barM, parity)) failed = true;
       fence_after_sync();
+      SPW_PH(3);
       if (has_next) store_hi<KJ>(x, lane_addr, colHi, q, NKS);
       uint32_t d[GJ][8];
       load_d<GJ>(d, lane_addr, colD, q, NB / 8);
@@ -235,6 +247,7 @@ __global__ void __launch_bounds__(kThreadsC, 1) k_edge_step_c(EdgeStepCArgs a) {
         fence_before_sync();
         nbar_arrive(kBarOps, kThreadsC);
       }
+      SPW_PH(4);
       // ---- epilogue of tile i: relu, sign bits, receiver-segmented scan across the lanes of the warp ----
       const long long e = (long long)(blockIdx.x + i * gridDim.x) * kTM + row;
       const int r = r_cur;
@@ -282,7 +295,13 @@ __global__ void __launch_bounds__(kThreadsC, 1) k_edge_step_c(EdgeStepCArgs a) {
         }
       }
       r_cur = r_built;
+      SPW_PH(5);                                         // p5: epilogue
     }
+#ifdef SPW_PHASE_TIMING
+    if (blockIdx.x == 0 && lane == 0 && (warp == 0 || warp == 9))
+      printf("k_edge_step_c warp %d: build %lld waitC %lld lo %lld waitM %lld hi+D %lld epi %lld loop %lld (%d tiles)\n", warp, ph_t[0], ph_t[1], ph_t[2],
+             ph_t[3], ph_t[4], ph_t[5], ph_t[7], cnt);
+#endif
     if (failed && tid == 0) a.poison[0] = __int_as_float(0x7fc00000);
   }
   fence_before_sync();

@@ -7,7 +7,7 @@ struct LayoutC {
   size_t tcp[T_COUNT];
   size_t W2hi, W2lo, W2Thi, W2Tlo, ENCT;
   size_t degf, Q1, Q, QV, GP, U, S, R, H2S, PF, PL;
-  size_t X0, X1, X2, C, A;
+  size_t X0, X1, X2, C, A, H1;            // H1: h1 of the five steps (training)
   size_t EB, M1, M2;                      // sign bits (bytes, addressed in floats here): 4 / 5 / 5 arrays of 20 x bits_rows bytes
   size_t dU, dG, T, dS, dR, dH2S, DP, dQ, dQ1, dA, DH1, GB, partE, part0, partN;
   int slots, slotsGP;                     // per-step slots of U / S / R / H2S (5 in training, 1 otherwise) and of GP (5 / 2)
@@ -44,6 +44,7 @@ LayoutC make_layout_c(int64_t n, int64_t E, int training) {
   L.bits_floats = (20 * L.bits_rows + 3) / 4;
   if (training) {
     L.X0 = take(earr); L.X1 = take(earr); L.X2 = take(earr); L.C = take(earr);
+    L.H1 = take((size_t)5 * earr);
     L.EB = take((size_t)4 * L.bits_floats); L.M1 = take((size_t)5 * L.bits_floats); L.M2 = take((size_t)5 * L.bits_floats);
     L.dU = take((size_t)kQ100 * 5 * n * 4);
     L.dG = take((size_t)kQ100 * 5 * n * 4);
@@ -61,7 +62,7 @@ LayoutC make_layout_c(int64_t n, int64_t E, int training) {
     L.part0 = take(nsk * 3 * kDEP);
   } else {
     L.X0 = L.X2 = L.A; L.X1 = L.C = take(earr);       // inference: the encoder ping-pongs between two buffers
-    L.EB = L.M1 = L.M2 = 0;
+    L.EB = L.M1 = L.M2 = 0; L.H1 = 0;
     L.dU = L.dG = L.T = L.dS = L.dR = L.dH2S = L.DP = L.dQ = L.dQ1 = L.dA = L.DH1 = L.GB = L.partE = L.part0 = L.partN = 0;
   }
   L.total = off;
@@ -106,7 +107,8 @@ int run_wgrad_c(cudaStream_t st, int M, const csl::View& X, int Kx, int xmod, co
   csl::WgradCArgs a;
   memset(&a, 0, sizeof(a));
   a.M = M; a.X = X.p; a.x_slab = X.slab; a.x_col0 = X.col0; a.Kx = Kx; a.xmod = xmod; a.rowscale = rowscale; a.rsmod = rsmod;
-  a.dY = dY.p; a.y_slab = dY.slab; a.y_col0 = dY.col0; a.Ny = Ny; a.NB = Ny <= 112 ? 112 : 160;
+  a.dY = dY.p; a.y_slab = dY.slab; a.y_col0 = dY.col0; a.Ny = Ny;
+  const int NB = Ny <= 112 ? 112 : 160;
   a.nmt = Kx + 1 > 128 ? 2 : 1; a.part = part; a.first = 1; a.poison = part;
   const int ntiles = (M + kTM - 1) / kTM;
   int streams = num_sms() / a.nmt;
@@ -115,10 +117,16 @@ int run_wgrad_c(cudaStream_t st, int M, const csl::View& X, int Kx, int xmod, co
   const int f1 = Kx + 1 - 128;
   const int nqx0 = ((Kx < 128 ? Kx : 128) + 3) >> 2, nqx1 = a.nmt == 2 ? ((Kx + 3) >> 2) - (f1 >> 2) : 0;
   const int nqx = nqx0 > nqx1 ? nqx0 : nqx1, nqy = (Ny + 3) >> 2;
-  const size_t smem = csl::wgrad_c_smem<0>(nqx, nqy, a.NB, 3);
-  auto kern = csl::k_wgrad_c<0, 0, 3>;
-  set_smem(kern, smem);
-  SPW_KLAUNCH(tag, kern, dim3(streams * a.nmt), dim3(csl::kThreadsC), smem, st, a);
+  const size_t smem = csl::wgrad_c_smem(nqx, nqy, NB, 3);
+  if (NB == 160) {
+    auto kern = csl::k_wgrad_c<0, 160, 3>;
+    set_smem(kern, smem);
+    SPW_KLAUNCH(tag, kern, dim3(streams * a.nmt), dim3(csl::kThreadsC), smem, st, a);
+  } else {
+    auto kern = csl::k_wgrad_c<0, 112, 3>;
+    set_smem(kern, smem);
+    SPW_KLAUNCH(tag, kern, dim3(streams * a.nmt), dim3(csl::kThreadsC), smem, st, a);
+  }
   launch_reduce(st, part, streams, (int)tc::kWgPartFloats, 0, -1, f1 > 0 ? f1 : 0, Kx, Ny, out);
   return SPW_OK;
 }
@@ -251,6 +259,7 @@ int forward_csl(const SpwParams* w, const SpwGraph* g, const float* obj, float* 
       t.part_first = ws + L.PF; t.part_last = ws + L.PL;
       t.bits_h2 = training ? bits_ptr(ws, L.M2, L, l) : nullptr; t.bits_h1 = training ? bits_ptr(ws, L.M1, L, l) : nullptr;
       t.bits_rows = L.bits_rows; t.poison = H.p;
+      t.H1 = training ? ws + L.H1 + (size_t)l * ((size_t)kQ150 * E * 4 + 64) : nullptr;
       set_smem(csl::k_edge_step_c, csl::kEdgeStepCSmem);
       SPW_KLAUNCH("k_edge_step_c", csl::k_edge_step_c, dim3(tgrid), dim3(csl::kThreadsC), csl::kEdgeStepCSmem, st, t);
     }
@@ -335,12 +344,12 @@ int backward_csl(const SpwParams* w, const SpwGraph* g, const float* obj, const 
       {   // dW2 += h1^T . d h2 with h1 rebuilt from the gather and d h2 = relu'(h2) * d(sum h2)[receiver]
         csl::WgradCArgs a;
         memset(&a, 0, sizeof(a));
-        a.M = E; a.X = ws + L.A; a.x_slab = (long long)E * 4; a.x_col0 = 0; a.Kx = kDE; a.xmod = 0;
-        a.S = ws + L.S + (size_t)l * n * 4; a.R = ws + L.R + (size_t)l * n * 4; a.sr_slab = r5 * 4; a.snd = g->in_snd; a.rcv = g->in_rcv;
+        a.M = E; a.X = ws + L.H1 + (size_t)l * ((size_t)kQ150 * E * 4 + 64); a.x_slab = (long long)E * 4; a.x_col0 = 0; a.Kx = kDE; a.xmod = 0;
+        a.rcv = g->in_rcv;
         a.dY = dH.p; a.y_slab = dH.slab; a.y_col0 = 0; a.Ny = kDE; a.bits = m2; a.bits_rows = L.bits_rows;
-        a.NB = 160; a.nmt = 2; a.part = ws + L.partE; a.first = (l == SPW_N_STEPS - 1); a.poison = ws + L.partE;
-        const size_t smem = csl::wgrad_c_smem<1>(33, 38, 160, 2);
-        auto kern = csl::k_wgrad_c<1, 1, 2>;
+        a.nmt = 2; a.part = ws + L.partE; a.first = (l == SPW_N_STEPS - 1); a.poison = ws + L.partE;
+        const size_t smem = csl::wgrad_c_smem(33, 38, 160, 3);
+        auto kern = csl::k_wgrad_c<1, 160, 3>;
         set_smem(kern, smem);
         SPW_KLAUNCH("k_wgrad_c:step", kern, dim3(2 * wstreams), dim3(csl::kThreadsC), smem, st, a);
       }

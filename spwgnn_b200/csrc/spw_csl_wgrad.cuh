@@ -12,8 +12,12 @@
 //     frees the buffers of chunk q;
 //   * D is double-buffered per 128-row tile: the tensor core truncates when it accumulates, so a tile's sum is added to the
 //     running sum in registers with round-to-nearest adds, one tile late, while the next tile accumulates in the other buffer;
-//   * raw chunk rows arrive by cp.async from the column-slab arrays ([quad][row][4]: 512 contiguous bytes per quad and chunk)
-//     into a ring of stages; the streamed array is prefetched into L2 three chunks ahead.
+//   * raw chunk rows arrive in a ring of stages: streamed column-slab arrays ([quad][row][4]: 512 contiguous bytes per quad
+//     and chunk) by TMA bulk copies issued by one warp (cp.async.bulk, completion counted in bytes on the stage's mbarrier);
+//     rows gathered by node index (the edge step's d h2 = relu'(h2) * dH2S[receiver]) by cp.async, 16 bytes per row and quad.
+//     A warp-wide cp.async costs the LSU ~20 cycles whatever it copies (measured: 1.4k cycles per chunk for the 71 quads of a
+//     plain layer, 3.8k when h1 = relu(A + S[snd] + R[rcv]) was re-gathered), so the forward edge step now stores h1 and the
+//     only gather left is dH2S.
 #pragma once
 #ifndef SPW_EMU
 #include "spw_csl.cuh"
@@ -28,34 +32,31 @@ constexpr uint32_t kWgColD = 0, kWgColA = 320;    // TMEM: D0 [0,160) D1 [160,32
 
 struct WgradCArgs {
   int M;
-  const float* X; long long x_slab; int x_col0; int Kx; int xmod;      // X view (XMODE 1: the A_e array); row = r % xmod if xmod
+  const float* X; long long x_slab; int x_col0; int Kx; int xmod;      // X view; row = r % xmod if xmod (a per-node array reused by every step)
   const float* rowscale; int rsmod;                                    // value of the virtual feature Kx (null: 1)
-  const float* S; const float* R; long long sr_slab;                   // XMODE 1: x = relu(X + S[snd] + R[rcv])
-  const int32_t* snd; const int32_t* rcv;
+  const int32_t* rcv;                                                  // YMODE 1: receiver of each row
   const float* dY; long long y_slab; int y_col0; int Ny;               // dY view; YMODE 1: node table gathered by rcv, masked by bits
   const uint8_t* bits; long long bits_rows;                            // YMODE 1: byte-slab relu bits [19][rows]
-  int NB;                                                              // MMA N: 112 or 160 (>= Ny)
   int nmt;                                                             // M-tiles: 1 (Kx + 1 <= 128) or 2
   float* part;                                                         // [gridDim.x / nmt][2][160][128]
   int first;                                                           // this launch initialises the partials (else it adds to them)
   float* poison;
 };
 
-__device__ __forceinline__ void l2_prefetch(const void* p, uint32_t bytes) {
-  asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(p), "r"(bytes) : "memory");
-}
-
-// stage layout (floats): X quads [nqx][132] | (XMODE 1: S quads, R quads) | Y quads [nqy][132] | RS [32] | bits [20][32] bytes
-template <int XMODE>
-__host__ __device__ constexpr int wg_stage_floats(int nqx, int nqy) { return ((XMODE ? 3 : 1) * nqx + nqy) * kQPitch + 32 + 160; }
-template <int XMODE>
+// stage layout (floats): X quads [nqx][132] | Y quads [nqy][132] | RS [32] | bits [20][32] bytes
+__host__ __device__ constexpr int wg_stage_floats(int nqx, int nqy) { return (nqx + nqy) * kQPitch + 32 + 160; }
 constexpr size_t wgrad_c_smem(int nqx, int nqy, int NB, int nst) {
-  return (size_t)(nst * wg_stage_floats<XMODE>(nqx, nqy) + 2 * 2 * (kWgCh / 8) * (2 * NB * 4)) * sizeof(float) + 128;
+  return (size_t)(nst * wg_stage_floats(nqx, nqy) + 2 * 2 * (kWgCh / 8) * (2 * NB * 4) + 8) * sizeof(float) + 128 + 8 * nst;
 }
 
-template <int XMODE, int YMODE, int NST>
+// The per-chunk work of a thread is a fixed pattern; everything that does not depend on the chunk (shared-memory offsets of
+// the words it reads and writes, which lanes are real / ones / padding features) is computed once, and padding is expressed as
+// "read a zero word with stride 0" instead of predicates: the kernel was instruction-issue bound (ncu: 61 % issue-active).
+template <int YMODE, int NB, int NST>
 __global__ void __launch_bounds__(kThreadsC, 1) k_wgrad_c(WgradCArgs a) {
   SPW_DYN_SMEM(smem_raw);
+  constexpr int kUnits = ((kWgCh / 4) * NB + kWorkers - 1) / kWorkers;      // B-operand units (4 rows x 1 column) per thread
+  constexpr int bfl = (kWgCh / 8) * (2 * NB * 4);                         // floats per hi or lo B operand of a chunk
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int mt = (int)blockIdx.x % a.nmt, stream = (int)blockIdx.x / a.nmt, nstreams = (int)gridDim.x / a.nmt;
   const int f0 = mt == 0 ? 0 : a.Kx + 1 - 128;                   // first feature of this CTA's M-tile
@@ -63,17 +64,23 @@ __global__ void __launch_bounds__(kThreadsC, 1) k_wgrad_c(WgradCArgs a) {
   const int fhi = mt == 0 ? (a.Kx < 128 ? a.Kx : 128) : a.Kx;    // features [f0, fhi) are read from X
   const int nqx = ((fhi + 3) >> 2) - qlo;
   const int nqy = (a.Ny + 3) >> 2;
-  const int NB = a.NB;
-  const int stf = wg_stage_floats<XMODE>(nqx, nqy);
-  const int bfl = (kWgCh / 8) * (2 * NB * 4);                    // floats per hi or lo B operand of a chunk
+  const int stf = wg_stage_floats(nqx, nqy);
   float* stages = reinterpret_cast<float*>(smem_raw);
   float* Bop = stages + NST * stf;                               // [2 buffers][hi | lo][bfl]
-  uint64_t* bars = reinterpret_cast<uint64_t*>(Bop + 4 * bfl);
-  uint64_t* barF = bars; uint64_t* barT = bars + 2;
-  uint32_t* tptr = reinterpret_cast<uint32_t*>(bars + 4);
+  float* zero = Bop + 4 * bfl;                                   // 8 zero words
+  uint64_t* bars = reinterpret_cast<uint64_t*>(zero + 8);
+  uint64_t* barF = bars; uint64_t* barT = bars + 2; uint64_t* barS = bars + 4;      // barS[NST]: stage filled (bulk copies)
+  uint32_t* tptr = reinterpret_cast<uint32_t*>(barS + NST);
 
   if (warp == 0) tmem_alloc(tptr, kTmemCols);
-  if (tid == 32) { mbar_init(barF, 1); mbar_init(barF + 1, 1); mbar_init(barT, 1); mbar_init(barT + 1, 1); fence_mbar_init(); }
+  if (tid == 32) {
+    mbar_init(barF, 1); mbar_init(barF + 1, 1); mbar_init(barT, 1); mbar_init(barT + 1, 1);
+    for (int i = 0; i < NST; ++i) mbar_init(barS + i, 1);
+    fence_mbar_init();
+  }
+  if (tid < 8) zero[tid] = 0.f;
+  if (!a.rowscale)                                               // the virtual feature Kx is a column of ones
+    for (int i = tid; i < NST * 32; i += kThreadsC) stages[(i >> 5) * stf + (nqx + nqy) * kQPitch + (i & 31)] = 1.f;
   fence_before_sync();
   __syncthreads();
   fence_after_sync();
@@ -86,7 +93,7 @@ __global__ void __launch_bounds__(kThreadsC, 1) k_wgrad_c(WgradCArgs a) {
 
   if (warp == kWorkers / 32) {
     // ---------------- MMA issuer warp ----------------
-    const uint32_t idesc = make_idesc_tf32(128, NB);
+    constexpr uint32_t idesc = make_idesc_tf32(128, NB);
     for (int q = 0; q < nq; ++q) {
       nbar_sync(kBarOps, kThreadsC);
       fence_after_sync();
@@ -112,146 +119,182 @@ __global__ void __launch_bounds__(kThreadsC, 1) k_wgrad_c(WgradCArgs a) {
     // ---------------- worker warps ----------------
     const int L = 32 * (warp & 3) + lane, sub = warp >> 2;      // TMEM lane = feature f0 + L; rows 8 sub .. 8 sub + 7 of a chunk
     const uint32_t lane_addr = tmem_base + ((uint32_t)(32 * (warp & 3)) << 16);
+    constexpr int ngroups = NB / 8;
+    const int y_off = nqx * kQPitch;
+    const int rs_off = (nqx + nqy) * kQPitch;                    // RS (virtual feature values) inside a stage
+    // A operand: word offset (within a stage) and row stride of this lane's feature; padding lanes read the zero word
     const int feat = f0 + L;
-    const int xoff = ((feat >> 2) - qlo) * kQPitch + (feat & 3);         // this feature's word inside a staged row quad
-    const int ngroups = NB / 8;
+    int xa_off, xa_str;
+    if (feat < fhi) { xa_off = ((feat >> 2) - qlo) * kQPitch + (feat & 3) + 32 * sub; xa_str = 4; }
+    else if (feat == a.Kx) { xa_off = rs_off + 8 * sub; xa_str = 1; }
+    else { xa_off = -1; xa_str = 0; }
+    // B operand units of this thread: column n, row quad kc  ->  source word, bit word, destination
+    int yo[kUnits], bo[kUnits], ysh[kUnits], ystr[kUnits];
+#pragma unroll
+    for (int u = 0; u < kUnits; ++u) {
+      const int idx = tid + u * kWorkers;
+      const int n = idx % NB, kc = idx / NB;
+      if (idx < (kWgCh / 4) * NB && n < a.Ny) { yo[u] = y_off + (n >> 2) * kQPitch + 16 * kc + (n & 3); ystr[u] = 4; }
+      else { yo[u] = -1; ystr[u] = 0; }
+      bo[u] = (rs_off + 32) * 4 + (n >> 3) * 32 + 4 * kc;          // byte offset of the 4 rows' relu bytes inside a stage
+      ysh[u] = n & 7;
+    }
     bool failed = false;
     float acc[5][8];
 #pragma unroll
     for (int j = 0; j < 5; ++j)
 #pragma unroll
       for (int k = 0; k < 8; ++k) acc[j][k] = 0.f;
-    int s_idx = 0, r_idx = 0;                                    // XMODE / YMODE 1: sender / receiver of row (chunk, lane), one chunk ahead
-    auto load_idx = [&](int q) {
-      s_idx = 0; r_idx = 0;
-      if ((XMODE == 1 || YMODE == 1) && q < nq) {
-        const long long r = row0_of(q) + lane;
-        if (r < a.M) { if (XMODE == 1) s_idx = a.snd[r]; r_idx = a.rcv[r]; }
+    int r_idx = 0;                                               // YMODE 1: receiver of row (chunk, lane), one chunk ahead
+    SPW_PH_DECL
+
+    // q = -(NST - 1) .. -1: fill the ring;  q = 0 .. nq - 1: chunk q;  q = nq: flush of the last tile only
+    if (YMODE == 1 && nq > 0) {
+      const long long r = row0_of(0) + lane;
+      if (r < a.M) r_idx = a.rcv[r];
+    }
+#pragma unroll 1
+    for (int q = -(NST - 1); q <= nq; ++q) {
+      SPW_PH(7);
+      if (q >= 0 && q < nq) {
+        if (YMODE == 1 || a.rowscale) cp_async_wait<NST - 2>();  // this thread's gathers of chunk q have landed
+        if (!mbar_wait(barS + (q % NST), (uint32_t)(q / NST) & 1u)) failed = true;   // ... and the bulk copies
+        nbar_sync(kBarWork, kWorkers);                           // everybody's; and chunk q - 1 is fully consumed
       }
-    };
-    // asynchronous copies of chunk q into its stage: thread -> (quad, row = lane); uses s_idx / r_idx loaded for chunk q
-    auto issue_chunk = [&](int q) {
-      if (q < nq) {
-        float* st = stages + (q % NST) * stf;
-        const long long r0 = row0_of(q), r = r0 + lane;
-        const bool valid = r < a.M;
-        const long long rr = valid ? r : 0;
-        const long long xr = a.xmod ? rr % a.xmod : rr;
-        const int qx0 = (a.x_col0 >> 2) + qlo;
-        for (int qd = warp; qd < nqx; qd += kWorkers / 32) {
-          cp_async16_zfill(st + qd * kQPitch + lane * 4, a.X + (long long)(qx0 + qd) * a.x_slab + xr * 4, valid);
-          if (XMODE == 1) {
-            cp_async16_zfill(st + (nqx + qd) * kQPitch + lane * 4, a.S + (long long)(qlo + qd) * a.sr_slab + (long long)s_idx * 4, valid);
-            cp_async16_zfill(st + (2 * nqx + qd) * kQPitch + lane * 4, a.R + (long long)(qlo + qd) * a.sr_slab + (long long)r_idx * 4, valid);
+      SPW_PH(0);
+      {   // chunk qi = q + NST - 1 into its stage
+        const int qi = q + NST - 1;
+        if (qi < nq) {
+          float* st = stages + (qi % NST) * stf;
+          const long long r0 = row0_of(qi);
+          const int nvalid = a.M - r0 >= kWgCh ? kWgCh : (a.M > r0 ? (int)(a.M - r0) : 0);
+          uint64_t* bs = barS + (qi % NST);
+          if (nvalid < kWgCh) {                                  // last chunk of the array: rows that do not exist read as zero
+            for (int i = tid; i < (nqx + nqy) * (kWgCh - nvalid); i += kWorkers) {
+              const int qd = i / (kWgCh - nvalid), rj = nvalid + i % (kWgCh - nvalid);
+              *reinterpret_cast<float4*>(st + qd * kQPitch + rj * 4) = make_float4(0.f, 0.f, 0.f, 0.f);
+            }
+          }
+          if (tid == 0) mbar_arrive_expect_tx(bs, (uint32_t)((nqx + (YMODE == 0 ? nqy : 0)) * nvalid * 16));
+          // streamed arrays: one bulk copy per quad and chunk (more where r % xmod wraps), issued by lane 0 of every warp: a bulk
+          // copy costs its issuing thread ~55 cycles, and a warp-wide issue is serialised over its lanes
+          if (lane == 0 && nvalid > 0) {
+            const float* xsrc = a.X + (long long)((a.x_col0 >> 2) + qlo) * a.x_slab;
+            for (int qd = warp; qd < nqx; qd += kWorkers / 32) {
+              if (!a.xmod) {
+                bulk_g2s(st + qd * kQPitch, xsrc + (long long)qd * a.x_slab + r0 * 4, (uint32_t)nvalid * 16, bs);
+              } else {
+                for (int done = 0; done < nvalid;) {
+                  const long long x0 = (r0 + done) % a.xmod;
+                  const int len = (int)(a.xmod - x0 < nvalid - done ? a.xmod - x0 : nvalid - done);
+                  bulk_g2s(st + qd * kQPitch + done * 4, xsrc + (long long)qd * a.x_slab + x0 * 4, (uint32_t)len * 16, bs);
+                  done += len;
+                }
+              }
+            }
+            if (YMODE == 0) {
+              const float* ysrc = a.dY + (long long)(a.y_col0 >> 2) * a.y_slab + r0 * 4;
+              for (int qd = warp; qd < nqy; qd += kWorkers / 32) bulk_g2s(st + y_off + qd * kQPitch, ysrc + (long long)qd * a.y_slab, (uint32_t)nvalid * 16, bs);
+            }
+          }
+          if (YMODE == 1) {                                      // gathered rows: thread -> (quad, row = lane), 16 bytes each
+            const bool valid = lane < nvalid;
+            const float* src = a.dY + (long long)((a.y_col0 >> 2) + warp) * a.y_slab + (long long)r_idx * 4;
+            float* dst = st + y_off + warp * kQPitch + lane * 4;
+            for (int qd = warp; qd < nqy; qd += kWorkers / 32) {
+              cp_async16_zfill(dst, src, valid);
+              src += (kWorkers / 32) * a.y_slab; dst += (kWorkers / 32) * kQPitch;
+            }
+            if (warp == 1) {                                     // relu bits of the chunk: 19 groups x 32 bytes, 16-byte pieces
+              uint8_t* BT = reinterpret_cast<uint8_t*>(st + rs_off + 32);
+              for (int i = lane; i < 2 * 19; i += 32)
+                cp_async16_zfill(reinterpret_cast<float*>(BT + (i >> 1) * 32 + 16 * (i & 1)),
+                                 reinterpret_cast<const float*>(a.bits + (long long)(i >> 1) * a.bits_rows + r0 + 16 * (i & 1)), true);
+            }
+          }
+          if (a.rowscale && warp == 2) {
+            const long long r = r0 + lane;
+            const bool valid = lane < nvalid;
+            cp_async4_zfill(st + rs_off + lane, a.rowscale + (valid ? (a.rsmod ? r % a.rsmod : r) : 0), valid);
           }
         }
-        float* YD = st + (XMODE ? 3 : 1) * nqx * kQPitch;
-        const int qy0 = a.y_col0 >> 2;
-        for (int qd = warp; qd < nqy; qd += kWorkers / 32) {
-          if (YMODE == 1) cp_async16_zfill(YD + qd * kQPitch + lane * 4, a.dY + (long long)(qy0 + qd) * a.y_slab + (long long)r_idx * 4, valid);
-          else cp_async16_zfill(YD + qd * kQPitch + lane * 4, a.dY + (long long)(qy0 + qd) * a.y_slab + rr * 4, valid);
-        }
-        float* RS = YD + nqy * kQPitch;
-        if (a.rowscale && warp == 0) cp_async4_zfill(RS + lane, a.rowscale + (a.rsmod ? rr % a.rsmod : rr), valid);
-        if (YMODE == 1 && warp == 1) {                           // relu bits of the chunk: 19 groups x 32 bytes
-          uint8_t* BT = reinterpret_cast<uint8_t*>(RS + 32);
-          // two 16-byte pieces per group; the bit arrays are allocated in whole 128-row tiles, so the read stays in bounds
-          for (int i = lane; i < 2 * 19; i += 32)
-            cp_async16_zfill(reinterpret_cast<float*>(BT + (i >> 1) * 32 + 16 * (i & 1)),
-                             reinterpret_cast<const float*>(a.bits + (long long)(i >> 1) * a.bits_rows + r0 + 16 * (i & 1)), true);
-        }
-        // stream prefetch into L2, three chunks ahead (one 512-byte piece per quad)
-        if (q + 3 < nq && lane == 0) {
-          const long long rp = row0_of(q + 3);
-          if (rp + kWgCh <= a.M && !a.xmod)
-            for (int qd = warp; qd < nqx; qd += kWorkers / 32) l2_prefetch(a.X + (long long)(qx0 + qd) * a.x_slab + rp * 4, kWgCh * 16);
-          if (YMODE == 0 && rp + kWgCh <= a.M)
-            for (int qd = warp; qd < nqy; qd += kWorkers / 32) l2_prefetch(a.dY + (long long)(qy0 + qd) * a.y_slab + rp * 4, kWgCh * 16);
+        if (YMODE == 1 || a.rowscale) cp_async_commit();
+        if (YMODE == 1 && qi + 1 < nq) {                         // receivers of the chunk after that one
+          const long long r = row0_of(qi + 1) + lane;
+          r_idx = r < a.M ? a.rcv[r] : 0;
         }
       }
-      cp_async_commit();
-    };
-    auto flush_tile = [&](int t) {                               // D[t & 1] of local tile t -> running sums (round-to-nearest adds)
-      if (!mbar_wait(barT + (t & 1), (uint32_t)(t >> 1) & 1u)) failed = true;
-      fence_after_sync();
-      uint32_t d[5][8];
-      load_d<5>(d, lane_addr, kWgColD + 160 * (t & 1), sub, ngroups);
-#pragma unroll
-      for (int j = 0; j < 5; ++j)
-#pragma unroll
-        for (int k = 0; k < 8; ++k)
-          if (sub + 4 * j < ngroups) acc[j][k] += __uint_as_float(d[j][k]);
-      fence_before_sync();
-    };
-
-    // prologue: chunks 0 .. NST - 2 in flight, indices one chunk ahead
-    load_idx(0);
-#pragma unroll 1
-    for (int p = 0; p < NST - 1; ++p) { issue_chunk(p); load_idx(p + 1); }
-    for (int q = 0; q < nq; ++q) {
+      SPW_PH(1);
+      if (q < 0) continue;
       const int t = q / kCh, c = q % kCh, buf = q & 1;
-      cp_async_wait<NST - 2>();                                  // this thread's copies of chunk q have landed
-      nbar_sync(kBarWork, kWorkers);                             // ... everybody's; and chunk q - 1 is fully consumed
-      issue_chunk(q + NST - 1);                                  // refill the stage chunk q - 1 used
-      load_idx(q + NST);
-      if (c == 1 && t >= 1) flush_tile(t - 1);
+      if ((c == 1 && t >= 1) || q == nq) {                       // D of the previous tile -> running sums (round-to-nearest adds)
+        const int tf = q == nq ? my_tiles - 1 : t - 1;
+        if (tf >= 0) {
+          if (!mbar_wait(barT + (tf & 1), (uint32_t)(tf >> 1) & 1u)) failed = true;
+          fence_after_sync();
+          uint32_t d[5][8];
+          load_d<5>(d, lane_addr, kWgColD + 160 * (tf & 1), sub, ngroups);
+#pragma unroll
+          for (int j = 0; j < 5; ++j)
+#pragma unroll
+            for (int k = 0; k < 8; ++k)
+              if (sub + 4 * j < ngroups) acc[j][k] += __uint_as_float(d[j][k]);
+          fence_before_sync();
+        }
+      }
+      SPW_PH(2);
+      if (q == nq) break;
       if (q >= 2) {                                              // operand buffers `buf` are free once chunk q - 2's MMAs are done
         if (!mbar_wait(barF + buf, (uint32_t)((q >> 1) - 1) & 1u)) failed = true;
         fence_after_sync();
       }
+      SPW_PH(3);
       const float* st = stages + (q % NST) * stf;
-      const float* XA = st; const float* XS = st + nqx * kQPitch; const float* XR = st + 2 * nqx * kQPitch;
-      const float* YD = st + (XMODE ? 3 : 1) * nqx * kQPitch;
-      const float* RS = YD + nqy * kQPitch;
-      const uint8_t* BT = reinterpret_cast<const uint8_t*>(RS + 32);
-      const long long r0 = row0_of(q);
-      // ---- A = X^T: this lane's feature, this thread's 8 rows of the chunk as 8 TMEM columns
-      {
+      {   // ---- A = X^T: this lane's feature, this thread's 8 rows of the chunk as 8 TMEM columns
+        const float* pa = xa_off >= 0 ? st + xa_off : zero;
         uint32_t h[8], l[8];
 #pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          const int j = 8 * sub + i;
-          float xv = 0.f;
-          if (feat < fhi) {
-            xv = XA[xoff + j * 4];
-            if (XMODE == 1) xv = relu_f(xv + XS[xoff + j * 4] + XR[xoff + j * 4]);
-          } else if (feat == a.Kx && r0 + j < a.M) {
-            xv = a.rowscale ? RS[j] : 1.f;
-          }
-          split_fast(xv, h[i], l[i]);
-        }
+        for (int i = 0; i < 8; ++i) split_fast(pa[i * xa_str], h[i], l[i]);
         const uint32_t colA = kWgColA + 64 * buf;
         tmem_st8(lane_addr + colA + 8 * sub, h);
         tmem_st8(lane_addr + colA + 32 + 8 * sub, l);
       }
-      // ---- B = dY^T: [k-step][2][n][4 rows]
-      {
+      SPW_PH(4);
+      {   // ---- B = dY^T: [k-step][2][n][4 rows]
         float* Bhi_s = Bop + (size_t)(2 * buf) * bfl; float* Blo_s = Bhi_s + bfl;
-        for (int idx = tid; idx < (kWgCh / 4) * NB; idx += kWorkers) {
-          const int n = idx % NB, kc = idx / NB;
-          uint32_t h[4], l[4];
-          uint32_t bw = 0xffffffffu;
-          if (YMODE == 1 && n < a.Ny) bw = *reinterpret_cast<const uint32_t*>(BT + (n >> 3) * 32 + 4 * kc);
+        const uint8_t* stb = reinterpret_cast<const uint8_t*>(st);
 #pragma unroll
-          for (int i = 0; i < 4; ++i) {
-            float y = 0.f;
-            if (n < a.Ny) {
-              y = YD[(n >> 2) * kQPitch + (4 * kc + i) * 4 + (n & 3)];
-              if (YMODE == 1) y = ((bw >> (8 * i + (n & 7))) & 1u) ? y : 0.f;
+        for (int u = 0; u < kUnits; ++u) {
+          const int idx = tid + u * kWorkers;
+          if (idx < (kWgCh / 4) * NB) {
+            const float* py = yo[u] >= 0 ? st + yo[u] : zero;
+            uint32_t h[4], l[4];
+            uint32_t bw = 0xffffffffu;
+            if (YMODE == 1) bw = *reinterpret_cast<const uint32_t*>(stb + bo[u]) >> ysh[u];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+              float y = py[i * ystr[u]];
+              if (YMODE == 1) y = ((bw >> (8 * i)) & 1u) ? y : 0.f;
+              split_fast(y, h[i], l[i]);
             }
-            split_fast(y, h[i], l[i]);
+            reinterpret_cast<uint4*>(Bhi_s)[idx] = make_uint4(h[0], h[1], h[2], h[3]);
+            reinterpret_cast<uint4*>(Blo_s)[idx] = make_uint4(l[0], l[1], l[2], l[3]);
           }
-          reinterpret_cast<uint4*>(Bhi_s)[idx] = make_uint4(h[0], h[1], h[2], h[3]);
-          reinterpret_cast<uint4*>(Blo_s)[idx] = make_uint4(l[0], l[1], l[2], l[3]);
         }
       }
+      SPW_PH(5);
       tmem_wait_st();
       fence_async_smem();
       fence_before_sync();
       nbar_arrive(kBarOps, kThreadsC);
+      SPW_PH(6);
     }
+#ifdef SPW_PHASE_TIMING
+    if (blockIdx.x == 0 && lane == 0 && (warp == 0 || warp == 9) && a.M > 100000)
+      printf("k_wgrad_c<%d> warp %d: wait copies %lld issue copies %lld flush %lld waitMMA %lld A %lld B %lld arrive %lld loop %lld (%d chunks)\n", YMODE, warp,
+             ph_t[0], ph_t[1], ph_t[2], ph_t[3], ph_t[4], ph_t[5], ph_t[6], ph_t[7], nq);
+#endif
     cp_async_wait<0>();
-    if (my_tiles >= 1) flush_tile(my_tiles - 1);                 // the last tile (every earlier one was flushed one tile late)
     {   // running sums -> per-CTA partial in global memory ([n][lane]: coalesced)
       float* pp = a.part + (size_t)stream * (2 * 160 * 128) + (size_t)mt * (160 * 128) + L;
 #pragma unroll
