@@ -31,8 +31,14 @@ namespace csl {
 using namespace spw::tc;
 
 constexpr int kWorkers = 512;                     // 16 worker warps: thread = (row = TMEM lane, quarter q of the 8-column groups)
-constexpr int kThreadsC = kWorkers + 32;          // + the MMA issuer warp
+constexpr int kThreadsC = kWorkers + 128;         // + a fifth warp group: the MMA issuer warp and three idle warps
+// Registers: 20 warps = 5 per scheduler = 96 registers per thread at launch (640 x 96 = 61 440 for the CTA).  The worker warp
+// groups raise their allotment with setmaxnreg once the fifth group (which only issues MMAs) has given most of its registers
+// back; the CTA's pool is what it was launched with, so 512 x 112 + 128 x 24 = 60 416 fits and 512 x 120 would block forever.
+__device__ __forceinline__ void regs_workers() { asm volatile("setmaxnreg.inc.sync.aligned.u32 112;" ::: "memory"); }
+__device__ __forceinline__ void regs_issuer() { asm volatile("setmaxnreg.dec.sync.aligned.u32 24;" ::: "memory"); }
 constexpr int kBarOps = 1;                        // workers arrive, issuer syncs
+constexpr int kBarOpsCount = 512 + 32;            // ... 16 worker warps + the issuer warp
 __device__ __forceinline__ void nbar_sync(int id, int count) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(count) : "memory"); }
 __device__ __forceinline__ void nbar_arrive(int id, int count) { asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(count) : "memory"); }
 
@@ -190,15 +196,17 @@ __global__ void __launch_bounds__(kThreadsC, 1) k_lin(LinCArgs a) {
   const int ntiles = (a.M + kTM - 1) / kTM;
   const int cnt = (int)blockIdx.x < ntiles ? (ntiles - 1 - (int)blockIdx.x) / (int)gridDim.x + 1 : 0;
 
-  if (warp == kWorkers / 32) {
-    // ---------------- MMA issuer warp ----------------
+  if (warp >= kWorkers / 32) {
+    // ---------------- MMA issuer warp (and its three idle siblings) ----------------
+    regs_issuer();
+    if (warp == kWorkers / 32) {
     if (lane == 0) bulk_load_weights(Bhi_s, Blo_s, a.Bhi, a.Blo, (uint32_t)bfl * 4, barW);
     bool ok = mbar_wait(barW, 0);
 #ifdef SPW_PHASE_TIMING
     long long t_wait = 0, t_issue = 0, t_c = 0, t_m = 0, t_last = clock64();
 #endif
     for (int i = 0; i < cnt; ++i) {
-      nbar_sync(kBarOps, kThreadsC);
+      nbar_sync(kBarOps, kBarOpsCount);
       fence_after_sync();
 #ifdef SPW_PHASE_TIMING
       { const long long t = clock64(); t_wait += t - t_last; t_last = t; }
@@ -219,8 +227,10 @@ __global__ void __launch_bounds__(kThreadsC, 1) k_lin(LinCArgs a) {
     if (blockIdx.x == 0 && lane == 0 && a.M > 100000) printf("k_lin issuer: waited for operands %lld, issuing %lld, issue end -> barC %lld, issue end -> barM %lld cycles over %d tiles\n", t_wait, t_issue, t_c, t_m, cnt);
 #endif
     if (!ok && lane == 0) a.poison[0] = __int_as_float(0x7fc00000);
+    }
   } else {
     // ---------------- worker warps ----------------
+    regs_workers();
     const uint32_t lane_addr = tmem_base + ((uint32_t)(32 * (warp & 3)) << 16);
     constexpr int ngroups = NB / 8;
     constexpr int nq8 = (N + 7) >> 3;                            // output column groups that exist
@@ -251,7 +261,7 @@ __global__ void __launch_bounds__(kThreadsC, 1) k_lin(LinCArgs a) {
       store_hi<KJ>(x, lane_addr, colHi, q, NKS);
       tmem_wait_st();
       fence_before_sync();
-      nbar_arrive(kBarOps, kThreadsC);
+      nbar_arrive(kBarOps, kBarOpsCount);
     }
     for (int i = 0; i < cnt; ++i) {
       const bool has_next = i + 1 < cnt;
@@ -273,7 +283,7 @@ __global__ void __launch_bounds__(kThreadsC, 1) k_lin(LinCArgs a) {
       if (has_next) {
         tmem_wait_st();
         fence_before_sync();
-        nbar_arrive(kBarOps, kThreadsC);                         // the issuer starts tile i + 1
+        nbar_arrive(kBarOps, kBarOpsCount);                         // the issuer starts tile i + 1
       }
       SPW_PH(4);                                                 // p4: hi words + D load: the tensor pipe idles
       // ---- epilogue of tile i from registers, under the MMAs of tile i + 1 ----

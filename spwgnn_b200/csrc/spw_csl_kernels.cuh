@@ -140,17 +140,21 @@ __global__ void __launch_bounds__(kThreadsC, 1) k_edge_step_c(EdgeStepCArgs a) {
   const int ntiles = (a.E + kTM - 1) / kTM;
   const int cnt = (int)blockIdx.x < ntiles ? (ntiles - 1 - (int)blockIdx.x) / (int)gridDim.x + 1 : 0;
 
-  if (warp == kWorkers / 32) {
+  if (warp >= kWorkers / 32) {
+    regs_issuer();
+    if (warp == kWorkers / 32) {
     if (lane == 0) bulk_load_weights(Bhi_s, Blo_s, a.W2hi, a.W2lo, (uint32_t)kBFloats * 4, barW);
     bool ok = mbar_wait(barW, 0);
     for (int i = 0; i < cnt; ++i) {
-      nbar_sync(kBarOps, kThreadsC);
+      nbar_sync(kBarOps, kBarOpsCount);
       fence_after_sync();
       if (lane == 0) issue_tile(tmem_base + colD, tmem_base + colHi, tmem_base + colLo, smem_u32(Bhi_s), smem_u32(Blo_s), NKS, NB, barC, barM);
       __syncwarp();
     }
     if (!ok && lane == 0) a.poison[0] = __int_as_float(0x7fc00000);
+    }
   } else {
+    regs_workers();
     const uint32_t lane_addr = tmem_base + ((uint32_t)(32 * (warp & 3)) << 16);
     const long long es = (long long)a.E * 4;
     bool failed = false;
@@ -218,7 +222,7 @@ __global__ void __launch_bounds__(kThreadsC, 1) k_edge_step_c(EdgeStepCArgs a) {
       store_hi<KJ>(x, lane_addr, colHi, q, NKS);
       tmem_wait_st();
       fence_before_sync();
-      nbar_arrive(kBarOps, kThreadsC);
+      nbar_arrive(kBarOps, kBarOpsCount);
     }
     for (int i = 0; i < cnt; ++i) {
       const bool has_next = i + 1 < cnt;
@@ -245,7 +249,7 @@ __global__ void __launch_bounds__(kThreadsC, 1) k_edge_step_c(EdgeStepCArgs a) {
       if (has_next) {
         tmem_wait_st();
         fence_before_sync();
-        nbar_arrive(kBarOps, kThreadsC);
+        nbar_arrive(kBarOps, kBarOpsCount);
       }
       SPW_PH(4);
       // ---- epilogue of tile i: relu, sign bits, receiver-segmented scan across the lanes of the warp ----
@@ -346,6 +350,7 @@ struct EdgeDgradCArgs {
   float* poison;
 };
 
+template <bool FIRST>
 __global__ void __launch_bounds__(kThreadsC, 1) k_edge_dgrad_c(EdgeDgradCArgs a) {
   constexpr int KJ = 5, GJ = 5, NKS = kKS, NB = kN;
   SPW_DYN_SMEM(smem_raw);
@@ -367,17 +372,21 @@ __global__ void __launch_bounds__(kThreadsC, 1) k_edge_dgrad_c(EdgeDgradCArgs a)
   const int ntiles = (a.E + kTM - 1) / kTM;
   const int cnt = (int)blockIdx.x < ntiles ? (ntiles - 1 - (int)blockIdx.x) / (int)gridDim.x + 1 : 0;
 
-  if (warp == kWorkers / 32) {
+  if (warp >= kWorkers / 32) {
+    regs_issuer();
+    if (warp == kWorkers / 32) {
     if (lane == 0) bulk_load_weights(Bhi_s, Blo_s, a.Whi, a.Wlo, (uint32_t)kBFloats * 4, barW);
     bool ok = mbar_wait(barW, 0);
     for (int i = 0; i < cnt; ++i) {
-      nbar_sync(kBarOps, kThreadsC);
+      nbar_sync(kBarOps, kBarOpsCount);
       fence_after_sync();
       if (lane == 0) issue_tile(tmem_base + colD, tmem_base + colHi, tmem_base + colLo, smem_u32(Bhi_s), smem_u32(Blo_s), NKS, NB, barC, barM);
       __syncwarp();
     }
     if (!ok && lane == 0) a.poison[0] = __int_as_float(0x7fc00000);
+    }
   } else {
+    regs_workers();
     const uint32_t lane_addr = tmem_base + ((uint32_t)(32 * (warp & 3)) << 16);
     const long long es = (long long)a.E * 4;
     bool failed = false;
@@ -387,7 +396,11 @@ __global__ void __launch_bounds__(kThreadsC, 1) k_edge_dgrad_c(EdgeDgradCArgs a)
       const long long e = (long long)(blockIdx.x + i * gridDim.x) * kTM + row;
       r = (i < cnt && e < a.E) ? a.in_rcv[e] : -1;
     };
-    auto build_x = [&](int i, int r) {                   // x = relu'(h2) ? dH2S[receiver] : 0
+    // Loads are issued in batches well before their first use (the kernel was long-scoreboard bound: ncu 22 stalled warps per
+    // issue): the gathered operand rows and their mask bytes at the top of an iteration, consumed after the wait for the
+    // correction MMAs; the old dA values and the h1 mask bytes before D is read, consumed by the epilogue.
+    uint32_t b2[KJ];
+    auto gather_x = [&](int i, int r) {                  // raw dH2S[receiver] quads + relu'(h2) bytes of local tile i
       const long long e = (long long)(blockIdx.x + i * gridDim.x) * kTM + row;
       const bool rv = r >= 0;
       const float* dp = a.dH2S + (long long)(2 * q) * a.d_slab + (long long)(rv ? r : 0) * 4;
@@ -395,69 +408,87 @@ __global__ void __launch_bounds__(kThreadsC, 1) k_edge_dgrad_c(EdgeDgradCArgs a)
 #pragma unroll
       for (int j = 0; j < KJ; ++j) {
         const int ks = q + 4 * j;
+        float4 t0 = make_float4(0.f, 0.f, 0.f, 0.f), t1 = t0;
+        b2[j] = 0u;
         if (ks < NKS && rv) {
-          const float4 t0 = *reinterpret_cast<const float4*>(dp + (long long)(8 * j) * a.d_slab);
-          const float4 t1 = *reinterpret_cast<const float4*>(dp + (long long)(8 * j + 1) * a.d_slab);
-          const uint32_t b = bp[(long long)(4 * j) * a.bits_rows];
-          const float t[8] = {t0.x, t0.y, t0.z, t0.w, t1.x, t1.y, t1.z, t1.w};
-#pragma unroll
-          for (int k = 0; k < 8; ++k) x.v[j][k] = ((b >> k) & 1u) ? t[k] : 0.f;
-        } else {
-#pragma unroll
-          for (int k = 0; k < 8; ++k) x.v[j][k] = 0.f;
+          t0 = *reinterpret_cast<const float4*>(dp + (long long)(8 * j) * a.d_slab);
+          t1 = *reinterpret_cast<const float4*>(dp + (long long)(8 * j + 1) * a.d_slab);
+          b2[j] = bp[(long long)(4 * j) * a.bits_rows];
         }
+        x.v[j][0] = t0.x; x.v[j][1] = t0.y; x.v[j][2] = t0.z; x.v[j][3] = t0.w;
+        x.v[j][4] = t1.x; x.v[j][5] = t1.y; x.v[j][6] = t1.z; x.v[j][7] = t1.w;
       }
     };
-    if (cnt > 0) {
-      load_idx(0, r_nx);
-      build_x(0, r_nx);
-      load_idx(1, r_nx);
-      store_lo<KJ>(x, lane_addr, colLo, q, NKS);
-      store_hi<KJ>(x, lane_addr, colHi, q, NKS);
-      tmem_wait_st();
-      fence_before_sync();
-      nbar_arrive(kBarOps, kThreadsC);
-    }
-    for (int i = 0; i < cnt; ++i) {
+    auto mask_x = [&]() {
+#pragma unroll
+      for (int j = 0; j < KJ; ++j)
+#pragma unroll
+        for (int k = 0; k < 8; ++k) x.v[j][k] = ((b2[j] >> k) & 1u) ? x.v[j][k] : 0.f;
+    };
+    load_idx(0, r_nx);
+#pragma unroll 1
+    for (int i = -1; i < cnt; ++i) {
       const bool has_next = i + 1 < cnt;
       const uint32_t parity = (uint32_t)i & 1u;
       if (has_next) {
-        build_x(i + 1, r_nx);
+        gather_x(i + 1, r_nx);
         load_idx(i + 2, r_nx);
       }
-      if (!mbar_wait(barC, parity)) failed = true;
-      fence_after_sync();
-      if (has_next) store_lo<KJ>(x, lane_addr, colLo, q, NKS);
-      if (!mbar_wait(barM, parity)) failed = true;
-      fence_after_sync();
-      if (has_next) store_hi<KJ>(x, lane_addr, colHi, q, NKS);
-      uint32_t d[GJ][8];
-      load_d<GJ>(d, lane_addr, colD, q, NB / 8);
-      if (has_next) {
-        tmem_wait_st();
-        fence_before_sync();
-        nbar_arrive(kBarOps, kThreadsC);
+      if (i >= 0) {
+        if (!mbar_wait(barC, parity)) failed = true;
+        fence_after_sync();
       }
-      // ---- epilogue of tile i: mask with relu'(h1), DH1 (write), dA (write or accumulate): coalesced 16-byte accesses
+      if (has_next) { mask_x(); store_lo<KJ>(x, lane_addr, colLo, q, NKS); }
+      if (i >= 0) {
+        if (!mbar_wait(barM, parity)) failed = true;
+        fence_after_sync();
+      }
+      if (has_next) store_hi<KJ>(x, lane_addr, colHi, q, NKS);
+      // epilogue inputs of tile i: relu'(h1) bytes and (unless this is the first processed step) the old dA values
       const long long e = (long long)(blockIdx.x + i * gridDim.x) * kTM + row;
-      if (e < a.E) {
-        float* hp = a.DH1 + (long long)(2 * q) * es + e * 4;
-        float* gp = a.dA + (long long)(2 * q) * es + e * 4;
+      const bool ev = i >= 0 && e < a.E;
+      float* hp = a.DH1 + (long long)(2 * q) * es + (ev ? e : 0) * 4;
+      float* gp = a.dA + (long long)(2 * q) * es + (ev ? e : 0) * 4;
+      uint32_t b1[GJ];
+      float4 o0[GJ], o1[GJ];
+      if (ev) {
         const uint8_t* bp = a.bits_h1 + (long long)q * a.bits_rows + e;
 #pragma unroll
         for (int j = 0; j < GJ; ++j) {
-          const int g = q + 4 * j;
-          if (g >= NKS) continue;
-          const uint32_t b = bp[(long long)(4 * j) * a.bits_rows];
+          b1[j] = 0u;
+          if (q + 4 * j < NKS) {
+            b1[j] = bp[(long long)(4 * j) * a.bits_rows];
+            if (!FIRST && j < 3) {                       // the last two groups' old values are requested inside the epilogue
+              o0[j] = *reinterpret_cast<const float4*>(gp + (long long)(8 * j) * es);
+              o1[j] = *reinterpret_cast<const float4*>(gp + (long long)(8 * j + 1) * es);
+            }
+          }
+        }
+      }
+      uint32_t d[GJ][8];
+      if (i >= 0) load_d<GJ>(d, lane_addr, colD, q, NB / 8);
+      if (has_next) {
+        tmem_wait_st();
+        fence_before_sync();
+        nbar_arrive(kBarOps, kBarOpsCount);
+      }
+      // ---- epilogue of tile i: mask with relu'(h1), DH1 (write), dA (write or accumulate): coalesced 16-byte accesses
+      if (ev) {
+#pragma unroll
+        for (int j = 0; j < GJ; ++j) {
+          if (!FIRST && j + 3 < GJ && q + 4 * (j + 3) < NKS) {
+            o0[j + 3] = *reinterpret_cast<const float4*>(gp + (long long)(8 * (j + 3)) * es);
+            o1[j + 3] = *reinterpret_cast<const float4*>(gp + (long long)(8 * (j + 3) + 1) * es);
+          }
+          if (q + 4 * j >= NKS) continue;
           float v[8];
 #pragma unroll
-          for (int k = 0; k < 8; ++k) v[k] = ((b >> k) & 1u) ? __uint_as_float(d[j][k]) : 0.f;
+          for (int k = 0; k < 8; ++k) v[k] = ((b1[j] >> k) & 1u) ? __uint_as_float(d[j][k]) : 0.f;
           *reinterpret_cast<float4*>(hp + (long long)(8 * j) * es) = make_float4(v[0], v[1], v[2], v[3]);
           *reinterpret_cast<float4*>(hp + (long long)(8 * j + 1) * es) = make_float4(v[4], v[5], v[6], v[7]);
-          if (!a.first) {
-            const float4 o0 = *reinterpret_cast<const float4*>(gp + (long long)(8 * j) * es);
-            const float4 o1 = *reinterpret_cast<const float4*>(gp + (long long)(8 * j + 1) * es);
-            v[0] += o0.x; v[1] += o0.y; v[2] += o0.z; v[3] += o0.w; v[4] += o1.x; v[5] += o1.y; v[6] += o1.z; v[7] += o1.w;
+          if (!FIRST) {
+            v[0] += o0[j].x; v[1] += o0[j].y; v[2] += o0[j].z; v[3] += o0[j].w;
+            v[4] += o1[j].x; v[5] += o1[j].y; v[6] += o1[j].z; v[7] += o1[j].w;
           }
           *reinterpret_cast<float4*>(gp + (long long)(8 * j) * es) = make_float4(v[0], v[1], v[2], v[3]);
           *reinterpret_cast<float4*>(gp + (long long)(8 * j + 1) * es) = make_float4(v[4], v[5], v[6], v[7]);

@@ -360,8 +360,13 @@ int backward_csl(const SpwParams* w, const SpwGraph* g, const float* obj, const 
         t.bits_h2 = m2; t.bits_h1 = m1; t.bits_rows = L.bits_rows; t.dA = ws + L.dA; t.DH1 = ws + L.DH1;
         t.first = (l == SPW_N_STEPS - 1); t.poison = ws + L.dA;
         const int tgrid = etiles < num_sms() ? etiles : num_sms();
-        set_smem(csl::k_edge_dgrad_c, csl::kEdgeStepCSmem);
-        SPW_KLAUNCH("k_edge_dgrad_c", csl::k_edge_dgrad_c, dim3(tgrid), dim3(csl::kThreadsC), csl::kEdgeStepCSmem, st, t);
+        if (t.first) {
+          set_smem(csl::k_edge_dgrad_c<true>, csl::kEdgeStepCSmem);
+          SPW_KLAUNCH("k_edge_dgrad_c", csl::k_edge_dgrad_c<true>, dim3(tgrid), dim3(csl::kThreadsC), csl::kEdgeStepCSmem, st, t);
+        } else {
+          set_smem(csl::k_edge_dgrad_c<false>, csl::kEdgeStepCSmem);
+          SPW_KLAUNCH("k_edge_dgrad_c", csl::k_edge_dgrad_c<false>, dim3(tgrid), dim3(csl::kThreadsC), csl::kEdgeStepCSmem, st, t);
+        }
       }
     }
     if (l > 0) {

@@ -91,11 +91,13 @@ __global__ void __launch_bounds__(kThreadsC, 1) k_wgrad_c(WgradCArgs a) {
   const int nq = my_tiles * kCh;
   auto row0_of = [&](int q) { return (long long)(stream + (q / kCh) * nstreams) * kTM + (q % kCh) * kWgCh; };
 
-  if (warp == kWorkers / 32) {
-    // ---------------- MMA issuer warp ----------------
+  if (warp >= kWorkers / 32) {
+    // ---------------- MMA issuer warp (and its three idle siblings) ----------------
+    regs_issuer();
     constexpr uint32_t idesc = make_idesc_tf32(128, NB);
+    if (warp == kWorkers / 32)
     for (int q = 0; q < nq; ++q) {
-      nbar_sync(kBarOps, kThreadsC);
+      nbar_sync(kBarOps, kBarOpsCount);
       fence_after_sync();
       if (lane == 0) {
         const int t = q / kCh, c = q % kCh, buf = q & 1;
@@ -117,6 +119,7 @@ __global__ void __launch_bounds__(kThreadsC, 1) k_wgrad_c(WgradCArgs a) {
     }
   } else {
     // ---------------- worker warps ----------------
+    regs_workers();
     const int L = 32 * (warp & 3) + lane, sub = warp >> 2;      // TMEM lane = feature f0 + L; rows 8 sub .. 8 sub + 7 of a chunk
     const uint32_t lane_addr = tmem_base + ((uint32_t)(32 * (warp & 3)) << 16);
     constexpr int ngroups = NB / 8;
@@ -286,7 +289,7 @@ __global__ void __launch_bounds__(kThreadsC, 1) k_wgrad_c(WgradCArgs a) {
       tmem_wait_st();
       fence_async_smem();
       fence_before_sync();
-      nbar_arrive(kBarOps, kThreadsC);
+      nbar_arrive(kBarOps, kBarOpsCount);
       SPW_PH(6);
     }
 #ifdef SPW_PHASE_TIMING
