@@ -527,6 +527,21 @@ __global__ void __launch_bounds__(256) k_gather_dsr_c(int n, int E, const int32_
   }
 }
 
+// out[i][:] = sum over `slots` of in[slot * n + i][:]  (column-slab arrays; thread = (quad, node), fixed order)
+__global__ void __launch_bounds__(256) k_sum_slots_c(int n, int slots, int nquads, const float* __restrict__ in, long long in_slab,
+                                                     float* __restrict__ out, long long out_slab) {
+  const long long total = (long long)n * nquads;
+  for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (long long)gridDim.x * blockDim.x) {
+    const int qd = (int)(idx / n), i = (int)(idx - (long long)qd * n);
+    float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int l = 0; l < slots; ++l) {
+      const float4 v = *reinterpret_cast<const float4*>(in + (long long)qd * in_slab + ((long long)l * n + i) * 4);
+      s.x += v.x; s.y += v.y; s.z += v.z; s.w += v.w;
+    }
+    *reinterpret_cast<float4*>(out + (long long)qd * out_slab + (long long)i * 4) = s;
+  }
+}
+
 // =========================================================================================================================
 // Skinny weight gradients: sums over rows of  s0 * Z[row][:],  s1 * Z[row][:]  and  Z[row][:]  with per-row scalars s0, s1.
 //   MODE 0  relation-encoder layer 0:  Z = G0 [E][150], (s0, s1) = pos_receiver - pos_sender       -> d rm_w0 [2][150], d rm_b0

@@ -100,34 +100,70 @@ int run_lin_c(cudaStream_t st, float* ws, const LayoutC& L, int M, const LinC& o
   return launch_lin(st, o.epi, a, o.tag);
 }
 
-// dW[Kx][Ny] (+ bias row) = X^T dY over M rows (plain mode), reduced in fixed order into the Keras-layout gradient
-int run_wgrad_c(cudaStream_t st, int M, const csl::View& X, int Kx, int xmod, const float* rowscale, int rsmod, const csl::View& dY,
-                int Ny, float* part, const WgOut& out, const char* tag) {
+// ---- TMA tensor maps (driver entry point resolved at run time: the library does not link libcuda) ---------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
+                                  const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+EncodeTiledFn encode_tiled() {
+  static EncodeTiledFn fn = nullptr;
+  if (!fn) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) == cudaSuccess && qres == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(p);
+  }
+  return fn;
+}
+// 2-D map of a column-slab view: [nquads][rows * 4 floats] (quad stride = slab floats), box [box_quads][33 rows x 4 floats]
+int make_csl_map(CUtensorMap* m, const csl::View& v, long long rows, int nquads, int box_quads) {
+  EncodeTiledFn enc = encode_tiled();
+  if (!enc) return fail(SPW_ERR_LAUNCH, "cuTensorMapEncodeTiled is not available");
+  const cuuint64_t gdim[2] = {(cuuint64_t)rows * 4, (cuuint64_t)nquads};
+  const cuuint64_t gstr[1] = {(cuuint64_t)v.slab * 4};
+  const cuuint32_t box[2] = {(cuuint32_t)csl::kQPitch, (cuuint32_t)box_quads};
+  const cuuint32_t estr[2] = {1, 1};
+  float* base = v.p + (long long)(v.col0 >> 2) * v.slab;
+  CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, base, gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
+                   CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return fail(SPW_ERR_LAUNCH, "cuTensorMapEncodeTiled failed (%d): rows %lld, %d quads, slab %lld", (int)r, rows, nquads, v.slab);
+  return SPW_OK;
+}
+
+// dW[Kx][Ny] (+ bias row) = X^T dY over M rows, reduced in fixed order into the Keras-layout gradient.
+//   gather_rcv == null: dY is a column-slab view streamed like X;  else: dY is a node table gathered by gather_rcv[row] and masked
+//   with the byte-slab relu bits (the edge step's d h2).  reduce == false: the launch only updates the per-CTA partials (first:
+//   initialises them) and the caller reduces them later (the five step launches of rmp layer 1).
+int run_wgrad_c(cudaStream_t st, int M, const csl::View& X, int Kx, const float* rowscale, int rsmod, const csl::View& dY, int Ny, float* part,
+                const WgOut& out, const char* tag, const int32_t* gather_rcv = nullptr, const uint8_t* bits = nullptr, long long bits_rows = 0,
+                int first = 1, bool reduce = true, int* streams_out = nullptr) {
   if (M <= 0) return SPW_OK;
   csl::WgradCArgs a;
   memset(&a, 0, sizeof(a));
-  a.M = M; a.X = X.p; a.x_slab = X.slab; a.x_col0 = X.col0; a.Kx = Kx; a.xmod = xmod; a.rowscale = rowscale; a.rsmod = rsmod;
-  a.dY = dY.p; a.y_slab = dY.slab; a.y_col0 = dY.col0; a.Ny = Ny;
+  a.M = M; a.Kx = Kx; a.rowscale = rowscale; a.rsmod = rsmod;
+  a.dY = dY.p; a.y_slab = dY.slab; a.y_col0 = dY.col0; a.Ny = Ny; a.rcv = gather_rcv; a.bits = bits; a.bits_rows = bits_rows;
   const int NB = Ny <= 112 ? 112 : 160;
-  a.nmt = Kx + 1 > 128 ? 2 : 1; a.part = part; a.first = 1; a.poison = part;
+  a.nmt = Kx + 1 > 128 ? 2 : 1; a.part = part; a.first = first; a.poison = part;
   const int ntiles = (M + kTM - 1) / kTM;
   int streams = num_sms() / a.nmt;
   if (streams > kMaxCtas) streams = kMaxCtas;
   if (streams > ntiles) streams = ntiles;
+  if (streams_out) *streams_out = streams;
   const int f1 = Kx + 1 - 128;
   const int nqx0 = ((Kx < 128 ? Kx : 128) + 3) >> 2, nqx1 = a.nmt == 2 ? ((Kx + 3) >> 2) - (f1 >> 2) : 0;
   const int nqx = nqx0 > nqx1 ? nqx0 : nqx1, nqy = (Ny + 3) >> 2;
+  CUtensorMap tmX, tmY;
+  int rc;
+  if ((rc = make_csl_map(&tmX, X, M, (Kx + 3) >> 2, nqx)) != SPW_OK) return rc;
+  if (gather_rcv) tmY = tmX;
+  else if ((rc = make_csl_map(&tmY, dY, M, nqy, nqy)) != SPW_OK) return rc;
   const size_t smem = csl::wgrad_c_smem(nqx, nqy, NB, 3);
-  if (NB == 160) {
-    auto kern = csl::k_wgrad_c<0, 160, 3>;
-    set_smem(kern, smem);
-    SPW_KLAUNCH(tag, kern, dim3(streams * a.nmt), dim3(csl::kThreadsC), smem, st, a);
-  } else {
-    auto kern = csl::k_wgrad_c<0, 112, 3>;
-    set_smem(kern, smem);
-    SPW_KLAUNCH(tag, kern, dim3(streams * a.nmt), dim3(csl::kThreadsC), smem, st, a);
-  }
-  launch_reduce(st, part, streams, (int)tc::kWgPartFloats, 0, -1, f1 > 0 ? f1 : 0, Kx, Ny, out);
+#define SPW_WG_LAUNCH(YM, NBV)                                                                                           \
+  do { auto kern = csl::k_wgrad_c<YM, NBV, 3>; set_smem(kern, smem);                                                      \
+       SPW_KLAUNCH(tag, kern, dim3(streams * a.nmt), dim3(csl::kThreadsC), smem, st, tmX, tmY, a, nqx); } while (0)
+  if (gather_rcv) SPW_WG_LAUNCH(1, 160);
+  else if (NB == 160) SPW_WG_LAUNCH(0, 160);
+  else SPW_WG_LAUNCH(0, 112);
+#undef SPW_WG_LAUNCH
+  if (reduce) launch_reduce(st, part, streams, (int)tc::kWgPartFloats, 0, -1, f1 > 0 ? f1 : 0, Kx, Ny, out);
   return SPW_OK;
 }
 
@@ -308,8 +344,7 @@ int backward_csl(const SpwParams* w, const SpwGraph* g, const float* obj, const 
   SPW_KLAUNCH("k_logit_bwd_c", csl::k_logit_bwd_c, dim3(grid_for((int64_t)n * csl::kQP, 256)), dim3(256), 0, st, dlogits, (const float*)U5.p, U5.slab, n,
               (const float*)w->omp_w[1], ws + L.dU + (size_t)4 * n * 4, r5 * 4);
 
-  int wstreams = num_sms() / 2;                                  // row streams of the edge-step weight gradient (2 M-tiles)
-  if (wstreams > etiles) wstreams = etiles;
+  int wstreams = 0;                                              // row streams of the edge-step weight gradient
   for (int l = SPW_N_STEPS - 1; l >= 0; --l) {   // step l+1 of the forward loop
     const csl::View dU = cview(ws + L.dU, r5, (long long)l * n, 0), dG = cview(ws + L.dG, r5, (long long)l * n, 0);
     const csl::View Ul = cview(ws + L.U, r5, (long long)l * n, 0);
@@ -341,17 +376,10 @@ int backward_csl(const SpwParams* w, const SpwGraph* g, const float* obj, const 
     }
     if (E > 0) {
       const uint8_t* m2 = bits_ptr(ws, L.M2, L, l); const uint8_t* m1 = bits_ptr(ws, L.M1, L, l);
-      {   // dW2 += h1^T . d h2 with h1 rebuilt from the gather and d h2 = relu'(h2) * d(sum h2)[receiver]
-        csl::WgradCArgs a;
-        memset(&a, 0, sizeof(a));
-        a.M = E; a.X = ws + L.H1 + (size_t)l * ((size_t)kQ150 * E * 4 + 64); a.x_slab = (long long)E * 4; a.x_col0 = 0; a.Kx = kDE; a.xmod = 0;
-        a.rcv = g->in_rcv;
-        a.dY = dH.p; a.y_slab = dH.slab; a.y_col0 = 0; a.Ny = kDE; a.bits = m2; a.bits_rows = L.bits_rows;
-        a.nmt = 2; a.part = ws + L.partE; a.first = (l == SPW_N_STEPS - 1); a.poison = ws + L.partE;
-        const size_t smem = csl::wgrad_c_smem(33, 38, 160, 3);
-        auto kern = csl::k_wgrad_c<1, 160, 3>;
-        set_smem(kern, smem);
-        SPW_KLAUNCH("k_wgrad_c:step", kern, dim3(2 * wstreams), dim3(csl::kThreadsC), smem, st, a);
+      {   // dW2 += h1^T . d h2 with h1 kept by the forward pass and d h2 = relu'(h2) * d(sum h2)[receiver]
+        const csl::View H1v = cview(ws + L.H1 + (size_t)l * ((size_t)kQ150 * E * 4 + 64), E, 0, 0);
+        if ((rc = run_wgrad_c(st, E, H1v, kDE, nullptr, 0, dH, kDE, ws + L.partE, WgOut{nullptr, 0, 0, 0, nullptr, 0}, "k_wgrad_c:step", g->in_rcv, m2,
+                              L.bits_rows, l == SPW_N_STEPS - 1, false, &wstreams)) != SPW_OK) return rc;
       }
       {
         csl::EdgeDgradCArgs t;
@@ -394,10 +422,13 @@ int backward_csl(const SpwParams* w, const SpwGraph* g, const float* obj, const 
   // ---- node-level weight gradients, each one contraction over all steps' rows -------------------
   const csl::View dUall = cview(ws + L.dU, r5, 0, 0);
   // omp layer 0 = [V1a; V1b; V1c], bias c1
-  run_wgrad_c(st, 5 * n, cview(ws + L.Q, n, 0, 0), kDP, n, nullptr, 0, dUall, kDP, partN, {grads->omp_w[0], 100, 0, 0, grads->omp_b[0], 0}, "k_wgrad_c:node");
-  run_wgrad_c(st, 5 * n, cview(ws + L.GP, r5, 0, 0), 2 * kDP, 0, nullptr, 0, dUall, kDP, partN, {grads->omp_w[0], 100, 100, 0, nullptr, 0}, "k_wgrad_c:node");
+  //   rows 0..99 (V1a): q is the same in all five steps, so q^T (sum over the steps of dUpre): the sum lands in DP (free by now)
+  SPW_KLAUNCH("k_sum_slots_c", csl::k_sum_slots_c, dim3(grid_for((int64_t)n * csl::kQP, 256)), dim3(256), 0, st, n, 5, csl::kQP, (const float*)(ws + L.dU), r5 * 4,
+              ws + L.DP, (long long)n * 4);
+  if ((rc = run_wgrad_c(st, n, cview(ws + L.Q, n, 0, 0), kDP, nullptr, 0, cview(ws + L.DP, n, 0, 0), kDP, partN, {grads->omp_w[0], 100, 0, 0, grads->omp_b[0], 0}, "k_wgrad_c:node")) != SPW_OK) return rc;
+  if ((rc = run_wgrad_c(st, 5 * n, cview(ws + L.GP, r5, 0, 0), 2 * kDP, nullptr, 0, dUall, kDP, partN, {grads->omp_w[0], 100, 100, 0, nullptr, 0}, "k_wgrad_c:node")) != SPW_OK) return rc;
   // omp layer 1: channels 1..100 from T (steps 1..4), channel 0 from the head
-  run_wgrad_c(st, 4 * n, cview(ws + L.U, r5, 0, 0), kDP, 0, nullptr, 0, cview(ws + L.T, r4, 0, 0), kDP, partN, {grads->omp_w[1], 101, 0, 1, grads->omp_b[1], 1}, "k_wgrad_c:node");
+  if ((rc = run_wgrad_c(st, 4 * n, cview(ws + L.U, r5, 0, 0), kDP, nullptr, 0, cview(ws + L.T, r4, 0, 0), kDP, partN, {grads->omp_w[1], 101, 0, 1, grads->omp_b[1], 1}, "k_wgrad_c:node")) != SPW_OK) return rc;
   {
     const int nw = (n + csl::kSkinnyRows - 1) / csl::kSkinnyRows;
     SPW_KLAUNCH("k_skinny_c", csl::k_skinny_c<2>, dim3((nw + 7) / 8), dim3(256), 0, st, n, (const float*)U5.p, U5.slab, csl::kQP, 104, (const int32_t*)nullptr,
@@ -405,12 +436,12 @@ int backward_csl(const SpwParams* w, const SpwGraph* g, const float* obj, const 
     launch_reduce(st, ws + L.part0, nw, 104, 1, 0, 0, kDP, 1, {grads->omp_w[1], 101, 0, 0, grads->omp_b[1], 0});
   }
   // rmp layer 2 (W3, b3 scaled by in-degree)
-  run_wgrad_c(st, 5 * n, cview(ws + L.H2S, r5, 0, 0), kDE, 0, ws + L.degf, n, cview(ws + L.dG, r5, 0, 0), kDP, partN, {grads->rmp_w[2], 100, 0, 0, grads->rmp_b[2], 0}, "k_wgrad_c:node");
+  if ((rc = run_wgrad_c(st, 5 * n, cview(ws + L.H2S, r5, 0, 0), kDE, ws + L.degf, n, cview(ws + L.dG, r5, 0, 0), kDP, partN, {grads->rmp_w[2], 100, 0, 0, grads->rmp_b[2], 0}, "k_wgrad_c:node")) != SPW_OK) return rc;
   // rmp layer 0 rows 150..349 (W1b, W1c): X = p^{l} for steps 2..5
-  run_wgrad_c(st, 4 * n, cview(ws + L.GP, r5, n, 100), kDP, 0, nullptr, 0, cview(ws + L.dS, r4, 0, 0), kDE, partN, {grads->rmp_w[0], 150, 150, 0, nullptr, 0}, "k_wgrad_c:node");
-  run_wgrad_c(st, 4 * n, cview(ws + L.GP, r5, n, 100), kDP, 0, nullptr, 0, cview(ws + L.dR, r4, 0, 0), kDE, partN, {grads->rmp_w[0], 150, 250, 0, nullptr, 0}, "k_wgrad_c:node");
+  if ((rc = run_wgrad_c(st, 4 * n, cview(ws + L.GP, r5, n, 100), kDP, nullptr, 0, cview(ws + L.dS, r4, 0, 0), kDE, partN, {grads->rmp_w[0], 150, 150, 0, nullptr, 0}, "k_wgrad_c:node")) != SPW_OK) return rc;
+  if ((rc = run_wgrad_c(st, 4 * n, cview(ws + L.GP, r5, n, 100), kDP, nullptr, 0, cview(ws + L.dR, r4, 0, 0), kDE, partN, {grads->rmp_w[0], 150, 250, 0, nullptr, 0}, "k_wgrad_c:node")) != SPW_OK) return rc;
   // object encoder
-  run_wgrad_c(st, n, cview(ws + L.Q1, n, 0, 0), kDP, 0, nullptr, 0, cview(ws + L.dQ, n, 0, 0), kDP, partN, {grads->om_w[1], 100, 0, 0, grads->om_b[1], 0}, "k_wgrad_c:node");
+  if ((rc = run_wgrad_c(st, n, cview(ws + L.Q1, n, 0, 0), kDP, nullptr, 0, cview(ws + L.dQ, n, 0, 0), kDP, partN, {grads->om_w[1], 100, 0, 0, grads->om_b[1], 0}, "k_wgrad_c:node")) != SPW_OK) return rc;
   {
     LinC o; o.tag = "k_lin:node"; o.id = T_OM1T; o.N = 100; o.K = 100; o.epi = csl::EPI_MUL_POS;
     o.X = cview(ws + L.dQ, n, 0, 0); o.Y = cview(ws + L.dQ1, n, 0, 0); o.mulsrc = cview(ws + L.Q1, n, 0, 0);
@@ -432,7 +463,7 @@ int backward_csl(const SpwParams* w, const SpwGraph* g, const float* obj, const 
     float* dY = ws + L.dA;
     float* gout[2] = {ws + L.DH1, ws + L.GB};
     for (int i = 0; i < 4; ++i) {
-      run_wgrad_c(st, E, cview(acts[i], E, 0, 0), kDE, 0, nullptr, 0, cview(dY, E, 0, 0), kDE, ws + L.partE, {gw[i], 150, 0, 0, gb[i], 0}, "k_wgrad_c:enc");
+      if ((rc = run_wgrad_c(st, E, cview(acts[i], E, 0, 0), kDE, nullptr, 0, cview(dY, E, 0, 0), kDE, ws + L.partE, {gw[i], 150, 0, 0, gb[i], 0}, "k_wgrad_c:enc")) != SPW_OK) return rc;
       // data gradient of the layer: (dY . W^T) * relu'(layer input), times 1/keep through the dropout on c_e
       LinC o; o.tag = "k_lin:enc_bwd"; o.id = -1; o.Bhi = ws + L.ENCT + (size_t)(2 * i) * 24320; o.Blo = ws + L.ENCT + (size_t)(2 * i + 1) * 24320;
       o.N = 150; o.K = 150; o.epi = csl::EPI_MUL_BITS | csl::EPI_SCALE; o.X = cview(dY, E, 0, 0); o.Y = cview(gout[i & 1], E, 0, 0);

@@ -12,14 +12,17 @@
 //     frees the buffers of chunk q;
 //   * D is double-buffered per 128-row tile: the tensor core truncates when it accumulates, so a tile's sum is added to the
 //     running sum in registers with round-to-nearest adds, one tile late, while the next tile accumulates in the other buffer;
-//   * raw chunk rows arrive in a ring of stages: streamed column-slab arrays ([quad][row][4]: 512 contiguous bytes per quad
-//     and chunk) by TMA bulk copies issued by one warp (cp.async.bulk, completion counted in bytes on the stage's mbarrier);
-//     rows gathered by node index (the edge step's d h2 = relu'(h2) * dH2S[receiver]) by cp.async, 16 bytes per row and quad.
-//     A warp-wide cp.async costs the LSU ~20 cycles whatever it copies (measured: 1.4k cycles per chunk for the 71 quads of a
-//     plain layer, 3.8k when h1 = relu(A + S[snd] + R[rcv]) was re-gathered), so the forward edge step now stores h1 and the
-//     only gather left is dH2S.
+//   * raw chunk rows arrive in a ring of stages.  Streamed column-slab arrays ([quad][row][4]) are described to the TMA as 2-D
+//     tensors [quad][rows * 4 floats]: ONE cp.async.bulk.tensor per array and chunk lands a [quads][33 rows x 4] box (pitch 132
+//     floats: bank-conflict-free for both operand builds; rows past the end of the array are zero-filled by the TMA),
+//     completion counted in bytes on the stage's mbarrier.  Measured alternatives: a warp-wide cp.async costs the LSU ~20
+//     cycles whatever it copies (1.4k cycles per chunk for the 71 quads of a plain layer, 3.8k when h1 = relu(A + S[snd] +
+//     R[rcv]) was re-gathered); one plain bulk copy per 512-byte quad piece costs ~55 cycles of a serialised issue path (3.9k).
+//     So the forward edge step now stores h1, and the only gather left -- d h2 = relu'(h2) * dH2S[receiver], 16 bytes per row
+//     and quad -- uses cp.async.
 #pragma once
 #ifndef SPW_EMU
+#include <cuda.h>
 #include "spw_csl.cuh"
 
 namespace spw {
@@ -32,10 +35,10 @@ constexpr uint32_t kWgColD = 0, kWgColA = 320;    // TMEM: D0 [0,160) D1 [160,32
 
 struct WgradCArgs {
   int M;
-  const float* X; long long x_slab; int x_col0; int Kx; int xmod;      // X view; row = r % xmod if xmod (a per-node array reused by every step)
+  int Kx;                                                              // X features (the X array itself: tensor map tmX)
   const float* rowscale; int rsmod;                                    // value of the virtual feature Kx (null: 1)
   const int32_t* rcv;                                                  // YMODE 1: receiver of each row
-  const float* dY; long long y_slab; int y_col0; int Ny;               // dY view; YMODE 1: node table gathered by rcv, masked by bits
+  const float* dY; long long y_slab; int y_col0; int Ny;               // YMODE 0: tensor map tmY; YMODE 1: node table gathered by rcv, masked by bits
   const uint8_t* bits; long long bits_rows;                            // YMODE 1: byte-slab relu bits [19][rows]
   int nmt;                                                             // M-tiles: 1 (Kx + 1 <= 128) or 2
   float* part;                                                         // [gridDim.x / nmt][2][160][128]
@@ -43,8 +46,16 @@ struct WgradCArgs {
   float* poison;
 };
 
-// stage layout (floats): X quads [nqx][132] | Y quads [nqy][132] | RS [32] | bits [20][32] bytes
-__host__ __device__ constexpr int wg_stage_floats(int nqx, int nqy) { return (nqx + nqy) * kQPitch + 32 + 160; }
+// stage layout (floats): X quads [nqx][132] | Y quads [nqy][132] | RS [32] | bits [20][32] bytes; each region 128-byte aligned
+__host__ __device__ constexpr int wg_up32(int f) { return (f + 31) & ~31; }
+__host__ __device__ constexpr int wg_stage_floats(int nqx, int nqy) { return wg_up32(nqx * kQPitch) + wg_up32(nqy * kQPitch) + 32 + 160; }
+
+// tile-mode TMA load of a 2-D box: coordinates {c0 (innermost: floats along the rows), c1 (quad)}
+__device__ __forceinline__ void tma_load_2d(void* sdst, const CUtensorMap* tm, int c0, int c1, uint64_t* bar) {
+  asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];" ::"r"(smem_u32(sdst)),
+               "l"(reinterpret_cast<uint64_t>(tm)), "r"(c0), "r"(c1), "r"(smem_u32(bar))
+               : "memory");
+}
 constexpr size_t wgrad_c_smem(int nqx, int nqy, int NB, int nst) {
   return (size_t)(nst * wg_stage_floats(nqx, nqy) + 2 * 2 * (kWgCh / 8) * (2 * NB * 4) + 8) * sizeof(float) + 128 + 8 * nst;
 }
@@ -52,8 +63,10 @@ constexpr size_t wgrad_c_smem(int nqx, int nqy, int NB, int nst) {
 // The per-chunk work of a thread is a fixed pattern; everything that does not depend on the chunk (shared-memory offsets of
 // the words it reads and writes, which lanes are real / ones / padding features) is computed once, and padding is expressed as
 // "read a zero word with stride 0" instead of predicates: the kernel was instruction-issue bound (ncu: 61 % issue-active).
+// tmX / tmY: 2-D tensor maps [quads][rows * 4] of the X and dY arrays (base = first row and first quad of the view), boxes of
+// [nqx_box][132] and [nqy][132] floats (launch code: run_wgrad_c).
 template <int YMODE, int NB, int NST>
-__global__ void __launch_bounds__(kThreadsC, 1) k_wgrad_c(WgradCArgs a) {
+__global__ void __launch_bounds__(kThreadsC, 1) k_wgrad_c(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmY, WgradCArgs a, int nqx) {
   SPW_DYN_SMEM(smem_raw);
   constexpr int kUnits = ((kWgCh / 4) * NB + kWorkers - 1) / kWorkers;      // B-operand units (4 rows x 1 column) per thread
   constexpr int bfl = (kWgCh / 8) * (2 * NB * 4);                         // floats per hi or lo B operand of a chunk
@@ -62,8 +75,7 @@ __global__ void __launch_bounds__(kThreadsC, 1) k_wgrad_c(WgradCArgs a) {
   const int f0 = mt == 0 ? 0 : a.Kx + 1 - 128;                   // first feature of this CTA's M-tile
   const int qlo = f0 >> 2;                                       // staged X quads: [qlo, qlo + nqx)
   const int fhi = mt == 0 ? (a.Kx < 128 ? a.Kx : 128) : a.Kx;    // features [f0, fhi) are read from X
-  const int nqx = ((fhi + 3) >> 2) - qlo;
-  const int nqy = (a.Ny + 3) >> 2;
+  const int nqy = (a.Ny + 3) >> 2;                               // nqx (kernel argument): quads of the X box, the same for both M-tiles
   const int stf = wg_stage_floats(nqx, nqy);
   float* stages = reinterpret_cast<float*>(smem_raw);
   float* Bop = stages + NST * stf;                               // [2 buffers][hi | lo][bfl]
@@ -80,7 +92,7 @@ __global__ void __launch_bounds__(kThreadsC, 1) k_wgrad_c(WgradCArgs a) {
   }
   if (tid < 8) zero[tid] = 0.f;
   if (!a.rowscale)                                               // the virtual feature Kx is a column of ones
-    for (int i = tid; i < NST * 32; i += kThreadsC) stages[(i >> 5) * stf + (nqx + nqy) * kQPitch + (i & 31)] = 1.f;
+    for (int i = tid; i < NST * 32; i += kThreadsC) stages[(i >> 5) * stf + wg_up32(nqx * kQPitch) + wg_up32(nqy * kQPitch) + (i & 31)] = 1.f;
   fence_before_sync();
   __syncthreads();
   fence_after_sync();
@@ -123,8 +135,8 @@ __global__ void __launch_bounds__(kThreadsC, 1) k_wgrad_c(WgradCArgs a) {
     const int L = 32 * (warp & 3) + lane, sub = warp >> 2;      // TMEM lane = feature f0 + L; rows 8 sub .. 8 sub + 7 of a chunk
     const uint32_t lane_addr = tmem_base + ((uint32_t)(32 * (warp & 3)) << 16);
     constexpr int ngroups = NB / 8;
-    const int y_off = nqx * kQPitch;
-    const int rs_off = (nqx + nqy) * kQPitch;                    // RS (virtual feature values) inside a stage
+    const int y_off = wg_up32(nqx * kQPitch);
+    const int rs_off = y_off + wg_up32(nqy * kQPitch);           // RS (virtual feature values) inside a stage
     // A operand: word offset (within a stage) and row stride of this lane's feature; padding lanes read the zero word
     const int feat = f0 + L;
     int xa_off, xa_str;
@@ -171,34 +183,11 @@ __global__ void __launch_bounds__(kThreadsC, 1) k_wgrad_c(WgradCArgs a) {
           float* st = stages + (qi % NST) * stf;
           const long long r0 = row0_of(qi);
           const int nvalid = a.M - r0 >= kWgCh ? kWgCh : (a.M > r0 ? (int)(a.M - r0) : 0);
-          uint64_t* bs = barS + (qi % NST);
-          if (nvalid < kWgCh) {                                  // last chunk of the array: rows that do not exist read as zero
-            for (int i = tid; i < (nqx + nqy) * (kWgCh - nvalid); i += kWorkers) {
-              const int qd = i / (kWgCh - nvalid), rj = nvalid + i % (kWgCh - nvalid);
-              *reinterpret_cast<float4*>(st + qd * kQPitch + rj * 4) = make_float4(0.f, 0.f, 0.f, 0.f);
-            }
-          }
-          if (tid == 0) mbar_arrive_expect_tx(bs, (uint32_t)((nqx + (YMODE == 0 ? nqy : 0)) * nvalid * 16));
-          // streamed arrays: one bulk copy per quad and chunk (more where r % xmod wraps), issued by lane 0 of every warp: a bulk
-          // copy costs its issuing thread ~55 cycles, and a warp-wide issue is serialised over its lanes
-          if (lane == 0 && nvalid > 0) {
-            const float* xsrc = a.X + (long long)((a.x_col0 >> 2) + qlo) * a.x_slab;
-            for (int qd = warp; qd < nqx; qd += kWorkers / 32) {
-              if (!a.xmod) {
-                bulk_g2s(st + qd * kQPitch, xsrc + (long long)qd * a.x_slab + r0 * 4, (uint32_t)nvalid * 16, bs);
-              } else {
-                for (int done = 0; done < nvalid;) {
-                  const long long x0 = (r0 + done) % a.xmod;
-                  const int len = (int)(a.xmod - x0 < nvalid - done ? a.xmod - x0 : nvalid - done);
-                  bulk_g2s(st + qd * kQPitch + done * 4, xsrc + (long long)qd * a.x_slab + x0 * 4, (uint32_t)len * 16, bs);
-                  done += len;
-                }
-              }
-            }
-            if (YMODE == 0) {
-              const float* ysrc = a.dY + (long long)(a.y_col0 >> 2) * a.y_slab + r0 * 4;
-              for (int qd = warp; qd < nqy; qd += kWorkers / 32) bulk_g2s(st + y_off + qd * kQPitch, ysrc + (long long)qd * a.y_slab, (uint32_t)nvalid * 16, bs);
-            }
+          if (tid == 0) {                                        // streamed arrays: one tensor copy each (rows past the end read as zero)
+            uint64_t* bs = barS + (qi % NST);
+            mbar_arrive_expect_tx(bs, (uint32_t)((nqx + (YMODE == 0 ? nqy : 0)) * kQPitch * 4));
+            tma_load_2d(st, &tmX, (int)(r0 * 4), qlo, bs);
+            if (YMODE == 0) tma_load_2d(st + y_off, &tmY, (int)(r0 * 4), 0, bs);
           }
           if (YMODE == 1) {                                      // gathered rows: thread -> (quad, row = lane), 16 bytes each
             const bool valid = lane < nvalid;
