@@ -144,6 +144,21 @@ int spw_sample_jenga(uint64_t seed, int32_t n_towers, const int32_t* node_off, d
 int spw_sample_tower(uint64_t seed, int32_t n_towers, const int32_t* node_off, double* raw, float* obj, double* pos,
                      int inference_glue, void* stream);
 
+/* ---- demolish searches -------------------------------------------------------------------
+ * The reference scores N candidate removals (JengaBuilder.remove_to_demolish, JengaBuilder.py:236-269) or 100 candidate drop
+ * poses (TowerCreator.drop_to_demolish, TowerCreator.py:276-319) with one batch-1 predict call each and takes
+ * argmin sum_i p_i.  Here the candidates are built on the device and scored as ONE packed inference batch:
+ *   spw_candidates_remove: raw [N][3] (pixels) -> N towers of N - 1 blocks (tower c lacks block c, order kept):
+ *                          obj [N (N-1)][3] = raw / 170, pos [N (N-1)][2] = positions for the relation test;
+ *   spw_candidates_drop:   raw [N][3], poses [K][2] -> K towers of N + 1 blocks, the dropped block (poses[c], `width`) is
+ *                          object 0 of tower c (TowerCreator.py:451);
+ *   spw_tower_sums:        sums[t] = sum of probs over the blocks of tower t (double, block order: the callers' Python loop),
+ *                          argmin (nullable, device int32) = index of the first minimum (np.argmin). */
+int spw_candidates_remove(const double* raw, int32_t n_blocks, float* obj, double* pos, int inference_glue, void* stream);
+int spw_candidates_drop(const double* raw, int32_t n_blocks, const double* poses, int32_t n_poses, double width, float* obj, double* pos,
+                        int inference_glue, void* stream);
+int spw_tower_sums(const float* probs, const int32_t* node_off, int32_t n_towers, double* sums, int32_t* argmin, void* stream);
+
 /* Bytes of workspace spw_forward/spw_backward need.  training != 0 also reserves the node-level
  * state the backward pass reads (5 propagation steps x per-node activations) and per-edge
  * gradient staging.  The same workspace must be passed, untouched, to spw_backward.            */

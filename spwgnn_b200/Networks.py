@@ -7,8 +7,10 @@ kernels in libspwgnn.so.  Differences by design:
     Networks.py:17-18,40-56); `getModel` still caches one facade per N like `self.Nets`;
   * besides the dense one-hot dict, `predict_towers` / `fit_towers` take ragged raw poses and build
     the relations on the GPU (no O(N^3) tensors);
-  * logits are exposed (`predict_logits`), and `predict_tower_sums` returns the per-tower sum of
-    block probabilities the demolish searches use (JengaBuilder.py:254-256, TowerCreator.py:299-300).
+  * logits are exposed (`predict_logits`); `predict_tower_sums` returns the per-tower sum of block
+    probabilities the demolish searches use (JengaBuilder.py:254-256, TowerCreator.py:299-300), and
+    `score_removals` / `score_drops` run a whole demolish search (candidate towers, scores, argmin)
+    as one packed inference instead of N or 100 batch-1 predicts.
 """
 import os
 import sys
@@ -20,13 +22,15 @@ try:
     from .engine import Engine
     from .graph import TowerBatch, REL_THRESHOLD
     from ._lib import SpwError
+    from .Blocks import RelationalModel, ObjectModel
 except ImportError:      # imported as top-level `Networks` (reference style: `from Networks import *`)
     sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
     from spwgnn_b200.engine import Engine
     from spwgnn_b200.graph import TowerBatch, REL_THRESHOLD
     from spwgnn_b200._lib import SpwError
+    from spwgnn_b200.Blocks import RelationalModel, ObjectModel
 
-__all__ = ['PropagationNetwork', 'PropagationModel', 'History']
+__all__ = ['PropagationNetwork', 'PropagationModel', 'History', 'RelationalModel', 'ObjectModel']
 
 
 class History:
@@ -41,13 +45,22 @@ class History:
 
 
 class PropagationNetwork:
-    """Networks.py:12-104.  Holds the shared weights (one Engine) and a per-N facade cache."""
+    """Networks.py:12-104.  Holds the shared weights (one Engine, created when a model first computes) and a per-N facade
+    cache like the reference's `self.Nets`; `relnet / objnet / relnetp / objnetp` are the four shared MLPs (Networks.py:40-56)
+    as Blocks descriptors."""
 
     def __init__(self, device='cuda', seed=0):
         self.Nets = {}
         self.set_weights = False
         self._device, self._seed = device, seed
-        self.engine = None
+        self._engine = None
+        self.relnet = self.objnet = self.relnetp = self.objnetp = None
+
+    @property
+    def engine(self):
+        if self._engine is None:                        # deferred: getModel() itself needs no GPU (main.py:36-37 runs before any data exists)
+            self._engine = Engine(self._device, self._seed)
+        return self._engine
 
     def getModel(self, n_objects, object_dim=3, relation_dim=1):
         if n_objects in self.Nets:                      # Networks.py:17-18
@@ -55,10 +68,14 @@ class PropagationNetwork:
         if object_dim != 3:
             raise SpwError('object_dim=%d: only object_dim=3 is well defined in the reference (with 2 the object '
                            'encoder is declared 2-wide but fed 1 feature, Networks.py:42,47,70-73)' % object_dim)
-        if self.engine is None:
-            self.engine = Engine(self._device, self._seed)
+        n_relations = n_objects * (n_objects - 1)       # Networks.py:20
+        if not self.set_weights:                        # Networks.py:46-56: the four MLPs are created once and shared by every model size
+            self.relnet = RelationalModel((n_relations,), 2, [150, 150, 150, 150], prefix='rm', network=self).getRelnet()
+            self.objnet = ObjectModel((n_objects,), 2, [100, 100], prefix='om', network=self).getObjnet()
+            self.relnetp = RelationalModel((n_relations,), 350, [150, 150, 100], prefix='rmp', network=self).getRelnet()
+            self.objnetp = ObjectModel((n_objects,), 300, [100, 101], prefix='omp', network=self).getObjnet()
             self.set_weights = True
-        model = PropagationModel(self.engine, n_objects)
+        model = PropagationModel(self, n_objects)
         self.Nets[n_objects] = model
         return model
 
@@ -66,12 +83,16 @@ class PropagationNetwork:
 class PropagationModel:
     """The compiled-model facade: Adam(lr=5e-4) + binary_crossentropy + binary_accuracy (Networks.py:101-102)."""
 
-    def __init__(self, engine, n_objects):
-        self.engine = engine
+    def __init__(self, network, n_objects):
+        self.network = network
         self.n_objects = n_objects
         self.lr = 5e-4               # optimizers.Adam(lr=0.0005), Networks.py:101
         self.dropout_rate = 0.1      # Dropout(0.1) on both encodings, train only, Networks.py:77-78
         self._drop_seed = 0x5EED0001
+
+    @property
+    def engine(self):
+        return self.network.engine
 
     # ---- inference -----------------------------------------------------------------------------
     def _batch_from_dict(self, x, sel=None):
@@ -107,13 +128,61 @@ class PropagationModel:
         off = batch.node_off_host
         return [p[off[t]:off[t + 1]] for t in range(batch.n_towers)]
 
+    def _tower_sums(self, batch, probs, want_argmin=True):
+        """Per-tower sum of block probabilities (double, block order) and the index of the first minimum, on the GPU."""
+        api, dev = self.engine.api, self.engine.device
+        sums = torch.empty(max(batch.n_towers, 1), dtype=torch.float64, device=dev)
+        amin = torch.zeros(1, dtype=torch.int32, device=dev)
+        with torch.cuda.device(dev):
+            api.check(api.dll.spw_tower_sums(probs.data_ptr(), batch.node_off.data_ptr(), batch.n_towers, sums.data_ptr(),
+                                             amin.data_ptr() if want_argmin else None, torch.cuda.current_stream(dev).cuda_stream))
+        return sums[:batch.n_towers], amin
+
     def predict_tower_sums(self, towers, **kw):
-        """Per-tower sum of block probabilities (the demolish searches' score), computed on the GPU."""
+        """Per-tower sum of block probabilities (the demolish searches' score, JengaBuilder.py:254-256), computed on the GPU."""
         batch = TowerBatch.from_towers(towers, device=self.engine.device, **kw)
         _, probs = self.engine.forward(batch, training=False)
-        seg = torch.repeat_interleave(torch.arange(batch.n_towers, device=probs.device),
-                                      torch.as_tensor(np.diff(batch.node_off_host), device=probs.device))
-        return torch.zeros(batch.n_towers, device=probs.device).index_add_(0, seg, probs).cpu().numpy()
+        return self._tower_sums(batch, probs, want_argmin=False)[0].cpu().numpy()
+
+    def _score_candidates(self, obj, pos, n_cand, n_each, inference_glue, thr):
+        node_off = np.arange(n_cand + 1, dtype=np.int64) * n_each
+        batch = TowerBatch.from_poses(obj, node_off, pos, thr=thr, fully_connected=False, device=self.engine.device, max_nodes=n_each)
+        _, probs = self.engine.forward(batch, training=False)
+        sums, amin = self._tower_sums(batch, probs)
+        return sums.cpu().numpy(), int(amin.item())
+
+    def score_removals(self, tower, inference_glue=True, thr=REL_THRESHOLD):
+        """JengaBuilder.remove_to_demolish (JengaBuilder.py:236-269) as ONE packed inference: candidate c is `tower`
+        ((N, 3) raw [x, y, width]) without block c.  The candidates are built on the device, scored together, summed per
+        candidate and arg-minimised by kernels.  Returns (box_stabilities (N,) float64, remove_index) -- the reference's
+        `box_stabilities` and `np.argmin(box_stabilities)`.  inference_glue=True builds the relations as the reference's
+        predict glue does (positions / 170 against the threshold 170: fully connected, JengaBuilder.py:309-323)."""
+        api, dev = self.engine.api, self.engine.device
+        raw = torch.as_tensor(np.ascontiguousarray(np.asarray(tower, dtype=np.float64).reshape(-1, 3))).to(dev)
+        N = raw.shape[0]
+        if N < 2:
+            raise SpwError('score_removals needs at least two blocks')
+        obj = torch.empty(N * (N - 1), 3, dtype=torch.float32, device=dev)
+        pos = torch.empty(N * (N - 1), 2, dtype=torch.float64, device=dev)
+        with torch.cuda.device(dev):
+            api.check(api.dll.spw_candidates_remove(raw.data_ptr(), N, obj.data_ptr(), pos.data_ptr(), int(bool(inference_glue)),
+                                                    torch.cuda.current_stream(dev).cuda_stream))
+        return self._score_candidates(obj, pos, N, N - 1, inference_glue, thr)
+
+    def score_drops(self, tower, poses, width=150.0, inference_glue=True, thr=REL_THRESHOLD):
+        """TowerCreator.drop_to_demolish (TowerCreator.py:276-319) as ONE packed inference: candidate c is `tower`
+        ((N, 3) raw) plus a dropped block at poses[c] = [x, y], which becomes object 0 (TowerCreator.py:451).
+        Returns (stability sums (K,) float64, index_min)."""
+        api, dev = self.engine.api, self.engine.device
+        raw = torch.as_tensor(np.ascontiguousarray(np.asarray(tower, dtype=np.float64).reshape(-1, 3))).to(dev)
+        ps = torch.as_tensor(np.ascontiguousarray(np.asarray(poses, dtype=np.float64).reshape(-1, 2))).to(dev)
+        N, K = raw.shape[0], ps.shape[0]
+        obj = torch.empty(max(K * (N + 1), 1), 3, dtype=torch.float32, device=dev)
+        pos = torch.empty(max(K * (N + 1), 1), 2, dtype=torch.float64, device=dev)
+        with torch.cuda.device(dev):
+            api.check(api.dll.spw_candidates_drop(raw.data_ptr(), N, ps.data_ptr(), K, float(width), obj.data_ptr(), pos.data_ptr(),
+                                                  int(bool(inference_glue)), torch.cuda.current_stream(dev).cuda_stream))
+        return self._score_candidates(obj[:K * (N + 1)], pos[:K * (N + 1)], K, N + 1, inference_glue, thr)
 
     # ---- training ------------------------------------------------------------------------------
     def train_on_batch(self, batch, target):

@@ -202,30 +202,12 @@ __global__ void __launch_bounds__(kThreadsC, 1) k_lin(LinCArgs a) {
     if (warp == kWorkers / 32) {
     if (lane == 0) bulk_load_weights(Bhi_s, Blo_s, a.Bhi, a.Blo, (uint32_t)bfl * 4, barW);
     bool ok = mbar_wait(barW, 0);
-#ifdef SPW_PHASE_TIMING
-    long long t_wait = 0, t_issue = 0, t_c = 0, t_m = 0, t_last = clock64();
-#endif
     for (int i = 0; i < cnt; ++i) {
       nbar_sync(kBarOps, kBarOpsCount);
       fence_after_sync();
-#ifdef SPW_PHASE_TIMING
-      { const long long t = clock64(); t_wait += t - t_last; t_last = t; }
-#endif
       if (lane == 0) issue_tile(tmem_base + colD, tmem_base + colHi, tmem_base + colLo, smem_u32(Bhi_s), smem_u32(Blo_s), NKS, NB, barC, barM);
       __syncwarp();
-#ifdef SPW_PHASE_TIMING
-      { const long long t = clock64(); t_issue += t - t_last; t_last = t; }
-      if (lane == 0) {
-        mbar_wait(barC, (uint32_t)i & 1u); const long long tc_ = clock64();
-        mbar_wait(barM, (uint32_t)i & 1u); const long long tm_ = clock64();
-        t_c += tc_ - t_last; t_m += tm_ - t_last; t_last = tm_;
-      }
-      __syncwarp();
-#endif
     }
-#ifdef SPW_PHASE_TIMING
-    if (blockIdx.x == 0 && lane == 0 && a.M > 100000) printf("k_lin issuer: waited for operands %lld, issuing %lld, issue end -> barC %lld, issue end -> barM %lld cycles over %d tiles\n", t_wait, t_issue, t_c, t_m, cnt);
-#endif
     if (!ok && lane == 0) a.poison[0] = __int_as_float(0x7fc00000);
     }
   } else {

@@ -251,7 +251,7 @@ __global__ void __launch_bounds__(128) k_sample_tower(uint64_t seed, int n_tower
     if (obj) { obj[3 * o] = (float)(x / 170.0); obj[3 * o + 1] = (float)(y / 170.0); obj[3 * o + 2] = (float)(rect_w / 170.0); }
     if (pos) { pos[2 * o] = inference_glue ? x / 170.0 : x; pos[2 * o + 1] = inference_glue ? y / 170.0 : y; }
   };
-  const int orientation = ctr_u32(seed, (uint64_t)t, ctr++) > 0x80000000u ? 1 : 0;     // rng.random() > 0.5
+  int orientation = ctr_u32(seed, (uint64_t)t, ctr++) > 0x80000000u ? 1 : 0;           // rng.random() > 0.5; flipped by a failed stability check
   // layer sizes
   unsigned char layers[kMaxNodes];
   int nl = 0;
@@ -285,19 +285,101 @@ __global__ void __launch_bounds__(128) k_sample_tower(uint64_t seed, int n_tower
     return ctr_randint(seed, (uint64_t)t, ctr, lo, hi) + (size % 2 == 0 ? mean_range / 2 : 0);
   };
   auto middle = [&](int ln) { return ln == 0 ? 750.0 : (double)(int)((double)((prev_min - rect_w / 2) + (prev_max + rect_w / 2)) / 2.0); };
+  // TowerCreator.is_box_stable (TowerCreator.py:250-263): with the candidate in place, the sum of int(x / count) over all
+  // boxes must lie between the edges of the ground layer; otherwise ONE re-draw with the build direction flipped (:201-207)
+  short xs[kMaxNodes + 1];
+  int placed = 0, g_max = 0, g_min = 0;
+  auto place_x = [&](int ln, int size, int idx, double mid, bool to_drop) {
+    int x = make_x(ln, size, idx, mid, to_drop);
+    if (ln > 0) {
+      const int cnt = placed + 1;
+      int com = x / cnt;
+      for (int i = 0; i < placed; ++i) com += xs[i] / cnt;
+      if (com < g_min - rect_w / 2 || com > g_max + rect_w / 2) {
+        orientation = 1 - orientation;
+        x = make_x(ln, size, idx, mid, to_drop);
+      }
+    }
+    return x;
+  };
   for (int ln = 0; ln < nl; ++ln) {
     const double mid = middle(ln);
     int cur_max = 0, cur_min = 0;
     for (int i = 0; i < layers[ln]; ++i) {
-      const int x = make_x(ln, layers[ln], i, mid, false);
+      const int x = place_x(ln, layers[ln], i, mid, false);
       cur_max = i == 0 ? x : (x > cur_max ? x : cur_max);
       cur_min = i == 0 ? x : (x < cur_min ? x : cur_min);
+      xs[placed++] = (short)x;
       emit(k++, (double)x, (double)bottom + rect_h / 2.0 + (double)(rect_h * ln));
     }
     prev_max = cur_max; prev_min = cur_min;
+    if (ln == 0) { g_max = cur_max; g_min = cur_min; }
   }
-  const int xd = make_x(nl, 1, 0, middle(nl), true);
+  const int xd = place_x(nl, 1, 0, middle(nl), true);
   emit(0, (double)xd, (double)bottom + rect_h / 2.0 + (double)(rect_h * nl));
+}
+
+// =================================================================================================
+// Demolish searches: candidate towers built on the device, one packed inference batch, per-tower
+// sum of block probabilities and its argmin -- instead of N (JengaBuilder.remove_to_demolish, JengaBuilder.py:236-269) or 100
+// (TowerCreator.drop_to_demolish, TowerCreator.py:276-319) sequential batch-1 predict calls.
+// =================================================================================================
+// candidate c (0 <= c < N) = the base tower without block c, block order kept (JengaBuilder.py:245-249): N towers of N - 1 blocks
+__global__ void __launch_bounds__(256) k_candidates_remove(const double* __restrict__ raw, int N, float* __restrict__ obj,
+                                                           double* __restrict__ pos, int inference_glue) {
+  const int total = N * (N - 1);
+  for (int idx = blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += gridDim.x * blockDim.x) {
+    const int c = idx / (N - 1), k = idx - c * (N - 1);
+    const int src = k < c ? k : k + 1;
+    const double x = raw[3 * src], y = raw[3 * src + 1], w = raw[3 * src + 2];
+    obj[3 * (size_t)idx] = (float)(x / 170.0); obj[3 * (size_t)idx + 1] = (float)(y / 170.0); obj[3 * (size_t)idx + 2] = (float)(w / 170.0);   // main.py:91
+    pos[2 * (size_t)idx] = inference_glue ? x / 170.0 : x; pos[2 * (size_t)idx + 1] = inference_glue ? y / 170.0 : y;
+  }
+}
+// candidate c (0 <= c < K) = the base tower plus a dropped block at poses[c], which is object 0 (TowerCreator.py:288-296,451):
+// K towers of N + 1 blocks; the dropped block carries `width` like every block of the construction environment
+__global__ void __launch_bounds__(256) k_candidates_drop(const double* __restrict__ raw, int N, const double* __restrict__ poses, int K,
+                                                         double width, float* __restrict__ obj, double* __restrict__ pos, int inference_glue) {
+  const long long total = (long long)K * (N + 1);
+  for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (long long)gridDim.x * blockDim.x) {
+    const int c = (int)(idx / (N + 1)), k = (int)(idx - (long long)c * (N + 1));
+    double x, y, w;
+    if (k == 0) { x = poses[2 * c]; y = poses[2 * c + 1]; w = width; }
+    else { x = raw[3 * (k - 1)]; y = raw[3 * (k - 1) + 1]; w = raw[3 * (k - 1) + 2]; }
+    obj[3 * idx] = (float)(x / 170.0); obj[3 * idx + 1] = (float)(y / 170.0); obj[3 * idx + 2] = (float)(w / 170.0);
+    pos[2 * idx] = inference_glue ? x / 170.0 : x; pos[2 * idx + 1] = inference_glue ? y / 170.0 : y;
+  }
+}
+// sums[t] = sum over the blocks of tower t of probs, accumulated in double in block order -- the callers' Python loop
+// `stability_sum += s[0]` (JengaBuilder.py:254-256, TowerCreator.py:299-300); one thread per tower
+__global__ void __launch_bounds__(256) k_tower_sums(const float* __restrict__ probs, const int32_t* __restrict__ node_off, int T,
+                                                    double* __restrict__ sums) {
+  for (int t = blockIdx.x * blockDim.x + threadIdx.x; t < T; t += gridDim.x * blockDim.x) {
+    double s = 0.0;
+    for (int i = node_off[t]; i < node_off[t + 1]; ++i) s += (double)probs[i];
+    sums[t] = s;
+  }
+}
+// np.argmin: index of the FIRST minimum (one CTA; T is a candidate count, tens to thousands)
+__global__ void __launch_bounds__(256) k_argmin(const double* __restrict__ v, int T, int32_t* __restrict__ out) {
+  __shared__ double sv[256];
+  __shared__ int si[256];
+  double best = 0.0; int bi = -1;
+  for (int t = threadIdx.x; t < T; t += blockDim.x)
+    if (bi < 0 || v[t] < best) { best = v[t]; bi = t; }     // ascending t per thread: keeps the first minimum
+  sv[threadIdx.x] = best; si[threadIdx.x] = bi;
+  __syncthreads();
+  for (int off = 128; off >= 1; off >>= 1) {
+    if ((int)threadIdx.x < off) {
+      const int j = si[threadIdx.x + off];
+      if (j >= 0 && (si[threadIdx.x] < 0 || sv[threadIdx.x + off] < sv[threadIdx.x] ||
+                     (sv[threadIdx.x + off] == sv[threadIdx.x] && j < si[threadIdx.x]))) {
+        sv[threadIdx.x] = sv[threadIdx.x + off]; si[threadIdx.x] = j;
+      }
+    }
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) out[0] = si[0];
 }
 
 }  // namespace spw

@@ -824,6 +824,34 @@ int spw_sample_tower(uint64_t seed, int32_t n_towers, const int32_t* node_off, d
   return check_launch("spw_sample_tower");
 }
 
+int spw_candidates_remove(const double* raw, int32_t n_blocks, float* obj, double* pos, int inference_glue, void* stream) {
+  if (n_blocks < 2 || n_blocks > SPW_MAX_NODES + 1) return fail(SPW_ERR_BAD_ARG, "spw_candidates_remove: %d blocks (need 2..%d)", n_blocks, SPW_MAX_NODES + 1);
+  if (!raw || !obj || !pos) return fail(SPW_ERR_BAD_ARG, "spw_candidates_remove: null pointer");
+  SPW_KLAUNCH("k_candidates_remove", k_candidates_remove, dim3(grid_for((int64_t)n_blocks * (n_blocks - 1), 256)), dim3(256), 0, (cudaStream_t)stream, raw,
+              (int)n_blocks, obj, pos, inference_glue);
+  return check_launch("spw_candidates_remove");
+}
+
+int spw_candidates_drop(const double* raw, int32_t n_blocks, const double* poses, int32_t n_poses, double width, float* obj, double* pos,
+                        int inference_glue, void* stream) {
+  if (n_blocks < 1 || n_blocks + 1 > SPW_MAX_NODES || n_poses < 0) return fail(SPW_ERR_BAD_ARG, "spw_candidates_drop: bad size");
+  if (n_poses == 0) return SPW_OK;
+  if (!raw || !poses || !obj || !pos) return fail(SPW_ERR_BAD_ARG, "spw_candidates_drop: null pointer");
+  SPW_KLAUNCH("k_candidates_drop", k_candidates_drop, dim3(grid_for((int64_t)n_poses * (n_blocks + 1), 256)), dim3(256), 0, (cudaStream_t)stream, raw,
+              (int)n_blocks, poses, (int)n_poses, width, obj, pos, inference_glue);
+  return check_launch("spw_candidates_drop");
+}
+
+int spw_tower_sums(const float* probs, const int32_t* node_off, int32_t n_towers, double* sums, int32_t* argmin, void* stream) {
+  if (n_towers < 0) return fail(SPW_ERR_BAD_ARG, "spw_tower_sums: negative size");
+  if (n_towers == 0) return SPW_OK;
+  if (!probs || !node_off || !sums) return fail(SPW_ERR_BAD_ARG, "spw_tower_sums: null pointer");
+  cudaStream_t st = (cudaStream_t)stream;
+  SPW_KLAUNCH("k_tower_sums", k_tower_sums, dim3(grid_for(n_towers, 256)), dim3(256), 0, st, probs, node_off, (int)n_towers, sums);
+  if (argmin) SPW_KLAUNCH("k_argmin", k_argmin, dim3(1), dim3(256), 0, st, (const double*)sums, (int)n_towers, argmin);
+  return check_launch("spw_tower_sums");
+}
+
 size_t spw_workspace_bytes(int32_t n_nodes, int32_t n_edges, int training) {
   if (n_nodes < 0 || n_edges < 0) return 0;
 #if SPW_USE_TC

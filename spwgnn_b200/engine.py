@@ -9,7 +9,7 @@ import torch
 
 from ._lib import lib, require_cuda, SpwError
 from .graph import TowerBatch, _stream_ptr
-from .params import ParamBuffer, FLAT_SIZE
+from .params import ParamBuffer, FLAT_SIZE, STATS_TAIL
 
 
 class Workspace:
@@ -26,6 +26,20 @@ class Workspace:
         return self.buf
 
 
+def keras_adam_update_(params, grads, state, lr=5e-4, beta1=0.9, beta2=0.999, eps=1e-7):
+    """One step of Keras 2.2 Adam (the optimiser main.py trains with: `optimizers.Adam(lr=0.0005)`, Networks.py:101) on flat
+    tensors, in place:  t += 1;  lr_t = lr sqrt(1 - b2^t) / (1 - b1^t);  m = b1 m + (1 - b1) g;  v = b2 v + (1 - b2) g^2;
+    p -= lr_t m / (sqrt(v) + eps)  with eps = K.epsilon() = 1e-7 OUTSIDE the square root and no bias-corrected m, v (that is
+    what distinguishes it from torch.optim.Adam).  state: dict(t, m, v)."""
+    state['t'] += 1
+    t = state['t']
+    state['m'].mul_(beta1).add_(grads, alpha=1 - beta1)
+    state['v'].mul_(beta2).addcmul_(grads, grads, value=1 - beta2)
+    lr_t = lr * (1 - beta2 ** t) ** 0.5 / (1 - beta1 ** t)
+    params.addcdiv_(state['m'], state['v'].sqrt().add_(eps), value=-lr_t)
+    return params
+
+
 class Engine:
     """One replica of the network on one GPU."""
 
@@ -34,7 +48,8 @@ class Engine:
         self.api = lib()
         self.device = torch.device(device)
         self.params = ParamBuffer(self.device).glorot_init(seed)
-        self.grads = ParamBuffer(self.device)
+        self.grads_buffer = torch.zeros(FLAT_SIZE + STATS_TAIL, dtype=torch.float32, device=self.device)   # gradients + stats tail
+        self.grads = ParamBuffer(self.device, flat=self.grads_buffer[:FLAT_SIZE])
         self.ws = Workspace(self.device)        # training: must survive until backward
         self.ws_inf = Workspace(self.device)    # inference: separate, so a predict() between forward and
                                                 # backward of a training step cannot clobber saved state
@@ -99,13 +114,7 @@ class Engine:
         """Keras 2.2 Adam (Networks.py:101): lr_t = lr*sqrt(1-b2^t)/(1-b1^t); p -= lr_t*m/(sqrt(v)+eps)."""
         if self._adam is None:
             self._adam = dict(t=0, m=torch.zeros(FLAT_SIZE, device=self.device), v=torch.zeros(FLAT_SIZE, device=self.device))
-        a = self._adam
-        a['t'] += 1
-        t, g = a['t'], self.grads.flat
-        a['m'].mul_(beta1).add_(g, alpha=1 - beta1)
-        a['v'].mul_(beta2).addcmul_(g, g, value=1 - beta2)
-        lr_t = lr * (1 - beta2 ** t) ** 0.5 / (1 - beta1 ** t)
-        self.params.flat.addcdiv_(a['m'], a['v'].sqrt().add_(eps), value=-lr_t)
+        keras_adam_update_(self.params.flat, self.grads.flat, self._adam, lr, beta1, beta2, eps)
 
 
 class PropNetFunction(torch.autograd.Function):

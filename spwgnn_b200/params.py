@@ -25,6 +25,7 @@ def _offsets():
 
 
 OFFSETS, FLAT_SIZE = _offsets()
+STATS_TAIL = 4   # floats behind the gradient buffer: the loss / accuracy sums ride in the gradient all-reduce (dp.py)
 N_PARAMS = sum(int(torch.Size(s).numel()) for _, s in PARAM_SPECS)   # 209501
 
 

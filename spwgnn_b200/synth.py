@@ -61,16 +61,35 @@ def g_tower(n, rng: random.Random):
             x = rng.randint(lo, hi) + (int(mean_range / 2) if layer_size % 2 == 0 else 0)
         return x, BOTTOM + RECT_H / 2 + RECT_H * layer_num
 
+    def stable(layer_num, x):
+        """TowerCreator.is_box_stable (TowerCreator.py:250-263): with the candidate in place, the sum of int(x / count) over all
+        boxes must lie between the edges of the ground layer."""
+        if layer_num == 0:
+            return True
+        xs = [v for layer in boxes for v in layer] + [x]
+        com = sum(int(v / len(xs)) for v in xs)
+        r, l = edges(0)
+        return l <= com <= r
+
+    def place(layer_num, layer_size, idx, mid, to_drop=False):
+        nonlocal orientation
+        x, y = make_pos(layer_num, layer_size, idx, mid, to_drop)
+        if not stable(layer_num, x):          # one re-draw with the build direction flipped (TowerCreator.py:201-207)
+            orientation = not orientation
+            x, y = make_pos(layer_num, layer_size, idx, mid, to_drop)
+        return x, y
+
     out = []
     for ln, size in enumerate(layers):
         boxes.append([])
         mid = middle(ln)
         for i in range(size):
-            x, y = make_pos(ln, size, i, mid)
+            x, y = place(ln, size, i, mid)
             boxes[ln].append(x)
             out.append([float(x), float(y), float(RECT_W)])
     ln = len(boxes)
-    x, y = make_pos(ln, 1, 0, middle(ln), to_drop=True)
+    boxes.append([])                          # drop_object appends the new (still empty) layer before it places the block
+    x, y = place(ln, 1, 0, middle(ln), to_drop=True)
     return np.array([[float(x), float(y), float(RECT_W)]] + out, dtype=np.float64)   # dropped block first
 
 

@@ -545,3 +545,108 @@ def test_dropout_matches_oracle_with_same_mask(eng):
     for k in O.tensor_names():
         e = _rel(eng.grads.views[k].cpu().numpy(), g64[k].numpy())
         assert e < max(TOL, 4 * _rel(g32[k].numpy(), g64[k].numpy())), (k, e)
+
+
+def _nccl_worker(rank, world, port, q):
+    """One rank of the 2-GPU data-parallel check (spawned by test_data_parallel_nccl_matches_single_gpu)."""
+    import torch.distributed as dist
+    os.environ['MASTER_ADDR'] = '127.0.0.1'
+    os.environ['MASTER_PORT'] = str(port)
+    torch.cuda.set_device(rank)
+    dist.init_process_group('nccl', rank=rank, world_size=world, device_id=torch.device('cuda', rank))
+    try:
+        from spwgnn_b200 import synth
+        from spwgnn_b200.dp import DataParallelTrainer, shard_towers, tower_edge_counts
+        from spwgnn_b200.engine import Engine
+        from spwgnn_b200.graph import TowerBatch
+        towers = synth.make_towers('uniform', 96, 11, lo=4, hi=20)
+        labels = [(np.random.default_rng(100 + i).random(len(t)) > 0.5).astype(np.float32) for i, t in enumerate(towers)]
+        dev = 'cuda:%d' % rank
+        eng = Engine(dev, seed=3)
+        full = TowerBatch.from_towers(towers, device=dev)
+        shards = shard_towers([len(t) for t in towers], world, edges=tower_edge_counts(full))
+        mine = shards[rank]
+        batch = TowerBatch.from_towers([towers[i] for i in mine], device=dev)
+        tgt = torch.as_tensor(np.concatenate([labels[i] for i in mine])).to(dev)
+        tr = DataParallelTrainer(eng, dropout_rate=0.0)
+        stats = eng.loss_and_grads(batch, tgt, count=full.n_nodes)
+        tr.comm.allreduce_(eng.grads.flat, stats, buffer=eng.grads_buffer)
+        torch.cuda.synchronize()
+        if rank == 0:
+            ref = Engine(dev, seed=3)
+            rs = ref.loss_and_grads(full, torch.as_tensor(np.concatenate(labels)).to(dev))
+            torch.cuda.synchronize()
+            g, r = eng.grads.flat.cpu().numpy(), ref.grads.flat.cpu().numpy()
+            q.put((float(np.abs(g - r).max() / np.abs(r).max()), stats.cpu().tolist(), rs.cpu().tolist()))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_data_parallel_nccl_matches_single_gpu():
+    """Two ranks over NCCL: towers sharded on the measured relation counts, ONE all-reduce of the gradient buffer (stats in
+    its tail) == the single-GPU gradient of the union batch."""
+    if torch.cuda.device_count() < 2:
+        pytest.skip('needs two GPUs')
+    import torch.multiprocessing as mp
+    ctx = mp.get_context('spawn')
+    q = ctx.Queue()
+    port = 29500 + (os.getpid() % 2000)
+    procs = [ctx.Process(target=_nccl_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    err, stats, ref_stats = q.get(timeout=300)
+    for p in procs:
+        p.join(timeout=120)
+        assert p.exitcode == 0
+    assert err < 2e-6, err
+    assert abs(stats[0] - ref_stats[0]) < 1e-3 * abs(ref_stats[0]) and stats[1] == ref_stats[1]
+
+
+def _dense_dict(raw, n):
+    """The dict the reference's predict glue feeds (JengaBuilder.py:307-329): positions / 170 against the threshold 170."""
+    boxes = (raw / 170.0)[None]
+    rs, rr = O.build_relations_dense(boxes[:, :, :2], 170.0)
+    return {'objects': boxes, 'sender_relations': rs, 'receiver_relations': rr, 'propagation': np.zeros((1, n, 100))}
+
+
+def test_demolish_searches_match_sequential_predicts_and_oracle():
+    """score_removals / score_drops (candidates built on the device, ONE packed inference, per-candidate sums
+    and argmin by kernels) == the reference's loop of batch-1 predict calls summed in Python (JengaBuilder.py:243-257,
+    TowerCreator.py:294-303) == the fp64 oracle."""
+    from spwgnn_b200.Networks import PropagationNetwork
+    from spwgnn_b200 import synth
+    net = PropagationNetwork(device='cuda', seed=5)
+    w64 = O.init_weights(5, nonzero_bias=True)
+    tower = synth.make_towers('jenga', 1, 21, n=9)[0]                 # main.py:121 default: n - 1 = 9 blocks
+    N = len(tower)
+    model_full, model_less = net.getModel(N), net.getModel(N - 1)
+    net.engine.params.load_dict(w64)
+    sums, idx = model_full.score_removals(tower)
+    seq, ora = np.zeros(N), np.zeros(N)
+    for c in range(N):
+        cand = np.delete(tower, c, axis=0)
+        out = model_less.predict(_dense_dict(cand, N - 1))           # one batch-1 predict per candidate, as the reference does
+        s = 0
+        for v in out[0]:
+            s += v[0]                                                 # JengaBuilder.py:254-256
+        seq[c] = s
+        eo, snd, rcv, slot = O.edge_list(cand[:, :2] / 170.0, np.array([0, N - 1]))
+        obj64 = torch.as_tensor((cand / 170.0).astype(np.float32).astype(np.float64))
+        _, probs, _, _ = O.loss_and_grads_sparse(w64, obj64, torch.as_tensor(snd), torch.as_tensor(rcv), torch.zeros(N - 1, dtype=torch.float64))
+        ora[c] = float(probs.sum())
+    assert np.abs(sums - seq).max() <= 1e-6 * np.abs(seq).max(), (sums, seq)
+    assert np.abs(sums - ora).max() <= 1e-5 * np.abs(ora).max()
+    assert idx == int(np.argmin(seq)) == int(np.argmin(sums))
+    # construction environment: 100 candidate drop poses on a 6-block tower (TowerCreator.py:290-303)
+    base = synth.make_towers('tower', 1, 4, n=6)[0][1:]              # the stacked blocks (object 0 of g_tower is a dropped block)
+    rng = np.random.default_rng(3)
+    poses = np.stack([rng.integers(500, 1000, 100).astype(np.float64), np.full(100, base[:, 1].max() + 80.0)], 1)
+    sums_d, idx_d = net.getModel(len(base) + 1).score_drops(base, poses)
+    model7 = net.getModel(len(base) + 1)
+    seq_d = np.zeros(100)
+    for c in range(100):
+        cand = np.concatenate([[[poses[c, 0], poses[c, 1], 150.0]], base])
+        out = model7.predict(_dense_dict(cand, len(cand)))
+        seq_d[c] = float(sum(float(v[0]) for v in out[0]))
+    assert np.abs(sums_d - seq_d).max() <= 1e-6 * np.abs(seq_d).max()
+    assert idx_d == int(np.argmin(seq_d))

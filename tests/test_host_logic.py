@@ -104,6 +104,23 @@ def test_shard_towers_balances_cost():
     loads = np.array([cost[s].sum() for s in shards])
     assert loads.max() / loads.mean() < 1.01
     assert all(np.array_equal(a, b) for a, b in zip(shards, shard_towers(sizes, 8)))
+    assert all((np.diff(s) > 0).all() for s in shards)
+    # real relation counts (what spw_edges_count measures) instead of the size-based estimate
+    edges = rng.integers(0, 200, size=4096)
+    shards = shard_towers(sizes, 8, edges=edges)
+    loads = np.array([tower_cost(sizes, edges)[s].sum() for s in shards])
+    assert sorted(np.concatenate(shards).tolist()) == list(range(4096)) and loads.max() / loads.mean() < 1.01
+
+
+def test_shard_towers_is_cheap():
+    """A 65 536-tower global batch (BASELINE config 4) is planned in a few milliseconds (round 1: 0.25 s)."""
+    import time
+    from spwgnn_b200.dp import shard_towers
+    sizes = np.random.default_rng(1).integers(6, 33, size=65536)
+    shard_towers(sizes, 8)
+    t0 = time.perf_counter()
+    shard_towers(sizes, 8)
+    assert time.perf_counter() - t0 < 0.05
 
 
 def _gloo_worker(rank, world, port, q):
@@ -120,6 +137,12 @@ def _gloo_worker(rank, world, port, q):
         params = torch.arange(FLAT_SIZE, dtype=torch.float32) * (1 if rank == 0 else -1)
         comm.broadcast_(params, 0)
         comm.allreduce_(flat, stats)
+        # the one-collective path: stats ride in the tail of the gradient buffer
+        from spwgnn_b200.params import STATS_TAIL
+        buf = torch.full((FLAT_SIZE + STATS_TAIL,), float(rank + 1))
+        stats2 = torch.tensor([0.5 * (rank + 1), 7.0], dtype=torch.float64)
+        comm.allreduce_(buf[:FLAT_SIZE], stats2, buffer=buf)
+        assert float(buf[0]) == 3.0 and stats2.tolist() == [1.5, 14.0]
         q.put((rank, float(flat[0]), float(flat[-1]), stats.tolist(), float(params[5])))
     finally:
         dist.destroy_process_group()

@@ -17,3 +17,6 @@ for l in open(path):
         r.get('executed_frac_of_pipe') or 0, (r.get('fp32_pipe') or {}).get('peak_tflops_measured') or 0, r.get('step_algorithmic_tflops') or 0))
     if d.get('cpu_baseline'):
         print('  cpu_baseline %.0f towers/s on %d cores' % (d['cpu_baseline']['value'], d['cpu_baseline']['cores']))
+    for name, c in sorted((d.get('configs') or {}).items()):
+        if c:
+            print('  %s: %s' % (name, ', '.join('%s %s' % (k, ('%.4g' % v) if isinstance(v, float) else v) for k, v in c.items() if k != 'workload')))
