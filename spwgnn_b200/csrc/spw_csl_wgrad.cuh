@@ -50,14 +50,6 @@ struct WgradCArgs {
 __host__ __device__ constexpr int wg_up32(int f) { return (f + 31) & ~31; }
 __host__ __device__ constexpr int wg_stage_floats(int nqx, int nqy) { return wg_up32(nqx * kQPitch) + wg_up32(nqy * kQPitch) + 32 + 160; }
 
-// 16-byte cp.async through L1 (.ca): the gathered rows of a chunk belong to a handful of receivers, so most lanes of a warp hit
-// the same few lines; the L2-only form (.cg) sent 32 separate requests per instruction (measured: ~1.1k cycles per chunk)
-__device__ __forceinline__ void cp_async16_ca_zfill(float* sdst, const float* gsrc, bool valid) {
-  const unsigned s = smem_u32(sdst);
-  const int sz = valid ? 16 : 0;
-  asm volatile("cp.async.ca.shared.global [%0], [%1], 16, %2;\n" ::"r"(s), "l"(gsrc), "r"(sz));
-}
-
 // tile-mode TMA load of a 2-D box: coordinates {c0 (innermost: floats along the rows), c1 (quad)}
 __device__ __forceinline__ void tma_load_2d(void* sdst, const CUtensorMap* tm, int c0, int c1, uint64_t* bar) {
   asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];" ::"r"(smem_u32(sdst)),
@@ -202,7 +194,7 @@ __global__ void __launch_bounds__(kThreadsC, 1) k_wgrad_c(const __grid_constant_
             const float* src = a.dY + (long long)((a.y_col0 >> 2) + warp) * a.y_slab + (long long)r_idx * 4;
             float* dst = st + y_off + warp * kQPitch + lane * 4;
             for (int qd = warp; qd < nqy; qd += kWorkers / 32) {
-              cp_async16_ca_zfill(dst, src, valid);
+              cp_async16_zfill(dst, src, valid);           // .cg: the L1-allocating form (.ca) measured slower here
               src += (kWorkers / 32) * a.y_slab; dst += (kWorkers / 32) * kQPitch;
             }
             if (warp == 1) {                                     // relu bits of the chunk: 19 groups x 32 bytes, 16-byte pieces
