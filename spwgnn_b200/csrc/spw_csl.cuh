@@ -50,6 +50,30 @@ __device__ __forceinline__ float* vaddr(const View& v, long long row, int c) {  
   return v.p + (long long)((v.col0 + c) >> 2) * v.slab + row * 4;
 }
 
+// ---- L2 prefetch by the otherwise idle warps of the issuer group -------------------------------------------------------------
+// The worker warps move in lock-step behind the same mbarriers, so HBM latency is not hidden by other warps: every operand or
+// epilogue load that misses L2 stalls the whole SM (ncu: long_scoreboard 6-18 warps per issue).  Warps 17-19 therefore run two
+// tiles ahead of the workers and pull the tiles' column-slab pieces (128 rows x 16 bytes = 2 KB per quad) into L2 with
+// cp.async.bulk.prefetch.L2: one instruction per piece, no registers, no shared memory; the workers' loads then hit L2.
+constexpr int kPfThreads = 96;                    // warps 17, 18, 19
+__device__ __forceinline__ void l2_prefetch(const void* p, uint32_t bytes) {
+  asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(p), "r"(bytes) : "memory");
+}
+// rows [r0, r0 + nrows) of the quads [0, nquads) of a column-slab array whose first quad starts at `base`; pl = 0 .. 95
+__device__ __forceinline__ void prefetch_quads(const float* base, long long slab, int nquads, long long r0, int nrows, int pl) {
+  for (int qd = pl; qd < nquads; qd += kPfThreads) l2_prefetch(base + (long long)qd * slab + r0 * 4, (uint32_t)nrows * 16u);
+}
+// rows [r0, r0 + 128) of the groups [0, ngroups) of a byte-slab bit array (the arrays are allocated in whole tiles)
+__device__ __forceinline__ void prefetch_bits(const uint8_t* base, long long bits_rows, int ngroups, long long r0, int pl) {
+  for (int g = pl; g < ngroups; g += kPfThreads) l2_prefetch(base + (long long)g * bits_rows + r0, 128u);
+}
+
+// x[0..3] += v at the L2 (one element is touched by exactly one thread per launch and launches are stream-ordered, so the
+// sum is the same round-to-nearest fp32 add in the same order as a load / add / store, without the load's latency)
+__device__ __forceinline__ void red_add_v4(float* p, float a, float b, float c, float d) {
+  asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(p), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
+}
+
 // ---- weights: TMA bulk copies (issued by one thread) -------------------------------------------------------------------
 __device__ __forceinline__ void bulk_load_weights(float* Bhi_s, float* Blo_s, const float* Bhi, const float* Blo, uint32_t bytes, uint64_t* bar) {
   mbar_arrive_expect_tx(bar, 2 * bytes);
@@ -209,6 +233,23 @@ __global__ void __launch_bounds__(kThreadsC, 1) k_lin(LinCArgs a) {
       __syncwarp();
     }
     if (!ok && lane == 0) a.poison[0] = __int_as_float(0x7fc00000);
+    } else {
+      // ---------------- L2 prefetch warps: tile i + 2 while the workers are in tile i ----------------
+      const int pl = tid - (kWorkers + 32);
+      auto prefetch_tile = [&](int i) {
+        const long long r0 = (long long)(blockIdx.x + i * gridDim.x) * kTM;
+        const int nrows = a.M - r0 >= kTM ? kTM : (int)(a.M - r0);
+        prefetch_quads(a.X.p + (long long)(a.X.col0 >> 2) * a.X.slab, a.X.slab, (K + 3) >> 2, r0, nrows, pl);
+        if (EPI & EPI_ADD) prefetch_quads(a.addend.p + (long long)(a.addend.col0 >> 2) * a.addend.slab, a.addend.slab, (N + 3) >> 2, r0, nrows, pl);
+        if (EPI & (EPI_MUL_POS | EPI_MUL_TANH)) prefetch_quads(a.mulsrc.p + (long long)(a.mulsrc.col0 >> 2) * a.mulsrc.slab, a.mulsrc.slab, (N + 3) >> 2, r0, nrows, pl);
+        if (EPI & EPI_ACC) prefetch_quads(a.Y.p + (long long)(a.Y.col0 >> 2) * a.Y.slab, a.Y.slab, (N + 3) >> 2, r0, nrows, pl);
+        if (EPI & EPI_MUL_BITS) prefetch_bits(a.bits_in, a.bits_in_rows, (N + 7) >> 3, r0, pl);
+      };
+      if (cnt > 1) prefetch_tile(1);
+      for (int i = 0; i + 2 < cnt; ++i) {
+        mbar_wait(barC, (uint32_t)i & 1u);
+        prefetch_tile(i + 2);
+      }
     }
   } else {
     // ---------------- worker warps ----------------
@@ -250,6 +291,15 @@ __global__ void __launch_bounds__(kThreadsC, 1) k_lin(LinCArgs a) {
       const uint32_t parity = (uint32_t)i & 1u;
       SPW_PH(7);
       if (has_next) load_x(i + 1);                               // in flight under the MMAs of tile i
+      uint32_t bin[GJ];                                          // relu bits of tile i's epilogue, requested well before their use
+      if (EPI & EPI_MUL_BITS) {
+        const long long rb = (long long)(blockIdx.x + i * gridDim.x) * kTM + row;
+#pragma unroll
+        for (int j = 0; j < GJ; ++j) {
+          const int g = q + 4 * j;
+          bin[j] = (g < ngroups && g < nq8 && rb < a.M) ? a.bits_in[(long long)g * a.bits_in_rows + rb] : 0u;
+        }
+      }
       SPW_PH(0);                                                 // p0: issue of the operand loads
       if (!mbar_wait(barC, parity)) failed = true;               // corrections done: A_lo free
       fence_after_sync();
@@ -309,9 +359,8 @@ __global__ void __launch_bounds__(kThreadsC, 1) k_lin(LinCArgs a) {
             for (int e = 0; e < 8; ++e) v[e] = tanhf(v[e]);
           }
           if (EPI & EPI_MUL_BITS) {
-            const uint32_t bits = a.bits_in[(long long)g * a.bits_in_rows + r];
 #pragma unroll
-            for (int e = 0; e < 8; ++e) v[e] = ((bits >> e) & 1u) ? v[e] : 0.f;
+            for (int e = 0; e < 8; ++e) v[e] = ((bin[j] >> e) & 1u) ? v[e] : 0.f;
           }
           if (EPI & (EPI_MUL_POS | EPI_MUL_TANH)) {
             float m[8];

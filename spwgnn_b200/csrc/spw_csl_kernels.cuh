@@ -152,6 +152,20 @@ __global__ void __launch_bounds__(kThreadsC, 1) k_edge_step_c(EdgeStepCArgs a) {
       __syncwarp();
     }
     if (!ok && lane == 0) a.poison[0] = __int_as_float(0x7fc00000);
+    } else {
+      // L2 prefetch warps (spw_csl.cuh): the A rows of tile i + 2 while the workers build tile i + 1
+      const int pl = tid - (kWorkers + 32);
+      auto prefetch_tile = [&](int i) {
+        const long long r0 = (long long)(blockIdx.x + i * gridDim.x) * kTM;
+        const int nrows = a.E - r0 >= kTM ? kTM : (int)(a.E - r0);
+        prefetch_quads(a.A, (long long)a.E * 4, kQE, r0, nrows, pl);
+      };
+      if (cnt > 1) prefetch_tile(1);
+      if (cnt > 2) prefetch_tile(2);
+      for (int i = 0; i + 3 < cnt; ++i) {
+        mbar_wait(barC, (uint32_t)i & 1u);
+        prefetch_tile(i + 3);
+      }
     }
   } else {
     regs_workers();
@@ -384,6 +398,19 @@ __global__ void __launch_bounds__(kThreadsC, 1) k_edge_dgrad_c(EdgeDgradCArgs a)
       __syncwarp();
     }
     if (!ok && lane == 0) a.poison[0] = __int_as_float(0x7fc00000);
+    } else {
+      // L2 prefetch warps (spw_csl.cuh): the relu bytes of tile i + 2 (the gathered node table is L2-resident anyway)
+      const int pl = tid - (kWorkers + 32);
+      auto prefetch_tile = [&](int i) {
+        const long long r0 = (long long)(blockIdx.x + i * gridDim.x) * kTM;
+        prefetch_bits(a.bits_h2, a.bits_rows, NKS, r0, pl);
+        prefetch_bits(a.bits_h1, a.bits_rows, NKS, r0, pl);
+      };
+      if (cnt > 1) prefetch_tile(1);
+      for (int i = 0; i + 2 < cnt; ++i) {
+        mbar_wait(barC, (uint32_t)i & 1u);
+        prefetch_tile(i + 2);
+      }
     }
   } else {
     regs_workers();
@@ -392,6 +419,7 @@ __global__ void __launch_bounds__(kThreadsC, 1) k_edge_dgrad_c(EdgeDgradCArgs a)
     bool failed = false;
     XR<KJ> x;
     int r_nx = -1;
+    SPW_PH_DECL
     auto load_idx = [&](int i, int& r) {
       const long long e = (long long)(blockIdx.x + i * gridDim.x) * kTM + row;
       r = (i < cnt && e < a.E) ? a.in_rcv[e] : -1;
@@ -430,19 +458,24 @@ __global__ void __launch_bounds__(kThreadsC, 1) k_edge_dgrad_c(EdgeDgradCArgs a)
     for (int i = -1; i < cnt; ++i) {
       const bool has_next = i + 1 < cnt;
       const uint32_t parity = (uint32_t)i & 1u;
+      SPW_PH(7);
       if (has_next) {
         gather_x(i + 1, r_nx);
         load_idx(i + 2, r_nx);
       }
+      SPW_PH(0);                                         // p0: issue of the gathers
       if (i >= 0) {
         if (!mbar_wait(barC, parity)) failed = true;
         fence_after_sync();
       }
+      SPW_PH(1);                                         // p1: wait for the correction MMAs
       if (has_next) { mask_x(); store_lo<KJ>(x, lane_addr, colLo, q, NKS); }
+      SPW_PH(2);                                         // p2: mask + lo words (first use of the gathers)
       if (i >= 0) {
         if (!mbar_wait(barM, parity)) failed = true;
         fence_after_sync();
       }
+      SPW_PH(3);                                         // p3: wait for the main MMAs
       if (has_next) store_hi<KJ>(x, lane_addr, colHi, q, NKS);
       // epilogue inputs of tile i: relu'(h1) bytes and (unless this is the first processed step) the old dA values
       const long long e = (long long)(blockIdx.x + i * gridDim.x) * kTM + row;
@@ -450,7 +483,6 @@ __global__ void __launch_bounds__(kThreadsC, 1) k_edge_dgrad_c(EdgeDgradCArgs a)
       float* hp = a.DH1 + (long long)(2 * q) * es + (ev ? e : 0) * 4;
       float* gp = a.dA + (long long)(2 * q) * es + (ev ? e : 0) * 4;
       uint32_t b1[GJ];
-      float4 o0[GJ], o1[GJ];
       if (ev) {
         const uint8_t* bp = a.bits_h1 + (long long)q * a.bits_rows + e;
 #pragma unroll
@@ -458,10 +490,6 @@ __global__ void __launch_bounds__(kThreadsC, 1) k_edge_dgrad_c(EdgeDgradCArgs a)
           b1[j] = 0u;
           if (q + 4 * j < NKS) {
             b1[j] = bp[(long long)(4 * j) * a.bits_rows];
-            if (!FIRST && j < 3) {                       // the last two groups' old values are requested inside the epilogue
-              o0[j] = *reinterpret_cast<const float4*>(gp + (long long)(8 * j) * es);
-              o1[j] = *reinterpret_cast<const float4*>(gp + (long long)(8 * j + 1) * es);
-            }
           }
         }
       }
@@ -472,29 +500,33 @@ __global__ void __launch_bounds__(kThreadsC, 1) k_edge_dgrad_c(EdgeDgradCArgs a)
         fence_before_sync();
         nbar_arrive(kBarOps, kBarOpsCount);
       }
+      SPW_PH(4);                                         // p4: hi words, epilogue loads issued, D load
       // ---- epilogue of tile i: mask with relu'(h1), DH1 (write), dA (write or accumulate): coalesced 16-byte accesses
       if (ev) {
 #pragma unroll
         for (int j = 0; j < GJ; ++j) {
-          if (!FIRST && j + 3 < GJ && q + 4 * (j + 3) < NKS) {
-            o0[j + 3] = *reinterpret_cast<const float4*>(gp + (long long)(8 * (j + 3)) * es);
-            o1[j + 3] = *reinterpret_cast<const float4*>(gp + (long long)(8 * (j + 3) + 1) * es);
-          }
           if (q + 4 * j >= NKS) continue;
           float v[8];
 #pragma unroll
           for (int k = 0; k < 8; ++k) v[k] = ((b1[j] >> k) & 1u) ? __uint_as_float(d[j][k]) : 0.f;
           *reinterpret_cast<float4*>(hp + (long long)(8 * j) * es) = make_float4(v[0], v[1], v[2], v[3]);
           *reinterpret_cast<float4*>(hp + (long long)(8 * j + 1) * es) = make_float4(v[4], v[5], v[6], v[7]);
-          if (!FIRST) {
-            v[0] += o0[j].x; v[1] += o0[j].y; v[2] += o0[j].z; v[3] += o0[j].w;
-            v[4] += o1[j].x; v[5] += o1[j].y; v[6] += o1[j].z; v[7] += o1[j].w;
+          if (FIRST) {
+            *reinterpret_cast<float4*>(gp + (long long)(8 * j) * es) = make_float4(v[0], v[1], v[2], v[3]);
+            *reinterpret_cast<float4*>(gp + (long long)(8 * j + 1) * es) = make_float4(v[4], v[5], v[6], v[7]);
+          } else {                                       // dA += d h1: reduction at the L2, nothing comes back to the SM
+            red_add_v4(gp + (long long)(8 * j) * es, v[0], v[1], v[2], v[3]);
+            red_add_v4(gp + (long long)(8 * j + 1) * es, v[4], v[5], v[6], v[7]);
           }
-          *reinterpret_cast<float4*>(gp + (long long)(8 * j) * es) = make_float4(v[0], v[1], v[2], v[3]);
-          *reinterpret_cast<float4*>(gp + (long long)(8 * j + 1) * es) = make_float4(v[4], v[5], v[6], v[7]);
         }
       }
+      SPW_PH(5);                                         // p5: epilogue
     }
+#ifdef SPW_PHASE_TIMING
+    if (blockIdx.x == 0 && lane == 0 && (warp == 0 || warp == 9))
+      printf("k_edge_dgrad_c<%d> warp %d: gathers %lld waitC %lld mask+lo %lld waitM %lld hi+D %lld epi %lld loop %lld (%d tiles)\n", (int)FIRST, warp, ph_t[0],
+             ph_t[1], ph_t[2], ph_t[3], ph_t[4], ph_t[5], ph_t[7], cnt);
+#endif
     if (failed && tid == 0) a.poison[0] = __int_as_float(0x7fc00000);
   }
   fence_before_sync();
