@@ -7,12 +7,44 @@
 #pragma once
 #include <stddef.h>
 #include <stdint.h>
+#include <string.h>
+#include <stdlib.h>
 #ifdef SPW_EMU
 #include "cuda_emu.h"
 #else
 #include <cuda_runtime.h>
 #define SPW_LAUNCH(kern, grid, block, smem, stream, ...) kern<<<(grid), (block), (smem), (stream)>>>(__VA_ARGS__)
 #define SPW_DYN_SMEM(name) extern __shared__ __align__(128) unsigned char name[]
+#endif
+
+// ---- programmatic dependent launch ---------------------------------------------------------------------------------------
+// A training step is ~135 dependent launches, most of them persistent grids of one CTA per SM that end ragged (a CTA owns
+// 2 or 3 tiles of a node-level layer).  Kernels launched with SPW_LAUNCH_PDL may become resident as soon as every CTA of the
+// previous kernel has called pdl_trigger() (first statement of every such kernel) and an SM has room, i.e. when the previous
+// kernel's CTA on that SM has exited; they run their prologue (barrier init, tensor-memory allocation, weight operands: data
+// no triggering kernel writes) and block in pdl_wait() until the previous kernel has completed and its writes are visible.
+// Nothing a predecessor reads or writes is touched before pdl_wait().  Kernels that do not trigger (packers, torch's) and
+// memsets are full barriers as before.
+#ifdef SPW_EMU
+__device__ __forceinline__ void pdl_trigger() {}
+__device__ __forceinline__ void pdl_wait() {}
+#define SPW_LAUNCH_PDL SPW_LAUNCH
+#else
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+template <typename... KArgs, typename... Args>
+inline void spw_launch_pdl(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream, Args&&... args) {
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof(cfg));
+  cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = stream;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  at[0].val.programmaticStreamSerializationAllowed = 1;
+  static const bool off = getenv("SPW_NO_PDL") != nullptr;      // A/B switch: plain stream order
+  cfg.attrs = at; cfg.numAttrs = off ? 0 : 1;
+  cudaLaunchKernelEx(&cfg, kern, KArgs(args)...);
+}
+#define SPW_LAUNCH_PDL(kern, grid, block, smem, stream, ...) spw_launch_pdl(kern, (grid), (block), (smem), (stream), __VA_ARGS__)
 #endif
 
 namespace spw {

@@ -209,6 +209,7 @@ __global__ void __launch_bounds__(kThreadsC, 1) k_lin(LinCArgs a) {
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int row = 32 * (warp & 3) + lane, q = warp >> 2;
 
+  pdl_trigger();                                                 // spw_common.cuh: the next kernel may set up behind this one
   if (warp == 0) tmem_alloc(tptr, kTmemCols);
   if (tid == 32) { mbar_init(barC, 1); mbar_init(barM, 1); mbar_init(barW, 1); fence_mbar_init(); }
   for (int i = tid; i < NB; i += kThreadsC) sbias[i] = ((EPI & EPI_BIAS) && i < N) ? a.bias[i] : 0.f;
@@ -236,6 +237,7 @@ __global__ void __launch_bounds__(kThreadsC, 1) k_lin(LinCArgs a) {
     } else {
       // ---------------- L2 prefetch warps: tile i + 2 while the workers are in tile i ----------------
       const int pl = tid - (kWorkers + 32);
+      pdl_wait();
       auto prefetch_tile = [&](int i) {
         const long long r0 = (long long)(blockIdx.x + i * gridDim.x) * kTM;
         const int nrows = a.M - r0 >= kTM ? kTM : (int)(a.M - r0);
@@ -278,6 +280,7 @@ __global__ void __launch_bounds__(kThreadsC, 1) k_lin(LinCArgs a) {
         }
       }
     };
+    pdl_wait();                                                  // the previous kernel's results are complete and visible
     if (cnt > 0) {
       load_x(0);
       store_lo<KJ>(x, lane_addr, colLo, q, NKS);

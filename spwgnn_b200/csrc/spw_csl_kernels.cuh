@@ -14,6 +14,8 @@ constexpr int kQP = 25;          // column quads of a 100-wide node array
 // ---- object encoder layer 0 (Networks.py:47,76; K = 2 on [y, w]): Q1 = relu(y W[0] + w W[1] + b) -------------------------
 __global__ void __launch_bounds__(256) k_obj_enc0_c(const float* __restrict__ obj, int n, const float* __restrict__ W,
                                                     const float* __restrict__ b, float* __restrict__ out, long long slab) {
+  pdl_trigger();
+  pdl_wait();
   const long long total = (long long)n * kQP;
   for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (long long)gridDim.x * blockDim.x) {
     const int qd = (int)(idx / n), i = (int)(idx - (long long)qd * n);
@@ -34,10 +36,12 @@ __global__ void __launch_bounds__(256) k_edge_enc0_c(int E, const int32_t* __res
                                                      const float* __restrict__ obj, const float* __restrict__ W0,
                                                      const float* __restrict__ b0, float* __restrict__ X0, uint8_t* __restrict__ bits, long long bits_rows) {
   __shared__ float sw[3][kDEP];
+  pdl_trigger();
   for (int i = threadIdx.x; i < kDEP; i += blockDim.x) {
     sw[0][i] = i < kDE ? W0[i] : 0.f; sw[1][i] = i < kDE ? W0[kDE + i] : 0.f; sw[2][i] = i < kDE ? b0[i] : 0.f;
   }
   __syncthreads();
+  pdl_wait();
   const long long slab = (long long)E * 4;
   for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < E; e += (long long)gridDim.x * blockDim.x) {
     const int s = in_snd[e], rc = in_rcv[e];
@@ -64,8 +68,10 @@ __global__ void __launch_bounds__(256) k_edge_enc0_c(int E, const int32_t* __res
 __global__ void __launch_bounds__(256) k_logit_c(const float* __restrict__ U, long long slab, int n, const float* __restrict__ V2raw,
                                                  const float* __restrict__ c2raw, float* __restrict__ logits, float* __restrict__ probs) {
   __shared__ float sv[kDP];
+  pdl_trigger();
   for (int i = threadIdx.x; i < kDP; i += blockDim.x) sv[i] = V2raw[(size_t)i * (kDP + 1)];
   __syncthreads();
+  pdl_wait();
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
     float s = 0.f;
 #pragma unroll 5
@@ -82,6 +88,8 @@ __global__ void __launch_bounds__(256) k_logit_c(const float* __restrict__ U, lo
 // dUpre5[i][c] = dlogit_i * V2[c][0] * [U5[i][c] > 0]; thread = (quad, node)
 __global__ void __launch_bounds__(256) k_logit_bwd_c(const float* __restrict__ dlogits, const float* __restrict__ U, long long u_slab, int n,
                                                      const float* __restrict__ V2raw, float* __restrict__ dU, long long du_slab) {
+  pdl_trigger();
+  pdl_wait();
   const long long total = (long long)n * kQP;
   for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (long long)gridDim.x * blockDim.x) {
     const int qd = (int)(idx / n), i = (int)(idx - (long long)qd * n);
@@ -130,6 +138,7 @@ __global__ void __launch_bounds__(kThreadsC, 1) k_edge_step_c(EdgeStepCArgs a) {
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int row = 32 * (warp & 3) + lane, q = warp >> 2;
 
+  pdl_trigger();
   if (warp == 0) tmem_alloc(tptr, kTmemCols);
   if (tid == 32) { mbar_init(barC, 1); mbar_init(barM, 1); mbar_init(barW, 1); fence_mbar_init(); }
   fence_before_sync();
@@ -155,6 +164,7 @@ __global__ void __launch_bounds__(kThreadsC, 1) k_edge_step_c(EdgeStepCArgs a) {
     } else {
       // L2 prefetch warps (spw_csl.cuh): the A rows of tile i + 2 while the workers build tile i + 1
       const int pl = tid - (kWorkers + 32);
+      pdl_wait();
       auto prefetch_tile = [&](int i) {
         const long long r0 = (long long)(blockIdx.x + i * gridDim.x) * kTM;
         const int nrows = a.E - r0 >= kTM ? kTM : (int)(a.E - r0);
@@ -227,6 +237,7 @@ __global__ void __launch_bounds__(kThreadsC, 1) k_edge_step_c(EdgeStepCArgs a) {
       }
     };
 
+    pdl_wait();
     if (cnt > 0) {
       load_idx(0, s_nx, r_nx);
       build_x(0, s_nx, r_nx);
@@ -330,6 +341,8 @@ __global__ void __launch_bounds__(kThreadsC, 1) k_edge_step_c(EdgeStepCArgs a) {
 // nodes whose in-edges cross a 32-row chunk: H2S_i = part_last[first chunk] + sum of whole middle chunks + part_first[last chunk]
 __global__ void __launch_bounds__(256) k_seg_fix_c(int n, const int32_t* __restrict__ in_off, const float* __restrict__ part_first,
                                                    const float* __restrict__ part_last, float* __restrict__ H2S, long long h_slab) {
+  pdl_trigger();
+  pdl_wait();
   const long long total = (long long)n * kQE;
   for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (long long)gridDim.x * blockDim.x) {
     const int qd = (int)(idx / n), i = (int)(idx - (long long)qd * n);
@@ -376,6 +389,7 @@ __global__ void __launch_bounds__(kThreadsC, 1) k_edge_dgrad_c(EdgeDgradCArgs a)
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int row = 32 * (warp & 3) + lane, q = warp >> 2;
 
+  pdl_trigger();
   if (warp == 0) tmem_alloc(tptr, kTmemCols);
   if (tid == 32) { mbar_init(barC, 1); mbar_init(barM, 1); mbar_init(barW, 1); fence_mbar_init(); }
   fence_before_sync();
@@ -401,6 +415,7 @@ __global__ void __launch_bounds__(kThreadsC, 1) k_edge_dgrad_c(EdgeDgradCArgs a)
     } else {
       // L2 prefetch warps (spw_csl.cuh): the relu bytes of tile i + 2 (the gathered node table is L2-resident anyway)
       const int pl = tid - (kWorkers + 32);
+      pdl_wait();
       auto prefetch_tile = [&](int i) {
         const long long r0 = (long long)(blockIdx.x + i * gridDim.x) * kTM;
         prefetch_bits(a.bits_h2, a.bits_rows, NKS, r0, pl);
@@ -453,6 +468,7 @@ __global__ void __launch_bounds__(kThreadsC, 1) k_edge_dgrad_c(EdgeDgradCArgs a)
 #pragma unroll
         for (int k = 0; k < 8; ++k) x.v[j][k] = ((b2[j] >> k) & 1u) ? x.v[j][k] : 0.f;
     };
+    pdl_wait();
     load_idx(0, r_nx);
 #pragma unroll 1
     for (int i = -1; i < cnt; ++i) {
@@ -538,6 +554,8 @@ __global__ void __launch_bounds__(kThreadsC, 1) k_edge_dgrad_c(EdgeDgradCArgs a)
 __global__ void __launch_bounds__(256) k_gather_dsr_c(int n, int E, const int32_t* __restrict__ in_off, const int32_t* __restrict__ out_off,
                                                       const int32_t* __restrict__ out_pos, const float* __restrict__ DH1,
                                                       float* __restrict__ dS, float* __restrict__ dR, long long sr_slab) {
+  pdl_trigger();
+  pdl_wait();
   const long long total = (long long)n * kQE;
   const long long es = (long long)E * 4;
   for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (long long)gridDim.x * blockDim.x) {
@@ -562,6 +580,8 @@ __global__ void __launch_bounds__(256) k_gather_dsr_c(int n, int E, const int32_
 // out[i][:] = sum over `slots` of in[slot * n + i][:]  (column-slab arrays; thread = (quad, node), fixed order)
 __global__ void __launch_bounds__(256) k_sum_slots_c(int n, int slots, int nquads, const float* __restrict__ in, long long in_slab,
                                                      float* __restrict__ out, long long out_slab) {
+  pdl_trigger();
+  pdl_wait();
   const long long total = (long long)n * nquads;
   for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (long long)gridDim.x * blockDim.x) {
     const int qd = (int)(idx / n), i = (int)(idx - (long long)qd * n);
@@ -587,6 +607,8 @@ template <int MODE>
 __global__ void __launch_bounds__(256) k_skinny_c(int M, const float* __restrict__ Z, long long z_slab, int nquads, int ld,
                                                   const int32_t* __restrict__ snd, const int32_t* __restrict__ rcv,
                                                   const float* __restrict__ obj, const float* __restrict__ s0v, float* __restrict__ part) {
+  pdl_trigger();
+  pdl_wait();
   const int lane = threadIdx.x & 31;
   const long long gw = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const long long nw = ((long long)M + kSkinnyRows - 1) / kSkinnyRows;

@@ -153,15 +153,22 @@ int run_wgrad_c(cudaStream_t st, int M, const csl::View& X, int Kx, const float*
   CUtensorMap tmX, tmY;
   int rc;
   if ((rc = make_csl_map(&tmX, X, M, (Kx + 3) >> 2, nqx)) != SPW_OK) return rc;
+  const bool pair = a.nmt == 2;                                 // two M-tiles: one CTA pair per row stream (k_wgrad_pair)
   if (gather_rcv) tmY = tmX;
-  else if ((rc = make_csl_map(&tmY, dY, M, nqy, nqy)) != SPW_OK) return rc;
-  const size_t smem = csl::wgrad_c_smem(nqx, nqy, NB, 3);
-#define SPW_WG_LAUNCH(YM, NBV)                                                                                           \
-  do { auto kern = csl::k_wgrad_c<YM, NBV, 3>; set_smem(kern, smem);                                                      \
-       SPW_KLAUNCH(tag, kern, dim3(streams * a.nmt), dim3(csl::kThreadsC), smem, st, tmX, tmY, a, nqx); } while (0)
-  if (gather_rcv) SPW_WG_LAUNCH(1, 160);
-  else if (NB == 160) SPW_WG_LAUNCH(0, 160);
-  else SPW_WG_LAUNCH(0, 112);
+  else if ((rc = make_csl_map(&tmY, dY, M, nqy, pair ? NB / 8 : nqy)) != SPW_OK) return rc;
+  const size_t smem = pair ? csl::wgrad_pair_smem(nqx, NB, 3) : csl::wgrad_c_smem(nqx, nqy, NB, 3);
+#define SPW_WG_LAUNCH(KERN, YM, NBV)                                                                                     \
+  do { auto kern = csl::KERN<YM, NBV, 3>; set_smem(kern, smem);                                                           \
+       SPW_KLAUNCH_PDL(tag, kern, dim3(streams * a.nmt), dim3(csl::kThreadsC), smem, st, tmX, tmY, a, nqx); } while (0)
+  if (pair) {
+    if (gather_rcv) SPW_WG_LAUNCH(k_wgrad_pair, 1, 160);
+    else if (NB == 160) SPW_WG_LAUNCH(k_wgrad_pair, 0, 160);
+    else SPW_WG_LAUNCH(k_wgrad_pair, 0, 112);
+  } else {
+    if (gather_rcv) SPW_WG_LAUNCH(k_wgrad_c, 1, 160);
+    else if (NB == 160) SPW_WG_LAUNCH(k_wgrad_c, 0, 160);
+    else SPW_WG_LAUNCH(k_wgrad_c, 0, 112);
+  }
 #undef SPW_WG_LAUNCH
   if (reduce) launch_reduce(st, part, streams, (int)tc::kWgPartFloats, 0, -1, f1 > 0 ? f1 : 0, Kx, Ny, out);
   return SPW_OK;
@@ -224,14 +231,14 @@ int forward_csl(const SpwParams* w, const SpwGraph* g, const float* obj, float* 
                     ws + L.ENCT + (size_t)(2 * i) * 24320, ws + L.ENCT + (size_t)(2 * i + 1) * 24320);
     }
   }
-  SPW_KLAUNCH("k_deg_to_float", k_deg_to_float, dim3(grid_for(n, 256)), dim3(256), 0, st, g->in_off, n, ws + L.degf);
+  SPW_KLAUNCH_PDL("k_deg_to_float", k_deg_to_float, dim3(grid_for(n, 256)), dim3(256), 0, st, g->in_off, n, ws + L.degf);
 
   const long long rGP = (long long)L.slotsGP * n, rS = (long long)L.slots * n;
   auto gp_slot = [&](int l) { return training ? l : (l & 1); };
   auto st_slot = [&](int l) { return training ? l : 0; };
 
   // object encoder (Networks.py:47,76): q1 = relu(om0([y, w])), q = relu(om1(q1)) (+ dropout, Networks.py:78); qv = q.V1a + c1
-  SPW_KLAUNCH("k_obj_enc0_c", csl::k_obj_enc0_c, dim3(grid_for((int64_t)n * csl::kQP, 256)), dim3(256), 0, st, obj, n, w->om_w[0], w->om_b[0],
+  SPW_KLAUNCH_PDL("k_obj_enc0_c", csl::k_obj_enc0_c, dim3(grid_for((int64_t)n * csl::kQP, 256)), dim3(256), 0, st, obj, n, w->om_w[0], w->om_b[0],
               ws + L.Q1, (long long)n * 4);
   {
     LinC o; o.tag = "k_lin:node"; o.id = T_OM1; o.N = 100; o.K = 100; o.epi = csl::EPI_BIAS | csl::EPI_RELU | (drop ? csl::EPI_DROP : 0u);
@@ -249,7 +256,7 @@ int forward_csl(const SpwParams* w, const SpwGraph* g, const float* obj, float* 
     float* Xs[4] = {ws + L.X0, ws + L.X1, ws + L.X2, ws + L.C};
     uint8_t* EB[4];
     for (int i = 0; i < 4; ++i) EB[i] = training ? bits_ptr(ws, L.EB, L, i) : nullptr;
-    SPW_KLAUNCH("k_edge_enc0_c", csl::k_edge_enc0_c, dim3(grid_for(E, 256)), dim3(256), 0, st, E, g->in_snd, g->in_rcv, obj,
+    SPW_KLAUNCH_PDL("k_edge_enc0_c", csl::k_edge_enc0_c, dim3(grid_for(E, 256)), dim3(256), 0, st, E, g->in_snd, g->in_rcv, obj,
                 (const float*)w->rm_w[0], (const float*)w->rm_b[0], Xs[0], EB[0], L.bits_rows);
     const int ids[3] = {T_RM1, T_RM2, T_RM3};
     const float* bs[3] = {w->rm_b[1], w->rm_b[2], w->rm_b[3]};
@@ -297,10 +304,10 @@ int forward_csl(const SpwParams* w, const SpwGraph* g, const float* obj, float* 
       t.bits_rows = L.bits_rows; t.poison = H.p;
       t.H1 = training ? ws + L.H1 + (size_t)l * ((size_t)kQ150 * E * 4 + 64) : nullptr;
       set_smem(csl::k_edge_step_c, csl::kEdgeStepCSmem);
-      SPW_KLAUNCH("k_edge_step_c", csl::k_edge_step_c, dim3(tgrid), dim3(csl::kThreadsC), csl::kEdgeStepCSmem, st, t);
+      SPW_KLAUNCH_PDL("k_edge_step_c", csl::k_edge_step_c, dim3(tgrid), dim3(csl::kThreadsC), csl::kEdgeStepCSmem, st, t);
     }
     // segments that cross a 32-row chunk, and nodes without incoming relations (all-zero aggregate)
-    SPW_KLAUNCH("k_seg_fix_c", csl::k_seg_fix_c, dim3(grid_for((int64_t)n * csl::kQE, 256)), dim3(256), 0, st, n, g->in_off,
+    SPW_KLAUNCH_PDL("k_seg_fix_c", csl::k_seg_fix_c, dim3(grid_for((int64_t)n * csl::kQE, 256)), dim3(256), 0, st, n, g->in_off,
                 (const float*)(ws + L.PF), (const float*)(ws + L.PL), H.p, H.slab);
     {   // g = tanh(W3.sum h2 + deg.b3)   (Networks.py:87-88), written into columns 0..99 of [g | p]
       LinC o; o.tag = "k_lin:node"; o.id = T_W3; o.N = 100; o.K = 150; o.epi = csl::EPI_BIAS | csl::EPI_ROWSCALE | csl::EPI_TANH;
@@ -319,7 +326,7 @@ int forward_csl(const SpwParams* w, const SpwGraph* g, const float* obj, float* 
       o.addend = cview(ws + L.GP, rGP, (long long)gl * n, 100); o.write_pad = 0;
       if ((rc = run_lin_c(st, ws, L, n, o)) != SPW_OK) return rc;
     } else {                     // head: channel 0 of the last z (Networks.py:93-96)
-      SPW_KLAUNCH("k_logit_c", csl::k_logit_c, dim3(grid_for(n, 256)), dim3(256), 0, st, (const float*)Uv.p, Uv.slab, n, (const float*)w->omp_w[1],
+      SPW_KLAUNCH_PDL("k_logit_c", csl::k_logit_c, dim3(grid_for(n, 256)), dim3(256), 0, st, (const float*)Uv.p, Uv.slab, n, (const float*)w->omp_w[1],
                   (const float*)w->omp_b[1], logits, probs);
     }
   }
@@ -341,7 +348,7 @@ int backward_csl(const SpwParams* w, const SpwGraph* g, const float* obj, const 
 
   // head: dUpre^5 = dlogit (x) V2[:,0] * relu'
   const csl::View U5 = cview(ws + L.U, r5, 4LL * n, 0);
-  SPW_KLAUNCH("k_logit_bwd_c", csl::k_logit_bwd_c, dim3(grid_for((int64_t)n * csl::kQP, 256)), dim3(256), 0, st, dlogits, (const float*)U5.p, U5.slab, n,
+  SPW_KLAUNCH_PDL("k_logit_bwd_c", csl::k_logit_bwd_c, dim3(grid_for((int64_t)n * csl::kQP, 256)), dim3(256), 0, st, dlogits, (const float*)U5.p, U5.slab, n,
               (const float*)w->omp_w[1], ws + L.dU + (size_t)4 * n * 4, r5 * 4);
 
   int wstreams = 0;                                              // row streams of the edge-step weight gradient
@@ -390,17 +397,17 @@ int backward_csl(const SpwParams* w, const SpwGraph* g, const float* obj, const 
         const int tgrid = etiles < num_sms() ? etiles : num_sms();
         if (t.first) {
           set_smem(csl::k_edge_dgrad_c<true>, csl::kEdgeStepCSmem);
-          SPW_KLAUNCH("k_edge_dgrad_c", csl::k_edge_dgrad_c<true>, dim3(tgrid), dim3(csl::kThreadsC), csl::kEdgeStepCSmem, st, t);
+          SPW_KLAUNCH_PDL("k_edge_dgrad_c", csl::k_edge_dgrad_c<true>, dim3(tgrid), dim3(csl::kThreadsC), csl::kEdgeStepCSmem, st, t);
         } else {
           set_smem(csl::k_edge_dgrad_c<false>, csl::kEdgeStepCSmem);
-          SPW_KLAUNCH("k_edge_dgrad_c", csl::k_edge_dgrad_c<false>, dim3(tgrid), dim3(csl::kThreadsC), csl::kEdgeStepCSmem, st, t);
+          SPW_KLAUNCH_PDL("k_edge_dgrad_c", csl::k_edge_dgrad_c<false>, dim3(tgrid), dim3(csl::kThreadsC), csl::kEdgeStepCSmem, st, t);
         }
       }
     }
     if (l > 0) {
       const csl::View dS = cview(ws + L.dS, r4, (long long)(l - 1) * n, 0), dR = cview(ws + L.dR, r4, (long long)(l - 1) * n, 0);
       if (E > 0) {
-        SPW_KLAUNCH("k_gather_dsr_c", csl::k_gather_dsr_c, dim3(grid_for((int64_t)n * csl::kQE, 256)), dim3(256), 0, st, n, E, g->in_off, g->out_off,
+        SPW_KLAUNCH_PDL("k_gather_dsr_c", csl::k_gather_dsr_c, dim3(grid_for((int64_t)n * csl::kQE, 256)), dim3(256), 0, st, n, E, g->in_off, g->out_off,
                     g->out_pos, (const float*)(ws + L.DH1), dS.p, dR.p, r4 * 4);
       } else {
         cudaMemset2DAsync(dS.p, (size_t)r4 * 16, 0, (size_t)n * 16, kQ150, st);
@@ -423,7 +430,7 @@ int backward_csl(const SpwParams* w, const SpwGraph* g, const float* obj, const 
   const csl::View dUall = cview(ws + L.dU, r5, 0, 0);
   // omp layer 0 = [V1a; V1b; V1c], bias c1
   //   rows 0..99 (V1a): q is the same in all five steps, so q^T (sum over the steps of dUpre): the sum lands in DP (free by now)
-  SPW_KLAUNCH("k_sum_slots_c", csl::k_sum_slots_c, dim3(grid_for((int64_t)n * csl::kQP, 256)), dim3(256), 0, st, n, 5, csl::kQP, (const float*)(ws + L.dU), r5 * 4,
+  SPW_KLAUNCH_PDL("k_sum_slots_c", csl::k_sum_slots_c, dim3(grid_for((int64_t)n * csl::kQP, 256)), dim3(256), 0, st, n, 5, csl::kQP, (const float*)(ws + L.dU), r5 * 4,
               ws + L.DP, (long long)n * 4);
   if ((rc = run_wgrad_c(st, n, cview(ws + L.Q, n, 0, 0), kDP, nullptr, 0, cview(ws + L.DP, n, 0, 0), kDP, partN, {grads->omp_w[0], 100, 0, 0, grads->omp_b[0], 0}, "k_wgrad_c:node")) != SPW_OK) return rc;
   if ((rc = run_wgrad_c(st, 5 * n, cview(ws + L.GP, r5, 0, 0), 2 * kDP, nullptr, 0, dUall, kDP, partN, {grads->omp_w[0], 100, 100, 0, nullptr, 0}, "k_wgrad_c:node")) != SPW_OK) return rc;
@@ -431,7 +438,7 @@ int backward_csl(const SpwParams* w, const SpwGraph* g, const float* obj, const 
   if ((rc = run_wgrad_c(st, 4 * n, cview(ws + L.U, r5, 0, 0), kDP, nullptr, 0, cview(ws + L.T, r4, 0, 0), kDP, partN, {grads->omp_w[1], 101, 0, 1, grads->omp_b[1], 1}, "k_wgrad_c:node")) != SPW_OK) return rc;
   {
     const int nw = (n + csl::kSkinnyRows - 1) / csl::kSkinnyRows;
-    SPW_KLAUNCH("k_skinny_c", csl::k_skinny_c<2>, dim3((nw + 7) / 8), dim3(256), 0, st, n, (const float*)U5.p, U5.slab, csl::kQP, 104, (const int32_t*)nullptr,
+    SPW_KLAUNCH_PDL("k_skinny_c", csl::k_skinny_c<2>, dim3((nw + 7) / 8), dim3(256), 0, st, n, (const float*)U5.p, U5.slab, csl::kQP, 104, (const int32_t*)nullptr,
                 (const int32_t*)nullptr, (const float*)nullptr, dlogits, ws + L.part0);
     launch_reduce(st, ws + L.part0, nw, 104, 1, 0, 0, kDP, 1, {grads->omp_w[1], 101, 0, 0, grads->omp_b[1], 0});
   }
@@ -447,7 +454,7 @@ int backward_csl(const SpwParams* w, const SpwGraph* g, const float* obj, const 
     o.X = cview(ws + L.dQ, n, 0, 0); o.Y = cview(ws + L.dQ1, n, 0, 0); o.mulsrc = cview(ws + L.Q1, n, 0, 0);
     if ((rc = run_lin_c(st, ws, L, n, o)) != SPW_OK) return rc;
     const int nw = (n + csl::kSkinnyRows - 1) / csl::kSkinnyRows;
-    SPW_KLAUNCH("k_skinny_c", csl::k_skinny_c<1>, dim3((nw + 7) / 8), dim3(256), 0, st, n, (const float*)(ws + L.dQ1), (long long)n * 4, csl::kQP, 104,
+    SPW_KLAUNCH_PDL("k_skinny_c", csl::k_skinny_c<1>, dim3((nw + 7) / 8), dim3(256), 0, st, n, (const float*)(ws + L.dQ1), (long long)n * 4, csl::kQP, 104,
                 (const int32_t*)nullptr, (const int32_t*)nullptr, obj, (const float*)nullptr, ws + L.part0);
     launch_reduce(st, ws + L.part0, nw, 3 * 104, 104, 0, 0, 2, kDP, {grads->om_w[0], 100, 0, 0, grads->om_b[0], 0});
   }
@@ -472,7 +479,7 @@ int backward_csl(const SpwParams* w, const SpwGraph* g, const float* obj, const 
       dY = gout[i & 1];
     }
     const int nw = (E + csl::kSkinnyRows - 1) / csl::kSkinnyRows;
-    SPW_KLAUNCH("k_skinny_c", csl::k_skinny_c<0>, dim3((nw + 7) / 8), dim3(256), 0, st, E, (const float*)dY, (long long)E * 4, csl::kQE, kDEP, g->in_snd, g->in_rcv,
+    SPW_KLAUNCH_PDL("k_skinny_c", csl::k_skinny_c<0>, dim3((nw + 7) / 8), dim3(256), 0, st, E, (const float*)dY, (long long)E * 4, csl::kQE, kDEP, g->in_snd, g->in_rcv,
                 obj, (const float*)nullptr, ws + L.part0);
     launch_reduce(st, ws + L.part0, nw, 3 * kDEP, kDEP, 0, 0, 2, kDE, {grads->rm_w[0], 150, 0, 0, grads->rm_b[0], 0});
   } else {

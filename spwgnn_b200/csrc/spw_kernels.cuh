@@ -72,6 +72,8 @@ __global__ void __launch_bounds__(256) k_obj_enc0(const float* __restrict__ obj,
 }
 
 __global__ void __launch_bounds__(256) k_deg_to_float(const int32_t* __restrict__ in_off, int n, float* __restrict__ degf) {
+  pdl_trigger();
+  pdl_wait();
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x)
     degf[i] = (float)(in_off[i + 1] - in_off[i]);
 }
@@ -314,6 +316,8 @@ struct RedArgs {
 // Eight lanes per output element: lane g sums parts g, g+8, g+16, ... in order, then the eight sub-sums are combined
 // in a fixed order -- deterministic, and 8 independent load chains per element instead of one long dependent one.
 __global__ void __launch_bounds__(256) k_reduce_parts(RedArgs a) {
+  pdl_trigger();
+  pdl_wait();
   const int total = (a.Kin + 1) * a.N;
   const int g = threadIdx.x & 7;
   const int per_block = blockDim.x >> 3;

@@ -589,7 +589,8 @@ __device__ __forceinline__ void mbar_arrive_remote(uint64_t* bar, uint32_t cta) 
 // bounded wait with acquire at cluster scope (the arrivals come from both CTAs of the pair)
 __device__ __forceinline__ bool mbar_wait_cluster(uint64_t* bar, uint32_t parity) {
   const uint32_t addr = smem_u32(bar);
-  for (int it = 0; it < (1 << 22); ++it) {
+#pragma unroll 1
+  for (int it = 0; it < kWaitSpin; ++it) {
     uint32_t ok;
     asm volatile(
         "{\n\t"

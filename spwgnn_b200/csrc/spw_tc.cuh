@@ -115,10 +115,15 @@ __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
 }
 __device__ __forceinline__ void fence_mbar_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
 // bounded wait: returns false on timeout instead of hanging the GPU
+#ifdef SPW_WAIT_DEBUG
+constexpr int kWaitSpin = 1 << 16;      // development builds (tools/build_phase.sh -DSPW_WAIT_DEBUG): fail fast
+#else
+constexpr int kWaitSpin = 1 << 22;
+#endif
 __device__ __forceinline__ bool mbar_wait(uint64_t* bar, uint32_t parity) {
   const uint32_t a = smem_u32(bar);
 #pragma unroll 1
-  for (int it = 0; it < (1 << 22); ++it) {
+  for (int it = 0; it < kWaitSpin; ++it) {
     uint32_t ok;
     asm volatile(
         "{\n\t"

@@ -69,6 +69,9 @@ struct Scope {
 }  // namespace prof
 #define SPW_KLAUNCH(name, kern, grid, block, smem, st, ...) \
   do { prof::Scope _scope(name, st); SPW_LAUNCH(kern, grid, block, smem, st, __VA_ARGS__); } while (0)
+// programmatic dependent launch (spw_common.cuh): only for kernels that call pdl_trigger() / pdl_wait()
+#define SPW_KLAUNCH_PDL(name, kern, grid, block, smem, st, ...) \
+  do { prof::Scope _scope(name, st); SPW_LAUNCH_PDL(kern, grid, block, smem, st, __VA_ARGS__); } while (0)
 
 thread_local char g_err[512] = "";
 
@@ -376,7 +379,7 @@ void launch_reduce(cudaStream_t st, const float* part, int nparts, int part_stri
   r.part = part; r.nparts = nparts; r.part_stride = part_stride; r.src_ld = src_ld; r.TA = TA; r.TB = TB; r.Kin = Kin; r.N = N;
   r.dW = out.dW; r.dst_ld = out.dst_ld; r.dst_row0 = out.dst_row0; r.dst_col0 = out.dst_col0;
   r.db = out.db; r.db_off = out.db_off;
-  SPW_KLAUNCH("k_reduce_parts", k_reduce_parts, dim3(grid_for((int64_t)(Kin + 1) * N, 32)), dim3(256), 0, st, r);
+  SPW_KLAUNCH_PDL("k_reduce_parts", k_reduce_parts, dim3(grid_for((int64_t)(Kin + 1) * N, 32)), dim3(256), 0, st, r);
 }
 
 constexpr int kTW = 64;   // rows per tile of the node-level weight-gradient kernel
@@ -558,7 +561,7 @@ int launch_lin(cudaStream_t st, uint32_t epi, const csl::LinCArgs& a, const char
   if (a.N == NV && a.K == KV && epi == (uint32_t)(EPIV)) {                                                                \
     auto kern = csl::k_lin<NV, KV, (uint32_t)(EPIV)>;                                                                     \
     const size_t sm = csl::lin_smem(NV <= 112 ? 112 : 160, (KV + 7) / 8); set_smem(kern, sm);                             \
-    SPW_KLAUNCH(tag, kern, dim3(grid), dim3(csl::kThreadsC), sm, st, a);                                                   \
+    SPW_KLAUNCH_PDL(tag, kern, dim3(grid), dim3(csl::kThreadsC), sm, st, a);                                               \
     return SPW_OK;                                                                                                        \
   }
   SPW_LIN_TABLE(SPW_LIN_X)
