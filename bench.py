@@ -255,13 +255,19 @@ def run_configs(args, torch, dist, world, rank, dev, eng, comm):
         for _ in range(5):
             model.predict_towers(one)
         ms_pred, _ = timed_events(torch, None, 1, dev, lambda: model.predict_towers(one), 50)
+        gmax, model.engine.graph_max_edges = model.engine.graph_max_edges, 0      # the same call as ~60 direct launches
+        for _ in range(5):
+            model.predict_towers(one)
+        ms_pred_direct, _ = timed_events(torch, None, 1, dev, lambda: model.predict_towers(one), 50)
+        model.engine.graph_max_edges = gmax
         t0 = time.perf_counter()
         model.fit_towers(towers, labels, batch_size=32, epochs=1, validation_split=0.2, shuffle=True, verbose=0, seed=0)
         torch.cuda.synchronize()
         epoch_s = time.perf_counter() - t0
         out['C1'] = {'workload': '7-block towers (TowerCreator layout), contact relations: fit step on a batch of 32 (edge build + fwd + bwd + Adam, '
-                                 'host-synchronous like Keras), batch-1 predict through the public API, one epoch of fit(batch 32, split 0.2) on 1000 samples',
+                                 'host-synchronous like Keras), batch-1 predict through the public API (forward replayed from a CUDA graph per shape), one epoch of fit(batch 32, split 0.2) on 1000 samples',
                      'fit_step_ms': ms_fit / 20, 'fit_towers_per_sec': 32 * 20 / (ms_fit * 1e-3), 'predict_batch1_us': ms_pred / 50 * 1e3,
+                     'predict_batch1_us_without_cuda_graph': ms_pred_direct / 50 * 1e3,
                      'epoch_1000_samples_s': epoch_s, 'edges_in_batch32': b32.n_edges}
     else:
         out['C1'] = None

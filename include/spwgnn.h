@@ -164,6 +164,15 @@ int spw_tower_sums(const float* probs, const int32_t* node_off, int32_t n_towers
  * gradient staging.  The same workspace must be passed, untouched, to spw_backward.            */
 size_t spw_workspace_bytes(int32_t n_nodes, int32_t n_edges, int training);
 
+/* Where a TRAINING forward pass leaves the relu states the backward pass uses (parity tests read them back to evaluate the
+ * fp64 oracle on the same piecewise-linear branch: tests/test_gpu_parity.py::test_gradient_deviation_is_relu_kinks).
+ * out[0] = rows of a sign-bit array (byte-slab u8 [20][rows]: bit c & 7 of byte [c >> 3][row], rows in receiver-major edge
+ * order); out[1] = bytes from one array of a group to the next; byte offsets into the workspace of: out[2] the 4 encoder
+ * arrays (relu of rm layers 0-3, Networks.py:75), out[3] the 5 per-step arrays of rmp layer 0 (h1), out[4] of rmp layer 1
+ * (h2, Networks.py:84-87); out[5] = U, float column-slab [25 quads][5 n][4] (omp layer 0 after relu, step l = rows l n ..),
+ * out[6] = Q and out[7] = Q1, float column-slab [25][n][4] (om layers 1 and 0 after relu, Networks.py:76).               */
+int spw_saved_state_layout(int32_t n_nodes, int32_t n_edges, int64_t* out /*[8]*/);
+
 /* Forward (Networks.py:58-96).  obj [n_nodes][3] = [x, y, width]/170 (main.py:91).
  * logits [n_nodes] (channel 0 of the last object-propagator output, Networks.py:94);
  * probs  [n_nodes] sigmoid(logits) or NULL.  training: keep state for spw_backward.

@@ -73,11 +73,19 @@ def init_weights(seed=0, dtype=torch.float64, nonzero_bias=False):
 
 
 _PROBE = None     # when a list: every relu records min|pre-activation| (distance to the kink)
+_FORCED = None    # when a list of 0/1 tensors: relu layer k multiplies by _FORCED[k] instead (a fixed linear branch)
+_FLIPS = None     # ... and records (units whose state differs from relu's own, max |pre-activation| over them)
 
 
 def _relu(x):
     if _PROBE is not None and x.numel():
         _PROBE.append(float(x.detach().abs().min()))
+    if _FORCED is not None:
+        m = _FORCED.pop(0).to(x.dtype)
+        assert m.shape == x.shape, (m.shape, x.shape)
+        diff = (x.detach() > 0) != (m > 0)
+        _FLIPS.append((int(diff.sum()), float(x.detach().abs()[diff].max()) if bool(diff.any()) else 0.0))
+        return x * m
     return torch.relu(x)
 
 
@@ -286,6 +294,26 @@ def loss_and_grads_sparse(w, obj, snd, rcv, target, c_scale=None, q_scale=None):
     names = tensor_names()
     grads = torch.autograd.grad(loss, [ws[k] for k in names])
     return loss.detach(), probs.detach(), logits.detach(), dict(zip(names, grads))
+
+
+def loss_and_grads_forced(w, obj, snd, rcv, target, masks):
+    """loss_and_grads_sparse on the linear branch given by `masks` (21 tensors in the order the relu layers are evaluated:
+    rm 0-3, om 0-1, then rmp 0, rmp 1, omp 0 per step): every relu is replaced by a multiplication with its mask.  Where a
+    mask equals the unit's own state nothing changes; where it differs the pre-activation is within rounding of 0 if the
+    masks come from an fp32 evaluation of the same network, which `flips` lets the caller verify.
+    Returns (loss, logits, grads, flips) with flips = [(number of differing units, max |pre-activation| over them)] per layer."""
+    global _FORCED, _FLIPS
+    _FORCED, _FLIPS = [m for m in masks], []
+    try:
+        ws = {k: v.detach().clone().requires_grad_(True) for k, v in w.items()}
+        probs, logits = forward_sparse(ws, obj, snd, rcv, return_logits=True)
+        assert not _FORCED, 'unused masks'
+        loss = bce_keras(probs, target)
+        names = tensor_names()
+        grads = torch.autograd.grad(loss, [ws[k] for k in names])
+        return loss.detach(), logits.detach(), dict(zip(names, grads)), _FLIPS
+    finally:
+        _FORCED, _FLIPS = None, None
 
 
 def normalise_objects(boxes_raw, thr=REL_THRESHOLD):

@@ -32,7 +32,7 @@ class SpwGraph(C.Structure):
     ]
 
 
-EXPORTS = ['spw_version', 'spw_last_error', 'spw_launch_count', 'spw_profile', 'spw_profile_report', 'spw_ffma_peak', 'spw_tc_selftest', 'spw_tc2_selftest', 'spw_tc_linear', 'spw_csl_linear', 'spw_edges_count', 'spw_edges_fill', 'spw_sample_sizes', 'spw_sample_jenga', 'spw_sample_tower', 'spw_candidates_remove', 'spw_candidates_drop', 'spw_tower_sums', 'spw_workspace_bytes',
+EXPORTS = ['spw_version', 'spw_last_error', 'spw_launch_count', 'spw_profile', 'spw_profile_report', 'spw_ffma_peak', 'spw_tc_selftest', 'spw_tc2_selftest', 'spw_tc_linear', 'spw_csl_linear', 'spw_edges_count', 'spw_edges_fill', 'spw_sample_sizes', 'spw_sample_jenga', 'spw_sample_tower', 'spw_candidates_remove', 'spw_candidates_drop', 'spw_tower_sums', 'spw_workspace_bytes', 'spw_saved_state_layout',
            'spw_forward', 'spw_bce_grad', 'spw_backward']
 
 
@@ -89,6 +89,8 @@ class CApi:
         d.spw_tower_sums.argtypes = [vp, vp, i32, vp, vp, vp]
         d.spw_workspace_bytes.restype = C.c_size_t
         d.spw_workspace_bytes.argtypes = [i32, i32, C.c_int]
+        d.spw_saved_state_layout.restype = C.c_int
+        d.spw_saved_state_layout.argtypes = [i32, i32, C.POINTER(C.c_int64)]
         d.spw_forward.restype = C.c_int
         d.spw_forward.argtypes = [C.POINTER(SpwParams), C.POINTER(SpwGraph), vp, vp, vp, vp, C.c_size_t, C.c_int,
                                   C.c_float, C.c_uint64, vp]

@@ -562,14 +562,30 @@ __global__ void __launch_bounds__(256) k_gather_dsr_c(int n, int E, const int32_
     const int qd = (int)(idx / n), i = (int)(idx - (long long)qd * n);
     const int i0 = in_off[i], i1 = in_off[i + 1], o0 = out_off[i], o1 = out_off[i + 1];
     const float* src = DH1 + (long long)qd * es;
+    // fixed summation order (slot order); the loads of four relations are in flight together
     float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
-    for (int e = i0; e < i1; ++e) {
+    int e = i0;
+    for (; e + 4 <= i1; e += 4) {
+      const float4 v0 = *reinterpret_cast<const float4*>(src + (long long)e * 4), v1 = *reinterpret_cast<const float4*>(src + (long long)(e + 1) * 4);
+      const float4 v2 = *reinterpret_cast<const float4*>(src + (long long)(e + 2) * 4), v3 = *reinterpret_cast<const float4*>(src + (long long)(e + 3) * 4);
+      s.x = (((s.x + v0.x) + v1.x) + v2.x) + v3.x; s.y = (((s.y + v0.y) + v1.y) + v2.y) + v3.y;
+      s.z = (((s.z + v0.z) + v1.z) + v2.z) + v3.z; s.w = (((s.w + v0.w) + v1.w) + v2.w) + v3.w;
+    }
+    for (; e < i1; ++e) {
       const float4 v = *reinterpret_cast<const float4*>(src + (long long)e * 4);
       s.x += v.x; s.y += v.y; s.z += v.z; s.w += v.w;
     }
     *reinterpret_cast<float4*>(dR + (long long)qd * sr_slab + (long long)i * 4) = s;
     s = make_float4(0.f, 0.f, 0.f, 0.f);
-    for (int o = o0; o < o1; ++o) {
+    int o = o0;
+    for (; o + 4 <= o1; o += 4) {
+      const int p0 = out_pos[o], p1 = out_pos[o + 1], p2 = out_pos[o + 2], p3 = out_pos[o + 3];
+      const float4 v0 = *reinterpret_cast<const float4*>(src + (long long)p0 * 4), v1 = *reinterpret_cast<const float4*>(src + (long long)p1 * 4);
+      const float4 v2 = *reinterpret_cast<const float4*>(src + (long long)p2 * 4), v3 = *reinterpret_cast<const float4*>(src + (long long)p3 * 4);
+      s.x = (((s.x + v0.x) + v1.x) + v2.x) + v3.x; s.y = (((s.y + v0.y) + v1.y) + v2.y) + v3.y;
+      s.z = (((s.z + v0.z) + v1.z) + v2.z) + v3.z; s.w = (((s.w + v0.w) + v1.w) + v2.w) + v3.w;
+    }
+    for (; o < o1; ++o) {
       const float4 v = *reinterpret_cast<const float4*>(src + (long long)out_pos[o] * 4);
       s.x += v.x; s.y += v.y; s.z += v.z; s.w += v.w;
     }

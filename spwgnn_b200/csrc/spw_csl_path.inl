@@ -134,7 +134,7 @@ int make_csl_map(CUtensorMap* m, const csl::View& v, long long rows, int nquads,
 //   initialises them) and the caller reduces them later (the five step launches of rmp layer 1).
 int run_wgrad_c(cudaStream_t st, int M, const csl::View& X, int Kx, const float* rowscale, int rsmod, const csl::View& dY, int Ny, float* part,
                 const WgOut& out, const char* tag, const int32_t* gather_rcv = nullptr, const uint8_t* bits = nullptr, long long bits_rows = 0,
-                int first = 1, bool reduce = true, int* streams_out = nullptr) {
+                int first = 1, bool reduce = true, int* streams_out = nullptr, long long y_rows = 0) {
   if (M <= 0) return SPW_OK;
   csl::WgradCArgs a;
   memset(&a, 0, sizeof(a));
@@ -154,19 +154,23 @@ int run_wgrad_c(cudaStream_t st, int M, const csl::View& X, int Kx, const float*
   int rc;
   if ((rc = make_csl_map(&tmX, X, M, (Kx + 3) >> 2, nqx)) != SPW_OK) return rc;
   const bool pair = a.nmt == 2;                                 // two M-tiles: one CTA pair per row stream (k_wgrad_pair)
-  if (gather_rcv) tmY = tmX;
-  else if ((rc = make_csl_map(&tmY, dY, M, nqy, pair ? NB / 8 : nqy)) != SPW_OK) return rc;
+  if (gather_rcv) {                                              // node table [nqy quads][y_rows nodes x 4]: node-range copies of the pair kernel
+    static const bool no_tma = getenv("SPW_WG_NO_TMA_GATHER") != nullptr;      // A/B switch, and the way the tests reach the cp.async path
+    a.gather_tma = pair && y_rows > 0 && !no_tma;
+    if (!a.gather_tma) tmY = tmX;
+    else if ((rc = make_csl_map(&tmY, dY, y_rows, nqy, NB / 8)) != SPW_OK) return rc;
+  } else if ((rc = make_csl_map(&tmY, dY, M, nqy, pair ? NB / 8 : nqy)) != SPW_OK) return rc;
   const size_t smem = pair ? csl::wgrad_pair_smem(nqx, NB, 3) : csl::wgrad_c_smem(nqx, nqy, NB, 3);
 #define SPW_WG_LAUNCH(KERN, YM, NBV)                                                                                     \
   do { auto kern = csl::KERN<YM, NBV, 3>; set_smem(kern, smem);                                                           \
        SPW_KLAUNCH_PDL(tag, kern, dim3(streams * a.nmt), dim3(csl::kThreadsC), smem, st, tmX, tmY, a, nqx); } while (0)
+  if (gather_rcv && !pair) return fail(SPW_ERR_UNSUPPORTED, "run_wgrad_c: the gathered form exists for two M-tiles only (Kx = %d)", Kx);
   if (pair) {
     if (gather_rcv) SPW_WG_LAUNCH(k_wgrad_pair, 1, 160);
     else if (NB == 160) SPW_WG_LAUNCH(k_wgrad_pair, 0, 160);
     else SPW_WG_LAUNCH(k_wgrad_pair, 0, 112);
   } else {
-    if (gather_rcv) SPW_WG_LAUNCH(k_wgrad_c, 1, 160);
-    else if (NB == 160) SPW_WG_LAUNCH(k_wgrad_c, 0, 160);
+    if (NB == 160) SPW_WG_LAUNCH(k_wgrad_c, 0, 160);
     else SPW_WG_LAUNCH(k_wgrad_c, 0, 112);
   }
 #undef SPW_WG_LAUNCH
@@ -386,7 +390,7 @@ int backward_csl(const SpwParams* w, const SpwGraph* g, const float* obj, const 
       {   // dW2 += h1^T . d h2 with h1 kept by the forward pass and d h2 = relu'(h2) * d(sum h2)[receiver]
         const csl::View H1v = cview(ws + L.H1 + (size_t)l * ((size_t)kQ150 * E * 4 + 64), E, 0, 0);
         if ((rc = run_wgrad_c(st, E, H1v, kDE, nullptr, 0, dH, kDE, ws + L.partE, WgOut{nullptr, 0, 0, 0, nullptr, 0}, "k_wgrad_c:step", g->in_rcv, m2,
-                              L.bits_rows, l == SPW_N_STEPS - 1, false, &wstreams)) != SPW_OK) return rc;
+                              L.bits_rows, l == SPW_N_STEPS - 1, false, &wstreams, n)) != SPW_OK) return rc;
       }
       {
         csl::EdgeDgradCArgs t;

@@ -44,12 +44,13 @@ struct WgradCArgs {
   int nmt;                                                             // M-tiles: 1 (Kx + 1 <= 128) or 2
   float* part;                                                         // [gridDim.x / nmt][2][160][128]
   int first;                                                           // this launch initialises the partials (else it adds to them)
+  int gather_tma;                                                      // k_wgrad_pair, YMODE 1: node-range tensor copies allowed (0: always cp.async)
   float* poison;
 };
 
-// stage layout (floats): X quads [nqx][132] | Y quads [nqy][132] | RS [32] | bits [20][32] bytes; each region 128-byte aligned
+// stage layout (floats): X quads [nqx][132] | Y quads [nqy][132] | RS [32] | bits [20][32] bytes | RL [32] ints; each region 128-byte aligned
 __host__ __device__ constexpr int wg_up32(int f) { return (f + 31) & ~31; }
-__host__ __device__ constexpr int wg_stage_floats(int nqx, int nqy) { return wg_up32(nqx * kQPitch) + wg_up32(nqy * kQPitch) + 32 + 160; }
+__host__ __device__ constexpr int wg_stage_floats(int nqx, int nqy) { return wg_up32(nqx * kQPitch) + wg_up32(nqy * kQPitch) + 32 + 160 + 32; }
 
 // tile-mode TMA load of a 2-D box: coordinates {c0 (innermost: floats along the rows), c1 (quad)}
 __device__ __forceinline__ void tma_load_2d(void* sdst, const CUtensorMap* tm, int c0, int c1, uint64_t* bar) {
@@ -423,6 +424,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreadsC, 1) k_wgra
     constexpr int ngroups = NB / 8;
     const int y_off = wg_up32(nqx * kQPitch);
     const int rs_off = y_off + wg_up32(nqy * kQPitch);           // RS (virtual feature values) inside a stage
+    const int rl_off = rs_off + 32 + 160;                        // RL: staged dY row of each chunk row (YMODE 1)
     // A operand: word offset (within a stage) and row stride of this lane's feature; padding lanes read the zero word
     const int feat = f0 + L;
     int xa_off, xa_str;
@@ -430,13 +432,15 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreadsC, 1) k_wgra
     else if (feat == a.Kx) { xa_off = rs_off + 8 * sub; xa_str = 1; }
     else { xa_off = -1; xa_str = 0; }
     // B operand units of this thread: column n, row quad kc  ->  source word, bit word, destination
-    int yo[kUnits], bo[kUnits], ysh[kUnits], ystr[kUnits];
+    int yo[kUnits], bo[kUnits], ysh[kUnits], ystr[kUnits], kcu[kUnits];
 #pragma unroll
     for (int u = 0; u < kUnits; ++u) {
       const int idx = tid + u * kWorkers;
       const int n = idx % HB, kc = idx / HB;                       // column n0 + n of dY
-      if (idx < (kWgCh / 4) * HB && n0 + n < a.Ny) { yo[u] = y_off + (n >> 2) * kQPitch + 16 * kc + (n & 3); ystr[u] = 4; }
+      // YMODE 0: rows 4 kc .. 4 kc + 3 of the staged chunk; YMODE 1: the staged rows RL[4 kc ..] (a node of the staged range, or the row itself)
+      if (idx < (kWgCh / 4) * HB && n0 + n < a.Ny) { yo[u] = y_off + (n >> 2) * kQPitch + (YMODE == 1 ? 0 : 16 * kc) + (n & 3); ystr[u] = 4; }
       else { yo[u] = -1; ystr[u] = 0; }
+      kcu[u] = kc < kWgCh / 4 ? kc : 0;
       bo[u] = (rs_off + 32) * 4 + ((n0 + n) >> 3) * 32 + 4 * kc;   // byte offset of the 4 rows' relu bytes inside a stage
       ysh[u] = n & 7;
     }
@@ -470,19 +474,37 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreadsC, 1) k_wgra
           float* st = stages + (qi % NST) * stf;
           const long long r0 = row0_of(qi);
           const int nvalid = a.M - r0 >= kWgCh ? kWgCh : (a.M > r0 ? (int)(a.M - r0) : 0);
+          // YMODE 1: the rows are receiver-sorted, so the receivers of a chunk are an ascending range of nodes: when it spans at most 33
+          // nodes, ONE tensor copy of the node table [quads][33 nodes x 4] replaces 16 x 2 warp-wide cp.async gathers, and RL[row] =
+          // receiver - first receiver says where a row's values are; otherwise (isolated nodes in between) the rows are gathered
+          // one by one as before and RL[row] = row.
+          bool node_tma = false;
+          int r_first = 0;
+          if (YMODE == 1) {
+            r_first = __shfl_sync(0xffffffffu, r_idx, 0);
+            const int r_last = __shfl_sync(0xffffffffu, r_idx, nvalid > 0 ? nvalid - 1 : 0);
+            node_tma = a.gather_tma && nvalid > 0 && r_last - r_first < kQPitch / 4;
+          }
           if (tid == 0) {                                        // streamed arrays: one tensor copy each (rows past the end read as zero)
             uint64_t* bs = barS + (qi % NST);
-            mbar_arrive_expect_tx(bs, (uint32_t)((nqx + (YMODE == 0 ? nqy : 0)) * kQPitch * 4));
+            mbar_arrive_expect_tx(bs, (uint32_t)((nqx + ((YMODE == 0 || node_tma) ? nqy : 0)) * kQPitch * 4));
             tma_load_2d(st, &tmX, (int)(r0 * 4), qlo, bs);
             if (YMODE == 0) tma_load_2d(st + y_off, &tmY, (int)(r0 * 4), rank * nqy, bs);       // quads past the array read as zero
+            else if (node_tma) tma_load_2d(st + y_off, &tmY, r_first * 4, rank * nqy, bs);
           }
-          if (YMODE == 1) {                                      // gathered rows: thread -> (quad, row = lane), 16 bytes each
+          if (YMODE == 1) {
             const bool valid = lane < nvalid;
-            const float* src = a.dY + (long long)((a.y_col0 >> 2) + rank * nqy + warp) * a.y_slab + (long long)r_idx * 4;
-            float* dst = st + y_off + warp * kQPitch + lane * 4;
-            for (int qd = warp; qd < nqy && rank * nqy + qd < nqy_all; qd += kWorkers / 32) {
-              cp_async16_zfill(dst, src, valid);           // .cg: the L1-allocating form (.ca) measured slower here
-              src += (kWorkers / 32) * a.y_slab; dst += (kWorkers / 32) * kQPitch;
+            if (warp == 0) reinterpret_cast<int*>(st + rl_off)[lane] = node_tma ? (valid ? r_idx - r_first : 0) : lane;
+            // rows past the end: X is zero-filled by the tensor copy, the virtual ones feature (bias row) is switched off here, so
+            // whatever finite value such a row picks up on the dY side contributes nothing
+            if (warp == 2 && !a.rowscale) st[rs_off + lane] = valid ? 1.f : 0.f;
+            if (!node_tma) {                                     // gathered rows: thread -> (quad, row = lane), 16 bytes each
+              const float* src = a.dY + (long long)((a.y_col0 >> 2) + rank * nqy + warp) * a.y_slab + (long long)r_idx * 4;
+              float* dst = st + y_off + warp * kQPitch + lane * 4;
+              for (int qd = warp; qd < nqy && rank * nqy + qd < nqy_all; qd += kWorkers / 32) {
+                cp_async16_zfill(dst, src, valid);           // .cg: the L1-allocating form (.ca) measured slower here
+                src += (kWorkers / 32) * a.y_slab; dst += (kWorkers / 32) * kQPitch;
+              }
             }
             if (warp == 1) {                                     // relu bits of the chunk: 19 groups x 32 bytes, 16-byte pieces
               uint8_t* BT = reinterpret_cast<uint8_t*>(st + rs_off + 32);
@@ -549,10 +571,15 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreadsC, 1) k_wgra
             const float* py = yo[u] >= 0 ? st + yo[u] : zero;
             uint32_t h[4], l[4];
             uint32_t bw = 0xffffffffu;
-            if (YMODE == 1) bw = *reinterpret_cast<const uint32_t*>(stb + bo[u]) >> ysh[u];
+            int ro[4] = {0, 1, 2, 3};
+            if (YMODE == 1) {
+              bw = *reinterpret_cast<const uint32_t*>(stb + bo[u]) >> ysh[u];
+              const int4 rr = *reinterpret_cast<const int4*>(st + rl_off + 4 * kcu[u]);
+              ro[0] = rr.x; ro[1] = rr.y; ro[2] = rr.z; ro[3] = rr.w;
+            }
 #pragma unroll
             for (int i = 0; i < 4; ++i) {
-              float y = py[i * ystr[u]];
+              float y = py[ro[i] * ystr[u]];
               if (YMODE == 1) y = ((bw >> (8 * i)) & 1u) ? y : 0.f;
               split_fast(y, h[i], l[i]);
             }

@@ -18,6 +18,8 @@
 
 #include <atomic>
 #include <map>
+#include <mutex>
+#include <utility>
 #include <string>
 #include <vector>
 
@@ -245,8 +247,21 @@ int check_graph(const SpwGraph* g) {
   return SPW_OK;
 }
 
+// opt-in dynamic shared memory of a kernel: set once per (device, kernel, size) -- a small training step is ~140 launches and
+// the attribute call costs about as much as a launch
 template <class K>
 void set_smem(K kern, size_t bytes) {
+#ifndef SPW_EMU
+  static std::mutex mu;
+  static std::map<std::pair<int, const void*>, size_t> done;
+  int dev = 0;
+  cudaGetDevice(&dev);
+  const std::pair<int, const void*> key(dev, reinterpret_cast<const void*>(kern));
+  std::lock_guard<std::mutex> lock(mu);
+  auto it = done.find(key);
+  if (it != done.end() && it->second >= bytes) return;
+  done[key] = bytes;
+#endif
   cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
 }
 
@@ -861,6 +876,20 @@ size_t spw_workspace_bytes(int32_t n_nodes, int32_t n_edges, int training) {
   if (use_csl()) return make_layout_c(n_nodes, n_edges, training).total * sizeof(float);
 #endif
   return make_layout(n_nodes, n_edges, training).total * sizeof(float);
+}
+
+int spw_saved_state_layout(int32_t n_nodes, int32_t n_edges, int64_t* out) {
+  if (n_nodes < 0 || n_edges < 0 || !out) return fail(SPW_ERR_BAD_ARG, "spw_saved_state_layout: bad argument");
+#if SPW_USE_TC
+  if (use_csl()) {
+    const LayoutC L = make_layout_c(n_nodes, n_edges, 1);
+    out[0] = L.bits_rows; out[1] = (int64_t)L.bits_floats * 4;
+    out[2] = (int64_t)L.EB * 4; out[3] = (int64_t)L.M1 * 4; out[4] = (int64_t)L.M2 * 4;
+    out[5] = (int64_t)L.U * 4; out[6] = (int64_t)L.Q * 4; out[7] = (int64_t)L.Q1 * 4;
+    return SPW_OK;
+  }
+#endif
+  return fail(SPW_ERR_UNSUPPORTED, "spw_saved_state_layout: column-slab path only");
 }
 
 int spw_forward(const SpwParams* w, const SpwGraph* g, const float* obj, float* logits, float* probs, void* workspace,

@@ -4,9 +4,11 @@ Everything numerical happens inside libspwgnn.so (include/spwgnn.h); torch suppl
 memory, streams and (for data parallelism) torch.distributed.  No CPU fallback exists.
 """
 import ctypes
+import os
 
 import torch
 
+from ._capi import CApi
 from ._lib import lib, require_cuda, SpwError
 from .graph import TowerBatch, _stream_ptr
 from .params import ParamBuffer, FLAT_SIZE, STATS_TAIL
@@ -55,11 +57,60 @@ class Engine:
                                                 # backward of a training step cannot clobber saved state
         self._adam = None
         self._fwd = None
+        # small inference batches are launch-bound (~60 launches for microseconds of work: the reference's GUI loops predict
+        # one tower at a time, JengaBuilder.py:328): the forward pass of a given (towers, blocks, relations) shape is
+        # captured once as a CUDA graph over static buffers and replayed
+        self._graphs = {}
+        self.graph_max_edges = 0 if os.environ.get('SPW_NO_GRAPHS') else 8192
 
     # ---- forward ------------------------------------------------------------------------------
+    def _forward_graph(self, batch, want_probs):
+        """Inference forward of a small batch through a captured CUDA graph (one per shape, least recently used evicted)."""
+        api, n, E, T = self.api, batch.n_nodes, batch.n_edges, batch.n_towers
+        key = (T, n, E, bool(want_probs))
+        srcs = (batch.obj, batch.node_off, batch.in_off, batch.in_snd, batch.in_rcv, batch.out_off, batch.out_pos)
+        ent = self._graphs.get(key)
+        if ent is None:
+            if len(self._graphs) >= 64:
+                self._graphs.pop(next(iter(self._graphs)))
+            with torch.cuda.device(self.device):
+                st = [torch.empty_like(t) for t in srcs]
+                logits = torch.empty(max(n, 1), dtype=torch.float32, device=self.device)
+                probs = torch.empty(max(n, 1), dtype=torch.float32, device=self.device) if want_probs else None
+                ws = torch.empty(int(api.dll.spw_workspace_bytes(n, E, 0)) + 256, dtype=torch.uint8, device=self.device)
+                cg = CApi.graph(T, n, E, *[t.data_ptr() for t in st[1:]])
+                wp = self.params.c_struct()
+
+                def run():
+                    api.check(api.dll.spw_forward(ctypes.byref(wp), ctypes.byref(cg), st[0].data_ptr(), logits.data_ptr(),
+                                                  probs.data_ptr() if want_probs else None, ws.data_ptr(), ws.numel(), 0, 0.0, 0,
+                                                  _stream_ptr(self.device)))
+                for d, t in zip(st, srcs):
+                    d.copy_(t)
+                side = torch.cuda.Stream(self.device)
+                side.wait_stream(torch.cuda.current_stream(self.device))
+                with torch.cuda.stream(side):
+                    run()                                   # un-captured once: function attributes, lazy statics
+                torch.cuda.current_stream(self.device).wait_stream(side)
+                g = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(g):
+                    run()
+            ent = (g, st, logits, probs, ws, cg, wp)
+            self._graphs[key] = ent
+        else:
+            self._graphs[key] = self._graphs.pop(key)       # most recently used last
+        g, st, logits, probs = ent[0], ent[1], ent[2], ent[3]
+        with torch.cuda.device(self.device):
+            for d, t in zip(st, srcs):
+                d.copy_(t, non_blocking=True)
+            g.replay()
+            return logits[:n].clone(), (probs[:n].clone() if want_probs else None)   # the static buffers are reused by the next replay
+
     def forward(self, batch: TowerBatch, training=False, want_probs=True, dropout_rate=0.0, dropout_seed=0):
         """Per-block logits (and sigmoid probabilities) for a packed batch (Networks.py:58-96)."""
         api, n = self.api, batch.n_nodes
+        if not training and 0 < batch.n_edges <= self.graph_max_edges and n > 0 and not torch.cuda.is_current_stream_capturing():
+            return self._forward_graph(batch, want_probs)
         with torch.cuda.device(self.device):        # kernels launch on the current device: make it this engine's
             logits = torch.empty(max(n, 1), dtype=torch.float32, device=self.device)
             probs = torch.empty(max(n, 1), dtype=torch.float32, device=self.device) if want_probs else None
@@ -99,6 +150,32 @@ class Engine:
                                            dl.data_ptr(), ws.data_ptr(), ws.numel(), ctypes.byref(gp), rate,
                                            _stream_ptr(self.device)))
         return self.grads
+
+    def saved_relu_states(self):
+        """The relu states the last training forward left for the backward pass, in the oracle's order of relu layers
+        (Networks.py:75-76, then :84-90 per step): a list of 21 bool tensors -- rm layers 0..3 [E][150], om layers 0..1
+        [n][100], then per propagation step rmp layer 0, rmp layer 1 [E][150] and omp layer 0 [n][100].  Edge rows are in
+        receiver-major order (batch.in_snd / batch.in_rcv).  Parity tests evaluate the fp64 oracle on the same linear branch."""
+        if self._fwd is None:
+            raise SpwError('saved_relu_states without a training forward')
+        batch, ws, _, _ = self._fwd
+        n, E = batch.n_nodes, batch.n_edges
+        lay = (ctypes.c_int64 * 8)()
+        self.api.check(self.api.dll.spw_saved_state_layout(n, E, lay))
+        rows, stride, eb, m1, m2, u_off, q_off, q1_off = [int(v) for v in lay]
+
+        def bits(off):                      # byte-slab u8 [20][rows] -> bool [E][150]
+            b = ws[off:off + 20 * rows].view(20, rows)[:19, :E]
+            return ((b.unsqueeze(-1) >> torch.arange(8, device=b.device, dtype=torch.uint8)) & 1).bool().permute(1, 0, 2).reshape(E, 152)[:, :150]
+
+        def pos(off, rows_alloc, row0):     # float column-slab [25 quads][rows_alloc][4] -> bool [n][100]
+            a = ws[off:off + 25 * rows_alloc * 16].view(torch.float32).view(25, rows_alloc, 4)[:, row0:row0 + n]
+            return (a.permute(1, 0, 2).reshape(n, 100) > 0)
+
+        out = [bits(eb + i * stride) for i in range(4)] + [pos(q1_off, n, 0), pos(q_off, n, 0)]
+        for l in range(5):
+            out += [bits(m1 + l * stride), bits(m2 + l * stride), pos(u_off, 5 * n, l * n)]
+        return out
 
     def loss_and_grads(self, batch, target, count=None, dropout_rate=0.0, dropout_seed=0):
         """forward(training) + BCE + backward.  `count` = number of blocks the mean runs over
