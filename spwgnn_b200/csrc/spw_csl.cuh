@@ -330,11 +330,35 @@ __global__ void __launch_bounds__(kThreadsC, 1) k_lin(LinCArgs a) {
         const float* ap = nullptr; const float* mp = nullptr;
         if (EPI & EPI_ADD) ap = a.addend.p + (long long)((a.addend.col0 >> 2) + 2 * q) * a.addend.slab + r * 4;
         if (EPI & (EPI_MUL_POS | EPI_MUL_TANH)) mp = a.mulsrc.p + (long long)((a.mulsrc.col0 >> 2) + 2 * q) * a.mulsrc.slab + r * 4;
+        // the epilogue's own loads (addend, multiplier source, old Y of an accumulation) of group j + 1 are issued BEFORE group j is
+        // stored: the stores may alias them as far as the compiler knows, so left inside the loop every group paid a full L2 latency
+        constexpr bool kEpiLoads = (EPI & (EPI_ADD | EPI_MUL_POS | EPI_MUL_TANH | EPI_ACC)) != 0;
+        float4 ta[2][2], tm[2][2], ty[2][2];                       // [stage][quad of the group]
+        auto epi_issue = [&](int j, int sg) {
+          const int g = q + 4 * j;
+          if (!kEpiLoads || g >= ngroups || g >= nq8) return;      // warp-uniform
+          const bool h1 = 8 * g + 4 < N;
+          const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (EPI & EPI_ADD) {
+            ta[sg][0] = *reinterpret_cast<const float4*>(ap + (long long)(8 * j) * a.addend.slab);
+            ta[sg][1] = h1 ? *reinterpret_cast<const float4*>(ap + (long long)(8 * j + 1) * a.addend.slab) : z;
+          }
+          if (EPI & (EPI_MUL_POS | EPI_MUL_TANH)) {
+            tm[sg][0] = *reinterpret_cast<const float4*>(mp + (long long)(8 * j) * a.mulsrc.slab);
+            tm[sg][1] = h1 ? *reinterpret_cast<const float4*>(mp + (long long)(8 * j + 1) * a.mulsrc.slab) : z;
+          }
+          if (EPI & EPI_ACC) {
+            ty[sg][0] = *reinterpret_cast<const float4*>(yp + (long long)(8 * j) * ys);
+            ty[sg][1] = h1 ? *reinterpret_cast<const float4*>(yp + (long long)(8 * j + 1) * ys) : z;
+          }
+        };
+        epi_issue(0, 0);
 #pragma unroll
         for (int j = 0; j < GJ; ++j) {
           const int g = q + 4 * j;
+          if (j + 1 < GJ) epi_issue(j + 1, (j + 1) & 1);
           if (g >= ngroups || g >= nq8) continue;                  // warp-uniform
-          const int col = 8 * g;
+          const int col = 8 * g, sg = j & 1;
           const bool h1 = col + 4 < N;                             // the second quad holds valid columns
           float v[8];
 #pragma unroll
@@ -346,12 +370,9 @@ __global__ void __launch_bounds__(kThreadsC, 1) k_lin(LinCArgs a) {
             for (int e = 0; e < 8; ++e) v[e] = (EPI & EPI_ROWSCALE) ? fmaf(rs, bb[e], v[e]) : v[e] + bb[e];
           }
           if (EPI & EPI_ADD) {
-            const float4 t0 = *reinterpret_cast<const float4*>(ap + (long long)(8 * j) * a.addend.slab);
+            const float4 t0 = ta[sg][0], t1 = ta[sg][1];
             v[0] += t0.x; v[1] += t0.y; v[2] += t0.z; v[3] += t0.w;
-            if (h1) {
-              const float4 t1 = *reinterpret_cast<const float4*>(ap + (long long)(8 * j + 1) * a.addend.slab);
-              v[4] += t1.x; v[5] += t1.y; v[6] += t1.z; v[7] += t1.w;
-            }
+            if (h1) { v[4] += t1.x; v[5] += t1.y; v[6] += t1.z; v[7] += t1.w; }
           }
           if (EPI & EPI_RELU) {
 #pragma unroll
@@ -366,12 +387,8 @@ __global__ void __launch_bounds__(kThreadsC, 1) k_lin(LinCArgs a) {
             for (int e = 0; e < 8; ++e) v[e] = ((bin[j] >> e) & 1u) ? v[e] : 0.f;
           }
           if (EPI & (EPI_MUL_POS | EPI_MUL_TANH)) {
-            float m[8];
-            const float4 t0 = *reinterpret_cast<const float4*>(mp + (long long)(8 * j) * a.mulsrc.slab);
-            m[0] = t0.x; m[1] = t0.y; m[2] = t0.z; m[3] = t0.w;
-            float4 t1 = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (h1) t1 = *reinterpret_cast<const float4*>(mp + (long long)(8 * j + 1) * a.mulsrc.slab);
-            m[4] = t1.x; m[5] = t1.y; m[6] = t1.z; m[7] = t1.w;
+            const float4 t0 = tm[sg][0], t1 = tm[sg][1];
+            const float m[8] = {t0.x, t0.y, t0.z, t0.w, t1.x, t1.y, t1.z, t1.w};
 #pragma unroll
             for (int e = 0; e < 8; ++e) v[e] = (EPI & EPI_MUL_POS) ? (m[e] > 0.f ? v[e] : 0.f) : v[e] * (1.f - m[e] * m[e]);
           }
@@ -384,12 +401,9 @@ __global__ void __launch_bounds__(kThreadsC, 1) k_lin(LinCArgs a) {
             for (int e = 0; e < 8; ++e) v[e] *= a.post_scale;
           }
           if (EPI & EPI_ACC) {
-            const float4 t0 = *reinterpret_cast<const float4*>(yp + (long long)(8 * j) * ys);
+            const float4 t0 = ty[sg][0], t1 = ty[sg][1];
             v[0] += t0.x; v[1] += t0.y; v[2] += t0.z; v[3] += t0.w;
-            if (h1) {
-              const float4 t1 = *reinterpret_cast<const float4*>(yp + (long long)(8 * j + 1) * ys);
-              v[4] += t1.x; v[5] += t1.y; v[6] += t1.z; v[7] += t1.w;
-            }
+            if (h1) { v[4] += t1.x; v[5] += t1.y; v[6] += t1.z; v[7] += t1.w; }
           }
           if (col + 8 > N) {                                       // warp-uniform: the group straddles N
 #pragma unroll

@@ -191,6 +191,7 @@ __global__ void __launch_bounds__(kThreadsC, 1) k_edge_step_c(EdgeStepCArgs a) {
       s = 0; r = -1;
       if (i < cnt && e < a.E) { s = a.in_snd[e]; r = a.in_rcv[e]; }
     };
+    int2 io_built = make_int2(0, 0), io_cur = make_int2(0, 0);   // in_off[r], in_off[r + 1] of the row: requested a tile before the epilogue needs them
     // x = relu(A_e + S_s + R_r) for this thread's k-steps; ones column (150) picks up the bias row; h1 sign bits
     auto build_x = [&](int i, int s, int r) {
       const long long e = (long long)(blockIdx.x + i * gridDim.x) * kTM + row;
@@ -198,24 +199,32 @@ __global__ void __launch_bounds__(kThreadsC, 1) k_edge_step_c(EdgeStepCArgs a) {
       const float* ap = a.A + (long long)(2 * q) * es + (rv ? e : 0) * 4;
       const float* sp = a.S + (long long)(2 * q) * a.sr_slab + (long long)s * 4;
       const float* rp = a.R + (long long)(2 * q) * a.sr_slab + (long long)(rv ? r : 0) * 4;
+      // the loads of k-step j + 1 are issued BEFORE k-step j is consumed and stored (h1, sign bits): the stores may alias the loads as far
+      // as the compiler knows, so it never moves a load above them by itself, and every k-step paid a full memory latency (ncu: ~40 % of
+      // the worker samples on the first FADD after each load group)
+      float4 va[2][2], vs[2][2], vr[2][2];               // [stage][half of the k-step]
+      auto issue = [&](int j, int sg) {
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+          va[sg][h] = make_float4(0.f, 0.f, 0.f, 0.f); vs[sg][h] = va[sg][h]; vr[sg][h] = va[sg][h];
+          if (rv && q + 4 * j < NKS) {
+            va[sg][h] = *reinterpret_cast<const float4*>(ap + (long long)(8 * j + h) * es);
+            vs[sg][h] = *reinterpret_cast<const float4*>(sp + (long long)(8 * j + h) * a.sr_slab);
+            vr[sg][h] = *reinterpret_cast<const float4*>(rp + (long long)(8 * j + h) * a.sr_slab);
+          }
+        }
+      };
+      issue(0, 0);
 #pragma unroll
       for (int j = 0; j < KJ; ++j) {
         const int ks = q + 4 * j;
+        if (j + 1 < KJ) issue(j + 1, (j + 1) & 1);
         if (ks < NKS) {                                  // warp-uniform
-          float4 va[2], vs[2], vr[2];
+          const int sg = j & 1;
 #pragma unroll
           for (int h = 0; h < 2; ++h) {
-            va[h] = make_float4(0.f, 0.f, 0.f, 0.f); vs[h] = va[h]; vr[h] = va[h];
-            if (rv) {
-              va[h] = *reinterpret_cast<const float4*>(ap + (long long)(8 * j + h) * es);
-              vs[h] = *reinterpret_cast<const float4*>(sp + (long long)(8 * j + h) * a.sr_slab);
-              vr[h] = *reinterpret_cast<const float4*>(rp + (long long)(8 * j + h) * a.sr_slab);
-            }
-          }
-#pragma unroll
-          for (int h = 0; h < 2; ++h) {
-            x.v[j][4 * h] = relu_f(va[h].x + vs[h].x + vr[h].x); x.v[j][4 * h + 1] = relu_f(va[h].y + vs[h].y + vr[h].y);
-            x.v[j][4 * h + 2] = relu_f(va[h].z + vs[h].z + vr[h].z); x.v[j][4 * h + 3] = relu_f(va[h].w + vs[h].w + vr[h].w);
+            x.v[j][4 * h] = relu_f(va[sg][h].x + vs[sg][h].x + vr[sg][h].x); x.v[j][4 * h + 1] = relu_f(va[sg][h].y + vs[sg][h].y + vr[sg][h].y);
+            x.v[j][4 * h + 2] = relu_f(va[sg][h].z + vs[sg][h].z + vr[sg][h].z); x.v[j][4 * h + 3] = relu_f(va[sg][h].w + vs[sg][h].w + vr[sg][h].w);
           }
           if (ks == NKS - 1) { x.v[j][6] = rv ? 1.f : 0.f; x.v[j][7] = 0.f; }      // columns 150 (ones) and 151 (pad)
           if (a.H1 && rv) {                             // h1 for the backward pass (the weight gradient streams it)
@@ -242,6 +251,7 @@ __global__ void __launch_bounds__(kThreadsC, 1) k_edge_step_c(EdgeStepCArgs a) {
       load_idx(0, s_nx, r_nx);
       build_x(0, s_nx, r_nx);
       r_cur = r_nx;
+      if (r_cur >= 0) io_cur = make_int2(a.in_off[r_cur], a.in_off[r_cur + 1]);
       load_idx(1, s_nx, r_nx);
       store_lo<KJ>(x, lane_addr, colLo, q, NKS);
       store_hi<KJ>(x, lane_addr, colHi, q, NKS);
@@ -255,6 +265,7 @@ __global__ void __launch_bounds__(kThreadsC, 1) k_edge_step_c(EdgeStepCArgs a) {
       int r_built = -1;
       SPW_PH(7);
       if (has_next) {                                    // under the MMAs of tile i
+        if (r_nx >= 0) io_built = make_int2(a.in_off[r_nx], a.in_off[r_nx + 1]);
         build_x(i + 1, s_nx, r_nx);
         r_built = r_nx;
         load_idx(i + 2, s_nx, r_nx);                     // indices one tile ahead of the gathers that need them
@@ -288,7 +299,7 @@ __global__ void __launch_bounds__(kThreadsC, 1) k_edge_step_c(EdgeStepCArgs a) {
       const uint32_t far = __ballot_sync(0xffffffffu, dist >= 16) ? 5u : (__ballot_sync(0xffffffffu, dist >= 8) ? 4u : 3u);
       float* dst = nullptr; long long dstep = 0;         // tail lanes: where the 4-column pieces of the segment sum go
       if (tail && rv) {
-        const int i0 = a.in_off[r], i1 = a.in_off[r + 1];
+        const int i0 = io_cur.x, i1 = io_cur.y;
         const long long chunk = e >> 5;
         if (e - dist == i0 && e == i1 - 1) { dst = a.H2S + (long long)r * 4; dstep = a.h_slab; }
         else if (e - dist != i0) { dst = a.part_first + chunk * kN; dstep = 4; }
@@ -323,7 +334,7 @@ __global__ void __launch_bounds__(kThreadsC, 1) k_edge_step_c(EdgeStepCArgs a) {
           *reinterpret_cast<float4*>(dst + (long long)(2 * g + 1) * dstep) = make_float4(v[4], v[5], v[6], v[7]);
         }
       }
-      r_cur = r_built;
+      r_cur = r_built; io_cur = io_built;
       SPW_PH(5);                                         // p5: epilogue
     }
 #ifdef SPW_PHASE_TIMING
@@ -525,8 +536,10 @@ __global__ void __launch_bounds__(kThreadsC, 1) k_edge_dgrad_c(EdgeDgradCArgs a)
           float v[8];
 #pragma unroll
           for (int k = 0; k < 8; ++k) v[k] = ((b1[j] >> k) & 1u) ? __uint_as_float(d[j][k]) : 0.f;
-          *reinterpret_cast<float4*>(hp + (long long)(8 * j) * es) = make_float4(v[0], v[1], v[2], v[3]);
-          *reinterpret_cast<float4*>(hp + (long long)(8 * j + 1) * es) = make_float4(v[4], v[5], v[6], v[7]);
+          if (a.DH1) {                                   // null in the last processed step: nothing sums d h1 by sender / receiver there
+            *reinterpret_cast<float4*>(hp + (long long)(8 * j) * es) = make_float4(v[0], v[1], v[2], v[3]);
+            *reinterpret_cast<float4*>(hp + (long long)(8 * j + 1) * es) = make_float4(v[4], v[5], v[6], v[7]);
+          }
           if (FIRST) {
             *reinterpret_cast<float4*>(gp + (long long)(8 * j) * es) = make_float4(v[0], v[1], v[2], v[3]);
             *reinterpret_cast<float4*>(gp + (long long)(8 * j + 1) * es) = make_float4(v[4], v[5], v[6], v[7]);
@@ -653,7 +666,11 @@ __global__ void __launch_bounds__(256) k_skinny_c(int M, const float* __restrict
     for (int m = 16; m >= 1; m >>= 1) v += __shfl_xor_sync(0xffffffffu, v, m);
     return v;
   };
-  for (int qd = 0; qd < nquads; ++qd) {
+  // the column quads are dealt to gridDim.y blocks (each recomputes the two input features of its rows): with one block per 2048 rows the
+  // largest launch (rm layer 0, all relations) ran 8 warps per SM and was latency bound
+  const int qper = (nquads + (int)gridDim.y - 1) / (int)gridDim.y;
+  const int q_lo = (int)blockIdx.y * qper, q_hi = q_lo + qper < nquads ? q_lo + qper : nquads;
+  for (int qd = q_lo; qd < q_hi; ++qd) {
     float g0[4] = {0.f, 0.f, 0.f, 0.f}, g1[4] = {0.f, 0.f, 0.f, 0.f}, gb[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
     for (int k = 0; k < 8; ++k) {
@@ -678,7 +695,7 @@ __global__ void __launch_bounds__(256) k_skinny_c(int M, const float* __restrict
       }
     }
   }
-  if (MODE == 2) {
+  if (MODE == 2 && blockIdx.y == 0) {
     float sb = 0.f;
 #pragma unroll
     for (int k = 0; k < 8; ++k) sb += a0[k];

@@ -396,7 +396,7 @@ int backward_csl(const SpwParams* w, const SpwGraph* g, const float* obj, const 
         csl::EdgeDgradCArgs t;
         memset(&t, 0, sizeof(t));
         t.E = E; t.in_rcv = g->in_rcv; t.dH2S = dH.p; t.d_slab = dH.slab; t.Whi = ws + L.W2Thi; t.Wlo = ws + L.W2Tlo;
-        t.bits_h2 = m2; t.bits_h1 = m1; t.bits_rows = L.bits_rows; t.dA = ws + L.dA; t.DH1 = ws + L.DH1;
+        t.bits_h2 = m2; t.bits_h1 = m1; t.bits_rows = L.bits_rows; t.dA = ws + L.dA; t.DH1 = l > 0 ? ws + L.DH1 : nullptr;       // step 0 starts from p = 0: no d S / d R to form
         t.first = (l == SPW_N_STEPS - 1); t.poison = ws + L.dA;
         const int tgrid = etiles < num_sms() ? etiles : num_sms();
         if (t.first) {
@@ -442,7 +442,7 @@ int backward_csl(const SpwParams* w, const SpwGraph* g, const float* obj, const 
   if ((rc = run_wgrad_c(st, 4 * n, cview(ws + L.U, r5, 0, 0), kDP, nullptr, 0, cview(ws + L.T, r4, 0, 0), kDP, partN, {grads->omp_w[1], 101, 0, 1, grads->omp_b[1], 1}, "k_wgrad_c:node")) != SPW_OK) return rc;
   {
     const int nw = (n + csl::kSkinnyRows - 1) / csl::kSkinnyRows;
-    SPW_KLAUNCH_PDL("k_skinny_c", csl::k_skinny_c<2>, dim3((nw + 7) / 8), dim3(256), 0, st, n, (const float*)U5.p, U5.slab, csl::kQP, 104, (const int32_t*)nullptr,
+    SPW_KLAUNCH_PDL("k_skinny_c", csl::k_skinny_c<2>, dim3((nw + 7) / 8, 4), dim3(256), 0, st, n, (const float*)U5.p, U5.slab, csl::kQP, 104, (const int32_t*)nullptr,
                 (const int32_t*)nullptr, (const float*)nullptr, dlogits, ws + L.part0);
     launch_reduce(st, ws + L.part0, nw, 104, 1, 0, 0, kDP, 1, {grads->omp_w[1], 101, 0, 0, grads->omp_b[1], 0});
   }
@@ -458,7 +458,7 @@ int backward_csl(const SpwParams* w, const SpwGraph* g, const float* obj, const 
     o.X = cview(ws + L.dQ, n, 0, 0); o.Y = cview(ws + L.dQ1, n, 0, 0); o.mulsrc = cview(ws + L.Q1, n, 0, 0);
     if ((rc = run_lin_c(st, ws, L, n, o)) != SPW_OK) return rc;
     const int nw = (n + csl::kSkinnyRows - 1) / csl::kSkinnyRows;
-    SPW_KLAUNCH_PDL("k_skinny_c", csl::k_skinny_c<1>, dim3((nw + 7) / 8), dim3(256), 0, st, n, (const float*)(ws + L.dQ1), (long long)n * 4, csl::kQP, 104,
+    SPW_KLAUNCH_PDL("k_skinny_c", csl::k_skinny_c<1>, dim3((nw + 7) / 8, 4), dim3(256), 0, st, n, (const float*)(ws + L.dQ1), (long long)n * 4, csl::kQP, 104,
                 (const int32_t*)nullptr, (const int32_t*)nullptr, obj, (const float*)nullptr, ws + L.part0);
     launch_reduce(st, ws + L.part0, nw, 3 * 104, 104, 0, 0, 2, kDP, {grads->om_w[0], 100, 0, 0, grads->om_b[0], 0});
   }
@@ -483,7 +483,7 @@ int backward_csl(const SpwParams* w, const SpwGraph* g, const float* obj, const 
       dY = gout[i & 1];
     }
     const int nw = (E + csl::kSkinnyRows - 1) / csl::kSkinnyRows;
-    SPW_KLAUNCH_PDL("k_skinny_c", csl::k_skinny_c<0>, dim3((nw + 7) / 8), dim3(256), 0, st, E, (const float*)dY, (long long)E * 4, csl::kQE, kDEP, g->in_snd, g->in_rcv,
+    SPW_KLAUNCH_PDL("k_skinny_c", csl::k_skinny_c<0>, dim3((nw + 7) / 8, 4), dim3(256), 0, st, E, (const float*)dY, (long long)E * 4, csl::kQE, kDEP, g->in_snd, g->in_rcv,
                 obj, (const float*)nullptr, ws + L.part0);
     launch_reduce(st, ws + L.part0, nw, 3 * kDEP, kDEP, 0, 0, 2, kDE, {grads->rm_w[0], 150, 0, 0, grads->rm_b[0], 0});
   } else {

@@ -313,18 +313,25 @@ struct RedArgs {
   float* dW; int dst_ld, dst_row0, dst_col0;   // null: skip the matrix
   float* db; int db_off;                       // null: skip the bias row
 };
-// Eight lanes per output element: lane g sums parts g, g+8, g+16, ... in order, then the eight sub-sums are combined
-// in a fixed order -- deterministic, and 8 independent load chains per element instead of one long dependent one.
+// Eight sub-sums per output element: sub-sum g covers parts g, g+8, g+16, ... in order, then the eight are combined in a fixed order --
+// deterministic, and 8 independent load chains per element instead of one long dependent one.  On the GPU warp g of a block holds
+// sub-sum g and lane = element, elements taken in the order they lie in the partial (tensor-core layout: the feature index runs
+// fastest), so that a warp reads 128 contiguous bytes of every part; with eight LANES per element every lane read its own sector.
 __global__ void __launch_bounds__(256) k_reduce_parts(RedArgs a) {
   pdl_trigger();
   pdl_wait();
   const int total = (a.Kin + 1) * a.N;
-  const int g = threadIdx.x & 7;
-  const int per_block = blockDim.x >> 3;
-  for (int base = blockIdx.x * per_block; base < total; base += gridDim.x * per_block) {
-    const int idx = base + (threadIdx.x >> 3);
+#ifndef SPW_EMU
+  __shared__ float sub[8][32];
+  const int g = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  for (int base = blockIdx.x * 32; base < total; base += gridDim.x * 32) {
+    const int idx = base + lane;
     const bool in_range = idx < total;
-    const int k = in_range ? idx / a.N : 0, n = in_range ? idx - k * a.N : 0;
+    int k = 0, n = 0;
+    if (in_range) {
+      if (a.TA < 0) { n = idx / (a.Kin + 1); k = idx - n * (a.Kin + 1); }
+      else { k = idx / a.N; n = idx - k * a.N; }
+    }
     const bool want = in_range && !((k == a.Kin && !a.db) || (k < a.Kin && !a.dW));
     float s = 0.f;
     if (want) {
@@ -337,30 +344,48 @@ __global__ void __launch_bounds__(256) k_reduce_parts(RedArgs a) {
       } else {
         p = a.part + (size_t)k * a.src_ld + n;
       }
-#ifndef SPW_EMU
+#pragma unroll 4
       for (int c = g; c < a.nparts; c += 8) s += p[(size_t)c * a.part_stride];
-#else
-      if (g == 0) {   // host emulator: the same eight sub-sums and combination order, computed by one thread (shuffles are slow there)
-        float sub[8];
-        for (int gg = 0; gg < 8; ++gg) {
-          sub[gg] = 0.f;
-          for (int c = gg; c < a.nparts; c += 8) sub[gg] += p[(size_t)c * a.part_stride];
-        }
-        s = ((sub[0] + sub[4]) + (sub[2] + sub[6])) + ((sub[1] + sub[5]) + (sub[3] + sub[7]));
-      }
-#endif
     }
-#ifndef SPW_EMU
-    // fixed combination order: ((s0 + s4) + (s2 + s6)) + ((s1 + s5) + (s3 + s7))
-    s += __shfl_xor_sync(0xffffffffu, s, 4);
-    s += __shfl_xor_sync(0xffffffffu, s, 2);
-    s += __shfl_xor_sync(0xffffffffu, s, 1);
-#endif
-    if (want && g == 0) {
+    sub[g][lane] = s;
+    __syncthreads();
+    if (g == 0 && want) {
+      // fixed combination order: ((s0 + s4) + (s2 + s6)) + ((s1 + s5) + (s3 + s7))
+      s = ((sub[0][lane] + sub[4][lane]) + (sub[2][lane] + sub[6][lane])) + ((sub[1][lane] + sub[5][lane]) + (sub[3][lane] + sub[7][lane]));
       if (k < a.Kin) a.dW[(size_t)(a.dst_row0 + k) * a.dst_ld + a.dst_col0 + n] = s;
       else a.db[a.db_off + n] = s;
     }
+    __syncthreads();
   }
+#else
+  // host emulator: the same eight sub-sums and combination order, computed by one thread per element
+  const int g = threadIdx.x & 7;
+  const int per_block = blockDim.x >> 3;
+  for (int base = blockIdx.x * per_block; base < total; base += gridDim.x * per_block) {
+    const int idx = base + (threadIdx.x >> 3);
+    const bool in_range = idx < total;
+    const int k = in_range ? idx / a.N : 0, n = in_range ? idx - k * a.N : 0;
+    const bool want = in_range && !((k == a.Kin && !a.db) || (k < a.Kin && !a.dW));
+    if (!want || g != 0) continue;
+    const float* p;
+    if (a.TA > 0) {
+      const int ja = k / a.TA, ea = k - ja * a.TA, jb = n / a.TB, eb = n - jb * a.TB;
+      p = a.part + (size_t)(ea * a.TB + eb) * kThreads + (ja * 16 + jb);
+    } else if (a.TA < 0) {
+      p = k < 128 ? a.part + (size_t)n * 128 + k : a.part + (size_t)(160 + n) * 128 + (k - a.TB);
+    } else {
+      p = a.part + (size_t)k * a.src_ld + n;
+    }
+    float sub[8];
+    for (int gg = 0; gg < 8; ++gg) {
+      sub[gg] = 0.f;
+      for (int c = gg; c < a.nparts; c += 8) sub[gg] += p[(size_t)c * a.part_stride];
+    }
+    const float s = ((sub[0] + sub[4]) + (sub[2] + sub[6])) + ((sub[1] + sub[5]) + (sub[3] + sub[7]));
+    if (k < a.Kin) a.dW[(size_t)(a.dst_row0 + k) * a.dst_ld + a.dst_col0 + n] = s;
+    else a.db[a.db_off + n] = s;
+  }
+#endif
 }
 
 // =================================================================================================
