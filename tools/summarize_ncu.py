@@ -20,8 +20,8 @@ STEPS_IN_RUN = 4        # bench.py --steps 1 --warmup 3 (+ 1 profiled step that 
 
 def tag_of(name):
     """bench.py's profile tag of a demangled / base kernel name."""
-    if 'k_wgrad_c' in name:
-        return 'k_wgrad_c'
+    if 'k_wgrad_c' in name or 'k_wgrad_pair' in name:
+        return 'k_wgrad_pair' if 'k_wgrad_pair' in name else 'k_wgrad_c'
     for k in ('k_edge_step_c', 'k_edge_dgrad_c', 'k_lin', 'k_gather_dsr_c', 'k_reduce_parts', 'k_skinny_c', 'k_seg_fix_c', 'k_edge_enc0_c'):
         if k in name:
             return k
@@ -77,7 +77,8 @@ WANT = ['gpu__time_duration.sum', 'dram__bytes_read.sum', 'dram__bytes_write.sum
         'launch__block_size', 'launch__shared_mem_per_block_dynamic', 'l1tex__t_sector_hit_rate.pct', 'lts__t_sector_hit_rate.pct',
         'l1tex__data_pipe_lsu_wavefronts_mem_shared.sum', 'l1tex__data_bank_conflicts_pipe_lsu_mem_shared.sum']
 BENCH_TAG = {  # full-capture kernel -> bench.py profile tag
-    'k_wgrad_c<1,': 'k_wgrad_c:step', 'k_wgrad_c<0, 160': 'k_wgrad_c:enc', 'k_edge_step_c': 'k_edge_step_c',
+    'k_wgrad_pair<1,': 'k_wgrad_c:step', 'k_wgrad_pair<0, 160': 'k_wgrad_c:enc', 'k_wgrad_c<0, 112': 'k_wgrad_c:node', 'k_gather_dsr_c': 'k_gather_dsr_c',
+    'k_edge_step_c': 'k_edge_step_c',
     'k_edge_dgrad_c': 'k_edge_dgrad_c', 'k_lin<150, 150, 6153>': 'k_lin:enc_fwd', 'k_lin<150, 150, 640>': 'k_lin:enc_bwd', 'k_lin<100, 200': 'k_lin:node'}
 
 
@@ -85,7 +86,7 @@ def full():
     out = ['# ncu --set full --clock-control none --import-source on [--kernel-name-base demangled] -k regex:<kernel> -s 3 -c 1 python bench.py --steps 1 --warmup 3 --no-configs',
            '# one launch per kernel of the C2 training step; the .ncu-rep files are not committed (binary); numbers per launch', '']
     kern = {}
-    for raw in sorted(glob.glob('gpurun_out/raw_%s*_*.csv' % tag)):
+    for raw in sorted(glob.glob('gpurun_out/raw_%s_*.csv' % tag)):
         rows = list(csv.reader(open(raw)))
         if len(rows) < 3:
             continue
