@@ -4,6 +4,7 @@
 #pragma once
 #ifndef SPW_EMU
 #include "spw_csl.cuh"
+#include <type_traits>
 
 namespace spw {
 namespace csl {
@@ -296,7 +297,7 @@ __global__ void __launch_bounds__(kThreadsC, 1) k_edge_step_c(EdgeStepCArgs a) {
       const bool head = lane == 0 || r != r_prev, tail = lane == 31 || r != r_next;
       const uint32_t hm = __ballot_sync(0xffffffffu, head);
       const int dist = lane - (31 - __clz(hm & (0xffffffffu >> (31 - lane))));     // rows since the head of this lane's segment
-      const uint32_t far = __ballot_sync(0xffffffffu, dist >= 16) ? 5u : (__ballot_sync(0xffffffffu, dist >= 8) ? 4u : 3u);
+      const bool far = __ballot_sync(0xffffffffu, dist >= 16) != 0u;             // warp-uniform: some segment is longer than 16 rows
       float* dst = nullptr; long long dstep = 0;         // tail lanes: where the 4-column pieces of the segment sum go
       if (tail && rv) {
         const int i0 = io_cur.x, i1 = io_cur.y;
@@ -305,35 +306,40 @@ __global__ void __launch_bounds__(kThreadsC, 1) k_edge_step_c(EdgeStepCArgs a) {
         else if (e - dist != i0) { dst = a.part_first + chunk * kN; dstep = 4; }
         else { dst = a.part_last + chunk * kN; dstep = 4; }
       }
+      // The number of scan steps is a compile-time constant of the loop body (4: segments of at most 16 rows, else 5), chosen by ONE branch
+      // per tile: with a run-time step count every shuffle sat behind its own branch (200 per tile and warp) and the 40 shuffle -> add
+      // chains ran one after the other; straight-line code lets the eight values of a group travel together.
+      auto epilogue = [&](auto steps_tag) {
+        constexpr int STEPS = decltype(steps_tag)::value;
 #pragma unroll
-      for (int j = 0; j < GJ; ++j) {
-        const int g = q + 4 * j;
-        if (g >= NKS) continue;                          // warp-uniform: columns >= 152 do not exist
-        float v[8];
-        uint32_t b = 0u;
+        for (int j = 0; j < GJ; ++j) {
+          const int g = q + 4 * j;
+          if (g >= NKS) continue;                        // warp-uniform: columns >= 152 do not exist
+          float v[8];
+          uint32_t b = 0u;
 #pragma unroll
-        for (int k = 0; k < 8; ++k) {
-          const float pre = __uint_as_float(d[j][k]);    // bias already inside (ones column x bias row)
-          const bool on = (8 * g + k < kDE) && pre > 0.f;
-          v[k] = on ? pre : 0.f;
-          b |= on ? (1u << k) : 0u;
-        }
-        if (a.bits_h2 && rv) a.bits_h2[(long long)g * a.bits_rows + e] = (uint8_t)b;
+          for (int k = 0; k < 8; ++k) {
+            const float pre = __uint_as_float(d[j][k]);  // bias already inside (ones column x bias row)
+            const bool on = (8 * g + k < kDE) && pre > 0.f;
+            v[k] = on ? pre : 0.f;
+            b |= on ? (1u << k) : 0u;
+          }
+          if (a.bits_h2 && rv) a.bits_h2[(long long)g * a.bits_rows + e] = (uint8_t)b;
 #pragma unroll
-        for (int k = 0; k < 8; ++k) {
+          for (int st = 0; st < STEPS; ++st) {
 #pragma unroll
-          for (int st = 0; st < 5; ++st) {
-            if ((uint32_t)st < far) {                    // warp-uniform
+            for (int k = 0; k < 8; ++k) {
               const float t = __shfl_up_sync(0xffffffffu, v[k], 1 << st);
               if (dist >= (1 << st)) v[k] += t;
             }
           }
+          if (dst) {
+            *reinterpret_cast<float4*>(dst + (long long)(2 * g) * dstep) = make_float4(v[0], v[1], v[2], v[3]);
+            *reinterpret_cast<float4*>(dst + (long long)(2 * g + 1) * dstep) = make_float4(v[4], v[5], v[6], v[7]);
+          }
         }
-        if (dst) {
-          *reinterpret_cast<float4*>(dst + (long long)(2 * g) * dstep) = make_float4(v[0], v[1], v[2], v[3]);
-          *reinterpret_cast<float4*>(dst + (long long)(2 * g + 1) * dstep) = make_float4(v[4], v[5], v[6], v[7]);
-        }
-      }
+      };
+      if (far) epilogue(std::integral_constant<int, 5>{}); else epilogue(std::integral_constant<int, 4>{});
       r_cur = r_built; io_cur = io_built;
       SPW_PH(5);                                         // p5: epilogue
     }
