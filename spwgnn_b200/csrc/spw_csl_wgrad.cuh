@@ -345,6 +345,16 @@ __device__ __forceinline__ void mbar_arrive_pair(uint64_t* bar, uint32_t cta) {
 // "read a zero word with stride 0" instead of predicates: the kernel was instruction-issue bound (ncu: 61 % issue-active).
 // tmX / tmY: 2-D tensor maps [quads][rows * 4] of the X and dY arrays (base = first row and first quad of the view), boxes of
 // [nqx_box][132] and [nqy][132] floats (launch code: run_wgrad_c).
+// local arrive (release at CTA scope) and "arrive when this thread's earlier cp.async copies have landed" (.noinc: counted in the
+// barrier's expected arrivals like an ordinary arrive)
+__device__ __forceinline__ void mbar_arrive_local(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void cp_async_mbar_arrive_noinc(uint64_t* bar) {
+  asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void regs_issuer32() { asm volatile("setmaxnreg.dec.sync.aligned.u32 32;" ::: "memory"); }
+
 template <int YMODE, int NB, int NST>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreadsC, 1) k_wgrad_pair(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmY, WgradCArgs a, int nqx) {
   SPW_DYN_SMEM(smem_raw);
@@ -367,14 +377,15 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreadsC, 1) k_wgra
   uint64_t* bars = reinterpret_cast<uint64_t*>(zero + 8);
   uint64_t* barF = bars; uint64_t* barT = bars + 2;
   uint64_t* barR = bars + 4;      // barR[2] (the leader's copy is used): the 2 x 16 worker warps of the pair have built a buffer
-  uint64_t* barS = bars + 6;      // barS[NST]: stage filled (bulk copies)
-  uint32_t* tptr = reinterpret_cast<uint32_t*>(barS + NST);
+  uint64_t* barS = bars + 6;      // barS[NST]: stage filled: the tensor copies' bytes + 2 arrivals of each lane of the producer warp
+  uint64_t* barE = barS + NST;    // barE[NST]: stage consumed: one arrival per worker warp
+  uint32_t* tptr = reinterpret_cast<uint32_t*>(barE + NST);
 
   pdl_trigger();
   if (warp == 0) tmem_alloc2(tptr, kTmemCols);
   if (tid == 32) {
     mbar_init(barF, 1); mbar_init(barF + 1, 1); mbar_init(barT, 1); mbar_init(barT + 1, 1); mbar_init(barR, 2 * (kWorkers / 32)); mbar_init(barR + 1, 2 * (kWorkers / 32));
-    for (int i = 0; i < NST; ++i) mbar_init(barS + i, 1);
+    for (int i = 0; i < NST; ++i) { mbar_init(barS + i, 1 + 2 * 32); mbar_init(barE + i, kWorkers / 32); }
     fence_mbar_init();
   }
   if (tid < 8) zero[tid] = 0.f;
@@ -393,7 +404,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreadsC, 1) k_wgra
 
   if (warp >= kWorkers / 32) {
     // ---------------- MMA issuer warp (and its three idle siblings) ----------------
-    regs_issuer();
+    regs_issuer32();
     constexpr uint32_t idesc = make_idesc_tf32(256, NB);
     bool ok = true;
     if (warp == kWorkers / 32 && rank == 0 && lane == 0)         // the leader's issuer thread issues for the pair
@@ -415,7 +426,76 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreadsC, 1) k_wgra
       mma2_commit_multicast(barF + buf);
       if (c == kCh - 1) mma2_commit_multicast(barT + (t & 1));
     }
-    if (!ok && lane == 0 && warp == kWorkers / 32) a.poison[0] = __int_as_float(0x7fc00000);
+    if (warp == kWorkers / 32 + 1) {
+      // ---------------- producer warp: fills the stage ring, up to NST chunks ahead of the workers ----------------
+      // (this used to be done by the worker warps between two chunks: ~100 instructions of index arithmetic, 1.1k of the 2.6k cycles
+      // of a chunk on every worker's critical path although the copies themselves are asynchronous)
+      const int y_off = wg_up32(nqx * kQPitch);
+      const int rs_off = y_off + wg_up32(nqy * kQPitch);
+      const int rl_off = rs_off + 32 + 160;
+      pdl_wait();
+      int slot = 0;
+      int r_nx = 0;                                              // YMODE 1: receiver of row (chunk, lane), loaded one chunk ahead of its use
+      if (YMODE == 1 && nq > 0) {
+        const long long r = row0_of(0) + lane;
+        if (r < a.M) r_nx = a.rcv[r];
+      }
+      for (int qi = 0; qi < nq; ++qi) {
+        if (qi >= NST && !mbar_wait(barE + slot, (uint32_t)(qi / NST - 1) & 1u)) ok = false;      // the workers are done with chunk qi - NST
+        float* st = stages + slot * stf;
+        uint64_t* bs = barS + slot;
+        const long long r0 = row0_of(qi);
+        const int nvalid = a.M - r0 >= kWgCh ? kWgCh : (a.M > r0 ? (int)(a.M - r0) : 0);
+        const bool valid = lane < nvalid;
+        // YMODE 1: the rows are receiver-sorted, so the receivers of a chunk are an ascending range of nodes: when it spans at most 33
+        // nodes, ONE tensor copy of the node table [quads][33 nodes x 4] brings the chunk's dY values, and RL[row] = receiver - first
+        // receiver says where a row's values are; otherwise (isolated nodes in between) the rows are gathered one by one and RL[row] = row.
+        bool node_tma = false;
+        int r_idx = 0, r_first = 0;
+        if (YMODE == 1) {
+          r_idx = r_nx;
+          if (qi + 1 < nq) {
+            const long long r = row0_of(qi + 1) + lane;
+            r_nx = r < a.M ? a.rcv[r] : 0;
+          }
+          r_first = __shfl_sync(0xffffffffu, r_idx, 0);
+          const int r_last = __shfl_sync(0xffffffffu, r_idx, nvalid > 0 ? nvalid - 1 : 0);
+          node_tma = a.gather_tma && nvalid > 0 && r_last - r_first < kQPitch / 4;
+        }
+        if (lane == 0) {                                         // streamed arrays: one tensor copy each (rows past the end read as zero)
+          mbar_arrive_expect_tx(bs, (uint32_t)((nqx + ((YMODE == 0 || node_tma) ? nqy : 0)) * kQPitch * 4));
+          tma_load_2d(st, &tmX, (int)(r0 * 4), qlo, bs);
+          if (YMODE == 0) tma_load_2d(st + y_off, &tmY, (int)(r0 * 4), rank * nqy, bs);         // quads past the array read as zero
+          else if (node_tma) tma_load_2d(st + y_off, &tmY, r_first * 4, rank * nqy, bs);
+        }
+        if (YMODE == 1) {
+          reinterpret_cast<int*>(st + rl_off)[lane] = node_tma ? (valid ? r_idx - r_first : 0) : lane;
+          // rows past the end: X is zero-filled by the tensor copy, the virtual ones feature (bias row) is switched off here, so
+          // whatever finite value such a row picks up on the dY side contributes nothing
+          if (!a.rowscale) st[rs_off + lane] = valid ? 1.f : 0.f;
+          if (!node_tma) {                                       // gathered rows: lane = row, 16 bytes per quad
+            const float* src = a.dY + (long long)((a.y_col0 >> 2) + rank * nqy) * a.y_slab + (long long)r_idx * 4;
+            float* dst = st + y_off + lane * 4;
+            for (int qd = 0; qd < nqy && rank * nqy + qd < nqy_all; ++qd) {
+              cp_async16_zfill(dst, src, valid);
+              src += a.y_slab; dst += kQPitch;
+            }
+          }
+          uint8_t* BT = reinterpret_cast<uint8_t*>(st + rs_off + 32);    // relu bits of the chunk: 19 groups x 32 bytes, 16-byte pieces
+          for (int i = lane; i < 2 * 19; i += 32)
+            cp_async16_zfill(reinterpret_cast<float*>(BT + (i >> 1) * 32 + 16 * (i & 1)),
+                             reinterpret_cast<const float*>(a.bits + (long long)(i >> 1) * a.bits_rows + r0 + 16 * (i & 1)), true);
+        }
+        if (a.rowscale) {
+          const long long r = r0 + lane;
+          cp_async4_zfill(st + rs_off + lane, a.rowscale + (valid ? (a.rsmod ? r % a.rsmod : r) : 0), valid);
+        }
+        cp_async_mbar_arrive_noinc(bs);                          // ... when this lane's copies have landed
+        mbar_arrive_local(bs);                                   // ... and its plain stores are published
+        if (++slot == NST) slot = 0;
+      }
+    }
+    if (!ok && lane == 0) a.poison[0] = __int_as_float(0x7fc00000);
   } else {
     // ---------------- worker warps ----------------
     regs_workers();
@@ -450,83 +530,17 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreadsC, 1) k_wgra
     for (int j = 0; j < 5; ++j)
 #pragma unroll
       for (int k = 0; k < 8; ++k) acc[j][k] = 0.f;
-    int r_idx = 0;                                               // YMODE 1: receiver of row (chunk, lane), one chunk ahead
     SPW_PH_DECL
 
-    // q = -(NST - 1) .. -1: fill the ring;  q = 0 .. nq - 1: chunk q;  q = nq: flush of the last tile only
+    // q = 0 .. nq - 1: chunk q;  q = nq: flush of the last tile only
     pdl_wait();
-    if (YMODE == 1 && nq > 0) {
-      const long long r = row0_of(0) + lane;
-      if (r < a.M) r_idx = a.rcv[r];
-    }
+    int sq = 0; uint32_t sph = 0;                                // ring slot of chunk q and the phase of its barriers
 #pragma unroll 1
-    for (int q = -(NST - 1); q <= nq; ++q) {
+    for (int q = 0; q <= nq; ++q) {
       SPW_PH(7);
-      if (q >= 0 && q < nq) {
-        if (YMODE == 1 || a.rowscale) cp_async_wait<NST - 2>();  // this thread's gathers of chunk q have landed
-        if (!mbar_wait(barS + (q % NST), (uint32_t)(q / NST) & 1u)) { failed = true; SPW_WDBG("barS", q); }   // ... and the bulk copies
-        nbar_sync(kBarWork, kWorkers);                           // everybody's; and chunk q - 1 is fully consumed
-      }
+      if (q < nq && !mbar_wait(barS + sq, sph)) { failed = true; SPW_WDBG("barS", q); }   // the stage of chunk q is filled
       SPW_PH(0);
-      {   // chunk qi = q + NST - 1 into its stage
-        const int qi = q + NST - 1;
-        if (qi < nq) {
-          float* st = stages + (qi % NST) * stf;
-          const long long r0 = row0_of(qi);
-          const int nvalid = a.M - r0 >= kWgCh ? kWgCh : (a.M > r0 ? (int)(a.M - r0) : 0);
-          // YMODE 1: the rows are receiver-sorted, so the receivers of a chunk are an ascending range of nodes: when it spans at most 33
-          // nodes, ONE tensor copy of the node table [quads][33 nodes x 4] replaces 16 x 2 warp-wide cp.async gathers, and RL[row] =
-          // receiver - first receiver says where a row's values are; otherwise (isolated nodes in between) the rows are gathered
-          // one by one as before and RL[row] = row.
-          bool node_tma = false;
-          int r_first = 0;
-          if (YMODE == 1) {
-            r_first = __shfl_sync(0xffffffffu, r_idx, 0);
-            const int r_last = __shfl_sync(0xffffffffu, r_idx, nvalid > 0 ? nvalid - 1 : 0);
-            node_tma = a.gather_tma && nvalid > 0 && r_last - r_first < kQPitch / 4;
-          }
-          if (tid == 0) {                                        // streamed arrays: one tensor copy each (rows past the end read as zero)
-            uint64_t* bs = barS + (qi % NST);
-            mbar_arrive_expect_tx(bs, (uint32_t)((nqx + ((YMODE == 0 || node_tma) ? nqy : 0)) * kQPitch * 4));
-            tma_load_2d(st, &tmX, (int)(r0 * 4), qlo, bs);
-            if (YMODE == 0) tma_load_2d(st + y_off, &tmY, (int)(r0 * 4), rank * nqy, bs);       // quads past the array read as zero
-            else if (node_tma) tma_load_2d(st + y_off, &tmY, r_first * 4, rank * nqy, bs);
-          }
-          if (YMODE == 1) {
-            const bool valid = lane < nvalid;
-            if (warp == 0) reinterpret_cast<int*>(st + rl_off)[lane] = node_tma ? (valid ? r_idx - r_first : 0) : lane;
-            // rows past the end: X is zero-filled by the tensor copy, the virtual ones feature (bias row) is switched off here, so
-            // whatever finite value such a row picks up on the dY side contributes nothing
-            if (warp == 2 && !a.rowscale) st[rs_off + lane] = valid ? 1.f : 0.f;
-            if (!node_tma) {                                     // gathered rows: thread -> (quad, row = lane), 16 bytes each
-              const float* src = a.dY + (long long)((a.y_col0 >> 2) + rank * nqy + warp) * a.y_slab + (long long)r_idx * 4;
-              float* dst = st + y_off + warp * kQPitch + lane * 4;
-              for (int qd = warp; qd < nqy && rank * nqy + qd < nqy_all; qd += kWorkers / 32) {
-                cp_async16_zfill(dst, src, valid);           // .cg: the L1-allocating form (.ca) measured slower here
-                src += (kWorkers / 32) * a.y_slab; dst += (kWorkers / 32) * kQPitch;
-              }
-            }
-            if (warp == 1) {                                     // relu bits of the chunk: 19 groups x 32 bytes, 16-byte pieces
-              uint8_t* BT = reinterpret_cast<uint8_t*>(st + rs_off + 32);
-              for (int i = lane; i < 2 * 19; i += 32)
-                cp_async16_zfill(reinterpret_cast<float*>(BT + (i >> 1) * 32 + 16 * (i & 1)),
-                                 reinterpret_cast<const float*>(a.bits + (long long)(i >> 1) * a.bits_rows + r0 + 16 * (i & 1)), true);
-            }
-          }
-          if (a.rowscale && warp == 2) {
-            const long long r = r0 + lane;
-            const bool valid = lane < nvalid;
-            cp_async4_zfill(st + rs_off + lane, a.rowscale + (valid ? (a.rsmod ? r % a.rsmod : r) : 0), valid);
-          }
-        }
-        if (YMODE == 1 || a.rowscale) cp_async_commit();
-        if (YMODE == 1 && qi + 1 < nq) {                         // receivers of the chunk after that one
-          const long long r = row0_of(qi + 1) + lane;
-          r_idx = r < a.M ? a.rcv[r] : 0;
-        }
-      }
       SPW_PH(1);
-      if (q < 0) continue;
       const int t = q / kCh, c = q % kCh, buf = q & 1;
       if ((c == 1 && t >= 1) || q == nq) {                       // D of the previous tile -> running sums (round-to-nearest adds)
         const int tf = q == nq ? my_tiles - 1 : t - 1;
@@ -550,7 +564,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreadsC, 1) k_wgra
         fence_after_sync();
       }
       SPW_PH(3);
-      const float* st = stages + (q % NST) * stf;
+      const float* st = stages + sq * stf;
       {   // ---- A = X^T: this lane's feature, this thread's 8 rows of the chunk as 8 TMEM columns
         const float* pa = xa_off >= 0 ? st + xa_off : zero;
         uint32_t h[8], l[8];
@@ -594,6 +608,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreadsC, 1) k_wgra
       fence_before_sync();
       __syncwarp();
       if (lane == 0) mbar_arrive_pair(barR + buf, 0);           // this warp's part of chunk q is in place (leader's barrier)
+      if (lane == 0) mbar_arrive_local(barE + sq);              // ... and it has read everything it needs from the stage
+      if (++sq == NST) { sq = 0; sph ^= 1u; }
       SPW_PH(6);
     }
 #ifdef SPW_PHASE_TIMING
@@ -601,7 +617,6 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreadsC, 1) k_wgra
       printf("k_wgrad_pair<%d> warp %d: wait copies %lld issue copies %lld flush %lld waitMMA %lld A %lld B %lld arrive %lld loop %lld (%d chunks)\n", YMODE, warp,
              ph_t[0], ph_t[1], ph_t[2], ph_t[3], ph_t[4], ph_t[5], ph_t[6], ph_t[7], nq);
 #endif
-    cp_async_wait<0>();
     {   // running sums -> per-CTA partial in global memory ([n][lane]: coalesced)
       float* pp = a.part + (size_t)stream * (2 * 160 * 128) + (size_t)mt * (160 * 128) + L;
 #pragma unroll
