@@ -750,3 +750,36 @@ def test_demolish_searches_match_sequential_predicts_and_oracle():
         seq_d[c] = float(sum(float(v[0]) for v in out[0]))
     assert np.abs(sums_d - seq_d).max() <= 1e-6 * np.abs(seq_d).max()
     assert idx_d == int(np.argmin(seq_d))
+
+
+def test_weight_gradient_row_gather_path_equals_node_range_copies(tmp_path):
+    """k_wgrad_pair stages the gathered dY operand of the edge step either as ONE node-range tensor copy per chunk (whenever the chunk's
+    receivers span at most 33 nodes: every named workload) or row by row with cp.async (isolated nodes in between).  The second path is
+    forced through the library's A/B switch in a fresh process; both must give the same gradients bit for bit."""
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    script = (
+        "import sys, numpy as np, torch\n"
+        "sys.path.insert(0, %r)\n"
+        "from spwgnn_b200.engine import Engine\n"
+        "from spwgnn_b200.graph import TowerBatch\n"
+        "from spwgnn_b200 import synth\n"
+        "eng = Engine('cuda:0', seed=3)\n"
+        "out = []\n"
+        "for kind, kw, cnt, fc in (('jenga', dict(n=10), 300, True), ('uniform', dict(lo=6, hi=32), 200, False)):\n"
+        "    towers = synth.make_towers(kind, cnt, 9, **kw)\n"
+        "    batch = TowerBatch.from_towers(towers, fully_connected=fc)\n"
+        "    tgt = torch.as_tensor((np.random.default_rng(2).random(batch.n_nodes) > 0.5).astype(np.float32)).cuda()\n"
+        "    eng.loss_and_grads(batch, tgt)\n"
+        "    out.append(eng.grads.flat.cpu().numpy().copy())\n"
+        "np.save(sys.argv[1], np.concatenate(out))\n" % root)
+    res = {}
+    for name, extra in (('tma', {}), ('rows', {'SPW_WG_NO_TMA_GATHER': '1'})):
+        env = dict(os.environ, **extra)
+        env.pop('SPW_WG_NO_TMA_GATHER', None) if not extra else None
+        path = str(tmp_path / (name + '.npy'))
+        subprocess.run([sys.executable, '-c', script, path], check=True, env=env, timeout=300)
+        res[name] = np.load(path)
+    assert np.isfinite(res['tma']).all() and np.abs(res['tma']).max() > 0
+    assert np.array_equal(res['tma'], res['rows'])
