@@ -74,6 +74,16 @@ constexpr size_t wgrad_pair_smem(int nqx, int NB, int nst) { return wgrad_c_smem
 // "read a zero word with stride 0" instead of predicates: the kernel was instruction-issue bound (ncu: 61 % issue-active).
 // tmX / tmY: 2-D tensor maps [quads][rows * 4] of the X and dY arrays (base = first row and first quad of the view), boxes of
 // [nqx_box][132] and [nqy][132] floats (launch code: run_wgrad_c).
+// local arrive (release at CTA scope) and "arrive when this thread's earlier cp.async copies have landed" (.noinc: counted in the
+// barrier's expected arrivals like an ordinary arrive)
+__device__ __forceinline__ void mbar_arrive_local(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void cp_async_mbar_arrive_noinc(uint64_t* bar) {
+  asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void regs_issuer32() { asm volatile("setmaxnreg.dec.sync.aligned.u32 32;" ::: "memory"); }
+
 template <int YMODE, int NB, int NST>
 __global__ void __launch_bounds__(kThreadsC, 1) k_wgrad_c(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmY, WgradCArgs a, int nqx) {
   SPW_DYN_SMEM(smem_raw);
@@ -90,14 +100,15 @@ __global__ void __launch_bounds__(kThreadsC, 1) k_wgrad_c(const __grid_constant_
   float* Bop = stages + NST * stf;                               // [2 buffers][hi | lo][bfl]
   float* zero = Bop + 4 * bfl;                                   // 8 zero words
   uint64_t* bars = reinterpret_cast<uint64_t*>(zero + 8);
-  uint64_t* barF = bars; uint64_t* barT = bars + 2; uint64_t* barS = bars + 4;      // barS[NST]: stage filled (bulk copies)
-  uint32_t* tptr = reinterpret_cast<uint32_t*>(barS + NST);
+  uint64_t* barF = bars; uint64_t* barT = bars + 2; uint64_t* barS = bars + 4;      // barS[NST]: stage filled (tensor copies + the producer's lanes)
+  uint64_t* barE = barS + NST;                                                      // barE[NST]: stage consumed (one arrival per worker warp)
+  uint32_t* tptr = reinterpret_cast<uint32_t*>(barE + NST);
 
   pdl_trigger();
   if (warp == 0) tmem_alloc(tptr, kTmemCols);
   if (tid == 32) {
     mbar_init(barF, 1); mbar_init(barF + 1, 1); mbar_init(barT, 1); mbar_init(barT + 1, 1);
-    for (int i = 0; i < NST; ++i) mbar_init(barS + i, 1);
+    for (int i = 0; i < NST; ++i) { mbar_init(barS + i, 1 + 2 * 32); mbar_init(barE + i, kWorkers / 32); }
     fence_mbar_init();
   }
   if (tid < 8) zero[tid] = 0.f;
@@ -115,7 +126,7 @@ __global__ void __launch_bounds__(kThreadsC, 1) k_wgrad_c(const __grid_constant_
 
   if (warp >= kWorkers / 32) {
     // ---------------- MMA issuer warp (and its three idle siblings) ----------------
-    regs_issuer();
+    regs_issuer32();
     constexpr uint32_t idesc = make_idesc_tf32(128, NB);
     if (warp == kWorkers / 32)
     for (int q = 0; q < nq; ++q) {
@@ -138,6 +149,35 @@ __global__ void __launch_bounds__(kThreadsC, 1) k_wgrad_c(const __grid_constant_
         if (c == kCh - 1) mma_commit(barT + (t & 1));
       }
       __syncwarp();
+    }
+    if (warp == kWorkers / 32 + 1) {
+      // ---------------- producer warp: fills the stage ring, up to NST chunks ahead of the workers (see k_wgrad_pair) ----------------
+      static_assert(YMODE == 0, "k_wgrad_c: streamed dY only (the gathered form is k_wgrad_pair's)");
+      const int y_off = wg_up32(nqx * kQPitch);
+      const int rs_off = y_off + wg_up32(nqy * kQPitch);
+      bool ok = true;
+      pdl_wait();
+      int slot = 0;
+      for (int qi = 0; qi < nq; ++qi) {
+        if (qi >= NST && !mbar_wait(barE + slot, (uint32_t)(qi / NST - 1) & 1u)) ok = false;      // the workers are done with chunk qi - NST
+        float* st = stages + slot * stf;
+        uint64_t* bs = barS + slot;
+        const long long r0 = row0_of(qi);
+        if (lane == 0) {                                         // one tensor copy per array (rows past the end read as zero)
+          mbar_arrive_expect_tx(bs, (uint32_t)((nqx + nqy) * kQPitch * 4));
+          tma_load_2d(st, &tmX, (int)(r0 * 4), qlo, bs);
+          tma_load_2d(st + y_off, &tmY, (int)(r0 * 4), 0, bs);
+        }
+        if (a.rowscale) {
+          const long long r = r0 + lane;
+          const bool valid = r < a.M;
+          cp_async4_zfill(st + rs_off + lane, a.rowscale + (valid ? (a.rsmod ? r % a.rsmod : r) : 0), valid);
+        }
+        cp_async_mbar_arrive_noinc(bs);
+        mbar_arrive_local(bs);
+        if (++slot == NST) slot = 0;
+      }
+      if (!ok && lane == 0) a.poison[0] = __int_as_float(0x7fc00000);
     }
   } else {
     // ---------------- worker warps ----------------
@@ -170,65 +210,17 @@ __global__ void __launch_bounds__(kThreadsC, 1) k_wgrad_c(const __grid_constant_
     for (int j = 0; j < 5; ++j)
 #pragma unroll
       for (int k = 0; k < 8; ++k) acc[j][k] = 0.f;
-    int r_idx = 0;                                               // YMODE 1: receiver of row (chunk, lane), one chunk ahead
     SPW_PH_DECL
 
-    // q = -(NST - 1) .. -1: fill the ring;  q = 0 .. nq - 1: chunk q;  q = nq: flush of the last tile only
+    // q = 0 .. nq - 1: chunk q;  q = nq: flush of the last tile only
     pdl_wait();
-    if (YMODE == 1 && nq > 0) {
-      const long long r = row0_of(0) + lane;
-      if (r < a.M) r_idx = a.rcv[r];
-    }
+    int sq = 0; uint32_t sph = 0;                                // ring slot of chunk q and the phase of its barriers
 #pragma unroll 1
-    for (int q = -(NST - 1); q <= nq; ++q) {
+    for (int q = 0; q <= nq; ++q) {
       SPW_PH(7);
-      if (q >= 0 && q < nq) {
-        if (YMODE == 1 || a.rowscale) cp_async_wait<NST - 2>();  // this thread's gathers of chunk q have landed
-        if (!mbar_wait(barS + (q % NST), (uint32_t)(q / NST) & 1u)) failed = true;   // ... and the bulk copies
-        nbar_sync(kBarWork, kWorkers);                           // everybody's; and chunk q - 1 is fully consumed
-      }
+      if (q < nq && !mbar_wait(barS + sq, sph)) failed = true;   // the stage of chunk q is filled
       SPW_PH(0);
-      {   // chunk qi = q + NST - 1 into its stage
-        const int qi = q + NST - 1;
-        if (qi < nq) {
-          float* st = stages + (qi % NST) * stf;
-          const long long r0 = row0_of(qi);
-          const int nvalid = a.M - r0 >= kWgCh ? kWgCh : (a.M > r0 ? (int)(a.M - r0) : 0);
-          if (tid == 0) {                                        // streamed arrays: one tensor copy each (rows past the end read as zero)
-            uint64_t* bs = barS + (qi % NST);
-            mbar_arrive_expect_tx(bs, (uint32_t)((nqx + (YMODE == 0 ? nqy : 0)) * kQPitch * 4));
-            tma_load_2d(st, &tmX, (int)(r0 * 4), qlo, bs);
-            if (YMODE == 0) tma_load_2d(st + y_off, &tmY, (int)(r0 * 4), 0, bs);
-          }
-          if (YMODE == 1) {                                      // gathered rows: thread -> (quad, row = lane), 16 bytes each
-            const bool valid = lane < nvalid;
-            const float* src = a.dY + (long long)((a.y_col0 >> 2) + warp) * a.y_slab + (long long)r_idx * 4;
-            float* dst = st + y_off + warp * kQPitch + lane * 4;
-            for (int qd = warp; qd < nqy; qd += kWorkers / 32) {
-              cp_async16_zfill(dst, src, valid);           // .cg: the L1-allocating form (.ca) measured slower here
-              src += (kWorkers / 32) * a.y_slab; dst += (kWorkers / 32) * kQPitch;
-            }
-            if (warp == 1) {                                     // relu bits of the chunk: 19 groups x 32 bytes, 16-byte pieces
-              uint8_t* BT = reinterpret_cast<uint8_t*>(st + rs_off + 32);
-              for (int i = lane; i < 2 * 19; i += 32)
-                cp_async16_zfill(reinterpret_cast<float*>(BT + (i >> 1) * 32 + 16 * (i & 1)),
-                                 reinterpret_cast<const float*>(a.bits + (long long)(i >> 1) * a.bits_rows + r0 + 16 * (i & 1)), true);
-            }
-          }
-          if (a.rowscale && warp == 2) {
-            const long long r = r0 + lane;
-            const bool valid = lane < nvalid;
-            cp_async4_zfill(st + rs_off + lane, a.rowscale + (valid ? (a.rsmod ? r % a.rsmod : r) : 0), valid);
-          }
-        }
-        if (YMODE == 1 || a.rowscale) cp_async_commit();
-        if (YMODE == 1 && qi + 1 < nq) {                         // receivers of the chunk after that one
-          const long long r = row0_of(qi + 1) + lane;
-          r_idx = r < a.M ? a.rcv[r] : 0;
-        }
-      }
       SPW_PH(1);
-      if (q < 0) continue;
       const int t = q / kCh, c = q % kCh, buf = q & 1;
       if ((c == 1 && t >= 1) || q == nq) {                       // D of the previous tile -> running sums (round-to-nearest adds)
         const int tf = q == nq ? my_tiles - 1 : t - 1;
@@ -252,7 +244,7 @@ __global__ void __launch_bounds__(kThreadsC, 1) k_wgrad_c(const __grid_constant_
         fence_after_sync();
       }
       SPW_PH(3);
-      const float* st = stages + (q % NST) * stf;
+      const float* st = stages + sq * stf;
       {   // ---- A = X^T: this lane's feature, this thread's 8 rows of the chunk as 8 TMEM columns
         const float* pa = xa_off >= 0 ? st + xa_off : zero;
         uint32_t h[8], l[8];
@@ -290,6 +282,9 @@ __global__ void __launch_bounds__(kThreadsC, 1) k_wgrad_c(const __grid_constant_
       fence_async_smem();
       fence_before_sync();
       nbar_arrive(kBarOps, kBarOpsCount);
+      __syncwarp();
+      if (lane == 0) mbar_arrive_local(barE + sq);              // this warp has read everything it needs from the stage
+      if (++sq == NST) { sq = 0; sph ^= 1u; }
       SPW_PH(6);
     }
 #ifdef SPW_PHASE_TIMING
@@ -297,7 +292,6 @@ __global__ void __launch_bounds__(kThreadsC, 1) k_wgrad_c(const __grid_constant_
       printf("k_wgrad_c<%d> warp %d: wait copies %lld issue copies %lld flush %lld waitMMA %lld A %lld B %lld arrive %lld loop %lld (%d chunks)\n", YMODE, warp,
              ph_t[0], ph_t[1], ph_t[2], ph_t[3], ph_t[4], ph_t[5], ph_t[6], ph_t[7], nq);
 #endif
-    cp_async_wait<0>();
     {   // running sums -> per-CTA partial in global memory ([n][lane]: coalesced)
       float* pp = a.part + (size_t)stream * (2 * 160 * 128) + (size_t)mt * (160 * 128) + L;
 #pragma unroll
@@ -345,16 +339,6 @@ __device__ __forceinline__ void mbar_arrive_pair(uint64_t* bar, uint32_t cta) {
 // "read a zero word with stride 0" instead of predicates: the kernel was instruction-issue bound (ncu: 61 % issue-active).
 // tmX / tmY: 2-D tensor maps [quads][rows * 4] of the X and dY arrays (base = first row and first quad of the view), boxes of
 // [nqx_box][132] and [nqy][132] floats (launch code: run_wgrad_c).
-// local arrive (release at CTA scope) and "arrive when this thread's earlier cp.async copies have landed" (.noinc: counted in the
-// barrier's expected arrivals like an ordinary arrive)
-__device__ __forceinline__ void mbar_arrive_local(uint64_t* bar) {
-  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
-}
-__device__ __forceinline__ void cp_async_mbar_arrive_noinc(uint64_t* bar) {
-  asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
-}
-__device__ __forceinline__ void regs_issuer32() { asm volatile("setmaxnreg.dec.sync.aligned.u32 32;" ::: "memory"); }
-
 template <int YMODE, int NB, int NST>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreadsC, 1) k_wgrad_pair(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmY, WgradCArgs a, int nqx) {
   SPW_DYN_SMEM(smem_raw);
