@@ -366,12 +366,7 @@ int backward_csl(const SpwParams* w, const SpwGraph* g, const float* obj, const 
       LinC o; o.tag = "k_lin:node"; o.id = T_V2PT; o.N = 100; o.K = 100; o.epi = csl::EPI_MUL_POS; o.X = Tl; o.Y = dU; o.mulsrc = Ul;
       if ((rc = run_lin_c(st, ws, L, n, o)) != SPW_OK) return rc;
     }
-    {   // dq_pre += (dUpre.V1a^T) * relu'(q), times 1/keep through the dropout on q
-      LinC o; o.tag = "k_lin:node"; o.id = T_V1AT; o.N = 100; o.K = 100;
-      o.epi = csl::EPI_MUL_POS | csl::EPI_SCALE | (l < SPW_N_STEPS - 1 ? csl::EPI_ACC : 0u);
-      o.X = dU; o.Y = cview(ws + L.dQ, n, 0, 0); o.mulsrc = cview(ws + L.Q, n, 0, 0); o.post_scale = inv_keep;
-      if ((rc = run_lin_c(st, ws, L, n, o)) != SPW_OK) return rc;
-    }
+    // (dq_pre, the gradient through the q part of omp layer 0, is the same linear map of every step's dUpre: one product of their sum, below)
     {   // dg_pre = (dUpre.V1b^T) * (1 - g^2)
       LinC o; o.tag = "k_lin:node"; o.id = T_V1BT; o.N = 100; o.K = 100; o.epi = csl::EPI_MUL_TANH; o.X = dU; o.Y = dG; o.mulsrc = Gl;
       if ((rc = run_lin_c(st, ws, L, n, o)) != SPW_OK) return rc;
@@ -436,6 +431,11 @@ int backward_csl(const SpwParams* w, const SpwGraph* g, const float* obj, const 
   //   rows 0..99 (V1a): q is the same in all five steps, so q^T (sum over the steps of dUpre): the sum lands in DP (free by now)
   SPW_KLAUNCH_PDL("k_sum_slots_c", csl::k_sum_slots_c, dim3(grid_for((int64_t)n * csl::kQP, 256)), dim3(256), 0, st, n, 5, csl::kQP, (const float*)(ws + L.dU), r5 * 4,
               ws + L.DP, (long long)n * 4);
+  {   // dq_pre = ((sum over the steps of dUpre).V1a^T) * relu'(q), times 1/keep through the dropout on q: V1a and relu'(q) do not depend on the step
+    LinC o; o.tag = "k_lin:node"; o.id = T_V1AT; o.N = 100; o.K = 100; o.epi = csl::EPI_MUL_POS | csl::EPI_SCALE;
+    o.X = cview(ws + L.DP, n, 0, 0); o.Y = cview(ws + L.dQ, n, 0, 0); o.mulsrc = cview(ws + L.Q, n, 0, 0); o.post_scale = inv_keep;
+    if ((rc = run_lin_c(st, ws, L, n, o)) != SPW_OK) return rc;
+  }
   if ((rc = run_wgrad_c(st, n, cview(ws + L.Q, n, 0, 0), kDP, nullptr, 0, cview(ws + L.DP, n, 0, 0), kDP, partN, {grads->omp_w[0], 100, 0, 0, grads->omp_b[0], 0}, "k_wgrad_c:node")) != SPW_OK) return rc;
   if ((rc = run_wgrad_c(st, 5 * n, cview(ws + L.GP, r5, 0, 0), 2 * kDP, nullptr, 0, dUall, kDP, partN, {grads->omp_w[0], 100, 100, 0, nullptr, 0}, "k_wgrad_c:node")) != SPW_OK) return rc;
   // omp layer 1: channels 1..100 from T (steps 1..4), channel 0 from the head
