@@ -12,9 +12,11 @@ struct LayoutC {
   size_t dU, dG, T, dS, dR, dH2S, DP, dQ, dQ1, dA, DH1, GB, partE, part0, partN;
   int slots, slotsGP;                     // per-step slots of U / S / R / H2S (5 in training, 1 otherwise) and of GP (5 / 2)
   long long bits_rows, bits_floats;       // rows (E rounded up to whole tiles) and floats of one sign-bit array
+  size_t part_stride, part0_stride;       // floats between the partial buffers of two weight-gradient jobs (partN[kPartJobs], part0[3])
   size_t total;
 };
 
+constexpr int kPartJobs = 11;            // 7 node-level + 4 relation-encoder weight gradients
 constexpr int kQ100 = 26, kQ150 = 38, kQ200 = 50;   // allocated column quads of 100 / 150 / 200-wide arrays
 
 LayoutC make_layout_c(int64_t n, int64_t E, int training) {
@@ -57,13 +59,16 @@ LayoutC make_layout_c(int64_t n, int64_t E, int training) {
     L.dQ1 = take((size_t)kQ100 * n * 4);
     L.dA = take(earr); L.DH1 = take(earr); L.GB = take(earr);
     L.partE = take((size_t)kMaxCtas * 2 * 160 * 128);
-    L.partN = take((size_t)kMaxCtas * 2 * 160 * 128);
+    L.part_stride = (size_t)kMaxCtas * 2 * 160 * 128;          // every weight gradient keeps its per-CTA partials until the ONE reduction launch
+    L.partN = take((size_t)kPartJobs * L.part_stride);
     const size_t nsk = (size_t)((E > n ? E : n) + csl::kSkinnyRows - 1) / csl::kSkinnyRows + 1;
-    L.part0 = take(nsk * 3 * kDEP);
+    L.part0_stride = nsk * 3 * kDEP;
+    L.part0 = take(3 * L.part0_stride);
   } else {
     L.X0 = L.X2 = L.A; L.X1 = L.C = take(earr);       // inference: the encoder ping-pongs between two buffers
     L.EB = L.M1 = L.M2 = 0; L.H1 = 0;
     L.dU = L.dG = L.T = L.dS = L.dR = L.dH2S = L.DP = L.dQ = L.dQ1 = L.dA = L.DH1 = L.GB = L.partE = L.part0 = L.partN = 0;
+    L.part_stride = L.part0_stride = 0;
   }
   L.total = off;
   return L;
@@ -348,7 +353,11 @@ int backward_csl(const SpwParams* w, const SpwGraph* g, const float* obj, const 
   int rc;
   const long long r5 = 5LL * n, r4 = 4LL * n;
   const int etiles = (E + kTM - 1) / kTM;
-  float* partN = ws + L.partN;
+  // every weight gradient keeps its own per-CTA partials; their fixed-order reductions run as ONE launch at the end of the pass
+  std::vector<RedArgs> red_jobs;
+  struct DeferGuard { DeferGuard(std::vector<RedArgs>* v) { t_deferred_reduces = v; } ~DeferGuard() { t_deferred_reduces = nullptr; } } defer_guard(&red_jobs);
+  int part_job = 0;
+  auto next_part = [&]() { return ws + L.partN + (size_t)(part_job++ % kPartJobs) * L.part_stride; };
 
   // head: dUpre^5 = dlogit (x) V2[:,0] * relu'
   const csl::View U5 = cview(ws + L.U, r5, 4LL * n, 0);
@@ -436,10 +445,10 @@ int backward_csl(const SpwParams* w, const SpwGraph* g, const float* obj, const 
     o.X = cview(ws + L.DP, n, 0, 0); o.Y = cview(ws + L.dQ, n, 0, 0); o.mulsrc = cview(ws + L.Q, n, 0, 0); o.post_scale = inv_keep;
     if ((rc = run_lin_c(st, ws, L, n, o)) != SPW_OK) return rc;
   }
-  if ((rc = run_wgrad_c(st, n, cview(ws + L.Q, n, 0, 0), kDP, nullptr, 0, cview(ws + L.DP, n, 0, 0), kDP, partN, {grads->omp_w[0], 100, 0, 0, grads->omp_b[0], 0}, "k_wgrad_c:node")) != SPW_OK) return rc;
-  if ((rc = run_wgrad_c(st, 5 * n, cview(ws + L.GP, r5, 0, 0), 2 * kDP, nullptr, 0, dUall, kDP, partN, {grads->omp_w[0], 100, 100, 0, nullptr, 0}, "k_wgrad_c:node")) != SPW_OK) return rc;
+  if ((rc = run_wgrad_c(st, n, cview(ws + L.Q, n, 0, 0), kDP, nullptr, 0, cview(ws + L.DP, n, 0, 0), kDP, next_part(), {grads->omp_w[0], 100, 0, 0, grads->omp_b[0], 0}, "k_wgrad_c:node")) != SPW_OK) return rc;
+  if ((rc = run_wgrad_c(st, 5 * n, cview(ws + L.GP, r5, 0, 0), 2 * kDP, nullptr, 0, dUall, kDP, next_part(), {grads->omp_w[0], 100, 100, 0, nullptr, 0}, "k_wgrad_c:node")) != SPW_OK) return rc;
   // omp layer 1: channels 1..100 from T (steps 1..4), channel 0 from the head
-  if ((rc = run_wgrad_c(st, 4 * n, cview(ws + L.U, r5, 0, 0), kDP, nullptr, 0, cview(ws + L.T, r4, 0, 0), kDP, partN, {grads->omp_w[1], 101, 0, 1, grads->omp_b[1], 1}, "k_wgrad_c:node")) != SPW_OK) return rc;
+  if ((rc = run_wgrad_c(st, 4 * n, cview(ws + L.U, r5, 0, 0), kDP, nullptr, 0, cview(ws + L.T, r4, 0, 0), kDP, next_part(), {grads->omp_w[1], 101, 0, 1, grads->omp_b[1], 1}, "k_wgrad_c:node")) != SPW_OK) return rc;
   {
     const int nw = (n + csl::kSkinnyRows - 1) / csl::kSkinnyRows;
     SPW_KLAUNCH_PDL("k_skinny_c", csl::k_skinny_c<2>, dim3((nw + 7) / 8, 4), dim3(256), 0, st, n, (const float*)U5.p, U5.slab, csl::kQP, 104, (const int32_t*)nullptr,
@@ -447,20 +456,20 @@ int backward_csl(const SpwParams* w, const SpwGraph* g, const float* obj, const 
     launch_reduce(st, ws + L.part0, nw, 104, 1, 0, 0, kDP, 1, {grads->omp_w[1], 101, 0, 0, grads->omp_b[1], 0});
   }
   // rmp layer 2 (W3, b3 scaled by in-degree)
-  if ((rc = run_wgrad_c(st, 5 * n, cview(ws + L.H2S, r5, 0, 0), kDE, ws + L.degf, n, cview(ws + L.dG, r5, 0, 0), kDP, partN, {grads->rmp_w[2], 100, 0, 0, grads->rmp_b[2], 0}, "k_wgrad_c:node")) != SPW_OK) return rc;
+  if ((rc = run_wgrad_c(st, 5 * n, cview(ws + L.H2S, r5, 0, 0), kDE, ws + L.degf, n, cview(ws + L.dG, r5, 0, 0), kDP, next_part(), {grads->rmp_w[2], 100, 0, 0, grads->rmp_b[2], 0}, "k_wgrad_c:node")) != SPW_OK) return rc;
   // rmp layer 0 rows 150..349 (W1b, W1c): X = p^{l} for steps 2..5
-  if ((rc = run_wgrad_c(st, 4 * n, cview(ws + L.GP, r5, n, 100), kDP, nullptr, 0, cview(ws + L.dS, r4, 0, 0), kDE, partN, {grads->rmp_w[0], 150, 150, 0, nullptr, 0}, "k_wgrad_c:node")) != SPW_OK) return rc;
-  if ((rc = run_wgrad_c(st, 4 * n, cview(ws + L.GP, r5, n, 100), kDP, nullptr, 0, cview(ws + L.dR, r4, 0, 0), kDE, partN, {grads->rmp_w[0], 150, 250, 0, nullptr, 0}, "k_wgrad_c:node")) != SPW_OK) return rc;
+  if ((rc = run_wgrad_c(st, 4 * n, cview(ws + L.GP, r5, n, 100), kDP, nullptr, 0, cview(ws + L.dS, r4, 0, 0), kDE, next_part(), {grads->rmp_w[0], 150, 150, 0, nullptr, 0}, "k_wgrad_c:node")) != SPW_OK) return rc;
+  if ((rc = run_wgrad_c(st, 4 * n, cview(ws + L.GP, r5, n, 100), kDP, nullptr, 0, cview(ws + L.dR, r4, 0, 0), kDE, next_part(), {grads->rmp_w[0], 150, 250, 0, nullptr, 0}, "k_wgrad_c:node")) != SPW_OK) return rc;
   // object encoder
-  if ((rc = run_wgrad_c(st, n, cview(ws + L.Q1, n, 0, 0), kDP, nullptr, 0, cview(ws + L.dQ, n, 0, 0), kDP, partN, {grads->om_w[1], 100, 0, 0, grads->om_b[1], 0}, "k_wgrad_c:node")) != SPW_OK) return rc;
+  if ((rc = run_wgrad_c(st, n, cview(ws + L.Q1, n, 0, 0), kDP, nullptr, 0, cview(ws + L.dQ, n, 0, 0), kDP, next_part(), {grads->om_w[1], 100, 0, 0, grads->om_b[1], 0}, "k_wgrad_c:node")) != SPW_OK) return rc;
   {
     LinC o; o.tag = "k_lin:node"; o.id = T_OM1T; o.N = 100; o.K = 100; o.epi = csl::EPI_MUL_POS;
     o.X = cview(ws + L.dQ, n, 0, 0); o.Y = cview(ws + L.dQ1, n, 0, 0); o.mulsrc = cview(ws + L.Q1, n, 0, 0);
     if ((rc = run_lin_c(st, ws, L, n, o)) != SPW_OK) return rc;
     const int nw = (n + csl::kSkinnyRows - 1) / csl::kSkinnyRows;
     SPW_KLAUNCH_PDL("k_skinny_c", csl::k_skinny_c<1>, dim3((nw + 7) / 8, 4), dim3(256), 0, st, n, (const float*)(ws + L.dQ1), (long long)n * 4, csl::kQP, 104,
-                (const int32_t*)nullptr, (const int32_t*)nullptr, obj, (const float*)nullptr, ws + L.part0);
-    launch_reduce(st, ws + L.part0, nw, 3 * 104, 104, 0, 0, 2, kDP, {grads->om_w[0], 100, 0, 0, grads->om_b[0], 0});
+                (const int32_t*)nullptr, (const int32_t*)nullptr, obj, (const float*)nullptr, ws + L.part0 + L.part0_stride);
+    launch_reduce(st, ws + L.part0 + L.part0_stride, nw, 3 * 104, 104, 0, 0, 2, kDP, {grads->om_w[0], 100, 0, 0, grads->om_b[0], 0});
   }
 
   // ---- edge-level weight gradients --------------------------------------------------------------
@@ -474,7 +483,7 @@ int backward_csl(const SpwParams* w, const SpwGraph* g, const float* obj, const 
     float* dY = ws + L.dA;
     float* gout[2] = {ws + L.DH1, ws + L.GB};
     for (int i = 0; i < 4; ++i) {
-      if ((rc = run_wgrad_c(st, E, cview(acts[i], E, 0, 0), kDE, nullptr, 0, cview(dY, E, 0, 0), kDE, ws + L.partE, {gw[i], 150, 0, 0, gb[i], 0}, "k_wgrad_c:enc")) != SPW_OK) return rc;
+      if ((rc = run_wgrad_c(st, E, cview(acts[i], E, 0, 0), kDE, nullptr, 0, cview(dY, E, 0, 0), kDE, next_part(), {gw[i], 150, 0, 0, gb[i], 0}, "k_wgrad_c:enc")) != SPW_OK) return rc;
       // data gradient of the layer: (dY . W^T) * relu'(layer input), times 1/keep through the dropout on c_e
       LinC o; o.tag = "k_lin:enc_bwd"; o.id = -1; o.Bhi = ws + L.ENCT + (size_t)(2 * i) * 24320; o.Blo = ws + L.ENCT + (size_t)(2 * i + 1) * 24320;
       o.N = 150; o.K = 150; o.epi = csl::EPI_MUL_BITS | csl::EPI_SCALE; o.X = cview(dY, E, 0, 0); o.Y = cview(gout[i & 1], E, 0, 0);
@@ -484,8 +493,8 @@ int backward_csl(const SpwParams* w, const SpwGraph* g, const float* obj, const 
     }
     const int nw = (E + csl::kSkinnyRows - 1) / csl::kSkinnyRows;
     SPW_KLAUNCH_PDL("k_skinny_c", csl::k_skinny_c<0>, dim3((nw + 7) / 8, 4), dim3(256), 0, st, E, (const float*)dY, (long long)E * 4, csl::kQE, kDEP, g->in_snd, g->in_rcv,
-                obj, (const float*)nullptr, ws + L.part0);
-    launch_reduce(st, ws + L.part0, nw, 3 * kDEP, kDEP, 0, 0, 2, kDE, {grads->rm_w[0], 150, 0, 0, grads->rm_b[0], 0});
+                obj, (const float*)nullptr, ws + L.part0 + 2 * L.part0_stride);
+    launch_reduce(st, ws + L.part0 + 2 * L.part0_stride, nw, 3 * kDEP, kDEP, 0, 0, 2, kDE, {grads->rm_w[0], 150, 0, 0, grads->rm_b[0], 0});
   } else {
     cudaMemsetAsync(grads->rmp_w[1], 0, 22500 * sizeof(float), st);
     cudaMemsetAsync(grads->rmp_b[1], 0, 150 * sizeof(float), st);
@@ -496,5 +505,6 @@ int backward_csl(const SpwParams* w, const SpwGraph* g, const float* obj, const 
       cudaMemsetAsync(grads->rm_b[i], 0, 150 * sizeof(float), st);
     }
   }
+  flush_reduces(st, red_jobs);
   return check_launch("spw_backward");
 }

@@ -317,9 +317,7 @@ struct RedArgs {
 // deterministic, and 8 independent load chains per element instead of one long dependent one.  On the GPU warp g of a block holds
 // sub-sum g and lane = element, elements taken in the order they lie in the partial (tensor-core layout: the feature index runs
 // fastest), so that a warp reads 128 contiguous bytes of every part; with eight LANES per element every lane read its own sector.
-__global__ void __launch_bounds__(256) k_reduce_parts(RedArgs a) {
-  pdl_trigger();
-  pdl_wait();
+__device__ __forceinline__ void reduce_parts_body(const RedArgs& a) {
   const int total = (a.Kin + 1) * a.N;
 #ifndef SPW_EMU
   __shared__ float sub[8][32];
@@ -387,6 +385,22 @@ __global__ void __launch_bounds__(256) k_reduce_parts(RedArgs a) {
   }
 #endif
 }
+__global__ void __launch_bounds__(256) k_reduce_parts(RedArgs a) {
+  pdl_trigger();
+  pdl_wait();
+  reduce_parts_body(a);
+}
+#ifndef SPW_EMU
+// every reduction of a backward pass in ONE launch (blockIdx.y = job): the fifteen small launches between the weight-gradient kernels
+// cost ~12 us each on the dependent-launch chain for ~4 us of memory traffic
+constexpr int kMaxRedJobs = 16;
+struct RedJobs { RedArgs j[kMaxRedJobs]; };
+__global__ void __launch_bounds__(256) k_reduce_multi(const __grid_constant__ RedJobs jobs) {
+  pdl_trigger();
+  pdl_wait();
+  reduce_parts_body(jobs.j[blockIdx.y]);
+}
+#endif
 
 // =================================================================================================
 // edge kernels

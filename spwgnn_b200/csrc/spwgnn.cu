@@ -388,14 +388,35 @@ void run_linear(cudaStream_t st, float* ws, const Layout& L, LinId id, int M, in
 // dW[Kin][N] (+ bias row) = X^T dY over M rows, reduced in fixed order into the Keras-layout gradient
 struct WgOut { float* dW; int dst_ld, dst_row0, dst_col0; float* db; int db_off; };
 
+// While a list is installed here (backward_csl), launch_reduce only records its job; flush_reduces launches them all at once.
+thread_local std::vector<RedArgs>* t_deferred_reduces = nullptr;
+
 void launch_reduce(cudaStream_t st, const float* part, int nparts, int part_stride, int src_ld, int TA, int TB, int Kin,
                    int N, const WgOut& out) {
   RedArgs r;
   r.part = part; r.nparts = nparts; r.part_stride = part_stride; r.src_ld = src_ld; r.TA = TA; r.TB = TB; r.Kin = Kin; r.N = N;
   r.dW = out.dW; r.dst_ld = out.dst_ld; r.dst_row0 = out.dst_row0; r.dst_col0 = out.dst_col0;
   r.db = out.db; r.db_off = out.db_off;
+  if (t_deferred_reduces) { t_deferred_reduces->push_back(r); return; }
   SPW_KLAUNCH_PDL("k_reduce_parts", k_reduce_parts, dim3(grid_for((int64_t)(Kin + 1) * N, 32)), dim3(256), 0, st, r);
 }
+
+#ifndef SPW_EMU
+void flush_reduces(cudaStream_t st, const std::vector<RedArgs>& jobs) {
+  for (size_t i0 = 0; i0 < jobs.size(); i0 += kMaxRedJobs) {
+    RedJobs rj;
+    memset(&rj, 0, sizeof(rj));
+    const int nj = (int)(jobs.size() - i0 < (size_t)kMaxRedJobs ? jobs.size() - i0 : (size_t)kMaxRedJobs);
+    int64_t most = 1;
+    for (int i = 0; i < nj; ++i) {
+      rj.j[i] = jobs[i0 + i];
+      const int64_t t = (int64_t)(rj.j[i].Kin + 1) * rj.j[i].N;
+      if (t > most) most = t;
+    }
+    SPW_KLAUNCH_PDL("k_reduce_parts", k_reduce_multi, dim3(grid_for(most, 32), nj), dim3(256), 0, st, rj);
+  }
+}
+#endif
 
 constexpr int kTW = 64;   // rows per tile of the node-level weight-gradient kernel
 
