@@ -102,13 +102,18 @@ __global__ void __launch_bounds__(kThreadsC, 1) k_wgrad_c(const __grid_constant_
   uint64_t* bars = reinterpret_cast<uint64_t*>(zero + 8);
   uint64_t* barF = bars; uint64_t* barT = bars + 2; uint64_t* barS = bars + 4;      // barS[NST]: stage filled (tensor copies + the producer's lanes)
   uint64_t* barE = barS + NST;                                                      // barE[NST]: stage consumed (one arrival per worker warp)
-  uint32_t* tptr = reinterpret_cast<uint32_t*>(barE + NST);
+  // barR[2]: the 16 worker warps have built operand buffer `buf`.  A phase-tracked mbarrier, not the bar.arrive / bar.sync pair of the
+  // pipelined kernels: without a CTA barrier per chunk a fast warp reaches chunk q + 1 (whose buffer is free once the MMAs of chunk
+  // q - 1 are done) while a slow one still builds chunk q, and a counting barrier would take its arrival for the slow warp's
+  uint64_t* barR = barE + NST;
+  uint32_t* tptr = reinterpret_cast<uint32_t*>(barR + 2);
 
   pdl_trigger();
   if (warp == 0) tmem_alloc(tptr, kTmemCols);
   if (tid == 32) {
     mbar_init(barF, 1); mbar_init(barF + 1, 1); mbar_init(barT, 1); mbar_init(barT + 1, 1);
     for (int i = 0; i < NST; ++i) { mbar_init(barS + i, 1 + 2 * 32); mbar_init(barE + i, kWorkers / 32); }
+    mbar_init(barR, kWorkers / 32); mbar_init(barR + 1, kWorkers / 32);
     fence_mbar_init();
   }
   if (tid < 8) zero[tid] = 0.f;
@@ -128,9 +133,10 @@ __global__ void __launch_bounds__(kThreadsC, 1) k_wgrad_c(const __grid_constant_
     // ---------------- MMA issuer warp (and its three idle siblings) ----------------
     regs_issuer32();
     constexpr uint32_t idesc = make_idesc_tf32(128, NB);
+    bool iss_ok = true;
     if (warp == kWorkers / 32)
     for (int q = 0; q < nq; ++q) {
-      nbar_sync(kBarOps, kBarOpsCount);
+      if (!mbar_wait(barR + (q & 1), (uint32_t)(q >> 1) & 1u)) iss_ok = false;   // the operands of chunk q are in tensor / shared memory
       fence_after_sync();
       if (lane == 0) {
         const int t = q / kCh, c = q % kCh, buf = q & 1;
@@ -150,6 +156,7 @@ __global__ void __launch_bounds__(kThreadsC, 1) k_wgrad_c(const __grid_constant_
       }
       __syncwarp();
     }
+    if (!iss_ok && lane == 0) a.poison[0] = __int_as_float(0x7fc00000);
     if (warp == kWorkers / 32 + 1) {
       // ---------------- producer warp: fills the stage ring, up to NST chunks ahead of the workers (see k_wgrad_pair) ----------------
       static_assert(YMODE == 0, "k_wgrad_c: streamed dY only (the gathered form is k_wgrad_pair's)");
@@ -281,9 +288,9 @@ __global__ void __launch_bounds__(kThreadsC, 1) k_wgrad_c(const __grid_constant_
       tmem_wait_st();
       fence_async_smem();
       fence_before_sync();
-      nbar_arrive(kBarOps, kBarOpsCount);
       __syncwarp();
-      if (lane == 0) mbar_arrive_local(barE + sq);              // this warp has read everything it needs from the stage
+      if (lane == 0) mbar_arrive_local(barR + buf);             // this warp's part of chunk q is in place
+      if (lane == 0) mbar_arrive_local(barE + sq);              // ... and it has read everything it needs from the stage
       if (++sq == NST) { sq = 0; sph ^= 1u; }
       SPW_PH(6);
     }

@@ -21,9 +21,14 @@ print('nodes', batch.n_nodes, 'edges', batch.n_edges, flush=True)
 tgt = torch.zeros(batch.n_nodes, device='cuda')
 ref = None
 bad = 0
+import time
+t_all = time.time()
 for it in range(steps):
+    t0 = time.time()
     stats = eng.loss_and_grads(batch, tgt)
     torch.cuda.synchronize()
+    if time.time() - t0 > 0.5:
+        print('step', it, 'took %.1f s' % (time.time() - t0), flush=True)
     g = eng.grads.flat.clone()
     if ref is None:
         ref = g
@@ -31,4 +36,4 @@ for it in range(steps):
     elif not torch.equal(g, ref):
         bad += 1
         print('step', it, 'differs: max abs', float((g - ref).abs().max()), 'finite', bool(torch.isfinite(g).all()), flush=True)
-print('steps', steps, 'mismatching', bad)
+print('steps', steps, 'mismatching', bad, 'seconds %.1f' % (time.time() - t_all))
