@@ -165,18 +165,18 @@ int run_wgrad_c(cudaStream_t st, int M, const csl::View& X, int Kx, const float*
     if (!a.gather_tma) tmY = tmX;
     else if ((rc = make_csl_map(&tmY, dY, y_rows, nqy, NB / 8)) != SPW_OK) return rc;
   } else if ((rc = make_csl_map(&tmY, dY, M, nqy, pair ? NB / 8 : nqy)) != SPW_OK) return rc;
-  const size_t smem = pair ? csl::wgrad_pair_smem(nqx, NB, 3) : csl::wgrad_c_smem(nqx, nqy, NB, 3);
-#define SPW_WG_LAUNCH(KERN, YM, NBV)                                                                                     \
-  do { auto kern = csl::KERN<YM, NBV, 3>; set_smem(kern, smem);                                                           \
+  const size_t smem = pair ? csl::wgrad_pair_smem(nqx, NB, 4) : csl::wgrad_c_smem(nqx, nqy, NB, 3);      // stage ring: 4 slots (pair) / 3
+#define SPW_WG_LAUNCH(KERN, YM, NBV, NSTV)                                                                                     \
+  do { auto kern = csl::KERN<YM, NBV, NSTV>; set_smem(kern, smem);                                                           \
        SPW_KLAUNCH_PDL(tag, kern, dim3(streams * a.nmt), dim3(csl::kThreadsC), smem, st, tmX, tmY, a, nqx); } while (0)
   if (gather_rcv && !pair) return fail(SPW_ERR_UNSUPPORTED, "run_wgrad_c: the gathered form exists for two M-tiles only (Kx = %d)", Kx);
   if (pair) {
-    if (gather_rcv) SPW_WG_LAUNCH(k_wgrad_pair, 1, 160);
-    else if (NB == 160) SPW_WG_LAUNCH(k_wgrad_pair, 0, 160);
-    else SPW_WG_LAUNCH(k_wgrad_pair, 0, 112);
+    if (gather_rcv) SPW_WG_LAUNCH(k_wgrad_pair, 1, 160, 4);
+    else if (NB == 160) SPW_WG_LAUNCH(k_wgrad_pair, 0, 160, 4);
+    else SPW_WG_LAUNCH(k_wgrad_pair, 0, 112, 4);
   } else {
-    if (NB == 160) SPW_WG_LAUNCH(k_wgrad_c, 0, 160);
-    else SPW_WG_LAUNCH(k_wgrad_c, 0, 112);
+    if (NB == 160) SPW_WG_LAUNCH(k_wgrad_c, 0, 160, 3);
+    else SPW_WG_LAUNCH(k_wgrad_c, 0, 112, 3);
   }
 #undef SPW_WG_LAUNCH
   if (reduce) launch_reduce(st, part, streams, (int)tc::kWgPartFloats, 0, -1, f1 > 0 ? f1 : 0, Kx, Ny, out);
